@@ -1,0 +1,121 @@
+/* legommenders_b200 — C ABI of the B200-native Legommenders hot path.
+ *
+ * The reference (Jyonn/Legommenders) is pure Python over PyTorch and has no FFI; every entry point below
+ * replaces the aten/library call(s) the reference makes at the cited file:line (paths relative to the
+ * reference root).  The Python host in legommenders_b200/ binds these with ctypes (see INTEGRATION.md for
+ * the stub a reference maintainer would add).
+ *
+ * Conventions: all pointers are DEVICE pointers owned by the caller; no allocation, no synchronisation;
+ * work is enqueued on `stream`; ids/masks are int64 (the reference's wire format, loader/resampler.py:134);
+ * floating point is fp32; row widths must be multiples of 4 floats (16-byte vector loads).  Every function
+ * returns 0 on success or a negative LK_ERR_* code; lk_last_error() returns the message for the calling thread.
+ */
+#ifndef LEGOMMENDERS_B200_H_
+#define LEGOMMENDERS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+const char* lk_version(void);
+const char* lk_last_error(void);
+/* 1 when the library was compiled for sm_100a and the current device is compute capability 10.x */
+int lk_device_ok(void);
+
+/* ---- (1) EmbeddingHub token gather — model/inputer/concat_inputer.py:105-113, simple_inputer.py:51-64,
+ *      loader/embedding_hub.py:378-385 (aten::embedding + mask multiply + add) ------------------------- */
+/* out[m,:] (+)= valid(m) ? table[ids[m],:] : 0, valid = mask ? mask[m]>0 : ids[m]>-1 */
+int lk_gather_rows(const int64_t* ids, const int64_t* mask, const float* table, float* out, int64_t M, int64_t E,
+                   int accumulate, cudaStream_t stream);
+/* gather + masked pooling over S tokens (model/operators/pooling_operator.py:46-56): mode 0 mean, 1 max, 2 sum */
+int lk_gather_pool(const int64_t* ids, const int64_t* mask, const float* table, float* out, int64_t N, int64_t S, int64_t E,
+                   int mode, cudaStream_t stream);
+/* backward of the gather for trainable tables (autograd of aten::embedding): sorted-index segmented
+ * scatter-add, deterministic.  dtable[ids[p],:] (+)= scale[p] * src[p / row_div,:] for valid p */
+size_t lk_scatter_add_workspace_bytes(int64_t P, int64_t V, int64_t E);
+int lk_scatter_add_sorted(const int64_t* ids, const int64_t* mask, const float* src, const float* scale, int64_t row_div,
+                          float* dtable, int64_t P, int64_t V, int64_t E, int accumulate, void* workspace,
+                          size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- dense contractions — nn.Linear (loader/embedding_hub.py:95-96, model/operators/attention_operator.py:56,
+ *      cnn_operator.py:62, model/common/attention.py:17-19), MHA in/out projections (attention_operator.py:32-37)
+ *      act: 0 none, 1 tanh, 2 relu; rowmask (nullable) zeroes rows with mask<=0 after the activation */
+int lk_linear_fwd(const float* X, const float* W, const float* bias, const int64_t* rowmask, float* Y, int64_t M, int64_t N,
+                  int64_t K, int act, int accumulate, float drop_p, uint64_t seed, cudaStream_t stream);
+/* dPre = dY * act'(Y) * dropout(seed) * rowmask, Y = saved epilogue output of lk_linear_fwd / lk_conv1d_fwd */
+int lk_act_bwd(const float* dY, const float* Y, const int64_t* rowmask, float* dPre, int64_t M, int64_t N, int act, float drop_p,
+               uint64_t seed, cudaStream_t stream);
+/* out[i] = ids[i] > -1 (model/inputer/concat_inputer.py:108) */
+int lk_valid_mask(const int64_t* ids, int64_t* out, int64_t n, cudaStream_t stream);
+int lk_linear_bwd_data(const float* dY, const float* W, float* dX, int64_t M, int64_t N, int64_t K, int accumulate,
+                       cudaStream_t stream);
+size_t lk_linear_bwd_weight_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int lk_linear_bwd_weight(const float* dY, const float* X, float* dW, float* db, int64_t M, int64_t N, int64_t K,
+                         int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t lk_colsum_workspace_bytes(int64_t M, int64_t N);
+int lk_colsum(const float* X, float* out, int64_t M, int64_t N, int accumulate, void* workspace, size_t workspace_bytes,
+              cudaStream_t stream);
+
+/* ---- NAML Conv1d(k,'same') as implicit-im2col GEMM — model/operators/cnn_operator.py:33-38,54-58.
+ *      Wr[o, j*Cin+i] = W[o,i,j];  Wd[i, j*Cout+o] = W[o,i,taps-1-j];  rows = N*S token rows */
+int lk_conv1d_fwd(const float* X, const float* Wr, const float* bias, const int64_t* rowmask, float* Y, int64_t rows,
+                  int64_t S, int64_t Cin, int64_t Cout, int taps, int act, float drop_p, uint64_t seed, cudaStream_t stream);
+int lk_conv1d_bwd_data(const float* dY, const float* Wd, float* dX, int64_t rows, int64_t S, int64_t Cin, int64_t Cout,
+                       int taps, int accumulate, cudaStream_t stream);
+size_t lk_conv1d_bwd_weight_workspace_bytes(int64_t rows, int64_t Cin, int64_t Cout, int taps);
+int lk_conv1d_bwd_weight(const float* dY, const float* X, float* dWr, float* db, int64_t rows, int64_t S, int64_t Cin,
+                         int64_t Cout, int taps, int accumulate, void* workspace, size_t workspace_bytes,
+                         cudaStream_t stream);
+
+/* ---- (2) NRMS multi-head self-attention core — nn.MultiheadAttention, attention_operator.py:49-55 ------ */
+int lk_mha_fwd(const float* qkv, const int64_t* mask, float* ctx, float* lse, int64_t N, int64_t S, int64_t D, int64_t H,
+               float drop_p, uint64_t seed, cudaStream_t stream);
+int lk_mha_bwd(const float* qkv, const int64_t* mask, const float* lse, const float* dctx, float* dqkv, int64_t N, int64_t S,
+               int64_t D, int64_t H, float drop_p, uint64_t seed, cudaStream_t stream);
+
+/* ---- (3) AdditiveAttention pooling — model/common/attention.py:31-38 ------------------------------------ */
+int lk_additive_pool_fwd(const float* X, const float* Hd, const float* w2, const int64_t* mask, float* out, float* alpha,
+                         int64_t N, int64_t S, int64_t D, int64_t A, cudaStream_t stream);
+int lk_additive_pool_bwd(const float* X, const float* Hd, const float* w2, const float* alpha, const float* dOut, float* dX,
+                         float* dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A, int accumulate_dx,
+                         cudaStream_t stream);
+/* PoolingOperator on gathered embeddings — model/operators/pooling_operator.py:46-56 (mode 0 mean, 1 max) */
+int lk_masked_pool(const float* X, const int64_t* mask, float* out, int64_t N, int64_t S, int64_t D, int mode,
+                   cudaStream_t stream);
+int lk_masked_mean_pool_bwd(const float* dOut, const int64_t* mask, float* dX, int64_t N, int64_t S, int64_t D,
+                            cudaStream_t stream);
+
+/* ---- (4) DotPredictor + loss — model/legommender.py:268-290, predictors/dot_predictor.py:7-10,
+ *      legommender.py:114-118,254,263 -------------------------------------------------------------------- */
+int lk_dot_scores(const float* U, const float* V, float* scores, int64_t B, int64_t C, int64_t D, cudaStream_t stream);
+int lk_dot_ce_fwd(const float* U, const float* V, float* scores, float* probs, float* rowloss, float* loss, int64_t B,
+                  int64_t C, int64_t D, cudaStream_t stream);
+int lk_dot_ce_bwd(const float* U, const float* V, const float* probs, const float* dloss, float* dU, float* dV, int64_t B,
+                  int64_t C, int64_t D, cudaStream_t stream);
+int lk_dot_bwd(const float* U, const float* V, const float* dS, float* dU, float* dV, int64_t B, int64_t C, int64_t D,
+               cudaStream_t stream);
+int lk_dot_bce_fwd(const float* U, const float* V, const float* y, float* scores, float* rowloss, float* loss, int64_t B,
+                   int64_t D, cudaStream_t stream);
+int lk_dot_bce_bwd(const float* U, const float* V, const float* y, const float* scores, const float* dloss, float* dz,
+                   float* dU, float* dV, int64_t B, int64_t D, cudaStream_t stream);
+
+/* ---- (5) cached evaluation — model/legommender.py:153-157, 202-203; base_lego.py:373-394 -------------- */
+int lk_cached_scores(const float* U, const float* I, const int64_t* uid, const int64_t* iid, float* out, int64_t R, int64_t D,
+                     cudaStream_t stream);
+int lk_index_rows(const float* table, const int64_t* ids, float* out, int64_t R, int64_t D, cudaStream_t stream);
+
+/* ---- optimiser — base_lego.py:198-204 (torch.optim.Adam defaults), one launch over a flat parameter buffer */
+int lk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                 int64_t step, float grad_scale, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEGOMMENDERS_B200_H_ */

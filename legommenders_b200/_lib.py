@@ -1,0 +1,116 @@
+"""ctypes binding of the C-ABI in include/legommenders_b200.h.
+
+The product path has NO fallback: if the shared library is missing (or a call fails) a RuntimeError is
+raised.  Tensors cross the boundary as raw device pointers + sizes; torch is only the owner of the memory
+and of the current stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'liblegommenders_b200.so')
+
+_P, _Q, _I, _F, _U, _Z = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_uint64, ctypes.c_size_t
+_T = {'p': _P, 'q': _Q, 'i': _I, 'f': _F, 'u': _U, 'z': _Z, 's': _P}
+
+# name -> (argument codes, restype code).  p pointer, q int64, i int, f float, u uint64, z size_t, s stream
+SIGNATURES = {
+    'lk_version': ('', 'c'),
+    'lk_last_error': ('', 'c'),
+    'lk_device_ok': ('', 'i'),
+    'lk_gather_rows': ('ppppqqis', 'i'),
+    'lk_gather_pool': ('ppppqqqis', 'i'),
+    'lk_scatter_add_workspace_bytes': ('qqq', 'z'),
+    'lk_scatter_add_sorted': ('ppppqpqqqipzs', 'i'),
+    'lk_linear_fwd': ('pppppqqqiifus', 'i'),
+    'lk_act_bwd': ('ppppqqifus', 'i'),
+    'lk_valid_mask': ('ppqs', 'i'),
+    'lk_linear_bwd_data': ('pppqqqis', 'i'),
+    'lk_linear_bwd_weight_workspace_bytes': ('qqq', 'z'),
+    'lk_linear_bwd_weight': ('ppppqqqipzs', 'i'),
+    'lk_colsum_workspace_bytes': ('qq', 'z'),
+    'lk_colsum': ('ppqqipzs', 'i'),
+    'lk_conv1d_fwd': ('pppppqqqqiifus', 'i'),
+    'lk_conv1d_bwd_data': ('pppqqqqiis', 'i'),
+    'lk_conv1d_bwd_weight_workspace_bytes': ('qqqi', 'z'),
+    'lk_conv1d_bwd_weight': ('ppppqqqqiipzs', 'i'),
+    'lk_mha_fwd': ('ppppqqqqfus', 'i'),
+    'lk_mha_bwd': ('pppppqqqqfus', 'i'),
+    'lk_additive_pool_fwd': ('ppppppqqqqs', 'i'),
+    'lk_additive_pool_bwd': ('ppppppppqqqqis', 'i'),
+    'lk_masked_pool': ('pppqqqis', 'i'),
+    'lk_masked_mean_pool_bwd': ('pppqqqs', 'i'),
+    'lk_dot_scores': ('pppqqqs', 'i'),
+    'lk_dot_ce_fwd': ('ppppppqqqs', 'i'),
+    'lk_dot_ce_bwd': ('ppppppqqqs', 'i'),
+    'lk_dot_bwd': ('pppppqqqs', 'i'),
+    'lk_dot_bce_fwd': ('ppppppqqs', 'i'),
+    'lk_dot_bce_bwd': ('ppppppppqqs', 'i'),
+    'lk_cached_scores': ('pppppqqs', 'i'),
+    'lk_index_rows': ('pppqqs', 'i'),
+    'lk_adam_step': ('ppppqffffqfs', 'i'),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library (once).  Raises if it has not been built — there is no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                '(nvcc, sm_100a).  legommenders_b200 has no CPU / eager fallback.')
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (args, res) in SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError if the header and the library disagree
+            fn.argtypes = [_T[a] for a in args]
+            fn.restype = ctypes.c_char_p if res == 'c' else _T[res]
+        _lib = lib
+    return _lib
+
+
+def ptr(t):
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args):
+    """Invoke an int-returning entry point on the current stream; raise on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args, stream())
+    if rc != 0:
+        raise RuntimeError(f'{name} failed ({rc}): {lib.lk_last_error().decode()}')
+
+
+def query(name: str, *args) -> int:
+    return int(getattr(load(), name)(*args))
+
+
+_ws = {}
+
+
+def workspace(nbytes: int, device, tag: str = 'default') -> torch.Tensor:
+    """Grow-only scratch buffer per (device, tag); the C ABI never allocates."""
+    key = (str(device), tag)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf

@@ -1,0 +1,190 @@
+// AdditiveAttention pooling (north_star piece 3; also the tail of every item encoder).
+//
+// Reference model/common/attention.py:31-38, restated literally (no max-subtraction):
+//   s[t] = w2 · tanh(W1 x[t] + b1);  a[t] = exp(s[t]) * mask[t];  alpha = a / (sum_t a + eps32);  out = sum_t alpha[t] x[t]
+// The W1 GEMM (+bias+tanh) is done by the linear kernels; this file fuses everything after it.
+// One CTA owns one sequence; masked positions are never loaded.
+#include "lk_common.cuh"
+#include "../../include/legommenders_b200.h"
+
+namespace lk {
+
+constexpr int AT = 128;        // threads per CTA
+constexpr int MAXS = 128;      // max sequence length
+constexpr float EPS32 = 1.1920928955078125e-07f;
+
+__global__ void __launch_bounds__(AT) additive_pool_fwd_kernel(const float* __restrict__ X, const float* __restrict__ Hd,
+                                                               const float* __restrict__ w2, const int64_t* __restrict__ mask,
+                                                               float* __restrict__ out, float* __restrict__ alpha, int S, int D,
+                                                               int A) {
+  __shared__ float a_s[MAXS];
+  const int64_t n = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int t = w; t < S; t += AT / 32) {
+    bool valid = mask ? mask[n * S + t] > 0 : true;
+    float s = 0.f;
+    if (valid) {
+      const float* h = Hd + (n * S + t) * (int64_t)A;
+      for (int c = lane * 4; c < A; c += 128) s += f4_dot(ldg4(h + c), ldg4(w2 + c));
+      s = warp_sum(s);
+    }
+    if (lane == 0) a_s[t] = valid ? expf(s) : 0.f;
+  }
+  __syncthreads();
+  float Z = 0.f;
+  for (int t = 0; t < S; t++) Z += a_s[t];
+  const float inv = 1.f / (Z + EPS32);
+  for (int t = threadIdx.x; t < S; t += AT) alpha[n * S + t] = a_s[t] * inv;
+  for (int c = threadIdx.x * 4; c < D; c += AT * 4) {
+    float4 acc = f4_zero();
+    for (int t = 0; t < S; t++) {
+      float al = a_s[t] * inv;
+      if (al != 0.f) f4_fma(acc, al, ldg4(X + (n * S + t) * (int64_t)D + c));
+    }
+    st4(out + n * (int64_t)D + c, acc);
+  }
+}
+
+// dX[t,:] (+)= alpha[t] * dOut ;  dpre[t,:] = ds[t] * w2 * (1 - h^2) ;  dw2_part[n,:] = sum_t ds[t] * h[t,:]
+__global__ void __launch_bounds__(AT) additive_pool_bwd_kernel(const float* __restrict__ X, const float* __restrict__ Hd,
+                                                               const float* __restrict__ w2, const float* __restrict__ alpha,
+                                                               const float* __restrict__ dOut, float* __restrict__ dX,
+                                                               float* __restrict__ dpre, float* __restrict__ dw2_part, int S,
+                                                               int D, int A, int accumulate_dx) {
+  __shared__ float al_s[MAXS], da_s[MAXS], ds_s[MAXS];
+  const int64_t n = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int t = threadIdx.x; t < S; t += AT) al_s[t] = alpha[n * S + t];
+  __syncthreads();
+  const float* g = dOut + n * (int64_t)D;
+  for (int t = w; t < S; t += AT / 32) {
+    float s = 0.f;
+    if (al_s[t] != 0.f) {
+      const float* x = X + (n * S + t) * (int64_t)D;
+      for (int c = lane * 4; c < D; c += 128) s += f4_dot(ldg4(x + c), ldg4(g + c));
+      s = warp_sum(s);
+    }
+    if (lane == 0) da_s[t] = s;
+  }
+  __syncthreads();
+  float cs = 0.f;
+  for (int t = 0; t < S; t++) cs = fmaf(al_s[t], da_s[t], cs);
+  for (int t = threadIdx.x; t < S; t += AT) ds_s[t] = al_s[t] * (da_s[t] - cs);
+  __syncthreads();
+  for (int c = threadIdx.x * 4; c < D; c += AT * 4) {
+    const float4 gv = ldg4(g + c);
+    for (int t = 0; t < S; t++) {
+      float al = al_s[t];
+      float4 v = make_float4(al * gv.x, al * gv.y, al * gv.z, al * gv.w);
+      float* o = dX + (n * S + t) * (int64_t)D + c;
+      if (accumulate_dx) f4_add(v, *reinterpret_cast<const float4*>(o));
+      st4(o, v);
+    }
+  }
+  for (int c = threadIdx.x * 4; c < A; c += AT * 4) {
+    const float4 wv = ldg4(w2 + c);
+    float4 acc = f4_zero();
+    for (int t = 0; t < S; t++) {
+      float ds = ds_s[t];
+      float4 o = f4_zero();
+      if (ds != 0.f) {
+        float4 h = ldg4(Hd + (n * S + t) * (int64_t)A + c);
+        f4_fma(acc, ds, h);
+        o.x = ds * wv.x * (1.f - h.x * h.x); o.y = ds * wv.y * (1.f - h.y * h.y);
+        o.z = ds * wv.z * (1.f - h.z * h.z); o.w = ds * wv.w * (1.f - h.w * h.w);
+      }
+      st4(dpre + (n * S + t) * (int64_t)A + c, o);
+    }
+    st4(dw2_part + n * (int64_t)A + c, acc);
+  }
+}
+
+// masked mean / max pooling of already-gathered embeddings (model/operators/pooling_operator.py:46-56)
+template <int MODE>
+__global__ void masked_pool_kernel(const float* __restrict__ X, const int64_t* __restrict__ mask, float* __restrict__ out,
+                                   int64_t N, int S, int D) {
+  int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int D4 = D >> 2;
+  if (i4 >= N * D4) return;
+  int64_t n = i4 / D4;
+  int c = (int)(i4 % D4) * 4;
+  float4 acc = MODE == 1 ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : f4_zero();
+  int cnt = 0;
+  for (int t = 0; t < S; t++) {
+    bool valid = mask[n * S + t] > 0;
+    float4 v = valid ? ldg4(X + (n * S + t) * (int64_t)D + c) : f4_zero();
+    cnt += valid;
+    if (MODE == 1) {
+      acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
+    } else {
+      f4_add(acc, v);
+    }
+  }
+  if (MODE == 0) {
+    float inv = 1.f / ((float)cnt + 1e-8f);
+    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+  }
+  st4(out + n * (int64_t)D + c, acc);
+}
+
+// backward of masked mean pooling: dX[n,t,:] = mask ? dOut[n,:] / (cnt + 1e-8) : 0
+__global__ void masked_mean_pool_bwd_kernel(const float* __restrict__ dOut, const int64_t* __restrict__ mask,
+                                            float* __restrict__ dX, int64_t N, int S, int D) {
+  int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int D4 = D >> 2;
+  if (i4 >= N * D4) return;
+  int64_t n = i4 / D4;
+  int c = (int)(i4 % D4) * 4;
+  int cnt = 0;
+  for (int t = 0; t < S; t++) cnt += mask[n * S + t] > 0;
+  float inv = 1.f / ((float)cnt + 1e-8f);
+  float4 g = ldg4(dOut + n * (int64_t)D + c);
+  g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
+  for (int t = 0; t < S; t++) st4(dX + (n * S + t) * (int64_t)D + c, mask[n * S + t] > 0 ? g : f4_zero());
+}
+
+}  // namespace lk
+
+using namespace lk;
+
+extern "C" {
+
+int lk_additive_pool_fwd(const float* X, const float* Hd, const float* w2, const int64_t* mask, float* out, float* alpha,
+                         int64_t N, int64_t S, int64_t D, int64_t A, cudaStream_t st) {
+  LK_REQUIRE(D % 4 == 0 && A % 4 == 0, LK_ERR_SHAPE, "lk_additive_pool_fwd: D=%ld, A=%ld must be multiples of 4", (long)D, (long)A);
+  LK_REQUIRE(S <= MAXS, LK_ERR_SHAPE, "lk_additive_pool_fwd: S=%ld exceeds %d", (long)S, MAXS);
+  if (N == 0) return LK_OK;
+  additive_pool_fwd_kernel<<<(unsigned)N, AT, 0, st>>>(X, Hd, w2, mask, out, alpha, (int)S, (int)D, (int)A);
+  return check_launch("additive_pool_fwd");
+}
+
+int lk_additive_pool_bwd(const float* X, const float* Hd, const float* w2, const float* alpha, const float* dOut, float* dX,
+                         float* dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A, int accumulate_dx,
+                         cudaStream_t st) {
+  LK_REQUIRE(D % 4 == 0 && A % 4 == 0, LK_ERR_SHAPE, "lk_additive_pool_bwd: D=%ld, A=%ld must be multiples of 4", (long)D, (long)A);
+  LK_REQUIRE(S <= MAXS, LK_ERR_SHAPE, "lk_additive_pool_bwd: S=%ld exceeds %d", (long)S, MAXS);
+  if (N == 0) return LK_OK;
+  additive_pool_bwd_kernel<<<(unsigned)N, AT, 0, st>>>(X, Hd, w2, alpha, dOut, dX, dpre, dw2_part, (int)S, (int)D, (int)A,
+                                                      accumulate_dx);
+  return check_launch("additive_pool_bwd");
+}
+
+int lk_masked_pool(const float* X, const int64_t* mask, float* out, int64_t N, int64_t S, int64_t D, int mode, cudaStream_t st) {
+  LK_REQUIRE(D % 4 == 0, LK_ERR_SHAPE, "lk_masked_pool: D=%ld must be a multiple of 4", (long)D);
+  LK_REQUIRE(mode == 0 || mode == 1, LK_ERR_ARG, "lk_masked_pool: mode must be 0 (mean) or 1 (max)");
+  if (N == 0) return LK_OK;
+  int64_t total = N * (D / 4);
+  if (mode == 0) masked_pool_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, mask, out, N, (int)S, (int)D);
+  else masked_pool_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, mask, out, N, (int)S, (int)D);
+  return check_launch("masked_pool");
+}
+
+int lk_masked_mean_pool_bwd(const float* dOut, const int64_t* mask, float* dX, int64_t N, int64_t S, int64_t D, cudaStream_t st) {
+  LK_REQUIRE(D % 4 == 0, LK_ERR_SHAPE, "lk_masked_mean_pool_bwd: D=%ld must be a multiple of 4", (long)D);
+  if (N == 0) return LK_OK;
+  int64_t total = N * (D / 4);
+  masked_mean_pool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dOut, mask, dX, N, (int)S, (int)D);
+  return check_launch("masked_mean_pool_bwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,84 @@
+// Shared device/host helpers for the legommenders_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define LK_OK 0
+#define LK_ERR_CUDA (-1)
+#define LK_ERR_SHAPE (-2)
+#define LK_ERR_ARG (-3)
+
+namespace lk {
+
+void set_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return LK_ERR_CUDA;
+  }
+  return LK_OK;
+}
+
+#define LK_REQUIRE(cond, code, ...)   \
+  do {                                \
+    if (!(cond)) {                    \
+      lk::set_error(__VA_ARGS__);     \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// streaming (read-once) 16-byte load that does not pollute L1
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void f4_fma(float4& a, float s, const float4& x) {
+  a.x = fmaf(s, x.x, a.x);
+  a.y = fmaf(s, x.y, a.y);
+  a.z = fmaf(s, x.z, a.z);
+  a.w = fmaf(s, x.w, a.w);
+}
+__device__ __forceinline__ void f4_add(float4& a, const float4& x) {
+  a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+}
+__device__ __forceinline__ float f4_dot(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+// Counter-based RNG for dropout (statistics, not bits, are what the reference defines).
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return (uint32_t)x;
+}
+// keep-scale for element `idx` of dropout stream `seed`: 0 with prob p, 1/(1-p) otherwise.
+__device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, float p, float inv_keep) {
+  uint32_t r = mix32(seed * 0x9E3779B97F4A7C15ULL + idx);
+  return ((r >> 8) * (1.0f / 16777216.0f)) < p ? 0.f : inv_keep;
+}
+
+}  // namespace lk

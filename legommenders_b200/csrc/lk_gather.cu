@@ -1,0 +1,271 @@
+// EmbeddingHub token gather (north_star piece 1).
+//
+// Reference semantics (model/inputer/concat_inputer.py:105-113, simple_inputer.py:51-64,
+// loader/embedding_hub.py:378-385, model/operators/pooling_operator.py:46-61):
+//   valid(m) = mask ? mask[m] > 0 : ids[m] > -1 ;  row(m) = valid ? table[ids[m]] : 0
+//   gather      : out[m,:]  (+)= row(m)
+//   gather+pool : out[n,:]  = sum_t row(n,t) / (sum_t valid + 1e-8)   (mean) | max_t row(n,t) | sum_t row(n,t)
+// Backward for trainable tables is a sorted-index segmented scatter-add (no atomics, deterministic):
+//   radix sort (id, position) -> run-length encode -> fixed-size partial sums -> per-id ordered reduction.
+#include <cub/cub.cuh>
+
+#include "lk_common.cuh"
+#include "../../include/legommenders_b200.h"
+
+namespace lk {
+
+constexpr int GW = 8;  // warps per block in the gather kernels
+
+// ------------------------------------------------------------------------------------------------
+// plain gather: one warp per row, 16-byte vector loads, fused validity mask
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GW * 32) gather_rows_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
+                                                              const float* __restrict__ table, float* __restrict__ out,
+                                                              int64_t M, int E, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * GW + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * GW;
+  const int E4 = E >> 2;
+  for (int64_t m = warp; m < M; m += nwarps) {
+    int64_t id = ids[m];
+    bool valid = mask ? (mask[m] > 0) : (id > -1);
+    float* o = out + m * E;
+    if (valid) {
+      const float* src = table + id * (int64_t)E;
+      for (int c = lane; c < E4; c += 32) {
+        float4 v = ldg4(src + c * 4);
+        if (accumulate) f4_add(v, *reinterpret_cast<const float4*>(o + c * 4));
+        st4(o + c * 4, v);
+      }
+    } else if (!accumulate) {
+      for (int c = lane; c < E4; c += 32) st4(o + c * 4, f4_zero());
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather + masked pooling: one warp per (item, 128-float column block); 4 tokens in flight
+// ------------------------------------------------------------------------------------------------
+template <int MODE>  // 0 mean, 1 max, 2 sum
+__global__ void __launch_bounds__(GW * 32) gather_pool_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
+                                                              const float* __restrict__ table, float* __restrict__ out,
+                                                              int64_t N, int S, int E) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * GW + (threadIdx.x >> 5);
+  const int c = (blockIdx.y * 32 + lane) * 4;
+  if (n >= N) return;
+  const bool col_ok = c < E;
+  const int64_t* idr = ids + n * S;
+  const int64_t* mr = mask ? mask + n * S : nullptr;
+  float4 acc = MODE == 1 ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : f4_zero();
+  int cnt = 0;
+  for (int t0 = 0; t0 < S; t0 += 4) {
+    float4 v[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      int t = t0 + u;
+      ok[u] = false;
+      v[u] = f4_zero();
+      if (t < S) {
+        int64_t id = idr[t];
+        ok[u] = mr ? (mr[t] > 0) : (id > -1);
+        if (ok[u] && col_ok) v[u] = ldg4(table + id * (int64_t)E + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (t0 + u >= S) continue;
+      cnt += ok[u] ? 1 : 0;
+      if (MODE == 1) {
+        acc.x = fmaxf(acc.x, v[u].x); acc.y = fmaxf(acc.y, v[u].y);
+        acc.z = fmaxf(acc.z, v[u].z); acc.w = fmaxf(acc.w, v[u].w);
+      } else {
+        f4_add(acc, v[u]);
+      }
+    }
+  }
+  if (!col_ok) return;
+  if (MODE == 0) {
+    float inv = 1.0f / ((float)cnt + 1e-8f);
+    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+  }
+  st4(out + n * (int64_t)E + c, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sorted-index segmented scatter-add
+// ------------------------------------------------------------------------------------------------
+constexpr int SEG = 32;  // rows per partial sum
+
+__global__ void make_keys_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask, int* __restrict__ keys,
+                                 int* __restrict__ vals, int64_t P, int V) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  int64_t id = ids[p];
+  bool valid = mask ? (mask[p] > 0) : (id > -1);
+  keys[p] = valid ? (int)id : V;   // invalid positions sort to the end under sentinel V
+  vals[p] = (int)p;
+}
+
+__global__ void partial_counts_kernel(const int* __restrict__ run_len, const int* __restrict__ num_runs, int* __restrict__ npart,
+                                      int cap) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  npart[i] = (i < *num_runs) ? (run_len[i] + SEG - 1) / SEG : 0;
+}
+
+// partial p of run r sums rows [run_off[r] + k*SEG, min(run_off[r+1], ...+SEG)) of the sorted order
+__global__ void __launch_bounds__(GW * 32) partial_sums_kernel(const int* __restrict__ sorted_pos, const int* __restrict__ run_off,
+                                                               const int* __restrict__ run_len, const int* __restrict__ part_off,
+                                                               const int* __restrict__ num_runs, const float* __restrict__ src,
+                                                               const float* __restrict__ scale, int row_div, int E,
+                                                               float* __restrict__ partial, int max_partials) {
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * GW + (threadIdx.x >> 5);
+  const int R = *num_runs;
+  if (p >= max_partials) return;
+  const int total = part_off[R - 1] + (run_len[R - 1] + SEG - 1) / SEG;
+  if (p >= total) return;
+  // binary search: last run r with part_off[r] <= p
+  int lo = 0, hi = R - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (part_off[mid] <= p) lo = mid; else hi = mid - 1;
+  }
+  const int r = lo;
+  const int beg = run_off[r] + (p - part_off[r]) * SEG;
+  const int end = min(run_off[r] + run_len[r], beg + SEG);
+  const int c = (blockIdx.y * 32 + lane) * 4;
+  if (c >= E) return;
+  float4 acc = f4_zero();
+  for (int i = beg; i < end; i++) {
+    int pos = sorted_pos[i];
+    float4 v = ldg4(src + (int64_t)(pos / row_div) * E + c);
+    if (scale) { float s = scale[pos]; v.x *= s; v.y *= s; v.z *= s; v.w *= s; }
+    f4_add(acc, v);
+  }
+  st4(partial + (int64_t)p * E + c, acc);
+}
+
+__global__ void __launch_bounds__(GW * 32) run_reduce_kernel(const int* __restrict__ run_key, const int* __restrict__ run_len,
+                                                             const int* __restrict__ part_off, const int* __restrict__ num_runs,
+                                                             const float* __restrict__ partial, float* __restrict__ dtable, int V,
+                                                             int E, int accumulate, int max_runs) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * GW + (threadIdx.x >> 5);
+  if (r >= max_runs || r >= *num_runs) return;
+  const int key = run_key[r];
+  if (key >= V) return;  // sentinel run of invalid positions
+  const int c = (blockIdx.y * 32 + lane) * 4;
+  if (c >= E) return;
+  const int np = (run_len[r] + SEG - 1) / SEG;
+  const float* src = partial + (int64_t)part_off[r] * E + c;
+  float4 acc = f4_zero();
+  for (int i = 0; i < np; i++) f4_add(acc, ldg4_stream(src + (int64_t)i * E));
+  float* o = dtable + (int64_t)key * E + c;
+  if (accumulate) f4_add(acc, *reinterpret_cast<const float4*>(o));
+  st4(o, acc);
+}
+
+struct ScatterWs {
+  int *keys, *vals, *skeys, *svals, *run_key, *run_len, *run_off, *npart, *part_off, *num_runs;
+  float* partial;
+  void* cub;
+  size_t cub_bytes;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t cub_bytes_for(int64_t P, int cap) {
+  size_t a = 0, b = 0, c = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int)P);
+  cub::DeviceRunLengthEncode::Encode(nullptr, b, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int)P);
+  cub::DeviceScan::ExclusiveSum(nullptr, c, (int*)nullptr, (int*)nullptr, cap);
+  size_t m = a > b ? a : b;
+  return align_up(m > c ? m : c);
+}
+
+static int run_cap(int64_t P, int64_t V) { return (int)((P < V + 1) ? P : V + 1); }
+static int64_t partial_cap(int64_t P, int64_t V) { return (P + SEG - 1) / SEG + run_cap(P, V); }
+
+static size_t carve(ScatterWs& w, void* base, int64_t P, int64_t V, int E) {
+  int cap = run_cap(P, V);
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* r = p ? p + off : nullptr; off += align_up(bytes); return r; };
+  w.keys = (int*)take(P * 4); w.vals = (int*)take(P * 4); w.skeys = (int*)take(P * 4); w.svals = (int*)take(P * 4);
+  w.run_key = (int*)take((size_t)cap * 4); w.run_len = (int*)take((size_t)cap * 4); w.run_off = (int*)take((size_t)cap * 4);
+  w.npart = (int*)take((size_t)cap * 4); w.part_off = (int*)take((size_t)cap * 4); w.num_runs = (int*)take(4);
+  w.partial = (float*)take((size_t)partial_cap(P, V) * E * 4);
+  w.cub_bytes = cub_bytes_for(P, cap);
+  w.cub = take(w.cub_bytes);
+  return off;
+}
+
+}  // namespace lk
+
+using namespace lk;
+
+extern "C" {
+
+int lk_gather_rows(const int64_t* ids, const int64_t* mask, const float* table, float* out, int64_t M, int64_t E,
+                   int accumulate, cudaStream_t st) {
+  LK_REQUIRE(E % 4 == 0, LK_ERR_SHAPE, "lk_gather_rows: row width %ld must be a multiple of 4 floats (16-byte loads)", (long)E);
+  if (M == 0) return LK_OK;
+  int64_t blocks = (M + GW - 1) / GW;
+  if (blocks > (int64_t)kNumSMs * 64) blocks = (int64_t)kNumSMs * 64;
+  gather_rows_kernel<<<(unsigned)blocks, GW * 32, 0, st>>>(ids, mask, table, out, M, (int)E, accumulate);
+  return check_launch("gather_rows");
+}
+
+int lk_gather_pool(const int64_t* ids, const int64_t* mask, const float* table, float* out, int64_t N, int64_t S, int64_t E,
+                   int mode, cudaStream_t st) {
+  LK_REQUIRE(E % 4 == 0, LK_ERR_SHAPE, "lk_gather_pool: row width %ld must be a multiple of 4 floats", (long)E);
+  LK_REQUIRE(mode >= 0 && mode <= 2, LK_ERR_ARG, "lk_gather_pool: mode must be 0 (mean), 1 (max) or 2 (sum)");
+  if (N == 0) return LK_OK;
+  dim3 grid((unsigned)((N + GW - 1) / GW), (unsigned)((E + 127) / 128));
+  if (mode == 0) gather_pool_kernel<0><<<grid, GW * 32, 0, st>>>(ids, mask, table, out, N, (int)S, (int)E);
+  else if (mode == 1) gather_pool_kernel<1><<<grid, GW * 32, 0, st>>>(ids, mask, table, out, N, (int)S, (int)E);
+  else gather_pool_kernel<2><<<grid, GW * 32, 0, st>>>(ids, mask, table, out, N, (int)S, (int)E);
+  return check_launch("gather_pool");
+}
+
+size_t lk_scatter_add_workspace_bytes(int64_t P, int64_t V, int64_t E) {
+  ScatterWs w;
+  return carve(w, nullptr, P, V, (int)E) + 256;
+}
+
+int lk_scatter_add_sorted(const int64_t* ids, const int64_t* mask, const float* src, const float* scale, int64_t row_div,
+                          float* dtable, int64_t P, int64_t V, int64_t E, int accumulate, void* workspace,
+                          size_t workspace_bytes, cudaStream_t st) {
+  LK_REQUIRE(E % 4 == 0, LK_ERR_SHAPE, "lk_scatter_add_sorted: row width %ld must be a multiple of 4 floats", (long)E);
+  LK_REQUIRE(P < (1LL << 31) && V < (1LL << 30), LK_ERR_SHAPE, "lk_scatter_add_sorted: P or V too large for 32-bit keys");
+  LK_REQUIRE(workspace_bytes >= lk_scatter_add_workspace_bytes(P, V, E), LK_ERR_ARG, "lk_scatter_add_sorted: workspace too small");
+  if (!accumulate) cudaMemsetAsync(dtable, 0, (size_t)V * E * sizeof(float), st);
+  if (P == 0) return LK_OK;
+  ScatterWs w;
+  carve(w, workspace, P, V, (int)E);
+  const int cap = run_cap(P, V);
+  make_keys_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(ids, mask, w.keys, w.vals, P, (int)V);
+  int end_bit = 1;
+  while ((1LL << end_bit) <= V) end_bit++;
+  size_t cb = w.cub_bytes;
+  cub::DeviceRadixSort::SortPairs(w.cub, cb, w.keys, w.skeys, w.vals, w.svals, (int)P, 0, end_bit, st);
+  cb = w.cub_bytes;
+  cub::DeviceRunLengthEncode::Encode(w.cub, cb, w.skeys, w.run_key, w.run_len, w.num_runs, (int)P, st);
+  cb = w.cub_bytes;
+  cub::DeviceScan::ExclusiveSum(w.cub, cb, w.run_len, w.run_off, cap, st);
+  partial_counts_kernel<<<(cap + 255) / 256, 256, 0, st>>>(w.run_len, w.num_runs, w.npart, cap);
+  cb = w.cub_bytes;
+  cub::DeviceScan::ExclusiveSum(w.cub, cb, w.npart, w.part_off, cap, st);
+  const int maxp = (int)partial_cap(P, V);
+  dim3 g1((maxp + GW - 1) / GW, (unsigned)((E + 127) / 128));
+  partial_sums_kernel<<<g1, GW * 32, 0, st>>>(w.svals, w.run_off, w.run_len, w.part_off, w.num_runs, src, scale, (int)row_div, (int)E,
+                                            w.partial, maxp);
+  dim3 g2((cap + GW - 1) / GW, (unsigned)((E + 127) / 128));
+  run_reduce_kernel<<<g2, GW * 32, 0, st>>>(w.run_key, w.run_len, w.part_off, w.num_runs, w.partial, dtable, (int)V, (int)E, 1, cap);
+  return check_launch("scatter_add_sorted");
+}
+
+}  // extern "C"

@@ -1,0 +1,12 @@
+from .base_operator import BaseOperator, BaseOperatorConfig
+from .attention_operator import AttentionOperator, AttentionOperatorConfig
+from .cnn_operator import CNNOperator, CNNOperatorConfig
+from .ada_operator import AdaOperator, AdaOperatorConfig
+from .pooling_operator import PoolingOperator, PoolingOperatorConfig
+
+REGISTRY = {'attention': AttentionOperator, 'cnn': CNNOperator, 'ada': AdaOperator, 'pooling': PoolingOperator}
+
+
+def get(name: str):
+    """Same keying as loader/class_hub.py:112-115: class name minus 'Operator', lower-cased."""
+    return REGISTRY[name.lower()]

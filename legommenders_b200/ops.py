@@ -1,0 +1,473 @@
+"""Differentiable host-side wrappers over the C-ABI kernels (torch.autograd.Function = plumbing only).
+
+Every forward/backward here is one or more calls into liblegommenders_b200.so on the current stream;
+no torch math runs on the hot path.  Each op cites the reference call site it replaces.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import call, ptr, query, workspace
+
+ACT_NONE, ACT_TANH, ACT_RELU = 0, 1, 2
+POOL_MEAN, POOL_MAX, POOL_SUM = 0, 1, 2
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise RuntimeError(f'expected a CUDA float32 tensor, got {t.dtype} on {t.device}')
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _i64(t):
+    if t is None:
+        return None
+    if t.dtype != torch.int64 or not t.is_cuda:
+        raise RuntimeError(f'expected a CUDA int64 tensor, got {t.dtype} on {t.device}')
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------
+# dense contractions
+# ----------------------------------------------------------------------------------------------------
+def linear_fwd_raw(x2, w, b, rowmask, act, out=None, accumulate=False, drop_p=0.0, seed=0):
+    M, K = x2.shape
+    N = w.shape[0]
+    y = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=x2.device)
+    call('lk_linear_fwd', ptr(x2), ptr(w), ptr(b), ptr(rowmask), ptr(y), M, N, K, act, int(accumulate), float(drop_p), int(seed))
+    return y
+
+
+def linear_bwd_data_raw(dy2, w, out=None, accumulate=False):
+    M, N = dy2.shape
+    K = w.shape[1]
+    dx = out if out is not None else torch.empty((M, K), dtype=torch.float32, device=dy2.device)
+    call('lk_linear_bwd_data', ptr(dy2), ptr(w), ptr(dx), M, N, K, int(accumulate))
+    return dx
+
+
+def linear_bwd_weight_raw(dy2, x2, want_bias=True):
+    M, N = dy2.shape
+    K = x2.shape[1]
+    dw = torch.empty((N, K), dtype=torch.float32, device=dy2.device)
+    db = torch.empty((N,), dtype=torch.float32, device=dy2.device) if want_bias else None
+    nbytes = query('lk_linear_bwd_weight_workspace_bytes', M, N, K)
+    ws = workspace(nbytes, dy2.device, 'wgrad')
+    call('lk_linear_bwd_weight', ptr(dy2), ptr(x2), ptr(dw), ptr(db), M, N, K, 0, ptr(ws), ws.numel())
+    return dw, db
+
+
+def colsum_raw(x2):
+    M, N = x2.shape
+    out = torch.empty((N,), dtype=torch.float32, device=x2.device)
+    nbytes = query('lk_colsum_workspace_bytes', M, N)
+    ws = workspace(nbytes, x2.device, 'colsum')
+    call('lk_colsum', ptr(x2), ptr(out), M, N, 0, ptr(ws), ws.numel())
+    return out
+
+
+def act_bwd_raw(dy2, y2, rowmask, act, drop_p=0.0, seed=0):
+    M, N = dy2.shape
+    out = torch.empty_like(dy2)
+    call('lk_act_bwd', ptr(dy2), ptr(y2), ptr(rowmask), ptr(out), M, N, act, float(drop_p), int(seed))
+    return out
+
+
+class _Linear(Function):
+    """y = dropout(act(x·Wᵀ + b)) * rowmask — nn.Linear call sites (embedding_hub.py:95-96,
+    attention_operator.py:56, cnn_operator.py:62, attention.py:17-19) and MHA in/out projections."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, rowmask, act, drop_p, seed):
+        x, w = _f32(x), _f32(w)
+        b = _f32(b) if b is not None else None
+        x2 = x.reshape(-1, x.shape[-1])
+        rm = _i64(rowmask.reshape(-1)) if rowmask is not None else None
+        y = linear_fwd_raw(x2, w, b, rm, act, drop_p=drop_p, seed=seed)
+        ctx.act, ctx.drop_p, ctx.seed, ctx.has_b = act, drop_p, seed, b is not None
+        plain = act == ACT_NONE and rm is None and drop_p == 0.0
+        ctx.plain = plain
+        ctx.save_for_backward(x2, w, None if plain else y, rm)
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, y, rm = ctx.saved_tensors
+        dy2 = _f32(dy).reshape(-1, dy.shape[-1])
+        if not ctx.plain:
+            dy2 = act_bwd_raw(dy2, y, rm, ctx.act, ctx.drop_p, ctx.seed)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = linear_bwd_data_raw(dy2, w).view(*dy.shape[:-1], w.shape[1])
+        if ctx.needs_input_grad[1] or (ctx.has_b and ctx.needs_input_grad[2]):
+            dw, db = linear_bwd_weight_raw(dy2, x2, want_bias=ctx.has_b)
+        return dx, dw, db, None, None, None, None
+
+
+def linear(x, w, b=None, rowmask=None, act=ACT_NONE, drop_p=0.0, seed=0):
+    return _Linear.apply(x, w, b, rowmask, act, drop_p, seed)
+
+
+# ----------------------------------------------------------------------------------------------------
+# embedding gather
+# ----------------------------------------------------------------------------------------------------
+def valid_mask(ids: torch.Tensor) -> torch.Tensor:
+    """mask = (ids > -1).long() — concat_inputer.py:108."""
+    ids = _i64(ids)
+    out = torch.empty_like(ids)
+    call('lk_valid_mask', ptr(ids), ptr(out), ids.numel())
+    return out
+
+
+def scatter_add_rows(ids, mask, src2, table_shape, scale=None, row_div=1):
+    """dtable = Σ_p valid(p)·scale[p]·src[p // row_div] at row ids[p] (sorted segmented reduction)."""
+    V, E = table_shape
+    P = ids.numel()
+    dt = torch.empty((V, E), dtype=torch.float32, device=src2.device)
+    nbytes = query('lk_scatter_add_workspace_bytes', P, V, E)
+    ws = workspace(nbytes, src2.device, 'scatter')
+    call('lk_scatter_add_sorted', ptr(ids), ptr(mask), ptr(src2), ptr(scale), row_div, ptr(dt), P, V, E, 0, ptr(ws), ws.numel())
+    return dt
+
+
+class _GatherAdd(Function):
+    """out = base + valid·table[ids] (base may be None) — aten::embedding + mask multiply + add at
+    concat_inputer.py:105-113 / simple_inputer.py:51-64."""
+
+    @staticmethod
+    def forward(ctx, base, ids, mask, table):
+        ids, mask, table = _i64(ids), _i64(mask), _f32(table)
+        M, E = ids.numel(), table.shape[1]
+        if base is None:
+            out = torch.empty((*ids.shape, E), dtype=torch.float32, device=table.device)
+            acc = 0
+        else:
+            out = _f32(base).clone()
+            acc = 1
+        call('lk_gather_rows', ptr(ids), ptr(mask), ptr(table), ptr(out), M, E, acc)
+        ctx.save_for_backward(ids, mask)
+        ctx.tshape = tuple(table.shape)
+        ctx.has_base = base is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ids, mask = ctx.saved_tensors
+        dbase = dout if (ctx.has_base and ctx.needs_input_grad[0]) else None
+        dtable = None
+        if ctx.needs_input_grad[3]:
+            d2 = _f32(dout).reshape(-1, dout.shape[-1])
+            dtable = scatter_add_rows(ids.reshape(-1), None if mask is None else mask.reshape(-1), d2, ctx.tshape)
+        return dbase, None, None, dtable
+
+
+def gather_add(base, ids, mask, table):
+    return _GatherAdd.apply(base, ids, mask, table)
+
+
+class _GatherPool(Function):
+    """Fused gather + masked pooling (north_star piece 1; pooling_operator.py:46-56 over an nn.Embedding)."""
+
+    @staticmethod
+    def forward(ctx, ids, mask, table, mode):
+        ids, mask, table = _i64(ids), _i64(mask), _f32(table)
+        N, S = ids.shape
+        E = table.shape[1]
+        out = torch.empty((N, E), dtype=torch.float32, device=table.device)
+        call('lk_gather_pool', ptr(ids), ptr(mask), ptr(table), ptr(out), N, S, E, mode)
+        ctx.save_for_backward(ids, mask)
+        ctx.tshape, ctx.mode = tuple(table.shape), mode
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ids, mask = ctx.saved_tensors
+        if not ctx.needs_input_grad[2]:
+            return None, None, None, None
+        if ctx.mode == POOL_MAX:
+            raise RuntimeError('gather_pool: backward of max pooling is not implemented')
+        N, S = ids.shape
+        scale = None
+        if ctx.mode == POOL_MEAN:
+            m = mask if mask is not None else valid_mask(ids)
+            cnt = m.sum(dim=1, keepdim=True).to(torch.float32)   # tiny [N,1] host-side bookkeeping
+            scale = (1.0 / (cnt + 1e-8)).expand(N, S).contiguous().reshape(-1)
+        dtable = scatter_add_rows(ids.reshape(-1), None if mask is None else mask.reshape(-1),
+                                  _f32(dout), ctx.tshape, scale=scale, row_div=S)
+        return None, None, dtable, None
+
+
+def gather_pool(ids, mask, table, mode=POOL_MEAN):
+    return _GatherPool.apply(ids, mask, table, mode)
+
+
+# ----------------------------------------------------------------------------------------------------
+# multi-head self-attention core
+# ----------------------------------------------------------------------------------------------------
+class _MHACore(Function):
+    """softmax((q·dh^-0.5)kᵀ + key padding)·v per head — nn.MultiheadAttention, attention_operator.py:49-55."""
+
+    @staticmethod
+    def forward(ctx, qkv, mask, heads, drop_p, seed):
+        qkv, mask = _f32(qkv), _i64(mask)
+        N, S, D3 = qkv.shape
+        D = D3 // 3
+        out = torch.empty((N, S, D), dtype=torch.float32, device=qkv.device)
+        lse = torch.empty((N, heads, S), dtype=torch.float32, device=qkv.device)
+        call('lk_mha_fwd', ptr(qkv), ptr(mask), ptr(out), ptr(lse), N, S, D, heads, float(drop_p), int(seed))
+        ctx.save_for_backward(qkv, mask, lse)
+        ctx.heads, ctx.drop_p, ctx.seed = heads, drop_p, seed
+        return out
+
+    @staticmethod
+    def backward(ctx, dctx):
+        qkv, mask, lse = ctx.saved_tensors
+        N, S, D3 = qkv.shape
+        dqkv = torch.empty_like(qkv)
+        call('lk_mha_bwd', ptr(qkv), ptr(mask), ptr(lse), ptr(_f32(dctx)), ptr(dqkv), N, S, D3 // 3, ctx.heads,
+             float(ctx.drop_p), int(ctx.seed))
+        return dqkv, None, None, None, None
+
+
+def mha_core(qkv, mask, heads, drop_p=0.0, seed=0):
+    return _MHACore.apply(qkv, mask, heads, drop_p, seed)
+
+
+# ----------------------------------------------------------------------------------------------------
+# additive attention
+# ----------------------------------------------------------------------------------------------------
+class _AdditiveAttention(Function):
+    """model/common/attention.py:23-38: W1 GEMM + tanh, then the fused score/exp/mask/normalise/pool kernel."""
+
+    @staticmethod
+    def forward(ctx, x, mask, w1, b1, w2):
+        x, w1, b1, w2 = _f32(x), _f32(w1), _f32(b1), _f32(w2)
+        mask = _i64(mask) if mask is not None else None
+        N, S, D = x.shape
+        A = w1.shape[0]
+        x2 = x.reshape(N * S, D)
+        hid = linear_fwd_raw(x2, w1, b1, None, ACT_TANH)
+        out = torch.empty((N, D), dtype=torch.float32, device=x.device)
+        alpha = torch.empty((N, S), dtype=torch.float32, device=x.device)
+        call('lk_additive_pool_fwd', ptr(x2), ptr(hid), ptr(w2), ptr(mask), ptr(out), ptr(alpha), N, S, D, A)
+        ctx.save_for_backward(x2, hid, alpha, w1, w2)
+        ctx.shape = (N, S, D, A)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, hid, alpha, w1, w2 = ctx.saved_tensors
+        N, S, D, A = ctx.shape
+        dev = x2.device
+        dx = torch.empty((N * S, D), dtype=torch.float32, device=dev)
+        dpre = torch.empty((N * S, A), dtype=torch.float32, device=dev)
+        dw2p = torch.empty((N, A), dtype=torch.float32, device=dev)
+        call('lk_additive_pool_bwd', ptr(x2), ptr(hid), ptr(w2), ptr(alpha), ptr(_f32(dout)), ptr(dx), ptr(dpre), ptr(dw2p),
+             N, S, D, A, 0)
+        dw2 = colsum_raw(dw2p).view(1, A)
+        dw1, db1 = linear_bwd_weight_raw(dpre, x2)
+        linear_bwd_data_raw(dpre, w1, out=dx, accumulate=True)
+        return dx.view(N, S, D), None, dw1, db1, dw2
+
+
+def additive_attention(x, mask, w1, b1, w2):
+    return _AdditiveAttention.apply(x, mask, w1, b1, w2)
+
+
+# ----------------------------------------------------------------------------------------------------
+# Conv1d('same') + ReLU + mask (NAML)
+# ----------------------------------------------------------------------------------------------------
+class _Conv1dReluMask(Function):
+    """dropout(relu(conv1d(x, W, b, 'same')) * mask) over [N,S,C] — cnn_operator.py:54-58."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, mask, drop_p, seed):
+        x, w, b = _f32(x), _f32(w), _f32(b)
+        N, S, Cin = x.shape
+        Cout, _, taps = w.shape
+        wr = w.permute(0, 2, 1).contiguous().view(Cout, taps * Cin)       # Wr[o, j*Cin+i] = W[o,i,j] (layout only)
+        rm = _i64(mask.reshape(-1)) if mask is not None else None
+        y = torch.empty((N * S, Cout), dtype=torch.float32, device=x.device)
+        x2 = x.reshape(N * S, Cin)
+        call('lk_conv1d_fwd', ptr(x2), ptr(wr), ptr(b), ptr(rm), ptr(y), N * S, S, Cin, Cout, taps, ACT_RELU, float(drop_p), int(seed))
+        ctx.save_for_backward(x2, w, y, rm)
+        ctx.dims = (N, S, Cin, Cout, taps)
+        ctx.drop_p, ctx.seed = drop_p, seed
+        return y.view(N, S, Cout)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, y, rm = ctx.saved_tensors
+        N, S, Cin, Cout, taps = ctx.dims
+        dy2 = act_bwd_raw(_f32(dy).reshape(N * S, Cout), y, rm, ACT_RELU, ctx.drop_p, ctx.seed)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wd = w.flip(2).permute(1, 2, 0).contiguous().view(Cin, taps * Cout)   # Wd[i, j*Cout+o] = W[o,i,taps-1-j]
+            dx = torch.empty((N * S, Cin), dtype=torch.float32, device=dy.device)
+            call('lk_conv1d_bwd_data', ptr(dy2), ptr(wd), ptr(dx), N * S, S, Cin, Cout, taps, 0)
+            dx = dx.view(N, S, Cin)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dwr = torch.empty((Cout, taps * Cin), dtype=torch.float32, device=dy.device)
+            db = torch.empty((Cout,), dtype=torch.float32, device=dy.device)
+            nbytes = query('lk_conv1d_bwd_weight_workspace_bytes', N * S, Cin, Cout, taps)
+            ws = workspace(nbytes, dy.device, 'wgrad')
+            call('lk_conv1d_bwd_weight', ptr(dy2), ptr(x2), ptr(dwr), ptr(db), N * S, S, Cin, Cout, taps, 0, ptr(ws), ws.numel())
+            dw = dwr.view(Cout, taps, Cin).permute(0, 2, 1).contiguous()
+        return dx, dw, db, None, None, None
+
+
+def conv1d_relu_mask(x, w, b, mask, drop_p=0.0, seed=0):
+    return _Conv1dReluMask.apply(x, w, b, mask, drop_p, seed)
+
+
+# ----------------------------------------------------------------------------------------------------
+# masked pooling of gathered embeddings
+# ----------------------------------------------------------------------------------------------------
+class _MaskedPool(Function):
+    """pooling_operator.py:46-56 on an [N,S,D] tensor."""
+
+    @staticmethod
+    def forward(ctx, x, mask, mode):
+        x, mask = _f32(x), _i64(mask)
+        N, S, D = x.shape
+        out = torch.empty((N, D), dtype=torch.float32, device=x.device)
+        call('lk_masked_pool', ptr(x), ptr(mask), ptr(out), N, S, D, mode)
+        ctx.save_for_backward(mask)
+        ctx.dims, ctx.mode = (N, S, D), mode
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (mask,) = ctx.saved_tensors
+        if ctx.mode != POOL_MEAN:
+            raise RuntimeError('masked_pool: backward of max pooling is not implemented')
+        N, S, D = ctx.dims
+        dx = torch.empty((N, S, D), dtype=torch.float32, device=dout.device)
+        call('lk_masked_mean_pool_bwd', ptr(_f32(dout)), ptr(mask), ptr(dx), N, S, D)
+        return dx, None, None
+
+
+def masked_pool(x, mask, mode=POOL_MEAN):
+    return _MaskedPool.apply(x, mask, mode)
+
+
+# ----------------------------------------------------------------------------------------------------
+# scoring + loss
+# ----------------------------------------------------------------------------------------------------
+class _DotScores(Function):
+    """scores[b,c] = <u[b], v[b,c]> — legommender.py:279-283 + dot_predictor.py:10 (no materialised repeat)."""
+
+    @staticmethod
+    def forward(ctx, user, items):
+        user, items = _f32(user), _f32(items)
+        B, C, D = items.shape
+        scores = torch.empty((B, C), dtype=torch.float32, device=user.device)
+        call('lk_dot_scores', ptr(user), ptr(items), ptr(scores), B, C, D)
+        ctx.save_for_backward(user, items)
+        return scores
+
+    @staticmethod
+    def backward(ctx, ds):
+        user, items = ctx.saved_tensors
+        B, C, D = items.shape
+        du, dv = torch.empty_like(user), torch.empty_like(items)
+        call('lk_dot_bwd', ptr(user), ptr(items), ptr(_f32(ds)), ptr(du), ptr(dv), B, C, D)
+        return du, dv
+
+
+def dot_scores(user, items):
+    return _DotScores.apply(user, items)
+
+
+class _DotCE(Function):
+    """loss = CrossEntropy(dot scores, label 0), mean — legommender.py:252-254, 263 fused with the predictor."""
+
+    @staticmethod
+    def forward(ctx, user, items):
+        user, items = _f32(user), _f32(items)
+        B, C, D = items.shape
+        dev = user.device
+        scores = torch.empty((B, C), dtype=torch.float32, device=dev)
+        probs = torch.empty((B, C), dtype=torch.float32, device=dev)
+        rowloss = torch.empty((B,), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        call('lk_dot_ce_fwd', ptr(user), ptr(items), ptr(scores), ptr(probs), ptr(rowloss), ptr(loss), B, C, D)
+        ctx.save_for_backward(user, items, probs)
+        ctx.mark_non_differentiable(scores)
+        return loss, scores
+
+    @staticmethod
+    def backward(ctx, dloss, _dscores):
+        user, items, probs = ctx.saved_tensors
+        B, C, D = items.shape
+        du, dv = torch.empty_like(user), torch.empty_like(items)
+        call('lk_dot_ce_bwd', ptr(user), ptr(items), ptr(probs), ptr(_f32(dloss)), ptr(du), ptr(dv), B, C, D)
+        return du, dv
+
+
+def dot_ce_loss(user, items):
+    """returns (loss, scores)"""
+    return _DotCE.apply(user, items)
+
+
+class _DotBCE(Function):
+    """loss = BCEWithLogits(<u,v>, click), mean — legommender.py:256-257, 285-290."""
+
+    @staticmethod
+    def forward(ctx, user, item, label):
+        user, item, label = _f32(user), _f32(item), _f32(label)
+        B, D = user.shape
+        dev = user.device
+        scores = torch.empty((B,), dtype=torch.float32, device=dev)
+        rowloss = torch.empty((B,), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        call('lk_dot_bce_fwd', ptr(user), ptr(item), ptr(label), ptr(scores), ptr(rowloss), ptr(loss), B, D)
+        ctx.save_for_backward(user, item, label, scores)
+        ctx.mark_non_differentiable(scores)
+        return loss, scores
+
+    @staticmethod
+    def backward(ctx, dloss, _ds):
+        user, item, label, scores = ctx.saved_tensors
+        B, D = user.shape
+        dz = torch.empty_like(scores)
+        du, dv = torch.empty_like(user), torch.empty_like(item)
+        call('lk_dot_bce_bwd', ptr(user), ptr(item), ptr(label), ptr(scores), ptr(_f32(dloss)), ptr(dz), ptr(du), ptr(dv), B, D)
+        return du, dv, None
+
+
+def dot_bce_loss(user, item, label):
+    return _DotBCE.apply(user, item, label)
+
+
+# ----------------------------------------------------------------------------------------------------
+# cached evaluation (no autograd: caches are detached — fast_item_pager.py:143, fast_user_pager.py:133)
+# ----------------------------------------------------------------------------------------------------
+def cached_scores(user_repr, item_repr, user_ids, item_ids, out=None):
+    """score[r] = <U[uid[r]], I[iid[r]]> — legommender.py:153-157, 202-203 + dot."""
+    user_repr, item_repr = _f32(user_repr), _f32(item_repr)
+    user_ids, item_ids = _i64(user_ids.reshape(-1)), _i64(item_ids.reshape(-1))
+    R, D = user_ids.numel(), user_repr.shape[1]
+    if out is None:
+        out = torch.empty((R,), dtype=torch.float32, device=user_repr.device)
+    call('lk_cached_scores', ptr(user_repr), ptr(item_repr), ptr(user_ids), ptr(item_ids), ptr(out), R, D)
+    return out
+
+
+def index_rows(table, ids):
+    """table[ids] for cache indexing — legommender.py:153-157."""
+    table, flat = _f32(table), _i64(ids.reshape(-1))
+    out = torch.empty((flat.numel(), table.shape[1]), dtype=torch.float32, device=table.device)
+    call('lk_index_rows', ptr(table), ptr(flat), ptr(out), flat.numel(), table.shape[1])
+    return out.view(*ids.shape, table.shape[1])
+
+
+def adam_step(p, g, m, v, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    """torch.optim.Adam defaults (base_lego.py:198-204) over one flat fp32 buffer."""
+    for t in (p, g, m, v):
+        if t.data_ptr() % 16:
+            raise RuntimeError('adam_step: buffers must be 16-byte aligned')
+    call('lk_adam_step', ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps), int(step),
+         float(grad_scale))

@@ -1,0 +1,84 @@
+"""Parity cases shared by the golden generator, the oracle tests and the GPU tests.
+
+A case is fully determined by its seeds: the world (`synth.MindWorld`) and the parameters (`synth.init_state`) are
+rebuilt on whichever box runs the test; only reference INPUT batches and OUTPUTS are stored in <case>.npz.
+"""
+from __future__ import annotations
+
+import os
+from collections import OrderedDict
+
+import numpy as np
+
+from legommenders_b200.synth import MindWorld, init_state
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+_small_world = dict(n_items=150, n_words=400, n_users=48, n_train=64, n_eval_groups=24, eval_group_mean=8,
+                    title_len=10, hist_len=12, min_title=3, max_neg=12, embed_dim=48)
+_full_world = dict(n_items=400, n_words=1500, n_users=64, n_train=64, n_eval_groups=16, eval_group_mean=10,
+                   title_len=30, hist_len=50, embed_dim=300)
+
+CASES = OrderedDict(
+    nrms_small=dict(kind='nrms', hidden=64, heads=8, additive=32, batch=6, seed=11, world=_small_world, cached_eval=True),
+    naml_small=dict(kind='naml', hidden=64, heads=8, additive=32, batch=6, seed=12, world=_small_world, cached_eval=True),
+    llmid_small=dict(kind='llmid', hidden=64, heads=8, additive=32, batch=6, seed=13, world=_small_world, llm_dim=96,
+                     cached_eval=True),
+    nrms_bce_small=dict(kind='nrms', hidden=64, heads=4, additive=32, batch=8, seed=14, world=_small_world,
+                        use_neg_sampling=False),
+    nrms_full=dict(kind='nrms', hidden=256, heads=8, additive=256, batch=4, seed=21, world=_full_world, full_grads=False),
+    naml_full=dict(kind='naml', hidden=256, heads=8, additive=256, batch=4, seed=22, world=_full_world, full_grads=False),
+)
+
+
+def make_world(c: dict):
+    world = MindWorld(seed=c['seed'], **c['world'])
+    llm = None
+    if c['kind'] == 'llmid':
+        rng = np.random.default_rng(c['seed'] + 1000)
+        llm = rng.standard_normal((world.n_items, c['llm_dim'])).astype(np.float32)
+    return world, llm
+
+
+def make_state(c: dict, world, shapes: dict, llm=None) -> dict:
+    """Deterministic parameters; pretrained tables come from the world, everything else from init_state."""
+    state = init_state(shapes, seed=c['seed'] + 7)
+    for k in shapes:
+        if k.endswith('.embedding.weight'):
+            state[k] = llm if c['kind'] == 'llmid' else world.word_table
+    return state
+
+
+def flatten_tree(tree, prefix='') -> dict:
+    out = {}
+    for k, v in tree.items():
+        if isinstance(v, dict):
+            out.update(flatten_tree(v, prefix + k + '/'))
+        else:
+            out[prefix + k] = v
+    return out
+
+
+def unflatten_batch(npz) -> dict:
+    """Rebuild the nested batch dict (torch int64 tensors) from 'batch/...' keys, preserving column order."""
+    import torch
+    root = OrderedDict()
+    for key in npz.files:
+        if not key.startswith('batch/'):
+            continue
+        parts = key[len('batch/'):].split('/')
+        d = root
+        for p in parts[:-1]:
+            d = d.setdefault(p, OrderedDict())
+        d[parts[-1]] = torch.from_numpy(npz[key])
+    return root
+
+
+def sample_strided(g: np.ndarray, n: int = 4096) -> np.ndarray:
+    flat = g.reshape(-1)
+    step = max(1, flat.size // n)
+    return flat[::step][:n].copy()
+
+
+def load(name: str):
+    return np.load(os.path.join(HERE, name + '.npz'))

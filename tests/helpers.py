@@ -1,0 +1,127 @@
+"""Shared parity plumbing: run the oracle on a golden case, compare tensors norm-wise."""
+from __future__ import annotations
+
+import copy
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+import cases
+from oracle import lego_oracle as O
+
+
+def normwise(a, b) -> float:
+    """max|a-b| / max|b| (SURVEY §8c parity protocol); 0 when both are identically zero."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = np.abs(b).max() if b.size else 0.0
+    num = np.abs(a - b).max() if b.size else 0.0
+    return float(num / den) if den > 0 else float(num)
+
+
+def case_spec(c, world):
+    return O.ModelSpec(c['kind'], c['heads'], {world.title_col: world.word_vocab, 'category': 'category'},
+                       use_neg_sampling=c.get('use_neg_sampling', True))
+
+
+def state_shapes(c, world, llm=None):
+    """Parameter shapes of the reference model for a case, without importing the reference."""
+    D, A, E = c['hidden'], c['additive'], world.embed_dim
+    s = OrderedDict()
+
+    def additive(prefix):
+        s[prefix + 'additive_attention.encoder.0.weight'] = (A, D)
+        s[prefix + 'additive_attention.encoder.0.bias'] = (A,)
+        s[prefix + 'additive_attention.encoder.2.weight'] = (1, A)
+
+    def mha(prefix):
+        s[prefix + 'multi_head_attention.in_proj_weight'] = (3 * D, D)
+        s[prefix + 'multi_head_attention.in_proj_bias'] = (3 * D,)
+        s[prefix + 'multi_head_attention.out_proj.weight'] = (D, D)
+        s[prefix + 'multi_head_attention.out_proj.bias'] = (D,)
+        s[prefix + 'linear.weight'] = (D, D)
+        s[prefix + 'linear.bias'] = (D,)
+        additive(prefix)
+
+    if c['kind'] in ('nrms', 'naml'):
+        s['embedding_vocab_table.glove.embedding.weight'] = (world.n_words, E)
+        s['embedding_vocab_table.glove.linear.weight'] = (D, E)
+        s['embedding_vocab_table.glove.linear.bias'] = (D,)
+        s['embedding_vocab_table.category.weight'] = (world.n_cats, D)
+    if c['kind'] == 'nrms':
+        s['embedding_vocab_table.__cat_inputer_special_ids.weight'] = (3, D)
+        mha('item_op.')
+        mha('user_op.')
+    elif c['kind'] == 'naml':
+        s['item_op.cnn.weight'] = (D, D, 3)
+        s['item_op.cnn.bias'] = (D,)
+        s['item_op.linear.weight'] = (D, D)
+        s['item_op.linear.bias'] = (D,)
+        additive('item_op.')
+        additive('user_op.')
+    else:
+        s['embedding_vocab_table.item_id.embedding.weight'] = (world.n_items, llm.shape[1])
+        s['embedding_vocab_table.item_id.linear.weight'] = (D, llm.shape[1])
+        s['embedding_vocab_table.item_id.linear.bias'] = (D,)
+        additive('user_op.')
+    return s
+
+
+def oracle_state(c, world, llm=None, dtype=torch.float32):
+    np_state = cases.make_state(c, world, state_shapes(c, world, llm), llm)
+    state = {}
+    for k, v in np_state.items():
+        t = torch.from_numpy(np.ascontiguousarray(v)).to(dtype)
+        frozen = k.endswith('.embedding.weight')
+        state[k] = t.requires_grad_(not frozen)
+    return np_state, state
+
+
+def oracle_run(c, world, llm, batch, dtype=torch.float32):
+    """loss + grads + scores + item/user representations from the oracle for one batch."""
+    _, state = oracle_state(c, world, llm, dtype)
+    spec = case_spec(c, world)
+    want = {}
+    loss = O.forward(state, spec, copy.deepcopy(batch), want=want)
+    loss.backward()
+    grads = {k: v.grad.detach().numpy() for k, v in state.items() if v.requires_grad}
+    with torch.no_grad():
+        scores = O.forward(state, spec, copy.deepcopy(batch), return_scores=True)
+    return dict(loss=float(loss.item()), grads=grads, scores=scores.numpy(), items=want['items'].detach().numpy(),
+                user=want['user'].detach().numpy(), state=state, spec=spec)
+
+
+def item_trees(world, kind, title_len=None):
+    """Per-item token layouts from the oracle's restatement of the inputers (a1/a2)."""
+    inputs = [world.title_col, 'category']
+    max_lens = {world.title_col: world.title_len, 'category': None}
+    tab = world.item_table()
+    out = []
+    for i in range(len(tab)):
+        s = tab[i]
+        if kind == 'nrms':
+            out.append(O.concat_layout(s, inputs, max_lens, use_cls_token=False, use_sep_token=True))
+        else:
+            out.append(O.simple_layout(s, inputs, max_lens))
+    return out
+
+
+def oracle_cached_eval(c, world, llm, state, spec):
+    hist = np.stack([O.pad_history(h, world.hist_len)[0] for h in world.histories])
+    hmask = np.stack([O.pad_history(h, world.hist_len)[1] for h in world.histories])
+    hist_t, hmask_t = torch.from_numpy(hist), torch.from_numpy(hmask)
+    item_repr = None
+    if c['kind'] != 'llmid':
+        item_repr = O.build_item_cache(state, spec, item_trees(world, c['kind']))
+    else:
+        # id path: history ids keep -1 padding through ConcatInputer (resampler.py:219-221 -> user_inputer(sample))
+        hist_t = torch.where(hmask_t > 0, hist_t, torch.full_like(hist_t, -1))
+    user_repr = O.build_user_cache(state, spec, item_repr, hist_t, hmask_t)
+    if c['kind'] == 'llmid':
+        with torch.no_grad():
+            item_all = O.table_lookup(state, spec.item_vocab, torch.arange(world.n_items))
+        scores = O.cached_scores(user_repr, item_all, torch.from_numpy(world.eval_users), torch.from_numpy(world.eval_items))
+    else:
+        scores = O.cached_scores(user_repr, item_repr, torch.from_numpy(world.eval_users), torch.from_numpy(world.eval_items))
+    return item_repr, user_repr, scores
