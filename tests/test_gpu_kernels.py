@@ -1,0 +1,347 @@
+"""Per-kernel parity of the CUDA path (through the C ABI) against the CPU oracle / plain torch fp32 math.
+Index and mask work must be bit-exact; floating point within the tolerance written at each assert."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import lego_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from legommenders_b200 import ops as _ops, _lib
+    assert _lib.load().lk_device_ok() == 1, 'not a compute-capability 10.x device'
+    return _ops
+
+
+def dev(t):
+    return t.cuda()
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    den = b.abs().max().item()
+    return ((a - b).abs().max().item() / den) if den > 0 else (a - b).abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------------ gather
+@pytest.mark.parametrize('E', [4, 64, 300, 256])
+def test_gather_rows_bit_exact(ops, E):
+    g = torch.Generator().manual_seed(E)
+    V, shape = 97, (7, 13)
+    table = torch.randn(V, E, generator=g)
+    ids = torch.randint(-1, V, shape, generator=g)
+    ids[0] = -1                                                   # a fully unset row block
+    out = ops.gather_add(None, dev(ids), None, dev(table)).cpu()
+    m = (ids > -1).long()
+    ref = F.embedding(ids * m, table) * m.unsqueeze(-1)
+    assert torch.equal(out, ref)
+    # explicit mask (SimpleInputer) + accumulate onto a base
+    mask = (torch.rand(shape, generator=g) < 0.6).long()
+    ids2 = torch.where(mask > 0, ids.clamp(min=0), torch.full_like(ids, -1))
+    base = torch.randn(*shape, E, generator=g)
+    out2 = ops.gather_add(dev(base), dev(ids2), dev(mask), dev(table)).cpu()
+    ref2 = base + F.embedding(ids2 * mask, table) * mask.unsqueeze(-1)
+    assert torch.equal(out2, ref2)
+
+
+def test_gather_empty(ops):
+    table = torch.randn(5, 8)
+    out = ops.gather_add(None, dev(torch.zeros((0, 3), dtype=torch.long)), None, dev(table))
+    assert out.shape == (0, 3, 8)
+
+
+@pytest.mark.parametrize('mode', [0, 1, 2])
+@pytest.mark.parametrize('E,S', [(300, 30), (64, 7), (512, 1)])
+def test_gather_pool(ops, mode, E, S):
+    g = torch.Generator().manual_seed(E + S + mode)
+    V, N = 211, 37
+    table = torch.randn(V, E, generator=g)
+    lens = torch.randint(0, S + 1, (N,), generator=g)              # includes empty (all-masked) rows
+    mask = (torch.arange(S)[None, :] < lens[:, None]).long()
+    ids = torch.where(mask > 0, torch.randint(0, V, (N, S), generator=g), torch.full((N, S), -1))
+    out = ops.gather_pool(dev(ids), dev(mask), dev(table), mode).cpu()
+    emb = F.embedding(ids * mask, table)
+    if mode == 2:
+        ref = (emb * mask.unsqueeze(-1)).sum(1)
+    else:
+        ref = O.pooling_operator(emb, mask, max_pooling=(mode == 1))
+    assert (out - ref).abs().max().item() <= 1e-5
+    # mask=None means ids > -1
+    out2 = ops.gather_pool(dev(ids), None, dev(table), mode).cpu()
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize('V,E,P', [(3, 64, 5000), (18, 256, 777), (5000, 300, 4096), (50, 8, 1)])
+def test_scatter_add_sorted(ops, V, E, P):
+    g = torch.Generator().manual_seed(V + P)
+    ids = torch.randint(-1, V, (P,), generator=g)
+    if P > 100:
+        ids[: P // 2] = 1                                          # one very hot row (PAD/SEP-like)
+    src = torch.randn(P, E, generator=g)
+    out = ops.scatter_add_rows(dev(ids), None, dev(src), (V, E)).cpu()
+    ref = torch.zeros(V, E, dtype=torch.float64)
+    valid = ids > -1
+    ref.index_add_(0, ids[valid], src[valid].double())
+    assert (out.double() - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item())
+    # determinism: bit-identical on a second run
+    out2 = ops.scatter_add_rows(dev(ids), None, dev(src), (V, E)).cpu()
+    assert torch.equal(out, out2)
+
+
+def test_embedding_backward_via_autograd(ops):
+    g = torch.Generator().manual_seed(3)
+    V, E = 40, 32
+    table = torch.randn(V, E, generator=g)
+    ids = torch.randint(-1, V, (6, 9), generator=g)
+    w = torch.randn(6, 9, E, generator=g)
+    t_gpu = dev(table).requires_grad_(True)
+    (ops.gather_add(None, dev(ids), None, t_gpu) * dev(w)).sum().backward()
+    t_cpu = table.clone().requires_grad_(True)
+    m = (ids > -1).long()
+    ((F.embedding(ids * m, t_cpu) * m.unsqueeze(-1)) * w).sum().backward()
+    assert rel(t_gpu.grad, t_cpu.grad) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ linear / conv
+@pytest.mark.parametrize('M,K,N', [(1, 4, 4), (130, 300, 64), (257, 256, 768), (1000, 64, 32), (65, 4096, 256)])
+@pytest.mark.parametrize('act', [0, 1, 2])
+def test_linear_fwd_bwd(ops, M, K, N, act):
+    g = torch.Generator().manual_seed(M + K + N + act)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    rowmask = (torch.rand(M, generator=g) < 0.7).long()
+    dy = torch.randn(M, N, generator=g)
+
+    def ref_fn(x, w, b):
+        y = F.linear(x, w, b)
+        y = torch.tanh(y) if act == 1 else (torch.relu(y) if act == 2 else y)
+        return y * rowmask.unsqueeze(-1)
+
+    xc, wc, bc = (t.double().requires_grad_(True) for t in (x, w, b))
+    yr = ref_fn(xc, wc, bc)
+    yr.backward(dy.double())
+    xg, wg, bg = (dev(t).requires_grad_(True) for t in (x, w, b))
+    y = ops.linear(xg, wg, bg, rowmask=dev(rowmask), act=act)
+    y.backward(dev(dy))
+    tol = 3e-6 * max(1.0, (K / 256) ** 0.5)
+    assert rel(y, yr) <= tol
+    assert rel(xg.grad, xc.grad) <= tol
+    assert rel(wg.grad, wc.grad) <= 1e-5
+    assert rel(bg.grad, bc.grad) <= 1e-5
+
+
+def test_linear_split_reduction_large_m(ops):
+    """grad-weight is a reduction over M token rows: exercise the split path at the NRMS shape."""
+    g = torch.Generator().manual_seed(5)
+    M, K, N = 33 * 400, 256, 256
+    x, dy = torch.randn(M, K, generator=g), torch.randn(M, N, generator=g)
+    w = torch.randn(N, K, generator=g) / 16
+    xg, wg = dev(x).requires_grad_(True), dev(w).requires_grad_(True)
+    ops.linear(xg, wg, None).backward(dev(dy))
+    assert rel(wg.grad, dy.double().t() @ x.double()) <= 1e-5
+    assert rel(xg.grad, dy.double() @ w.double()) <= 3e-6
+
+
+@pytest.mark.parametrize('N_,S,Cin,Cout', [(5, 30, 64, 64), (3, 7, 32, 48), (9, 2, 256, 256)])
+def test_conv1d_relu_mask(ops, N_, S, Cin, Cout):
+    g = torch.Generator().manual_seed(S + Cin)
+    x = torch.randn(N_, S, Cin, generator=g)
+    w = torch.randn(Cout, Cin, 3, generator=g) / (3 * Cin) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    lens = torch.randint(0, S + 1, (N_,), generator=g)
+    mask = (torch.arange(S)[None, :] < lens[:, None]).long()
+    dy = torch.randn(N_, S, Cout, generator=g)
+    xc, wc, bc = (t.double().requires_grad_(True) for t in (x, w, b))
+    yr = torch.relu(F.conv1d(xc.permute(0, 2, 1), wc, bc, padding=1).permute(0, 2, 1)) * mask.unsqueeze(-1)
+    yr.backward(dy.double())
+    xg, wg, bg = (dev(t).requires_grad_(True) for t in (x, w, b))
+    y = ops.conv1d_relu_mask(xg, wg, bg, dev(mask))
+    y.backward(dev(dy))
+    assert rel(y, yr) <= 3e-6
+    assert rel(xg.grad, xc.grad) <= 3e-6
+    assert rel(wg.grad, wc.grad) <= 1e-5
+    assert rel(bg.grad, bc.grad) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize('N_,S,D,H', [(11, 33, 256, 8), (4, 50, 256, 8), (7, 12, 64, 8), (3, 70, 64, 2), (2, 1, 32, 4)])
+def test_mha_core(ops, N_, S, D, H):
+    g = torch.Generator().manual_seed(S + D)
+    x = torch.randn(N_, S, D, generator=g)
+    in_w = torch.randn(3 * D, D, generator=g) / D ** 0.5
+    in_b = torch.randn(3 * D, generator=g) * 0.1
+    lens = torch.randint(1, S + 1, (N_,), generator=g)           # >= 1 valid key (Appendix C)
+    mask = (torch.arange(S)[None, :] < lens[:, None]).long()
+    dctx = torch.randn(N_, S, D, generator=g)
+    eye, zero = torch.eye(D, dtype=torch.float64), torch.zeros(D, dtype=torch.float64)
+    qkv_c = F.linear(x.double(), in_w.double(), in_b.double()).requires_grad_(True)
+
+    # oracle MHA with identity out-projection applied to a precomputed qkv
+    def ref(qkv):
+        q, k, v = qkv.split(D, dim=-1)
+        dh = D // H
+        q = q.view(N_, S, H, dh).transpose(1, 2) * dh ** -0.5
+        k = k.view(N_, S, H, dh).transpose(1, 2)
+        v = v.view(N_, S, H, dh).transpose(1, 2)
+        lg = (q @ k.transpose(-1, -2)).masked_fill((1 - mask).bool()[:, None, None, :], float('-inf'))
+        return (torch.softmax(lg, -1) @ v).transpose(1, 2).reshape(N_, S, D)
+
+    cr = ref(qkv_c)
+    cr.backward(dctx.double())
+    # cross-check the restated formula against the oracle's full MHA (identity out_proj)
+    full = O.multi_head_self_attention(x.double(), mask, in_w.double(), in_b.double(), eye, zero, H)
+    assert rel(cr, full) <= 1e-12
+    qkv_g = dev(qkv_c.detach().float()).requires_grad_(True)
+    c = ops.mha_core(qkv_g, dev(mask), H)
+    c.backward(dev(dctx))
+    assert rel(c, cr) <= 3e-6
+    assert rel(qkv_g.grad, qkv_c.grad) <= 5e-6
+
+
+@pytest.mark.parametrize('N_,S,D,A', [(13, 33, 256, 256), (5, 50, 256, 256), (9, 11, 64, 32), (3, 1, 64, 32)])
+def test_additive_attention(ops, N_, S, D, A):
+    g = torch.Generator().manual_seed(S + D + A)
+    x = torch.randn(N_, S, D, generator=g)
+    w1 = torch.randn(A, D, generator=g) / D ** 0.5
+    b1 = torch.randn(A, generator=g) * 0.1
+    w2 = torch.randn(1, A, generator=g) / A ** 0.5
+    lens = torch.randint(0, S + 1, (N_,), generator=g)             # an all-masked row must give zeros, not NaN
+    lens[0] = 0
+    mask = (torch.arange(S)[None, :] < lens[:, None]).long()
+    do = torch.randn(N_, D, generator=g)
+    cs = [t.double().requires_grad_(True) for t in (x, w1, b1, w2)]
+    yr = O.additive_attention(cs[0], mask, cs[1], cs[2], cs[3])
+    yr.backward(do.double())
+    gs = [dev(t).requires_grad_(True) for t in (x, w1, b1, w2)]
+    y = ops.additive_attention(gs[0], dev(mask), gs[1], gs[2], gs[3])
+    y.backward(dev(do))
+    assert torch.isfinite(y).all() and (y[0] == 0).all()
+    assert rel(y, yr) <= 3e-6
+    for a, b_ in zip(gs, cs):
+        assert rel(a.grad, b_.grad) <= 1e-5
+    # no mask at all
+    y2 = ops.additive_attention(gs[0].detach(), None, gs[1].detach(), gs[2].detach(), gs[3].detach())
+    assert rel(y2, O.additive_attention(x.double(), None, w1.double(), b1.double(), w2.double())) <= 3e-6
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+def test_masked_pool(ops, mode):
+    g = torch.Generator().manual_seed(mode)
+    N_, S, D = 17, 9, 64
+    x = torch.randn(N_, S, D, generator=g)
+    lens = torch.randint(0, S + 1, (N_,), generator=g)
+    mask = (torch.arange(S)[None, :] < lens[:, None]).long()
+    ref = O.pooling_operator(x, mask, max_pooling=(mode == 1))
+    out = ops.masked_pool(dev(x), dev(mask), mode).cpu()
+    assert (out - ref).abs().max().item() <= 1e-6
+    if mode == 0:
+        xg = dev(x).requires_grad_(True)
+        w = torch.randn(N_, D, generator=g)
+        (ops.masked_pool(xg, dev(mask), 0) * dev(w)).sum().backward()
+        xc = x.clone().requires_grad_(True)
+        (O.pooling_operator(xc, mask) * w).sum().backward()
+        assert rel(xg.grad, xc.grad) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ scoring / loss
+@pytest.mark.parametrize('B,C,D', [(64, 5, 256), (7, 3, 64), (1, 1, 32), (513, 5, 256)])
+def test_dot_ce(ops, B, C, D):
+    g = torch.Generator().manual_seed(B + C)
+    u, v = torch.randn(B, D, generator=g) * 0.3, torch.randn(B, C, D, generator=g) * 0.3
+    uc, vc = u.double().requires_grad_(True), v.double().requires_grad_(True)
+    sr = O.dot_scores(uc, vc)
+    lr = F.cross_entropy(sr, torch.zeros(B, dtype=torch.long))
+    lr.backward()
+    ug, vg = dev(u).requires_grad_(True), dev(v).requires_grad_(True)
+    loss, scores = ops.dot_ce_loss(ug, vg)
+    (loss * 1.0).backward()
+    assert rel(scores, sr) <= 2e-6
+    assert abs(loss.item() - lr.item()) <= 1e-6 * abs(lr.item())
+    assert rel(ug.grad, uc.grad) <= 5e-6 and rel(vg.grad, vc.grad) <= 5e-6
+    s2 = ops.dot_scores(dev(u), dev(v))
+    assert torch.equal(s2, scores)
+
+
+def test_dot_scores_backward(ops):
+    g = torch.Generator().manual_seed(9)
+    u, v, ds = torch.randn(6, 64, generator=g), torch.randn(6, 4, 64, generator=g), torch.randn(6, 4, generator=g)
+    uc, vc = u.double().requires_grad_(True), v.double().requires_grad_(True)
+    O.dot_scores(uc, vc).backward(ds.double())
+    ug, vg = dev(u).requires_grad_(True), dev(v).requires_grad_(True)
+    ops.dot_scores(ug, vg).backward(dev(ds))
+    assert rel(ug.grad, uc.grad) <= 2e-6 and rel(vg.grad, vc.grad) <= 2e-6
+
+
+def test_dot_bce(ops):
+    g = torch.Generator().manual_seed(2)
+    B, D = 37, 64
+    u, v = torch.randn(B, D, generator=g) * 0.4, torch.randn(B, D, generator=g) * 0.4
+    y = (torch.rand(B, generator=g) < 0.4).long()
+    uc, vc = u.double().requires_grad_(True), v.double().requires_grad_(True)
+    lr = O.bce_loss((uc * vc).sum(-1), y)
+    lr.backward()
+    ug, vg = dev(u).requires_grad_(True), dev(v).requires_grad_(True)
+    loss, scores = ops.dot_bce_loss(ug, vg, dev(y).float())
+    loss.backward()
+    assert abs(loss.item() - lr.item()) <= 2e-6 * abs(lr.item())
+    assert rel(ug.grad, uc.grad) <= 5e-6 and rel(vg.grad, vc.grad) <= 5e-6
+
+
+@pytest.mark.parametrize('R', [0, 1, 2, 1001, 70000])
+def test_cached_scores(ops, R):
+    g = torch.Generator().manual_seed(R)
+    NU, NI, D = 300, 500, 256
+    U, I = torch.randn(NU, D, generator=g), torch.randn(NI, D, generator=g)
+    uid, iid = torch.randint(0, NU, (R,), generator=g), torch.randint(0, NI, (R,), generator=g)
+    out = ops.cached_scores(dev(U), dev(I), dev(uid), dev(iid)).cpu()
+    ref = O.cached_scores(U.double(), I.double(), uid, iid)
+    assert out.shape == (R,)
+    if R:
+        assert rel(out, ref) <= 2e-6
+        assert torch.equal(ops.index_rows(dev(I), dev(iid.view(-1, 1))).cpu(), I[iid].view(R, 1, D))   # cache indexing: bit-exact
+
+
+def test_adam_matches_torch(ops):
+    g = torch.Generator().manual_seed(4)
+    n = 10007
+    p0 = torch.randn(n, generator=g)
+    pc = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pc], lr=1e-3)
+    pg = dev(p0.clone())
+    m, v = torch.zeros_like(pg), torch.zeros_like(pg)
+    for step in range(1, 6):
+        grad = torch.randn(n, generator=g)
+        pc.grad = grad.clone()
+        opt.step()
+        ops.adam_step(pg, dev(grad), m, v, step, lr=1e-3)
+    assert (pg.cpu() - pc.detach()).abs().max().item() <= 1e-6
+
+
+def test_dropout_statistics_and_backward(ops):
+    """Training-mode dropout is defined by its statistics: keep-rate 1-p, scale 1/(1-p), and the backward
+    uses the same mask as the forward."""
+    M, K, N, p = 512, 64, 256, 0.1
+    x = torch.ones(M, K)
+    w = torch.ones(N, K) / K
+    xg, wg = dev(x).requires_grad_(True), dev(w).requires_grad_(True)
+    y = ops.linear(xg, wg, None, drop_p=p, seed=1234)
+    yc = y.detach().cpu()
+    kept = (yc != 0)
+    assert abs(kept.float().mean().item() - (1 - p)) < 0.01
+    assert torch.allclose(yc[kept], torch.full_like(yc[kept], 1 / (1 - p)), rtol=1e-5)
+    y.sum().backward()
+    # dX[m,k] = sum_n mask[m,n]/(1-p) * w[n,k]
+    ref = (kept.float() / (1 - p)) @ w
+    assert rel(xg.grad, ref) <= 1e-5
+    y2 = ops.linear(xg.detach(), wg.detach(), None, drop_p=p, seed=99).cpu()
+    assert not torch.equal(y2 != 0, kept)                          # a different seed gives a different mask
+
+
+def test_error_reporting(ops):
+    with pytest.raises(RuntimeError, match='multiple'):
+        ops.gather_add(None, dev(torch.zeros(3, dtype=torch.long)), None, dev(torch.randn(4, 6)))

@@ -1,0 +1,161 @@
+"""End-to-end parity of the CUDA path behind the reference's plugin surface: loss, scores, representations, every
+parameter gradient, the two caches, cached scoring and the five default metrics — against the committed golden
+vectors (minted from the live reference) and against the oracle on the same inputs."""
+import copy
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import helpers
+from oracle import lego_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4   # BASELINE.json north_star: 1e-4 relative on fp32 logits and losses (norm-wise)
+
+
+def build(c, world, llm):
+    from legommenders_b200 import builder
+    model, resampler, cfg = builder.build_model(world, c['kind'], hidden=c['hidden'], heads=c['heads'], additive=c['additive'],
+                                                dropout=0.0, use_neg_sampling=c.get('use_neg_sampling', True),
+                                                llm_item_table=llm)
+    np_state, _ = helpers.oracle_state(c, world, llm)
+    builder.load_state(model, np_state)
+    return model, resampler, cfg
+
+
+@pytest.mark.parametrize('name', list(cases.CASES))
+def test_train_step_parity(name):
+    from legommenders_b200 import Env
+    c = cases.CASES[name]
+    g = cases.load(name)
+    world, llm = cases.make_world(c)
+    model, resampler, cfg = build(c, world, llm)
+    batch = cases.unflatten_batch(g)
+    ora = helpers.oracle_run(c, world, llm, batch)
+
+    Env.train()
+    model.train()
+    loss = model(batch=copy.deepcopy(batch))
+    loss.backward()
+    for ref_loss in (float(g['loss']), ora['loss']):
+        assert abs(loss.item() - ref_loss) <= TOL * abs(ref_loss)
+    grads = {n: p.grad.detach().cpu().numpy() for n, p in model.named_parameters() if p.requires_grad}
+    assert set(grads) == set(ora['grads'])
+    scale = max(np.abs(v).max() for v in ora['grads'].values())
+    for k, ref in ora['grads'].items():
+        assert np.abs(grads[k] - ref).max() <= TOL * max(np.abs(ref).max(), 5e-2 * scale), k
+        if 'grad/' + k in g.files:
+            gref = g['grad/' + k]
+            assert np.abs(grads[k] - gref).max() <= TOL * max(np.abs(gref).max(), 5e-2 * scale), k
+        else:
+            assert np.abs(cases.sample_strided(grads[k]) - g['gradsample/' + k]).max() <= TOL * max(float(g['gradmax/' + k]), 5e-2 * scale), k
+
+    Env.test()
+    with torch.no_grad():
+        scores = model(batch=copy.deepcopy(batch)).cpu().numpy()
+        user = model.get_user_content(copy.deepcopy(batch)).cpu().numpy()
+        assert helpers.normwise(scores, g['scores']) <= TOL and helpers.normwise(scores, ora['scores']) <= TOL
+        assert helpers.normwise(user, g['user']) <= TOL
+        if 'items' in g.files:
+            items = model.get_item_content(copy.deepcopy(batch), 'item_id').cpu().numpy()
+            assert helpers.normwise(items, g['items']) <= TOL
+    Env.train()
+
+
+@pytest.mark.parametrize('name', ['nrms_small', 'naml_small'])
+def test_batch_builder_bit_exact(name):
+    """Resampler + inputers + default_collate reproduce the reference batch bit for bit under the same `random` seed."""
+    from torch.utils.data import DataLoader
+    from legommenders_b200 import DataSet, Env
+    c = cases.CASES[name]
+    g = cases.load(name)
+    world, llm = cases.make_world(c)
+    model, resampler, cfg = build(c, world, llm)
+    Env.train()
+    random.seed(c['seed'])
+    batch = next(iter(DataLoader(DataSet(world.train_table(), resampler), batch_size=c['batch'], num_workers=0, shuffle=False)))
+    flat = cases.flatten_tree(batch)
+    keys = [k for k in g.files if k.startswith('batch/')]
+    assert sorted('batch/' + k for k in flat) == sorted(keys)
+    for k, v in flat.items():
+        assert v.dtype == torch.int64
+        assert np.array_equal(v.numpy(), g['batch/' + k]), k
+
+
+@pytest.mark.parametrize('name', [n for n, c in cases.CASES.items() if c.get('cached_eval')])
+def test_cached_eval_parity(name):
+    from torch.utils.data import DataLoader
+    from legommenders_b200 import DataSet, Env, ops
+    c = cases.CASES[name]
+    g = cases.load(name)
+    world, llm = cases.make_world(c)
+    model, resampler, cfg = build(c, world, llm)
+    Env.test()
+    model.eval()
+    model.cacher.cache(item_contents=resampler.item_cache, user_contents=DataSet(world.fast_table(), resampler))
+    assert Env.user_cache and model.cacher.user.cached
+    if cfg.use_item_content:
+        assert Env.item_cache and model.cacher.item.cached
+        assert np.abs(model.cacher.item.repr.cpu().numpy() - g['item_repr']).max() <= 1e-5
+    assert np.abs(model.cacher.user.repr.cpu().numpy() - g['user_repr']).max() <= 1e-5
+
+    # the reference's own loop: 64-row batches of (user, item) ids through forward()
+    sc = []
+    with torch.no_grad():
+        for eb in DataLoader(DataSet(world.eval_table(), resampler), batch_size=64, num_workers=0, shuffle=False):
+            assert set(eb) == {'index', 'user_id', 'item_id', 'click'}
+            sc.append(model(batch=eb).reshape(-1).cpu())
+    sc = torch.cat(sc).numpy()
+    assert helpers.normwise(sc, g['eval_scores']) <= TOL
+    m = O.metric_pool(sc, g['eval_labels'], g['eval_groups'])
+    for (k, v), ref in zip(m.items(), g['metrics']):
+        assert round(v, 4) == round(float(ref), 4), k
+
+    # one-launch scoring of every row (the cached-eval kernel proper)
+    if cfg.use_item_content:
+        allsc = ops.cached_scores(model.cacher.user.repr, model.cacher.item.repr,
+                                  torch.from_numpy(world.eval_users).cuda(), torch.from_numpy(world.eval_items).cuda()).cpu().numpy()
+        assert np.array_equal(allsc, sc)
+    model.cacher.clean()
+    assert not Env.item_cache and not Env.user_cache
+    Env.train()
+
+
+def test_state_dict_names_match_reference():
+    c = cases.CASES['nrms_small']
+    world, llm = cases.make_world(c)
+    model, _, _ = build(c, world, llm)
+    assert set(model.state_dict()) == set(helpers.state_shapes(c, world))
+    c = cases.CASES['naml_small']
+    world, llm = cases.make_world(c)
+    model, _, _ = build(c, world, llm)
+    assert set(model.state_dict()) == set(helpers.state_shapes(c, world))
+
+
+def test_training_reduces_loss_with_dropout():
+    """A few Adam steps with the reference's dropout rates on: loss is finite and goes down on a fixed batch."""
+    from legommenders_b200 import Env, ops
+    from legommenders_b200.trainer import FlatAdam
+    c = cases.CASES['nrms_small']
+    g = cases.load('nrms_small')
+    world, llm = cases.make_world(c)
+    from legommenders_b200 import builder
+    torch.manual_seed(0)
+    model, _, _ = builder.build_model(world, 'nrms', hidden=64, heads=8, additive=32, dropout=0.1)
+    opt = FlatAdam(model, lr=1e-3)
+    batch = cases.unflatten_batch(g)
+    Env.train()
+    model.train()
+    losses = []
+    for _ in range(30):
+        opt.zero_grad()
+        loss = model(batch=copy.deepcopy(batch))
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(np.isfinite(losses))
+    assert np.mean(losses[-5:]) < np.mean(losses[:5])
