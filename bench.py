@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — NRMS training throughput on synthetic MIND-small-shaped data (BASELINE.json metric), one process per GPU.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
+
+A step = one pass of the hot path over one batch of B=64 impressions per GPU: EmbeddingHub gather + projection, NRMS
+item encoder over 55 items/impression, NRMS user encoder, dot scoring + softmax-CE, backward, Adam (and the gradient
+allreduce when N>1).  Training mode with the reference's dropout rates (0.1) on.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# MIND-small shape
+WORKLOAD = dict(n_items=65238, n_words=400000, n_users=91935, n_cats=18, title_len=30, hist_len=50, n_train=208238,
+                n_eval_groups=73152, eval_group_mean=36, embed_dim=300)
+HIDDEN, HEADS, ADDITIVE, NEG, DROPOUT = 256, 8, 256, 4, 0.1
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=64, help='impressions per GPU per step')
+    ap.add_argument('--small', action='store_true', help='tiny world (debug only; not a valid bench line)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-seconds', type=float, default=15.0)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p['hbm_gbs'], tensor=p.get('bf16_tflops_sustained', p['bf16_tflops']), which='measured')
+    return dict(hbm=6650.0, tensor=1400.0, which='fallback')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [l.split(', ') for t, l in self.lines if t0 <= t <= t1 + 0.2] or [l.split(', ') for _, l in self.lines[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+def build_world(small: bool, seed=2023):
+    from legommenders_b200.synth import MindWorld
+    if small:
+        return MindWorld(n_items=2000, n_words=5000, n_users=500, n_train=4096, n_eval_groups=200, seed=seed)
+    return MindWorld(seed=seed, **WORKLOAD)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the reference's CPU path (oracle port): fwd + bwd + Adam with all host threads, training-mode dropout
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference(world, batches, budget_s=None, steps=None, warmup=1):
+    from oracle import lego_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    shapes = O.state_shapes('nrms', HIDDEN, ADDITIVE, world.embed_dim, world.n_words, world.n_cats)
+    state = O.default_state(shapes, {'embedding_vocab_table.glove.embedding.weight': torch.from_numpy(world.word_table)})
+    spec = O.ModelSpec('nrms', HEADS, {world.title_col: world.word_vocab, 'category': 'category'})
+    opt = torch.optim.Adam([v for v in state.values() if v.requires_grad], lr=1e-3)
+    O.DROPOUT = DROPOUT
+    B = next(iter(batches[0]['history']['input_ids'].values())).shape[0]
+
+    def step(i):
+        opt.zero_grad()
+        loss = O.forward(state, spec, batches[i % len(batches)])
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    for i in range(warmup):
+        step(i)
+    t0 = time.time()
+    n = 0
+    while True:
+        step(warmup + n)
+        n += 1
+        if steps is not None and n >= steps:
+            break
+        if steps is None and (time.time() - t0 >= budget_s and n >= 2):
+            break
+    dt = time.time() - t0
+    O.DROPOUT = 0.0
+    return dict(value=n * B / dt, steps=n, seconds=dt, batch=B)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0))
+    world_size = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    workload_name = 'NRMS train step, synthetic MIND-small shape (65,238 items, 400k x 300 GloVe-shaped table, title 30, history 50, 1+4 candidates, hidden 256)'
+    base_cfg = dict(workload=workload_name, batch_per_gpu=args.batch, global_batch=args.batch * max(world_size, 1),
+                    items_per_step_per_gpu=args.batch * (1 + NEG + WORKLOAD['hist_len']), dropout=DROPOUT,
+                    parallelism=f'dp{world_size}' if world_size > 1 else 'single')
+
+    # ---------------- reference arm: CPU only, rank 0 only ----------------------------------------------------
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        from legommenders_b200.synth import MindWorld  # data generator only (numpy)
+        world = build_world(args.small)
+        batches = host_batches_cpu(world, args.batch, 4)
+        bsz = args.batch
+        r = cpu_reference(world, batches, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+        line = dict(metric='NRMS train impressions/s', value=r['value'], unit='impressions/s', n_gpus=args.gpus, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=1000 * r['seconds'] / r['steps'], higher_is_better=True, scaling='weak',
+                    vs_baseline=None, dtype='f32', data='synthetic', impl='reference', config=base_cfg,
+                    cpu_baseline=dict(value=r['value'], unit='impressions/s', cores=os.cpu_count(), kind='port',
+                                      sample=f'{r["steps"]} steps x {bsz} impressions, fwd+bwd+Adam, dropout {DROPOUT}, torch CPU fp32'),
+                    e2e=dict(value=r['value'], unit='impressions/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    # ---------------- B200 arm ---------------------------------------------------------------------------------------
+    import torch.distributed as dist
+    if world_size > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world_size > 1:
+        dist.barrier()
+    from legommenders_b200 import Env, _lib, builder
+    from legommenders_b200.batching import BatchBuilder, tree_bytes, tree_to_device
+    from legommenders_b200.trainer import FlatAdam
+
+    torch.manual_seed(2023)
+    world = build_world(args.small)
+    model, resampler, cfg = builder.build_model(world, 'nrms', hidden=HIDDEN, heads=HEADS, additive=ADDITIVE, dropout=DROPOUT,
+                                                neg_count=NEG, device_index=local_rank)
+    dev = Env.device
+    opt = FlatAdam(model, lr=1e-3)
+    Env.train()
+    model.train()
+
+    bb = BatchBuilder(resampler, world, neg_count=NEG, seed=1000 + rank)
+    rng = np.random.default_rng(77 + rank)
+    POOL = 8
+    host = [bb.train_batch(rng.integers(0, world.n_train, size=args.batch)) for _ in range(POOL)]
+    devb = [tree_to_device(b, dev, non_blocking=False) for b in host]
+    h2d = tree_bytes(host[0])
+
+    def step(batch):
+        opt.zero_grad()
+        loss = model(batch=batch)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, k):
+        """K steps bracketed by barrier + synchronize; device time by CUDA events; max over ranks."""
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        sync_all()
+        w1 = time.time()
+        ms = e0.elapsed_time(e1)
+        if world_size > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, w0, w1
+
+    for i in range(max(args.warmup, 3)):
+        step(devb[i % POOL])
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = _lib.load().lk_launch_count()
+    ms, w0, w1 = timed(lambda i: step(devb[i % POOL]), args.steps)
+    launches = int(_lib.load().lk_launch_count() - l0)
+    clocks = sampler.stop(w0, w1) if sampler else None
+    value = world_size * args.batch * args.steps / (ms / 1000.0)
+
+    # e2e: host (pinned) batch -> H2D -> step -> D2H loss read, every step
+    def e2e_step(i):
+        b = tree_to_device(host[i % POOL], dev, non_blocking=True)
+        return step(b).item()
+
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e, _, _ = timed(e2e_step, args.steps)
+    e2e_value = world_size * args.batch * args.steps / (ms_e2e / 1000.0)
+
+    # per-entry-point device time over two extra steps (CUDA events around every C-ABI call on the launching stream)
+    roof, shares = None, None
+    if rank == 0:
+        prof = _lib.profile_begin()
+        for i in range(2):
+            step(devb[i % POOL])
+        torch.cuda.synchronize()
+        shares, gemm = _lib.profile_end(prof)
+        pk = peaks()
+        if gemm['ms'] > 0:
+            ach = gemm['flops'] / (gemm['ms'] / 1e3) / 1e12
+            roof = dict(bound='tensor', kernel='gemm_simt_kernel (lk_linear_* / MHA projections)', achieved=ach, peak=pk['tensor'],
+                        unit='TFLOP/s', frac=ach / pk['tensor'], traffic=None, peak_source=pk['which'],
+                        share_of_step=gemm['ms'] / max(sum(shares.values()), 1e-9), launches=gemm['calls'],
+                        note='algorithmic flops 2*M*N*K per call / CUDA-event time per call; fp32 FFMA path')
+
+    line = dict(metric='NRMS train impressions/s', value=value, unit='impressions/s', n_gpus=world_size, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f32', data='synthetic', impl='b200',
+                config=dict(base_cfg, l2='per-step working set (~1 GB of activations) exceeds the 126 MB L2; batches rotate through a pool of 8'),
+                clocks=clocks,
+                e2e=dict(value=e2e_value, unit='impressions/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                         ms_per_step=ms_e2e / args.steps),
+                gpu_launches=launches, roofline=roof, kernel_ms_share=shares)
+
+    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+        hb = [{k: v for k, v in b.items()} for b in host[:4]]
+        r = cpu_reference(world, hb, budget_s=args.cpu_seconds)
+        line['cpu_baseline'] = dict(value=r['value'], unit='impressions/s', cores=os.cpu_count(), kind='port',
+                                    sample=f'{r["steps"]} steps x {r["batch"]} impressions ({r["seconds"]:.1f} s), fwd+bwd+Adam, dropout {DROPOUT}, torch CPU fp32')
+    if rank == 0:
+        print(json.dumps(line))
+    if world_size > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def host_batches_cpu(world, batch, n):
+    """Wire-format batches without touching CUDA (reference arm): inputer layouts via the oracle's integer restatement."""
+    from collections import OrderedDict
+    from oracle import lego_oracle as O
+    inputs = [world.title_col, 'category']
+    max_lens = {world.title_col: world.title_len, 'category': None}
+    tab = world.item_table()
+    cols = None
+    rows = []
+    for i in range(len(tab)):
+        rows.append(O.concat_layout(tab[i], inputs, max_lens, False, True))
+    ids = OrderedDict((c, torch.from_numpy(np.stack([r['input_ids'][c] for r in rows]))) for c in rows[0]['input_ids'])
+    am = torch.from_numpy(np.stack([r['attention_mask'] for r in rows]))
+    rng = np.random.default_rng(5)
+    out = []
+    for _ in range(n):
+        r = rng.integers(0, world.n_train, size=batch)
+        users = world.train_users[r]
+        cand = np.concatenate([world.train_pos[r][:, None], rng.integers(0, world.n_items, size=(batch, NEG))], axis=1)
+        hist = np.zeros((batch, world.hist_len), dtype=np.int64)
+        hm = np.zeros((batch, world.hist_len), dtype=np.int64)
+        for b, u in enumerate(users):
+            h = world.histories[int(u)]
+            hist[b, :len(h)] = h
+            hm[b, :len(h)] = 1
+        ct, ht = torch.from_numpy(cand), torch.from_numpy(hist)
+        out.append({'item_id': dict(input_ids=OrderedDict((c, v[ct]) for c, v in ids.items()), attention_mask=am[ct]),
+                    'history': dict(input_ids=OrderedDict((c, v[ht]) for c, v in ids.items()), attention_mask=am[ht]),
+                    '__clicks_mask__': torch.from_numpy(hm), 'user_id': torch.from_numpy(users),
+                    'click': torch.ones(batch, dtype=torch.int64)})
+    return out
+
+
+if __name__ == '__main__':
+    main()

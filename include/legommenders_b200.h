@@ -28,6 +28,8 @@ const char* lk_version(void);
 const char* lk_last_error(void);
 /* 1 when the library was compiled for sm_100a and the current device is compute capability 10.x */
 int lk_device_ok(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long lk_launch_count(void);
 
 /* ---- (1) EmbeddingHub token gather — model/inputer/concat_inputer.py:105-113, simple_inputer.py:51-64,
  *      loader/embedding_hub.py:378-385 (aten::embedding + mask multiply + add) ------------------------- */

@@ -23,6 +23,7 @@ SIGNATURES = {
     'lk_version': ('', 'c'),
     'lk_last_error': ('', 'c'),
     'lk_device_ok': ('', 'i'),
+    'lk_launch_count': ('', 'u'),
     'lk_gather_rows': ('ppppqqis', 'i'),
     'lk_gather_pool': ('ppppqqqis', 'i'),
     'lk_scatter_add_workspace_bytes': ('qqq', 'z'),
@@ -91,12 +92,55 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+_profile = None   # when a list: (name, flops, start_event, stop_event) per C-ABI call (bench.py's per-kernel timing)
+
+# algorithmic flops of the dense-contraction entry points, from their (M, N, K) arguments
+_FLOPS = {
+    'lk_linear_fwd': lambda a: 2 * a[5] * a[6] * a[7],
+    'lk_linear_bwd_data': lambda a: 2 * a[3] * a[4] * a[5],
+    'lk_linear_bwd_weight': lambda a: 2 * a[4] * a[5] * a[6],
+    'lk_conv1d_fwd': lambda a: 2 * a[5] * a[7] * a[8] * a[9],
+    'lk_conv1d_bwd_data': lambda a: 2 * a[3] * a[5] * a[6] * a[7],
+    'lk_conv1d_bwd_weight': lambda a: 2 * a[4] * a[6] * a[7] * a[8],
+}
+
+
 def call(name: str, *args):
     """Invoke an int-returning entry point on the current stream; raise on a non-zero status."""
     lib = load()
-    rc = getattr(lib, name)(*args, stream())
+    if _profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream())
+        e1.record()
+        f = _FLOPS.get(name)
+        _profile.append((name, f(args) if f else 0, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args, stream())
     if rc != 0:
         raise RuntimeError(f'{name} failed ({rc}): {lib.lk_last_error().decode()}')
+
+
+def profile_begin():
+    global _profile
+    _profile = []
+    return _profile
+
+
+def profile_end(records):
+    """-> ({entry point: total ms}, {'ms','flops','calls'} of the dense-contraction entry points)."""
+    global _profile
+    _profile = None
+    torch.cuda.synchronize()
+    shares, gemm = {}, dict(ms=0.0, flops=0, calls=0)
+    for name, flops, e0, e1 in records:
+        ms = e0.elapsed_time(e1)
+        shares[name] = shares.get(name, 0.0) + ms
+        if flops:
+            gemm['ms'] += ms
+            gemm['flops'] += flops
+            gemm['calls'] += 1
+    return {k: round(v, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])}, gemm
 
 
 def query(name: str, *args) -> int:

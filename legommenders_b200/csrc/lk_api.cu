@@ -13,9 +13,13 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static unsigned long long g_launches = 0;
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 }  // namespace lk
 
 extern "C" {
+
+unsigned long long lk_launch_count(void) { return __atomic_load_n(&lk::g_launches, __ATOMIC_RELAXED); }
 
 const char* lk_version(void) { return "legommenders_b200 0.1 (sm_100a)"; }
 

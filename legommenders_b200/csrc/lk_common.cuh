@@ -12,8 +12,10 @@
 namespace lk {
 
 void set_error(const char* fmt, ...);
+void count_launches(int n);   // kernels launched by this library (reported by lk_launch_count)
 
-inline int check_launch(const char* what) {
+inline int check_launch(const char* what, int n = 1) {
+  count_launches(n);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));

@@ -265,7 +265,7 @@ int lk_scatter_add_sorted(const int64_t* ids, const int64_t* mask, const float* 
                                             w.partial, maxp);
   dim3 g2((cap + GW - 1) / GW, (unsigned)((E + 127) / 128));
   run_reduce_kernel<<<g2, GW * 32, 0, st>>>(w.run_key, w.run_len, w.part_off, w.num_runs, w.partial, dtable, (int)V, (int)E, 1, cap);
-  return check_launch("scatter_add_sorted");
+  return check_launch("scatter_add_sorted", 4);
 }
 
 }  // extern "C"

@@ -347,7 +347,7 @@ int lk_linear_bwd_weight(const float* dY, const float* X, float* dW, float* db, 
     dim3 g1((unsigned)((N + 127) / 128), nparts);
     colsum_stage1<<<g1, 128, 0, st>>>(dY, part, (int)M, (int)N, rpb);
     colsum_stage2<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(part, db, nparts, (int)N, accumulate);
-    rc = check_launch("colsum");
+    rc = check_launch("colsum", 2);
   }
   return rc;
 }
@@ -381,7 +381,7 @@ int lk_colsum(const float* X, float* out, int64_t M, int64_t N, int accumulate, 
   dim3 g1((unsigned)((N + 127) / 128), nparts);
   colsum_stage1<<<g1, 128, 0, st>>>(X, (float*)workspace, (int)M, (int)N, rpb);
   colsum_stage2<<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const float*)workspace, out, nparts, (int)N, accumulate);
-  return check_launch("colsum");
+  return check_launch("colsum", 2);
 }
 
 // ---- Conv1d(k, 'same') over S-long sequences as implicit-im2col GEMMs --------------------------------
@@ -444,7 +444,7 @@ int lk_conv1d_bwd_weight(const float* dY, const float* X, float* dWr, float* db,
     dim3 g1((unsigned)((Cout + 127) / 128), nparts);
     colsum_stage1<<<g1, 128, 0, st>>>(dY, part, (int)rows, (int)Cout, rpb);
     colsum_stage2<<<(unsigned)((Cout + 127) / 128), 128, 0, st>>>(part, db, nparts, (int)Cout, accumulate);
-    rc = check_launch("colsum");
+    rc = check_launch("colsum", 2);
   }
   return rc;
 }

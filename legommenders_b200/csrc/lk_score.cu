@@ -210,7 +210,7 @@ int lk_dot_ce_fwd(const float* U, const float* V, float* scores, float* probs, f
   LK_REQUIRE(B > 0 && C > 0, LK_ERR_SHAPE, "lk_dot_ce_fwd: empty batch");
   dot_ce_fwd_kernel<<<(unsigned)((B + SW - 1) / SW), SW * 32, 0, st>>>(U, V, scores, probs, rowloss, B, (int)C, (int)D);
   mean_kernel<<<1, 256, 0, st>>>(rowloss, loss, B);
-  return check_launch("dot_ce_fwd");
+  return check_launch("dot_ce_fwd", 2);
 }
 
 int lk_dot_ce_bwd(const float* U, const float* V, const float* probs, const float* dloss, float* dU, float* dV, int64_t B,
@@ -235,7 +235,7 @@ int lk_dot_bce_fwd(const float* U, const float* V, const float* y, float* scores
   LK_REQUIRE(B > 0, LK_ERR_SHAPE, "lk_dot_bce_fwd: empty batch");
   dot_bce_fwd_kernel<<<(unsigned)((B + SW - 1) / SW), SW * 32, 0, st>>>(U, V, y, scores, rowloss, B, (int)D);
   mean_kernel<<<1, 256, 0, st>>>(rowloss, loss, B);
-  return check_launch("dot_bce_fwd");
+  return check_launch("dot_bce_fwd", 2);
 }
 
 int lk_dot_bce_bwd(const float* U, const float* V, const float* y, const float* scores, const float* dloss, float* dz, float* dU,
@@ -244,7 +244,7 @@ int lk_dot_bce_bwd(const float* U, const float* V, const float* y, const float* 
   if (B == 0) return LK_OK;
   bce_dscore_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(scores, y, dloss, dz, B);
   dot_bwd_kernel<<<(unsigned)((B + SW - 1) / SW), SW * 32, 0, st>>>(U, V, dz, dU, dV, B, 1, (int)D);
-  return check_launch("dot_bce_bwd");
+  return check_launch("dot_bce_bwd", 2);
 }
 
 int lk_cached_scores(const float* U, const float* I, const int64_t* uid, const int64_t* iid, float* out, int64_t R, int64_t D,

@@ -88,6 +88,7 @@ class MindWorld:
         self.seed = seed
         self.n_items, self.n_words, self.n_users, self.n_cats = n_items, n_words, n_users, n_cats
         self.title_len, self.hist_len, self.embed_dim = title_len, hist_len, embed_dim
+        self.n_train = n_train
         self.title_col, self.word_vocab = title_col, word_vocab
 
         # ---- items ------------------------------------------------------------------

@@ -29,6 +29,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+DROPOUT = 0.0                   # parity runs keep 0; bench's CPU baseline sets the reference's 0.1 (training mode)
 UNSET = -1                      # loader/env.py:7
 EPS32 = 1.1920928955078125e-07  # torch.finfo(float32).eps, model/common/attention.py:36
 PAD, CLS, SEP = 0, 1, 2         # model/inputer/concat_inputer.py:27-30
@@ -110,7 +111,7 @@ def table_lookup(state: dict, vocab: str, ids: torch.Tensor, prefix='embedding_v
     k = prefix + vocab
     if k + '.embedding.weight' in state:
         e = F.embedding(ids, state[k + '.embedding.weight'])
-        return F.linear(e, state[k + '.linear.weight'], state[k + '.linear.bias'])
+        return F.dropout(F.linear(e, state[k + '.linear.weight'], state[k + '.linear.bias']), DROPOUT, training=DROPOUT > 0)
     return F.embedding(ids, state[k + '.weight'])
 
 
@@ -177,7 +178,7 @@ def multi_head_self_attention(x, mask, in_w, in_b, out_w, out_b, heads: int) -> 
     logits = q @ k.transpose(-1, -2)                                   # [N,h,S,S]
     key_pad = (1 - mask).bool()                                         # attention_operator.py:53
     logits = logits.masked_fill(key_pad[:, None, None, :], float('-inf'))
-    probs = torch.softmax(logits, dim=-1)
+    probs = F.dropout(torch.softmax(logits, dim=-1), DROPOUT, training=DROPOUT > 0)
     ctx = (probs @ v).transpose(1, 2).reshape(N, S, D)
     return F.linear(ctx, out_w, out_b)
 
@@ -205,7 +206,7 @@ def cnn_operator(state: dict, prefix: str, embeddings: "OrderedDict[str, torch.T
             pad = (w.shape[-1] - 1) // 2
             assert w.shape[-1] % 2 == 1
             y = F.conv1d(e.permute(0, 2, 1), w, state[prefix + 'cnn.bias'], padding=pad).permute(0, 2, 1)
-            y = torch.relu(y) * mask[col].unsqueeze(-1)
+            y = F.dropout(torch.relu(y) * mask[col].unsqueeze(-1), DROPOUT, training=DROPOUT > 0)
         else:
             y = F.linear(e, state[prefix + 'linear.weight'], state[prefix + 'linear.bias'])
         outs.append(y)
@@ -477,3 +478,65 @@ def adam_step(p, g, m, v, step: int, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
     bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
     denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
     p.addcdiv_(m, denom, value=-lr / bc1)
+
+
+# --------------------------------------------------------------------------------------------
+# parameter shapes / default initialisation for the CPU timing port
+# --------------------------------------------------------------------------------------------
+def state_shapes(kind: str, D: int, A: int, E: int, n_words: int, n_cats: int, n_items: int = 0) -> "OrderedDict[str, tuple]":
+    s = OrderedDict()
+
+    def additive(prefix):
+        s[prefix + 'additive_attention.encoder.0.weight'] = (A, D)
+        s[prefix + 'additive_attention.encoder.0.bias'] = (A,)
+        s[prefix + 'additive_attention.encoder.2.weight'] = (1, A)
+
+    def mha(prefix):
+        s[prefix + 'multi_head_attention.in_proj_weight'] = (3 * D, D)
+        s[prefix + 'multi_head_attention.in_proj_bias'] = (3 * D,)
+        s[prefix + 'multi_head_attention.out_proj.weight'] = (D, D)
+        s[prefix + 'multi_head_attention.out_proj.bias'] = (D,)
+        s[prefix + 'linear.weight'] = (D, D)
+        s[prefix + 'linear.bias'] = (D,)
+        additive(prefix)
+
+    if kind in ('nrms', 'naml'):
+        s['embedding_vocab_table.glove.embedding.weight'] = (n_words, E)
+        s['embedding_vocab_table.glove.linear.weight'] = (D, E)
+        s['embedding_vocab_table.glove.linear.bias'] = (D,)
+        s['embedding_vocab_table.category.weight'] = (n_cats, D)
+    if kind == 'nrms':
+        s['embedding_vocab_table.' + SPECIAL_VOCAB + '.weight'] = (3, D)
+        mha('item_op.')
+        mha('user_op.')
+    elif kind == 'naml':
+        s['item_op.cnn.weight'] = (D, D, 3)
+        s['item_op.cnn.bias'] = (D,)
+        s['item_op.linear.weight'] = (D, D)
+        s['item_op.linear.bias'] = (D,)
+        additive('item_op.')
+        additive('user_op.')
+    else:
+        s['embedding_vocab_table.item_id.embedding.weight'] = (n_items, E)
+        s['embedding_vocab_table.item_id.linear.weight'] = (D, E)
+        s['embedding_vocab_table.item_id.linear.bias'] = (D,)
+        additive('user_op.')
+    return s
+
+
+def default_state(shapes: dict, pretrained: Dict[str, torch.Tensor], seed: int = 2023) -> Dict[str, torch.Tensor]:
+    """Random parameters of the right shapes and scales (U(+-1/sqrt(fan_in))); pretrained tables are frozen."""
+    g = torch.Generator().manual_seed(seed)
+    state = {}
+    for k, shp in shapes.items():
+        if k in pretrained:
+            state[k] = pretrained[k]
+            continue
+        fan_in = shp[1] * (shp[2] if len(shp) > 2 else 1) if len(shp) > 1 else shp[0]
+        bound = 1.0 / math.sqrt(max(fan_in, 1))
+        if k.endswith('.weight') and 'embedding_vocab_table' in k and 'linear' not in k:
+            t = torch.randn(shp, generator=g)
+        else:
+            t = (torch.rand(shp, generator=g) * 2 - 1) * bound
+        state[k] = t.requires_grad_(True)
+    return state

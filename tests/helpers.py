@@ -27,45 +27,8 @@ def case_spec(c, world):
 
 def state_shapes(c, world, llm=None):
     """Parameter shapes of the reference model for a case, without importing the reference."""
-    D, A, E = c['hidden'], c['additive'], world.embed_dim
-    s = OrderedDict()
-
-    def additive(prefix):
-        s[prefix + 'additive_attention.encoder.0.weight'] = (A, D)
-        s[prefix + 'additive_attention.encoder.0.bias'] = (A,)
-        s[prefix + 'additive_attention.encoder.2.weight'] = (1, A)
-
-    def mha(prefix):
-        s[prefix + 'multi_head_attention.in_proj_weight'] = (3 * D, D)
-        s[prefix + 'multi_head_attention.in_proj_bias'] = (3 * D,)
-        s[prefix + 'multi_head_attention.out_proj.weight'] = (D, D)
-        s[prefix + 'multi_head_attention.out_proj.bias'] = (D,)
-        s[prefix + 'linear.weight'] = (D, D)
-        s[prefix + 'linear.bias'] = (D,)
-        additive(prefix)
-
-    if c['kind'] in ('nrms', 'naml'):
-        s['embedding_vocab_table.glove.embedding.weight'] = (world.n_words, E)
-        s['embedding_vocab_table.glove.linear.weight'] = (D, E)
-        s['embedding_vocab_table.glove.linear.bias'] = (D,)
-        s['embedding_vocab_table.category.weight'] = (world.n_cats, D)
-    if c['kind'] == 'nrms':
-        s['embedding_vocab_table.__cat_inputer_special_ids.weight'] = (3, D)
-        mha('item_op.')
-        mha('user_op.')
-    elif c['kind'] == 'naml':
-        s['item_op.cnn.weight'] = (D, D, 3)
-        s['item_op.cnn.bias'] = (D,)
-        s['item_op.linear.weight'] = (D, D)
-        s['item_op.linear.bias'] = (D,)
-        additive('item_op.')
-        additive('user_op.')
-    else:
-        s['embedding_vocab_table.item_id.embedding.weight'] = (world.n_items, llm.shape[1])
-        s['embedding_vocab_table.item_id.linear.weight'] = (D, llm.shape[1])
-        s['embedding_vocab_table.item_id.linear.bias'] = (D,)
-        additive('user_op.')
-    return s
+    E = llm.shape[1] if c['kind'] == 'llmid' else world.embed_dim
+    return O.state_shapes(c['kind'], c['hidden'], c['additive'], E, world.n_words, world.n_cats, world.n_items)
 
 
 def oracle_state(c, world, llm=None, dtype=torch.float32):

@@ -223,7 +223,11 @@ def test_additive_attention(ops, N_, S, D, A):
     assert torch.isfinite(y).all() and (y[0] == 0).all()
     assert rel(y, yr) <= 3e-6
     for a, b_ in zip(gs, cs):
-        assert rel(a.grad, b_.grad) <= 1e-5
+        # S == 1 makes alpha = a/(a+eps) ~ 1: the W1/w2 gradients are O(eps) round-off, compare those absolutely
+        if S == 1 and b_.grad.abs().max().item() < 1e-6:
+            assert (a.grad.double().cpu() - b_.grad).abs().max().item() <= 1e-9
+        else:
+            assert rel(a.grad, b_.grad) <= 1e-5
     # no mask at all
     y2 = ops.additive_attention(gs[0].detach(), None, gs[1].detach(), gs[2].detach(), gs[3].detach())
     assert rel(y2, O.additive_attention(x.double(), None, w1.double(), b1.double(), w2.double())) <= 3e-6
