@@ -222,10 +222,10 @@ def test_additive_attention(ops, N_, S, D, A):
     y.backward(dev(do))
     assert torch.isfinite(y).all() and (y[0] == 0).all()
     assert rel(y, yr) <= 3e-6
-    for a, b_ in zip(gs, cs):
-        # S == 1 makes alpha = a/(a+eps) ~ 1: the W1/w2 gradients are O(eps) round-off, compare those absolutely
-        if S == 1 and b_.grad.abs().max().item() < 1e-6:
-            assert (a.grad.double().cpu() - b_.grad).abs().max().item() <= 1e-9
+    for i, (a, b_) in enumerate(zip(gs, cs)):
+        # S == 1 makes alpha = a/(a+eps) ~ 1: the W1/b1/w2 gradients are O(eps) round-off, compare those absolutely
+        if S == 1 and i > 0:
+            assert (a.grad.double().cpu() - b_.grad).abs().max().item() <= 1e-8
         else:
             assert rel(a.grad, b_.grad) <= 1e-5
     # no mask at all
