@@ -61,9 +61,24 @@ int lk_linear_bwd_data(const float* dY, const float* W, float* dX, int64_t M, in
 size_t lk_linear_bwd_weight_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int lk_linear_bwd_weight(const float* dY, const float* X, float* dW, float* db, int64_t M, int64_t N, int64_t K,
                          int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* C[m,n] (+)= sum_z partial[z,m,n] in fixed z order (deterministic split reduction) */
+int lk_splitk_reduce(const float* partial, float* C, int64_t M, int64_t N, int64_t ldc, int splits, int accumulate,
+                     cudaStream_t stream);
 size_t lk_colsum_workspace_bytes(int64_t M, int64_t N);
 int lk_colsum(const float* X, float* out, int64_t M, int64_t N, int accumulate, void* workspace, size_t workspace_bytes,
               cudaStream_t stream);
+
+/* ---- tensor-core path for the same contractions (tcgen05.mma + TMEM + TMA, sm_100a).  Operands are split-bf16
+ *      planes (hi = bf16(x), lo = bf16(x - hi)) so that three MMAs per k-step reproduce fp32 products to ~2^-17.
+ *      lk_split_bf16: fp32 [rows, cols] (pitch ld_in) -> hi/lo [rows, ld_out] (transpose=0) or [cols, ld_out] (transpose=1).
+ *      lk_tc_gemm: C[GM,GN] (+)= A·B with both operands K-major (a_mn=b_mn=0: A [GM,GK], B [GN,GK], reduction contiguous)
+ *      or both MN-major (a_mn=b_mn=1: A [GK,GM], B [GK,GN]; the weight-gradient case, reduction over token rows). */
+int lk_split_bf16(const float* X, int64_t rows, int64_t cols, int64_t ld_in, void* hi, void* lo, int64_t ld_out, int transpose,
+                  cudaStream_t stream);
+size_t lk_tc_gemm_workspace_bytes(int64_t GM, int64_t GN, int64_t GK);
+int lk_tc_gemm(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo, int64_t ldb, int b_mn,
+               float* C, int64_t ldc, int64_t GM, int64_t GN, int64_t GK, const float* bias, const int64_t* rowmask, int act,
+               float drop_p, uint64_t seed, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* ---- NAML Conv1d(k,'same') as implicit-im2col GEMM — model/operators/cnn_operator.py:33-38,54-58.
  *      Wr[o, j*Cin+i] = W[o,i,j];  Wd[i, j*Cout+o] = W[o,i,taps-1-j];  rows = N*S token rows */

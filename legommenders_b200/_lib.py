@@ -34,6 +34,10 @@ SIGNATURES = {
     'lk_linear_bwd_data': ('pppqqqis', 'i'),
     'lk_linear_bwd_weight_workspace_bytes': ('qqq', 'z'),
     'lk_linear_bwd_weight': ('ppppqqqipzs', 'i'),
+    'lk_splitk_reduce': ('ppqqqiis', 'i'),
+    'lk_split_bf16': ('pqqqppqis', 'i'),
+    'lk_tc_gemm_workspace_bytes': ('qqq', 'z'),
+    'lk_tc_gemm': ('ppqippqipqqqqppifuipzs', 'i'),
     'lk_colsum_workspace_bytes': ('qq', 'z'),
     'lk_colsum': ('ppqqipzs', 'i'),
     'lk_conv1d_fwd': ('pppppqqqqiifus', 'i'),

@@ -367,6 +367,14 @@ int lk_valid_mask(const int64_t* ids, int64_t* out, int64_t n, cudaStream_t st) 
   return check_launch("valid_mask");
 }
 
+int lk_splitk_reduce(const float* partial, float* C, int64_t M, int64_t N, int64_t ldc, int splits, int accumulate, cudaStream_t st) {
+  LK_REQUIRE(N % 4 == 0 && ldc % 4 == 0, LK_ERR_SHAPE, "lk_splitk_reduce: N and ldc must be multiples of 4");
+  size_t total4 = (size_t)M * N / 4;
+  if (total4 == 0) return LK_OK;
+  splitk_reduce_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(partial, C, (int)M, (int)N, (int)ldc, splits, accumulate);
+  return check_launch("splitk_reduce");
+}
+
 size_t lk_colsum_workspace_bytes(int64_t M, int64_t N) { return ((size_t)(M + 511) / 512) * N * sizeof(float) + 256; }
 
 int lk_colsum(const float* X, float* out, int64_t M, int64_t N, int accumulate, void* workspace, size_t workspace_bytes,

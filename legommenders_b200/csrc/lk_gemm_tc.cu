@@ -1,0 +1,464 @@
+// tcgen05 / TMEM / TMA GEMM for the dense contractions of the hot path (QKV / out-proj / linear / additive-W1 /
+// GloVe + LLM projections and their gradients; reference call sites: nn.Linear + nn.MultiheadAttention projections in
+// model/operators/attention_operator.py:32-57, model/common/attention.py:17-19, loader/embedding_hub.py:95-96).
+//
+// Numerics: the reference computes in fp32 and parity is 1e-4 (BASELINE.json), which single-pass bf16/tf32 tensor-core
+// math misses.  Operands are therefore carried as TWO bf16 planes (hi = bf16(x), lo = bf16(x - hi); 16
+// mantissa bits, the same 4 bytes/element as fp32) and every k-step issues three MMAs into one fp32 TMEM accumulator:
+//     D += A_hi·B_hi + A_hi·B_lo + A_lo·B_hi          (the dropped lo·lo term is ~2^-18 relative)
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles of the four planes into a 3-stage smem ring
+//   warp 1      MMA issuer:   one elected lane issues tcgen05.mma (M=128,N=128,K=16, kind::f16, bf16 in / fp32 out)
+//   warps 2-5   epilogue:     tcgen05.ld of the fp32 accumulator (double-buffered in TMEM, 2 x 128 columns) ->
+//                             bias / tanh / relu / dropout / row mask -> 16-byte stores
+// Operand layouts: K-major tiles ([rows, k] with k contiguous) and MN-major tiles ([k, rows] with rows contiguous, used by
+// the weight-gradient contraction whose reduction runs over token rows) — both through 128-byte-swizzle UMMA descriptors.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "lk_common.cuh"
+#include "../../include/legommenders_b200.h"
+
+namespace lk {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3, UMMA_K = 16, ACC_STAGES = 2;
+constexpr int TILE_BYTES = BM * BK * 2;        // one plane of one operand: 16 KiB
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi, A_lo, B_hi, B_lo
+constexpr int TMEM_COLS = ACC_STAGES * BN;     // 256 fp32 columns
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct Params {
+  float* C;                 // [GM, ldc] (or split partials [splits, GM, GN] when partial != null)
+  float* partial;
+  int GM, GN, GK, ldc;
+  int m_tiles, n_tiles, k_blocks, splits, kb_per_split;
+  const float* bias;        // [GN] or null
+  const int64_t* rowmask;   // [GM] or null
+  int act, accumulate;
+  float drop_p;
+  unsigned long long seed;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 128-byte-swizzle UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor).
+//   K-major : rows of 64 bf16 (128 B); 8-row groups 1024 B apart (SBO); LBO unused.
+//   MN-major: k-rows of 64 MN-elements (128 B); 8-k groups 1024 B apart (SBO); next 64 MN-elements BK*128 B away (LBO).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(mn_major ? ((BK * 128) >> 4) : 0) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor (cute/arch/mma_sm100_desc.hpp: InstrDescriptor): fp32 accumulate, bf16 A/B
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+               const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024-byte alignment
+  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                     // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;           // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;       // [ACC_STAGES]
+  uint64_t* tempty_bar = tfull_bar + ACC_STAGES; // [ACC_STAGES]
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapAh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapAl) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapBh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapBl) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; i++) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    for (int i = 0; i < ACC_STAGES; i++) {
+      mbar_init(smem_u32(&tfull_bar[i]), 1);
+      mbar_init(smem_u32(&tempty_bar[i]), 4);   // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer ------------------------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / (p.m_tiles * p.n_tiles);
+        const int rem = tile - split * (p.m_tiles * p.n_tiles);
+        const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * BN;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; kb++) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (A_MN) {
+            tma_load_2d(sa, &mapAh, fb, m0, k0);
+            tma_load_2d(sa + TILE_BYTES / 2, &mapAh, fb, m0 + 64, k0);
+            tma_load_2d(sa + TILE_BYTES, &mapAl, fb, m0, k0);
+            tma_load_2d(sa + TILE_BYTES + TILE_BYTES / 2, &mapAl, fb, m0 + 64, k0);
+          } else {
+            tma_load_2d(sa, &mapAh, fb, k0, m0);
+            tma_load_2d(sa + TILE_BYTES, &mapAl, fb, k0, m0);
+          }
+          if (B_MN) {
+            tma_load_2d(sa + 2 * TILE_BYTES, &mapBh, fb, n0, k0);
+            tma_load_2d(sa + 2 * TILE_BYTES + TILE_BYTES / 2, &mapBh, fb, n0 + 64, k0);
+            tma_load_2d(sa + 3 * TILE_BYTES, &mapBl, fb, n0, k0);
+            tma_load_2d(sa + 3 * TILE_BYTES + TILE_BYTES / 2, &mapBl, fb, n0 + 64, k0);
+          } else {
+            tma_load_2d(sa + 2 * TILE_BYTES, &mapBh, fb, k0, n0);
+            tma_load_2d(sa + 3 * TILE_BYTES, &mapBl, fb, k0, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer ---------------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
+      constexpr uint32_t a_kstep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2);   // bytes per UMMA_K step inside a tile
+      constexpr uint32_t b_kstep = B_MN ? (UMMA_K * 128) : (UMMA_K * 2);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / (p.m_tiles * p.n_tiles);
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; kb++) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; k++) {
+            const uint64_t ah = make_desc(sa + k * a_kstep, A_MN);
+            const uint64_t al = make_desc(sa + TILE_BYTES + k * a_kstep, A_MN);
+            const uint64_t bh = make_desc(sa + 2 * TILE_BYTES + k * b_kstep, B_MN);
+            const uint64_t bl = make_desc(sa + 3 * TILE_BYTES + k * b_kstep, B_MN);
+            umma_bf16(d_tmem, al, bh, idesc, (kb > kb0 || k > 0) ? 1u : 0u);   // small terms first
+            umma_bf16(d_tmem, ah, bl, idesc, 1u);
+            umma_bf16(d_tmem, ah, bh, idesc, 1u);
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));      // frees the smem stage once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&tfull_bar[acc]));          // accumulator complete -> epilogue
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue (warps 2..5) ----------------------------------------
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = tile / (p.m_tiles * p.n_tiles);
+      const int rem = tile - split * (p.m_tiles * p.n_tiles);
+      const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * BN;
+      const int kb0 = split * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+      const bool has_k = kb1 > kb0;
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.GM;
+      float* out;
+      int ldo;
+      if (p.partial) { out = p.partial + (size_t)split * p.GM * p.GN; ldo = p.GN; } else { out = p.C; ldo = p.ldc; }
+      float rm = 1.f;
+      if (!p.partial && p.rowmask && row_ok) rm = p.rowmask[row] > 0 ? 1.f : 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c++) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = n0 + c * 32 + j;
+            if (n >= p.GN) break;
+            float x[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              float t = has_k ? __uint_as_float(v[j + e]) : 0.f;
+              if (!p.partial) {
+                if (p.bias) t += __ldg(p.bias + n + e);
+                if (p.act == 1) t = tanhf(t);
+                else if (p.act == 2) t = fmaxf(t, 0.f);
+                if (p.drop_p > 0.f) t *= dropout_scale(p.seed, (uint64_t)row * p.GN + n + e, p.drop_p, inv_keep);
+                t *= rm;
+              }
+              x[e] = t;
+            }
+            float* o = out + (size_t)row * ldo + n;
+            if (!p.partial && p.accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(o);
+              x[0] += old.x; x[1] += old.y; x[2] += old.z; x[3] += old.w;
+            }
+            st4(o, make_float4(x[0], x[1], x[2], x[3]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// fp32 -> (hi, lo) bf16 planes; optional transpose; output pitch ld_out (>= cols, multiple of 8), pad columns zeroed
+__global__ void split_bf16_kernel(const float* __restrict__ X, int64_t rows, int cols, int64_t ld_in, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, int64_t ld_out) {
+  const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = (int)(ld_out >> 2);
+  if (i4 >= rows * q) return;
+  const int64_t r = i4 / q;
+  const int c = (int)(i4 % q) * 4;
+  float x[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c + 3 < cols) {
+    const float4 v = ldg4_stream(X + r * ld_in + c);
+    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+  } else {
+    for (int e = 0; e < 4; e++) if (c + e < cols) x[e] = X[r * ld_in + c + e];
+  }
+  __nv_bfloat16 h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    h[e] = __float2bfloat16_rn(x[e]);
+    l[e] = __float2bfloat16_rn(x[e] - __bfloat162float(h[e]));
+  }
+  *reinterpret_cast<uint2*>(hi + r * ld_out + c) = *reinterpret_cast<uint2*>(h);
+  *reinterpret_cast<uint2*>(lo + r * ld_out + c) = *reinterpret_cast<uint2*>(l);
+}
+
+// transposed split through a 32x32 smem tile: out[c, r]
+__global__ void split_bf16_t_kernel(const float* __restrict__ X, int rows, int cols, int64_t ld_in, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, int64_t ld_out) {
+  __shared__ float t[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < rows && c < cols) ? X[(int64_t)r * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, r = r0 + threadIdx.x;   // output row = c, output col = r
+    if (c < cols && r < ld_out) {
+      float x = (r < rows) ? t[threadIdx.x][i] : 0.f;
+      __nv_bfloat16 h = __float2bfloat16_rn(x);
+      hi[(int64_t)c * ld_out + r] = h;
+      lo[(int64_t)c * ld_out + r] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch `pitch_elems`; 128B-swizzled box.
+static int make_map(CUtensorMap* m, const void* base, int64_t inner, int64_t outer, int64_t pitch_elems, int box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  LK_REQUIRE(fn != nullptr, LK_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LK_REQUIRE(r == CUDA_SUCCESS, LK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): inner=%ld outer=%ld pitch=%ld", (int)r, (long)inner,
+             (long)outer, (long)pitch_elems);
+  return LK_OK;
+}
+
+static int pick_splits(int64_t GM, int64_t GN, int64_t GK) {
+  int64_t tiles = ((GM + BM - 1) / BM) * ((GN + BN - 1) / BN);
+  int64_t kb = (GK + BK - 1) / BK;
+  if (tiles >= kNumSMs || kb < 8) return 1;
+  int64_t s = (2 * kNumSMs + tiles - 1) / tiles;
+  if (s > kb / 4) s = kb / 4;
+  return (int)(s < 1 ? 1 : s);
+}
+
+}  // namespace tc
+}  // namespace lk
+
+using namespace lk;
+using namespace lk::tc;
+
+extern "C" {
+
+int lk_split_bf16(const float* X, int64_t rows, int64_t cols, int64_t ld_in, void* hi, void* lo, int64_t ld_out, int transpose,
+                  cudaStream_t st) {
+  LK_REQUIRE(ld_out % 8 == 0, LK_ERR_SHAPE, "lk_split_bf16: output pitch %ld must be a multiple of 8 (16-byte TMA rows)", (long)ld_out);
+  if (rows == 0 || cols == 0) return LK_OK;
+  if (!transpose) {
+    LK_REQUIRE(ld_out >= cols && ld_in % 4 == 0, LK_ERR_SHAPE, "lk_split_bf16: bad pitches");
+    int64_t total = rows * (ld_out / 4);
+    split_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, rows, (int)cols, ld_in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_out);
+  } else {
+    LK_REQUIRE(ld_out >= rows, LK_ERR_SHAPE, "lk_split_bf16: transposed pitch too small");
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((ld_out + 31) / 32));
+    split_bf16_t_kernel<<<grid, dim3(32, 8), 0, st>>>(X, (int)rows, (int)cols, ld_in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_out);
+  }
+  return check_launch("split_bf16");
+}
+
+size_t lk_tc_gemm_workspace_bytes(int64_t GM, int64_t GN, int64_t GK) {
+  int s = pick_splits(GM, GN, GK);
+  return s > 1 ? (size_t)s * GM * GN * sizeof(float) + 256 : 256;
+}
+
+int lk_tc_gemm(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo, int64_t ldb, int b_mn,
+               float* C, int64_t ldc, int64_t GM, int64_t GN, int64_t GK, const float* bias, const int64_t* rowmask, int act,
+               float drop_p, uint64_t seed, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  LK_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 && GN % 4 == 0, LK_ERR_SHAPE, "lk_tc_gemm: pitches must be 16-byte multiples");
+  LK_REQUIRE(a_mn == b_mn, LK_ERR_ARG, "lk_tc_gemm: mixed operand majors are not instantiated");
+  LK_REQUIRE(((uintptr_t)A_hi | (uintptr_t)A_lo | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C) % 16 == 0, LK_ERR_ARG,
+             "lk_tc_gemm: operands must be 16-byte aligned");
+  if (GM == 0 || GN == 0) return LK_OK;
+  CUtensorMap mAh, mAl, mBh, mBl;
+  int rc;
+  if (a_mn) {   // A stored [GK, GM] (GM contiguous), B stored [GK, GN]
+    if ((rc = make_map(&mAh, A_hi, GM, GK, lda, 64))) return rc;
+    if ((rc = make_map(&mAl, A_lo, GM, GK, lda, 64))) return rc;
+    if ((rc = make_map(&mBh, B_hi, GN, GK, ldb, 64))) return rc;
+    if ((rc = make_map(&mBl, B_lo, GN, GK, ldb, 64))) return rc;
+  } else {      // A stored [GM, GK] (GK contiguous), B stored [GN, GK]
+    if ((rc = make_map(&mAh, A_hi, GK, GM, lda, BM))) return rc;
+    if ((rc = make_map(&mAl, A_lo, GK, GM, lda, BM))) return rc;
+    if ((rc = make_map(&mBh, B_hi, GK, GN, ldb, BN))) return rc;
+    if ((rc = make_map(&mBl, B_lo, GK, GN, ldb, BN))) return rc;
+  }
+  Params p;
+  p.C = C; p.GM = (int)GM; p.GN = (int)GN; p.GK = (int)GK; p.ldc = (int)ldc;
+  p.m_tiles = (int)((GM + BM - 1) / BM);
+  p.n_tiles = (int)((GN + BN - 1) / BN);
+  p.k_blocks = (int)((GK + BK - 1) / BK);
+  p.splits = pick_splits(GM, GN, GK);
+  p.kb_per_split = (p.k_blocks + p.splits - 1) / p.splits;
+  p.splits = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
+  p.partial = nullptr;
+  if (p.splits > 1) {
+    LK_REQUIRE(workspace && workspace_bytes >= (size_t)p.splits * GM * GN * sizeof(float), LK_ERR_ARG, "lk_tc_gemm: workspace too small");
+    LK_REQUIRE(!bias && !rowmask && act == 0 && drop_p == 0.f, LK_ERR_ARG, "lk_tc_gemm: split reduction has no fused epilogue");
+    p.partial = (float*)workspace;
+  }
+  p.bias = bias; p.rowmask = rowmask; p.act = act; p.accumulate = accumulate; p.drop_p = drop_p; p.seed = (unsigned long long)seed;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tc_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_set = true;
+  }
+  int total = p.m_tiles * p.n_tiles * p.splits;
+  int grid = total < kNumSMs ? total : kNumSMs;
+  if (a_mn) tc_gemm_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
+  else tc_gemm_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
+  rc = check_launch("tc_gemm");
+  if (rc) return rc;
+  if (p.splits > 1) return lk_splitk_reduce(p.partial, C, GM, GN, ldc, p.splits, accumulate, st);
+  return LK_OK;
+}
+
+}  // extern "C"

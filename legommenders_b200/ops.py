@@ -5,6 +5,9 @@ no torch math runs on the hot path.  Each op cites the reference call site it re
 """
 from __future__ import annotations
 
+import os
+import weakref
+
 import torch
 from torch.autograd import Function
 
@@ -30,27 +33,107 @@ def _i64(t):
 
 
 # ----------------------------------------------------------------------------------------------------
-# dense contractions
+# dense contractions.  Two engines behind one interface:
+#   * tensor-core path (lk_tc_gemm: tcgen05 + TMEM + TMA on split-bf16 planes) for every shape it supports
+#   * exact-fp32 SIMT path (lk_linear_*) for tiny / odd shapes and when LK_TC=0
 # ----------------------------------------------------------------------------------------------------
-def linear_fwd_raw(x2, w, b, rowmask, act, out=None, accumulate=False, drop_p=0.0, seed=0):
-    M, K = x2.shape
-    N = w.shape[0]
-    y = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=x2.device)
-    call('lk_linear_fwd', ptr(x2), ptr(w), ptr(b), ptr(rowmask), ptr(y), M, N, K, act, int(accumulate), float(drop_p), int(seed))
+USE_TC = os.environ.get('LK_TC', '1') != '0'
+TC_MIN_ROWS = 256
+
+
+class Planes:
+    """Split-bf16 image of an fp32 matrix [rows, cols]: hi/lo bf16 planes with pitch `ld` (multiple of 8, zero padded)."""
+    __slots__ = ('hi', 'lo', 'rows', 'cols', 'ld')
+
+    def __init__(self, hi, lo, rows, cols, ld):
+        self.hi, self.lo, self.rows, self.cols, self.ld = hi, lo, rows, cols, ld
+
+
+def split_planes(x2: torch.Tensor, transpose: bool = False) -> Planes:
+    rows, cols = x2.shape
+    orows, ocols = (cols, rows) if transpose else (rows, cols)
+    ld = (ocols + 7) // 8 * 8
+    buf = torch.empty((2, orows, ld), dtype=torch.bfloat16, device=x2.device)
+    call('lk_split_bf16', ptr(x2), rows, cols, x2.stride(0), ptr(buf[0]), ptr(buf[1]), ld, int(transpose))
+    return Planes(buf[0], buf[1], orows, ocols, ld)
+
+
+_wplanes = {}
+
+
+def weight_planes(w: torch.Tensor, transpose: bool = False) -> Planes:
+    """Planes of a parameter, cached per tensor OBJECT until it is modified in place (optimizer steps bump `_version`;
+    kernels that update parameters behind torch's back call invalidate_weight_planes)."""
+    key = (id(w), transpose)
+    ent = _wplanes.get(key)
+    if ent is not None:
+        ver, ref, dptr, planes = ent
+        if ref() is w and ver == w._version and dptr == w.data_ptr():
+            return planes
+    if len(_wplanes) > 256:
+        for k in [k for k, e in _wplanes.items() if e[1]() is None]:
+            del _wplanes[k]
+    planes = split_planes(w.detach(), transpose)
+    _wplanes[key] = (w._version, weakref.ref(w), w.data_ptr(), planes)
+    return planes
+
+
+def invalidate_weight_planes():
+    _wplanes.clear()
+
+
+def tc_ok(M, N, K) -> bool:
+    return USE_TC and M >= TC_MIN_ROWS and N % 4 == 0 and K % 4 == 0 and N >= 16 and K >= 16
+
+
+def tc_gemm(A: Planes, B: Planes, mn_major: bool, GM, GN, GK, out=None, bias=None, rowmask=None, act=0, drop_p=0.0, seed=0,
+            accumulate=False):
+    y = out if out is not None else torch.empty((GM, GN), dtype=torch.float32, device=A.hi.device)
+    nbytes = query('lk_tc_gemm_workspace_bytes', GM, GN, GK)
+    ws = workspace(nbytes, y.device, 'tc')
+    call('lk_tc_gemm', ptr(A.hi), ptr(A.lo), A.ld, int(mn_major), ptr(B.hi), ptr(B.lo), B.ld, int(mn_major), ptr(y), y.stride(0),
+         GM, GN, GK, ptr(bias), ptr(rowmask), act, float(drop_p), int(seed), int(accumulate), ptr(ws), ws.numel())
     return y
 
 
-def linear_bwd_data_raw(dy2, w, out=None, accumulate=False):
+def linear_fwd_raw(x2, w, b, rowmask, act, out=None, accumulate=False, drop_p=0.0, seed=0, xp=None):
+    """y = epilogue(x·Wᵀ).  Returns (y, planes-of-x or None)."""
+    M, K = x2.shape
+    N = w.shape[0]
+    if tc_ok(M, N, K):
+        xp = xp if xp is not None else split_planes(x2)
+        y = tc_gemm(xp, weight_planes(w), False, M, N, K, out=out, bias=b, rowmask=rowmask, act=act, drop_p=drop_p, seed=seed,
+                    accumulate=accumulate)
+        return y, xp
+    y = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=x2.device)
+    call('lk_linear_fwd', ptr(x2), ptr(w), ptr(b), ptr(rowmask), ptr(y), M, N, K, act, int(accumulate), float(drop_p), int(seed))
+    return y, None
+
+
+def linear_bwd_data_raw(dy2, w, out=None, accumulate=False, dyp=None):
+    """dX = dY·W  (contraction over N: B operand is Wᵀ's planes, K-major)."""
     M, N = dy2.shape
     K = w.shape[1]
+    if tc_ok(M, K, N):
+        dyp = dyp if dyp is not None else split_planes(dy2)
+        return tc_gemm(dyp, weight_planes(w, transpose=True), False, M, K, N, out=out, accumulate=accumulate)
     dx = out if out is not None else torch.empty((M, K), dtype=torch.float32, device=dy2.device)
     call('lk_linear_bwd_data', ptr(dy2), ptr(w), ptr(dx), M, N, K, int(accumulate))
     return dx
 
 
-def linear_bwd_weight_raw(dy2, x2, want_bias=True):
+def linear_bwd_weight_raw(dy2, x2, want_bias=True, dyp=None, xp=None):
+    """dW = dYᵀ·X (contraction over the M token rows: both operands MN-major), db = column sums of dY."""
     M, N = dy2.shape
-    K = x2.shape[1]
+    K = x2.shape[1] if x2 is not None else xp.cols
+    if tc_ok(M, N, K):
+        dyp = dyp if dyp is not None else split_planes(dy2)
+        xp = xp if xp is not None else split_planes(x2)
+        dw = tc_gemm(dyp, xp, True, N, K, M)
+        db = colsum_raw(dy2) if want_bias else None
+        return dw, db
+    if x2 is None:
+        raise RuntimeError('linear_bwd_weight_raw: fp32 input required for the SIMT path')
     dw = torch.empty((N, K), dtype=torch.float32, device=dy2.device)
     db = torch.empty((N,), dtype=torch.float32, device=dy2.device) if want_bias else None
     nbytes = query('lk_linear_bwd_weight_workspace_bytes', M, N, K)
@@ -85,11 +168,12 @@ class _Linear(Function):
         b = _f32(b) if b is not None else None
         x2 = x.reshape(-1, x.shape[-1])
         rm = _i64(rowmask.reshape(-1)) if rowmask is not None else None
-        y = linear_fwd_raw(x2, w, b, rm, act, drop_p=drop_p, seed=seed)
+        y, xp = linear_fwd_raw(x2, w, b, rm, act, drop_p=drop_p, seed=seed)
         ctx.act, ctx.drop_p, ctx.seed, ctx.has_b = act, drop_p, seed, b is not None
         plain = act == ACT_NONE and rm is None and drop_p == 0.0
         ctx.plain = plain
-        ctx.save_for_backward(x2, w, None if plain else y, rm)
+        ctx.xp = xp                      # split-bf16 image of x (same bytes as x) reused by the weight gradient
+        ctx.save_for_backward(x2 if xp is None else None, w, None if plain else y, rm)
         return y.view(*x.shape[:-1], w.shape[0])
 
     @staticmethod
@@ -99,10 +183,14 @@ class _Linear(Function):
         if not ctx.plain:
             dy2 = act_bwd_raw(dy2, y, rm, ctx.act, ctx.drop_p, ctx.seed)
         dx = dw = db = None
+        M, N = dy2.shape
+        K = w.shape[1]
+        dyp = split_planes(dy2) if (tc_ok(M, K, N) or tc_ok(M, N, K)) else None
         if ctx.needs_input_grad[0]:
-            dx = linear_bwd_data_raw(dy2, w).view(*dy.shape[:-1], w.shape[1])
+            dx = linear_bwd_data_raw(dy2, w, dyp=dyp).view(*dy.shape[:-1], K)
         if ctx.needs_input_grad[1] or (ctx.has_b and ctx.needs_input_grad[2]):
-            dw, db = linear_bwd_weight_raw(dy2, x2, want_bias=ctx.has_b)
+            dw, db = linear_bwd_weight_raw(dy2, x2, want_bias=ctx.has_b, dyp=dyp, xp=ctx.xp)
+        ctx.xp = None
         return dx, dw, db, None, None, None, None
 
 
@@ -248,7 +336,8 @@ class _AdditiveAttention(Function):
         N, S, D = x.shape
         A = w1.shape[0]
         x2 = x.reshape(N * S, D)
-        hid = linear_fwd_raw(x2, w1, b1, None, ACT_TANH)
+        hid, xp = linear_fwd_raw(x2, w1, b1, None, ACT_TANH)
+        ctx.xp = xp
         out = torch.empty((N, D), dtype=torch.float32, device=x.device)
         alpha = torch.empty((N, S), dtype=torch.float32, device=x.device)
         call('lk_additive_pool_fwd', ptr(x2), ptr(hid), ptr(w2), ptr(mask), ptr(out), ptr(alpha), N, S, D, A)
@@ -267,8 +356,10 @@ class _AdditiveAttention(Function):
         call('lk_additive_pool_bwd', ptr(x2), ptr(hid), ptr(w2), ptr(alpha), ptr(_f32(dout)), ptr(dx), ptr(dpre), ptr(dw2p),
              N, S, D, A, 0)
         dw2 = colsum_raw(dw2p).view(1, A)
-        dw1, db1 = linear_bwd_weight_raw(dpre, x2)
-        linear_bwd_data_raw(dpre, w1, out=dx, accumulate=True)
+        dpp = split_planes(dpre) if (tc_ok(N * S, D, A) or tc_ok(N * S, A, D)) else None
+        dw1, db1 = linear_bwd_weight_raw(dpre, x2, dyp=dpp, xp=ctx.xp)
+        linear_bwd_data_raw(dpre, w1, out=dx, accumulate=True, dyp=dpp)
+        ctx.xp = None
         return dx.view(N, S, D), None, dw1, db1, dw2
 
 

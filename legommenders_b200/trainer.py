@@ -53,3 +53,4 @@ class FlatAdam:
         self.allreduce()
         ops.adam_step(self.flat, self.grad, self.m, self.v, self.step_count, lr=self.lr if lr is None else lr,
                       beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, grad_scale=1.0 / self.world)
+        ops.invalidate_weight_planes()   # the kernel updated the parameters behind torch's version counters

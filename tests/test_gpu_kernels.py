@@ -107,9 +107,23 @@ def test_embedding_backward_via_autograd(ops):
 
 
 # ------------------------------------------------------------------------------------------------ linear / conv
-@pytest.mark.parametrize('M,K,N', [(1, 4, 4), (130, 300, 64), (257, 256, 768), (1000, 64, 32), (65, 4096, 256)])
+@pytest.fixture(params=['tc', 'simt'])
+def engine(request, ops):
+    """Run the dense-contraction tests on both engines: tcgen05 split-bf16 (default) and exact-fp32 SIMT."""
+    old = ops.USE_TC
+    ops.USE_TC = request.param == 'tc'
+    yield request.param
+    ops.USE_TC = old
+
+
+def gemm_tol(engine, exact):
+    # split-bf16 x3 keeps 16 mantissa bits per operand: ~1.5e-5 relative per product, averaged over the reduction
+    return exact if engine == 'simt' else 4e-5
+
+
+@pytest.mark.parametrize('M,K,N', [(1, 4, 4), (130, 300, 64), (257, 256, 768), (1000, 64, 32), (65, 4096, 256), (4000, 300, 256)])
 @pytest.mark.parametrize('act', [0, 1, 2])
-def test_linear_fwd_bwd(ops, M, K, N, act):
+def test_linear_fwd_bwd(ops, engine, M, K, N, act):
     g = torch.Generator().manual_seed(M + K + N + act)
     x = torch.randn(M, K, generator=g)
     w = torch.randn(N, K, generator=g) / K ** 0.5
@@ -128,14 +142,14 @@ def test_linear_fwd_bwd(ops, M, K, N, act):
     xg, wg, bg = (dev(t).requires_grad_(True) for t in (x, w, b))
     y = ops.linear(xg, wg, bg, rowmask=dev(rowmask), act=act)
     y.backward(dev(dy))
-    tol = 3e-6 * max(1.0, (K / 256) ** 0.5)
+    tol = gemm_tol(engine, 3e-6 * max(1.0, (K / 256) ** 0.5))
     assert rel(y, yr) <= tol
     assert rel(xg.grad, xc.grad) <= tol
-    assert rel(wg.grad, wc.grad) <= 1e-5
+    assert rel(wg.grad, wc.grad) <= gemm_tol(engine, 1e-5)
     assert rel(bg.grad, bc.grad) <= 1e-5
 
 
-def test_linear_split_reduction_large_m(ops):
+def test_linear_split_reduction_large_m(ops, engine):
     """grad-weight is a reduction over M token rows: exercise the split path at the NRMS shape."""
     g = torch.Generator().manual_seed(5)
     M, K, N = 33 * 400, 256, 256
@@ -143,8 +157,8 @@ def test_linear_split_reduction_large_m(ops):
     w = torch.randn(N, K, generator=g) / 16
     xg, wg = dev(x).requires_grad_(True), dev(w).requires_grad_(True)
     ops.linear(xg, wg, None).backward(dev(dy))
-    assert rel(wg.grad, dy.double().t() @ x.double()) <= 1e-5
-    assert rel(xg.grad, dy.double() @ w.double()) <= 3e-6
+    assert rel(wg.grad, dy.double().t() @ x.double()) <= gemm_tol(engine, 1e-5)
+    assert rel(xg.grad, dy.double() @ w.double()) <= gemm_tol(engine, 3e-6)
 
 
 @pytest.mark.parametrize('N_,S,Cin,Cout', [(5, 30, 64, 64), (3, 7, 32, 48), (9, 2, 256, 256)])
@@ -204,7 +218,7 @@ def test_mha_core(ops, N_, S, D, H):
 
 
 @pytest.mark.parametrize('N_,S,D,A', [(13, 33, 256, 256), (5, 50, 256, 256), (9, 11, 64, 32), (3, 1, 64, 32)])
-def test_additive_attention(ops, N_, S, D, A):
+def test_additive_attention(ops, engine, N_, S, D, A):
     g = torch.Generator().manual_seed(S + D + A)
     x = torch.randn(N_, S, D, generator=g)
     w1 = torch.randn(A, D, generator=g) / D ** 0.5
@@ -221,16 +235,16 @@ def test_additive_attention(ops, N_, S, D, A):
     y = ops.additive_attention(gs[0], dev(mask), gs[1], gs[2], gs[3])
     y.backward(dev(do))
     assert torch.isfinite(y).all() and (y[0] == 0).all()
-    assert rel(y, yr) <= 3e-6
+    assert rel(y, yr) <= gemm_tol(engine, 3e-6)
     for i, (a, b_) in enumerate(zip(gs, cs)):
         # S == 1 makes alpha = a/(a+eps) ~ 1: the W1/b1/w2 gradients are O(eps) round-off, compare those absolutely
         if S == 1 and i > 0:
             assert (a.grad.double().cpu() - b_.grad).abs().max().item() <= 1e-8
         else:
-            assert rel(a.grad, b_.grad) <= 1e-5
+            assert rel(a.grad, b_.grad) <= gemm_tol(engine, 1e-5)
     # no mask at all
     y2 = ops.additive_attention(gs[0].detach(), None, gs[1].detach(), gs[2].detach(), gs[3].detach())
-    assert rel(y2, O.additive_attention(x.double(), None, w1.double(), b1.double(), w2.double())) <= 3e-6
+    assert rel(y2, O.additive_attention(x.double(), None, w1.double(), b1.double(), w2.double())) <= gemm_tol(engine, 3e-6)
 
 
 @pytest.mark.parametrize('mode', [0, 1])

@@ -100,8 +100,8 @@ def test_cached_eval_parity(name):
     assert Env.user_cache and model.cacher.user.cached
     if cfg.use_item_content:
         assert Env.item_cache and model.cacher.item.cached
-        assert np.abs(model.cacher.item.repr.cpu().numpy() - g['item_repr']).max() <= 1e-5
-    assert np.abs(model.cacher.user.repr.cpu().numpy() - g['user_repr']).max() <= 1e-5
+        assert helpers.normwise(model.cacher.item.repr.cpu().numpy(), g['item_repr']) <= TOL
+    assert helpers.normwise(model.cacher.user.repr.cpu().numpy(), g['user_repr']) <= TOL
 
     # the reference's own loop: 64-row batches of (user, item) ids through forward()
     sc = []
