@@ -254,10 +254,13 @@ def main():
         pk = peaks()
         if gemm['ms'] > 0:
             ach = gemm['flops'] / (gemm['ms'] / 1e3) / 1e12
-            roof = dict(bound='tensor', kernel='gemm_simt_kernel (lk_linear_* / MHA projections)', achieved=ach, peak=pk['tensor'],
+            tc = gemm['name'] == 'lk_tc_gemm'
+            roof = dict(bound='tensor', kernel='tc_gemm_kernel (tcgen05.mma, split-bf16 x3, fp32 TMEM accumulate)' if tc
+                        else 'gemm_simt_kernel (fp32 FFMA)', achieved=ach, peak=pk['tensor'],
                         unit='TFLOP/s', frac=ach / pk['tensor'], traffic=None, peak_source=pk['which'],
                         share_of_step=gemm['ms'] / max(sum(shares.values()), 1e-9), launches=gemm['calls'],
-                        note='algorithmic flops 2*M*N*K per call / CUDA-event time per call; fp32 FFMA path')
+                        note='achieved = algorithmic flops (2*M*N*K per call, counted once) / CUDA-event time of the calls in a live step'
+                             + ('; the kernel executes 3 bf16 MMAs per algorithmic product to hold fp32 parity, so the tensor pipe runs at 3x this rate' if tc else ''))
 
     line = dict(metric='NRMS train impressions/s', value=value, unit='impressions/s', n_gpus=world_size, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,

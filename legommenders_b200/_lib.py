@@ -103,6 +103,7 @@ _FLOPS = {
     'lk_linear_fwd': lambda a: 2 * a[5] * a[6] * a[7],
     'lk_linear_bwd_data': lambda a: 2 * a[3] * a[4] * a[5],
     'lk_linear_bwd_weight': lambda a: 2 * a[4] * a[5] * a[6],
+    'lk_tc_gemm': lambda a: 2 * a[10] * a[11] * a[12],
     'lk_conv1d_fwd': lambda a: 2 * a[5] * a[7] * a[8] * a[9],
     'lk_conv1d_bwd_data': lambda a: 2 * a[3] * a[5] * a[6] * a[7],
     'lk_conv1d_bwd_weight': lambda a: 2 * a[4] * a[6] * a[7] * a[8],
@@ -136,14 +137,16 @@ def profile_end(records):
     global _profile
     _profile = None
     torch.cuda.synchronize()
-    shares, gemm = {}, dict(ms=0.0, flops=0, calls=0)
+    shares, per = {}, {}
     for name, flops, e0, e1 in records:
         ms = e0.elapsed_time(e1)
         shares[name] = shares.get(name, 0.0) + ms
         if flops:
-            gemm['ms'] += ms
-            gemm['flops'] += flops
-            gemm['calls'] += 1
+            g = per.setdefault(name, dict(ms=0.0, flops=0, calls=0, name=name))
+            g['ms'] += ms
+            g['flops'] += flops
+            g['calls'] += 1
+    gemm = max(per.values(), key=lambda g: g['ms']) if per else dict(ms=0.0, flops=0, calls=0, name=None)
     return {k: round(v, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])}, gemm
 
 
