@@ -91,17 +91,23 @@ int lk_conv1d_bwd_weight(const float* dY, const float* X, float* dWr, float* db,
                          int64_t Cout, int taps, int accumulate, void* workspace, size_t workspace_bytes,
                          cudaStream_t stream);
 
-/* ---- (2) NRMS multi-head self-attention core — nn.MultiheadAttention, attention_operator.py:49-55 ------ */
-int lk_mha_fwd(const float* qkv, const int64_t* mask, float* ctx, float* lse, int64_t N, int64_t S, int64_t D, int64_t H,
-               float drop_p, uint64_t seed, cudaStream_t stream);
-int lk_mha_bwd(const float* qkv, const int64_t* mask, const float* lse, const float* dctx, float* dqkv, int64_t N, int64_t S,
-               int64_t D, int64_t H, float drop_p, uint64_t seed, cudaStream_t stream);
+/* Sequence layouts shared by (2) and (3): dense [N, S, *] with an optional int64 validity mask [N,S] (the reference's padded
+ * layout), or — when `cu` is non-null — PACKED rows with int32 cumulative offsets cu[N+1] (sequence n = rows cu[n]..cu[n+1]),
+ * S then being an upper bound on the sequence length.  Packed execution skips the pad tokens / pad history slots that the
+ * reference computes and masks away; results on valid positions are identical. */
 
-/* ---- (3) AdditiveAttention pooling — model/common/attention.py:31-38 ------------------------------------ */
-int lk_additive_pool_fwd(const float* X, const float* Hd, const float* w2, const int64_t* mask, float* out, float* alpha,
-                         int64_t N, int64_t S, int64_t D, int64_t A, cudaStream_t stream);
-int lk_additive_pool_bwd(const float* X, const float* Hd, const float* w2, const float* alpha, const float* dOut, float* dX,
-                         float* dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A, int accumulate_dx,
+/* ---- (2) NRMS multi-head self-attention core — nn.MultiheadAttention, attention_operator.py:49-55.
+ *      qkv [rows,3D], ctx [rows,D], lse [rows,H]; head dim D/H in {8,16,32,64} ---------------------------------- */
+int lk_mha_fwd(const float* qkv, const int64_t* mask, const int32_t* cu, float* ctx, float* lse, int64_t N, int64_t S, int64_t D,
+               int64_t H, float drop_p, uint64_t seed, cudaStream_t stream);
+int lk_mha_bwd(const float* qkv, const int64_t* mask, const int32_t* cu, const float* lse, const float* dctx, float* dqkv, int64_t N,
+               int64_t S, int64_t D, int64_t H, float drop_p, uint64_t seed, cudaStream_t stream);
+
+/* ---- (3) AdditiveAttention pooling — model/common/attention.py:31-38.  X [rows,D], Hd = tanh(W1 x + b1) [rows,A] ------ */
+int lk_additive_pool_fwd(const float* X, const float* Hd, const float* w2, const int64_t* mask, const int32_t* cu, float* out,
+                         float* alpha, int64_t N, int64_t S, int64_t D, int64_t A, cudaStream_t stream);
+int lk_additive_pool_bwd(const float* X, const float* Hd, const float* w2, const float* alpha, const int32_t* cu, const float* dOut,
+                         float* dX, float* dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A, int accumulate_dx,
                          cudaStream_t stream);
 /* PoolingOperator on gathered embeddings — model/operators/pooling_operator.py:46-56 (mode 0 mean, 1 max) */
 int lk_masked_pool(const float* X, const int64_t* mask, float* out, int64_t N, int64_t S, int64_t D, int mode,

@@ -44,10 +44,10 @@ SIGNATURES = {
     'lk_conv1d_bwd_data': ('pppqqqqiis', 'i'),
     'lk_conv1d_bwd_weight_workspace_bytes': ('qqqi', 'z'),
     'lk_conv1d_bwd_weight': ('ppppqqqqiipzs', 'i'),
-    'lk_mha_fwd': ('ppppqqqqfus', 'i'),
-    'lk_mha_bwd': ('pppppqqqqfus', 'i'),
-    'lk_additive_pool_fwd': ('ppppppqqqqs', 'i'),
-    'lk_additive_pool_bwd': ('ppppppppqqqqis', 'i'),
+    'lk_mha_fwd': ('pppppqqqqfus', 'i'),
+    'lk_mha_bwd': ('ppppppqqqqfus', 'i'),
+    'lk_additive_pool_fwd': ('pppppppqqqqs', 'i'),
+    'lk_additive_pool_bwd': ('pppppppppqqqqis', 'i'),
     'lk_masked_pool': ('pppqqqis', 'i'),
     'lk_masked_mean_pool_bwd': ('pppqqqs', 'i'),
     'lk_dot_scores': ('pppqqqs', 'i'),

@@ -60,14 +60,20 @@ class BaseCacher:
 class ItemCacher(BaseCacher):
     """contents = list of per-item inputer outputs (Resampler.item_cache) in item-id order (resampler.py:113-126)."""
 
+    encode_packed = None   # set by ReprCacher when the item encoder supports padding-free execution
+
     def _cache(self, contents):
         op = self.operator
         out = op.get_full_placeholder(len(contents)).to(Env.device)
         with torch.no_grad():
             for s in range(0, len(contents), self.page_size):
                 page = stack_trees(contents[s:s + self.page_size])
-                emb = op.inputer.get_embeddings(page, training=False)
-                out[s:s + len(contents[s:s + self.page_size])] = op(emb, mask=op.inputer.get_mask(page))
+                n = len(contents[s:s + self.page_size])
+                if self.encode_packed is not None:
+                    out[s:s + n] = self.encode_packed(page['input_ids'], op.inputer.get_mask(page))[0]
+                else:
+                    emb = op.inputer.get_embeddings(page, training=False)
+                    out[s:s + n] = op(emb, mask=op.inputer.get_mask(page))
         return out
 
 
@@ -97,6 +103,8 @@ class ReprCacher:
         self.item = ItemCacher(operator=legommender.item_op, page_size=config.cache_page_size, hidden_size=config.hidden_size,
                                activate=legommender.item_op is not None and legommender.item_op.allow_caching,
                                trigger=Env.set_item_cache)
+        if legommender._packed_items():
+            self.item.encode_packed = legommender.encode_items_packed
         self.user = UserCacher(operator=legommender.get_user_content, page_size=config.cache_page_size,
                                hidden_size=config.hidden_size, activate=legommender.user_op.allow_caching,
                                placeholder=legommender.user_op.get_full_placeholder(self.user_size),

@@ -15,16 +15,21 @@ constexpr float EPS32 = 1.1920928955078125e-07f;
 
 __global__ void __launch_bounds__(AT) additive_pool_fwd_kernel(const float* __restrict__ X, const float* __restrict__ Hd,
                                                                const float* __restrict__ w2, const int64_t* __restrict__ mask,
-                                                               float* __restrict__ out, float* __restrict__ alpha, int S, int D,
-                                                               int A) {
+                                                               const int* __restrict__ cu, float* __restrict__ out,
+                                                               float* __restrict__ alpha, int Smax, int D, int A) {
   __shared__ float a_s[MAXS];
   const int64_t n = blockIdx.x;
+  const int64_t r0 = cu ? cu[n] : n * Smax;            // first row of this sequence
+  const int S = cu ? cu[n + 1] - cu[n] : Smax;
+  if (cu) mask = nullptr;                               // packed rows are all valid
+  const int64_t mrow = n * Smax;
+  X += r0 * D; Hd += r0 * A; alpha += r0;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int t = w; t < S; t += AT / 32) {
-    bool valid = mask ? mask[n * S + t] > 0 : true;
+    bool valid = mask ? mask[mrow + t] > 0 : true;
     float s = 0.f;
     if (valid) {
-      const float* h = Hd + (n * S + t) * (int64_t)A;
+      const float* h = Hd + t * (int64_t)A;
       for (int c = lane * 4; c < A; c += 128) s += f4_dot(ldg4(h + c), ldg4(w2 + c));
       s = warp_sum(s);
     }
@@ -34,12 +39,12 @@ __global__ void __launch_bounds__(AT) additive_pool_fwd_kernel(const float* __re
   float Z = 0.f;
   for (int t = 0; t < S; t++) Z += a_s[t];
   const float inv = 1.f / (Z + EPS32);
-  for (int t = threadIdx.x; t < S; t += AT) alpha[n * S + t] = a_s[t] * inv;
+  for (int t = threadIdx.x; t < S; t += AT) alpha[t] = a_s[t] * inv;
   for (int c = threadIdx.x * 4; c < D; c += AT * 4) {
     float4 acc = f4_zero();
     for (int t = 0; t < S; t++) {
       float al = a_s[t] * inv;
-      if (al != 0.f) f4_fma(acc, al, ldg4(X + (n * S + t) * (int64_t)D + c));
+      if (al != 0.f) f4_fma(acc, al, ldg4(X + t * (int64_t)D + c));
     }
     st4(out + n * (int64_t)D + c, acc);
   }
@@ -48,19 +53,23 @@ __global__ void __launch_bounds__(AT) additive_pool_fwd_kernel(const float* __re
 // dX[t,:] (+)= alpha[t] * dOut ;  dpre[t,:] = ds[t] * w2 * (1 - h^2) ;  dw2_part[n,:] = sum_t ds[t] * h[t,:]
 __global__ void __launch_bounds__(AT) additive_pool_bwd_kernel(const float* __restrict__ X, const float* __restrict__ Hd,
                                                                const float* __restrict__ w2, const float* __restrict__ alpha,
-                                                               const float* __restrict__ dOut, float* __restrict__ dX,
-                                                               float* __restrict__ dpre, float* __restrict__ dw2_part, int S,
-                                                               int D, int A, int accumulate_dx) {
+                                                               const int* __restrict__ cu, const float* __restrict__ dOut,
+                                                               float* __restrict__ dX, float* __restrict__ dpre,
+                                                               float* __restrict__ dw2_part, int Smax, int D, int A,
+                                                               int accumulate_dx) {
   __shared__ float al_s[MAXS], da_s[MAXS], ds_s[MAXS];
   const int64_t n = blockIdx.x;
+  const int64_t r0 = cu ? cu[n] : n * Smax;
+  const int S = cu ? cu[n + 1] - cu[n] : Smax;
+  X += r0 * D; Hd += r0 * A; alpha += r0; dX += r0 * D; dpre += r0 * A;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int t = threadIdx.x; t < S; t += AT) al_s[t] = alpha[n * S + t];
+  for (int t = threadIdx.x; t < S; t += AT) al_s[t] = alpha[t];
   __syncthreads();
   const float* g = dOut + n * (int64_t)D;
   for (int t = w; t < S; t += AT / 32) {
     float s = 0.f;
     if (al_s[t] != 0.f) {
-      const float* x = X + (n * S + t) * (int64_t)D;
+      const float* x = X + t * (int64_t)D;
       for (int c = lane * 4; c < D; c += 128) s += f4_dot(ldg4(x + c), ldg4(g + c));
       s = warp_sum(s);
     }
@@ -76,7 +85,7 @@ __global__ void __launch_bounds__(AT) additive_pool_bwd_kernel(const float* __re
     for (int t = 0; t < S; t++) {
       float al = al_s[t];
       float4 v = make_float4(al * gv.x, al * gv.y, al * gv.z, al * gv.w);
-      float* o = dX + (n * S + t) * (int64_t)D + c;
+      float* o = dX + t * (int64_t)D + c;
       if (accumulate_dx) f4_add(v, *reinterpret_cast<const float4*>(o));
       st4(o, v);
     }
@@ -88,12 +97,12 @@ __global__ void __launch_bounds__(AT) additive_pool_bwd_kernel(const float* __re
       float ds = ds_s[t];
       float4 o = f4_zero();
       if (ds != 0.f) {
-        float4 h = ldg4(Hd + (n * S + t) * (int64_t)A + c);
+        float4 h = ldg4(Hd + t * (int64_t)A + c);
         f4_fma(acc, ds, h);
         o.x = ds * wv.x * (1.f - h.x * h.x); o.y = ds * wv.y * (1.f - h.y * h.y);
         o.z = ds * wv.z * (1.f - h.z * h.z); o.w = ds * wv.w * (1.f - h.w * h.w);
       }
-      st4(dpre + (n * S + t) * (int64_t)A + c, o);
+      st4(dpre + t * (int64_t)A + c, o);
     }
     st4(dw2_part + n * (int64_t)A + c, acc);
   }
@@ -149,22 +158,22 @@ using namespace lk;
 
 extern "C" {
 
-int lk_additive_pool_fwd(const float* X, const float* Hd, const float* w2, const int64_t* mask, float* out, float* alpha,
-                         int64_t N, int64_t S, int64_t D, int64_t A, cudaStream_t st) {
+int lk_additive_pool_fwd(const float* X, const float* Hd, const float* w2, const int64_t* mask, const int32_t* cu, float* out,
+                         float* alpha, int64_t N, int64_t S, int64_t D, int64_t A, cudaStream_t st) {
   LK_REQUIRE(D % 4 == 0 && A % 4 == 0, LK_ERR_SHAPE, "lk_additive_pool_fwd: D=%ld, A=%ld must be multiples of 4", (long)D, (long)A);
   LK_REQUIRE(S <= MAXS, LK_ERR_SHAPE, "lk_additive_pool_fwd: S=%ld exceeds %d", (long)S, MAXS);
   if (N == 0) return LK_OK;
-  additive_pool_fwd_kernel<<<(unsigned)N, AT, 0, st>>>(X, Hd, w2, mask, out, alpha, (int)S, (int)D, (int)A);
+  additive_pool_fwd_kernel<<<(unsigned)N, AT, 0, st>>>(X, Hd, w2, mask, cu, out, alpha, (int)S, (int)D, (int)A);
   return check_launch("additive_pool_fwd");
 }
 
-int lk_additive_pool_bwd(const float* X, const float* Hd, const float* w2, const float* alpha, const float* dOut, float* dX,
-                         float* dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A, int accumulate_dx,
+int lk_additive_pool_bwd(const float* X, const float* Hd, const float* w2, const float* alpha, const int32_t* cu, const float* dOut,
+                         float* dX, float* dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A, int accumulate_dx,
                          cudaStream_t st) {
   LK_REQUIRE(D % 4 == 0 && A % 4 == 0, LK_ERR_SHAPE, "lk_additive_pool_bwd: D=%ld, A=%ld must be multiples of 4", (long)D, (long)A);
   LK_REQUIRE(S <= MAXS, LK_ERR_SHAPE, "lk_additive_pool_bwd: S=%ld exceeds %d", (long)S, MAXS);
   if (N == 0) return LK_OK;
-  additive_pool_bwd_kernel<<<(unsigned)N, AT, 0, st>>>(X, Hd, w2, alpha, dOut, dX, dpre, dw2_part, (int)S, (int)D, (int)A,
+  additive_pool_bwd_kernel<<<(unsigned)N, AT, 0, st>>>(X, Hd, w2, alpha, cu, dOut, dX, dpre, dw2_part, (int)S, (int)D, (int)A,
                                                       accumulate_dx);
   return check_launch("additive_pool_bwd");
 }

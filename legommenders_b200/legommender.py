@@ -9,6 +9,7 @@ from . import ops
 from .cacher import ReprCacher
 from .env import Env
 from .lego_config import LegoConfig
+from .packing import pack_offsets, pack_tokens
 
 
 def _flatten_tree(x):
@@ -61,6 +62,45 @@ class Legommender(nn.Module):
         self.cacher = ReprCacher(self)
         self.cacher.activate(config.use_fast_eval)
 
+    # -- padding-free execution --------------------------------------------------------------------------------
+    packed = True    # class-level switch: False forces the reference's padded layout through the same kernels
+
+    def _packed_items(self) -> bool:
+        return (self.packed and self.item_op is not None and getattr(self.item_op, 'supports_packed', False)
+                and getattr(self.item_op.inputer, 'output_single_sequence', False))
+
+    def encode_items_packed(self, input_ids: dict, mask: torch.Tensor, item_valid=None, keep_empty=True):
+        """Encode items given per-column ids [N,S] + mask [N,S] without touching pad tokens -> ([n,D], Packed)."""
+        pk = pack_tokens(input_ids, mask, item_valid, keep_empty=keep_empty)
+        emb = self.item_op.inputer.get_embeddings({'input_ids': pk.ids})
+        return self.item_op(emb, cu=pk.cu, max_len=pk.max_len), pk
+
+    def _forward_packed(self, batch: dict):
+        """Candidates + valid history items in ONE packed item-encoder pass; the packed history encodings are directly
+        the user encoder's token rows.  -> (items [B,C,D], user [B,D])"""
+        cm = self.cm
+        cand, hist = batch[cm.item_col], batch[cm.history_col]
+        meta = batch.get('__lk_packed__')
+        if meta is None:
+            B, C, S = cand['attention_mask'].shape
+            H = hist['attention_mask'].shape[1]
+            clicks = batch[cm.mask_col]
+            ids = {c: torch.cat([cand['input_ids'][c].reshape(B * C, S), hist['input_ids'][c].reshape(B * H, S)])
+                   for c in cand['input_ids']}
+            mask = torch.cat([cand['attention_mask'].reshape(B * C, S), hist['attention_mask'].reshape(B * H, S)])
+            valid = torch.cat([torch.ones(B * C, dtype=clicks.dtype, device=clicks.device), clicks.reshape(-1)])
+            pk = pack_tokens(ids, mask, valid, keep_empty=False)
+            cu_u, max_u = pack_offsets(clicks)
+            meta = (pk, cu_u, max_u, B, C)
+            if mask.is_cuda:          # device-resident batch: the bookkeeping cost a sync, keep it with the batch
+                batch['__lk_packed__'] = meta
+        pk, cu_u, max_u, B, C = meta
+        emb = self.item_op.inputer.get_embeddings({'input_ids': pk.ids})
+        rep = self.item_op(emb, cu=pk.cu, max_len=pk.max_len)
+        items = rep[:B * C].view(B, C, -1)
+        user = self.user_op(rep[B * C:], cu=cu_u, max_len=max_u)
+        return items, user
+
     # -- item side (model/legommender.py:138-192) ----------------------------------------------------------
     def get_item_content(self, batch: dict, col: str):
         if self.cacher.item.cached:
@@ -69,6 +109,9 @@ class Legommender(nn.Module):
         content, bsz = _flatten_tree(batch[col])
         inputer = self.item_op.inputer
         mask = inputer.get_mask(content)
+        if self._packed_items():
+            rep, _ = self.encode_items_packed(content['input_ids'], mask)
+            return rep.view(bsz, -1, rep.shape[-1])
         emb = inputer.get_embeddings(content)
 
         n = _rows(emb)
@@ -96,12 +139,17 @@ class Legommender(nn.Module):
         if isinstance(batch[cm.item_col], torch.Tensor) and batch[cm.item_col].dim() == 1:
             batch[cm.item_col] = batch[cm.item_col].unsqueeze(1)
 
-        if self.config.use_item_content:
-            items = self.get_item_content(batch, cm.item_col)
+        if (self._packed_items() and getattr(self.user_op, 'supports_packed', False) and not self.flatten_mode
+                and not self.cacher.item.cached and not self.cacher.user.cached and isinstance(batch[cm.item_col], dict)
+                and cm.history_col in batch):
+            items, user = self._forward_packed(batch)
         else:
-            vocab = self.config.user_ut.meta.features[cm.history_col].tokenizer.vocab.name
-            items = self.eh(vocab, col_name=cm.history_col)(batch[cm.item_col].to(Env.device))
-        user = self.get_user_content(batch)
+            if self.config.use_item_content:
+                items = self.get_item_content(batch, cm.item_col)
+            else:
+                vocab = self.config.user_ut.meta.features[cm.history_col].tokenizer.vocab.name
+                items = self.eh(vocab, col_name=cm.history_col)(batch[cm.item_col].to(Env.device))
+            user = self.get_user_content(batch)
 
         want_scores = Env.is_testing or (Env.is_evaluating and not Env.simple_dev)
         fused = getattr(self.predictor, 'fused_scoring', False)

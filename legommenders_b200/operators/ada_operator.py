@@ -21,7 +21,11 @@ class AdaOperator(BaseOperator):
         self.additive_attention = AdditiveAttention(embed_dim=self.config.input_dim,
                                                     hidden_size=self.config.additive_hidden_size)
 
-    def forward(self, embeddings, mask=None, **kwargs):
+    supports_packed = True
+
+    def forward(self, embeddings, mask=None, cu=None, max_len=None, **kwargs):
+        if cu is not None:
+            return self.additive_attention(embeddings, None, cu=cu, max_len=max_len)
         return self.additive_attention(embeddings, mask.to(Env.device))
 
     @property

@@ -28,12 +28,16 @@ class AttentionOperator(BaseOperator):
         self.linear = _Affine(c.input_dim, c.hidden_size)
         self.additive_attention = AdditiveAttention(embed_dim=c.hidden_size, hidden_size=c.additive_hidden_size)
 
-    def forward(self, embeddings, mask=None, **kwargs):
-        mask = mask.to(Env.device)
+    supports_packed = True
+
+    def forward(self, embeddings, mask=None, cu=None, max_len=None, **kwargs):
+        """Dense: embeddings [N,S,D] + mask [N,S] (the reference's call).  Packed: embeddings [T,D] + cu int32 [N+1]."""
+        if cu is None:
+            mask = mask.to(Env.device)
         mha = self.multi_head_attention
         p = mha.dropout if self.training else 0.0
         qkv = ops.linear(embeddings, mha.in_proj_weight, mha.in_proj_bias)
-        ctx = ops.mha_core(qkv, mask, mha.num_heads, drop_p=p, seed=self._next_seed() if p else 0)
+        ctx = ops.mha_core(qkv, mask, mha.num_heads, drop_p=p, seed=self._next_seed() if p else 0, cu=cu, max_len=max_len)
         out = ops.linear(ctx, mha.out_proj.weight, mha.out_proj.bias)
         lin = ops.linear(out, self.linear.weight, self.linear.bias)
-        return self.additive_attention(lin, mask)
+        return self.additive_attention(lin, mask, cu=cu, max_len=max_len)

@@ -16,9 +16,9 @@ class AdditiveAttention(nn.Module):
         self.embed_dim, self.hidden_size = embed_dim, hidden_size
         self.encoder = nn.ModuleDict({'0': _Affine(embed_dim, hidden_size), '2': _Affine(hidden_size, 1, bias=False)})
 
-    def forward(self, inputs, attention_mask=None):
+    def forward(self, inputs, attention_mask=None, cu=None, max_len=None):
         e = self.encoder
-        return ops.additive_attention(inputs, attention_mask, e['0'].weight, e['0'].bias, e['2'].weight)
+        return ops.additive_attention(inputs, attention_mask, e['0'].weight, e['0'].bias, e['2'].weight, cu=cu, max_len=max_len)
 
 
 class MultiheadAttentionParams(nn.Module):

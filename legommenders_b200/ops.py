@@ -295,76 +295,87 @@ def gather_pool(ids, mask, table, mode=POOL_MEAN):
 # multi-head self-attention core
 # ----------------------------------------------------------------------------------------------------
 class _MHACore(Function):
-    """softmax((q·dh^-0.5)kᵀ + key padding)·v per head — nn.MultiheadAttention, attention_operator.py:49-55."""
+    """softmax((q·dh^-0.5)kᵀ + key padding)·v per head — nn.MultiheadAttention, attention_operator.py:49-55.
+    Dense: qkv [N,S,3D] + mask [N,S].  Packed: qkv [T,3D] + cu int32 [N+1] (rows of sequence n = cu[n]..cu[n+1])."""
 
     @staticmethod
-    def forward(ctx, qkv, mask, heads, drop_p, seed):
-        qkv, mask = _f32(qkv), _i64(mask)
-        N, S, D3 = qkv.shape
-        D = D3 // 3
-        out = torch.empty((N, S, D), dtype=torch.float32, device=qkv.device)
-        lse = torch.empty((N, heads, S), dtype=torch.float32, device=qkv.device)
-        call('lk_mha_fwd', ptr(qkv), ptr(mask), ptr(out), ptr(lse), N, S, D, heads, float(drop_p), int(seed))
-        ctx.save_for_backward(qkv, mask, lse)
-        ctx.heads, ctx.drop_p, ctx.seed = heads, drop_p, seed
+    def forward(ctx, qkv, mask, cu, max_len, heads, drop_p, seed):
+        qkv = _f32(qkv)
+        mask = _i64(mask) if mask is not None else None
+        D = qkv.shape[-1] // 3
+        if cu is None:
+            N, S = qkv.shape[0], qkv.shape[1]
+            rows = N * S
+        else:
+            N, S, rows = cu.numel() - 1, int(max_len), qkv.shape[0]
+        out = torch.empty((*qkv.shape[:-1], D), dtype=torch.float32, device=qkv.device)
+        lse = torch.empty((rows, heads), dtype=torch.float32, device=qkv.device)
+        call('lk_mha_fwd', ptr(qkv), ptr(mask), ptr(cu), ptr(out), ptr(lse), N, S, D, heads, float(drop_p), int(seed))
+        ctx.save_for_backward(qkv, mask, cu, lse)
+        ctx.dims = (N, S, D, heads, drop_p, seed)
         return out
 
     @staticmethod
     def backward(ctx, dctx):
-        qkv, mask, lse = ctx.saved_tensors
-        N, S, D3 = qkv.shape
+        qkv, mask, cu, lse = ctx.saved_tensors
+        N, S, D, heads, drop_p, seed = ctx.dims
         dqkv = torch.empty_like(qkv)
-        call('lk_mha_bwd', ptr(qkv), ptr(mask), ptr(lse), ptr(_f32(dctx)), ptr(dqkv), N, S, D3 // 3, ctx.heads,
-             float(ctx.drop_p), int(ctx.seed))
-        return dqkv, None, None, None, None
+        call('lk_mha_bwd', ptr(qkv), ptr(mask), ptr(cu), ptr(lse), ptr(_f32(dctx)), ptr(dqkv), N, S, D, heads, float(drop_p), int(seed))
+        return dqkv, None, None, None, None, None, None
 
 
-def mha_core(qkv, mask, heads, drop_p=0.0, seed=0):
-    return _MHACore.apply(qkv, mask, heads, drop_p, seed)
+def mha_core(qkv, mask, heads, drop_p=0.0, seed=0, cu=None, max_len=None):
+    return _MHACore.apply(qkv, mask, cu, max_len, heads, drop_p, seed)
 
 
 # ----------------------------------------------------------------------------------------------------
 # additive attention
 # ----------------------------------------------------------------------------------------------------
 class _AdditiveAttention(Function):
-    """model/common/attention.py:23-38: W1 GEMM + tanh, then the fused score/exp/mask/normalise/pool kernel."""
+    """model/common/attention.py:23-38: W1 GEMM + tanh, then the fused score/exp/mask/normalise/pool kernel.
+    Dense: x [N,S,D] + mask [N,S] (or None).  Packed: x [T,D] + cu int32 [N+1]."""
 
     @staticmethod
-    def forward(ctx, x, mask, w1, b1, w2):
+    def forward(ctx, x, mask, cu, max_len, w1, b1, w2):
         x, w1, b1, w2 = _f32(x), _f32(w1), _f32(b1), _f32(w2)
         mask = _i64(mask) if mask is not None else None
-        N, S, D = x.shape
-        A = w1.shape[0]
-        x2 = x.reshape(N * S, D)
+        D, A = x.shape[-1], w1.shape[0]
+        if cu is None:
+            N, S = x.shape[0], x.shape[1]
+        else:
+            N, S = cu.numel() - 1, int(max_len)
+        x2 = x.reshape(-1, D)
+        rows = x2.shape[0]
         hid, xp = linear_fwd_raw(x2, w1, b1, None, ACT_TANH)
         ctx.xp = xp
         out = torch.empty((N, D), dtype=torch.float32, device=x.device)
-        alpha = torch.empty((N, S), dtype=torch.float32, device=x.device)
-        call('lk_additive_pool_fwd', ptr(x2), ptr(hid), ptr(w2), ptr(mask), ptr(out), ptr(alpha), N, S, D, A)
-        ctx.save_for_backward(x2, hid, alpha, w1, w2)
-        ctx.shape = (N, S, D, A)
+        alpha = torch.empty((rows,), dtype=torch.float32, device=x.device)
+        call('lk_additive_pool_fwd', ptr(x2), ptr(hid), ptr(w2), ptr(mask), ptr(cu), ptr(out), ptr(alpha), N, S, D, A)
+        ctx.save_for_backward(x2, hid, alpha, w1, w2, cu)
+        ctx.shape = (N, S, D, A, tuple(x.shape))
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x2, hid, alpha, w1, w2 = ctx.saved_tensors
-        N, S, D, A = ctx.shape
+        x2, hid, alpha, w1, w2, cu = ctx.saved_tensors
+        N, S, D, A, xshape = ctx.shape
         dev = x2.device
-        dx = torch.empty((N * S, D), dtype=torch.float32, device=dev)
-        dpre = torch.empty((N * S, A), dtype=torch.float32, device=dev)
+        rows = x2.shape[0]
+        dx = torch.empty((rows, D), dtype=torch.float32, device=dev)
+        dpre = torch.empty((rows, A), dtype=torch.float32, device=dev)
         dw2p = torch.empty((N, A), dtype=torch.float32, device=dev)
-        call('lk_additive_pool_bwd', ptr(x2), ptr(hid), ptr(w2), ptr(alpha), ptr(_f32(dout)), ptr(dx), ptr(dpre), ptr(dw2p),
+        call('lk_additive_pool_bwd', ptr(x2), ptr(hid), ptr(w2), ptr(alpha), ptr(cu), ptr(_f32(dout)), ptr(dx), ptr(dpre), ptr(dw2p),
              N, S, D, A, 0)
         dw2 = colsum_raw(dw2p).view(1, A)
-        dpp = split_planes(dpre) if (tc_ok(N * S, D, A) or tc_ok(N * S, A, D)) else None
+        dpp = split_planes(dpre) if (tc_ok(rows, D, A) or tc_ok(rows, A, D)) else None
         dw1, db1 = linear_bwd_weight_raw(dpre, x2, dyp=dpp, xp=ctx.xp)
         linear_bwd_data_raw(dpre, w1, out=dx, accumulate=True, dyp=dpp)
         ctx.xp = None
-        return dx.view(N, S, D), None, dw1, db1, dw2
+        return dx.view(xshape), None, None, None, dw1, db1, dw2
 
 
-def additive_attention(x, mask, w1, b1, w2):
-    return _AdditiveAttention.apply(x, mask, w1, b1, w2)
+def additive_attention(x, mask, w1, b1, w2, cu=None, max_len=None):
+    return _AdditiveAttention.apply(x, mask, cu, max_len, w1, b1, w2)
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -247,6 +247,45 @@ def test_additive_attention(ops, engine, N_, S, D, A):
     assert rel(y2, O.additive_attention(x.double(), None, w1.double(), b1.double(), w2.double())) <= gemm_tol(engine, 3e-6)
 
 
+@pytest.mark.parametrize('N_,S,D,H,A', [(9, 33, 256, 8, 256), (6, 50, 256, 8, 256), (5, 12, 64, 8, 32)])
+def test_packed_layout_matches_dense(ops, N_, S, D, H, A):
+    """Padding-free execution: the packed (cu) form of MHA + additive attention equals the dense masked form on every
+    valid position, forward and backward (pad rows carry no gradient in either)."""
+    g = torch.Generator().manual_seed(N_ + S)
+    lens = torch.randint(1, S + 1, (N_,), generator=g)
+    lens[1] = S
+    mask = (torch.arange(S)[None, :] < lens[:, None]).long()
+    qkv = torch.randn(N_, S, 3 * D, generator=g)
+    w1 = torch.randn(A, D, generator=g) / D ** 0.5
+    b1 = torch.randn(A, generator=g) * 0.1
+    w2 = torch.randn(1, A, generator=g) / A ** 0.5
+    do = torch.randn(N_, D, generator=g)
+    sel = mask.bool()
+    cu = torch.zeros(N_ + 1, dtype=torch.int32)
+    cu[1:] = torch.cumsum(lens, 0)
+
+    def run(packed):
+        q = (qkv[sel] if packed else qkv).cuda().requires_grad_(True)
+        ws = [t.cuda().requires_grad_(True) for t in (w1, b1, w2)]
+        if packed:
+            ctx = ops.mha_core(q, None, H, cu=cu.cuda(), max_len=S)
+            out = ops.additive_attention(ctx, None, *ws, cu=cu.cuda(), max_len=S)
+        else:
+            ctx = ops.mha_core(q, mask.cuda(), H)
+            out = ops.additive_attention(ctx, mask.cuda(), *ws)
+        out.backward(do.cuda())
+        return ctx.detach().cpu(), out.detach().cpu(), q.grad.cpu(), [w.grad.cpu() for w in ws]
+
+    ctx_d, out_d, dq_d, dw_d = run(False)
+    ctx_p, out_p, dq_p, dw_p = run(True)
+    assert rel(ctx_p, ctx_d[sel]) <= 1e-6
+    assert rel(out_p, out_d) <= 2e-5
+    assert rel(dq_p, dq_d[sel]) <= 2e-5
+    assert dq_d[~sel].abs().max().item() == 0.0 if (~sel).any() else True
+    for a, b_ in zip(dw_p, dw_d):
+        assert rel(a, b_) <= 5e-5
+
+
 @pytest.mark.parametrize('mode', [0, 1])
 def test_masked_pool(ops, mode):
     g = torch.Generator().manual_seed(mode)

@@ -27,8 +27,18 @@ def build(c, world, llm):
     return model, resampler, cfg
 
 
+@pytest.fixture(params=['packed', 'padded'])
+def layout(request):
+    """Every model-level parity test runs padding-free (default) and in the reference's padded layout."""
+    from legommenders_b200 import Legommender
+    old = Legommender.packed
+    Legommender.packed = request.param == 'packed'
+    yield request.param
+    Legommender.packed = old
+
+
 @pytest.mark.parametrize('name', list(cases.CASES))
-def test_train_step_parity(name):
+def test_train_step_parity(name, layout):
     from legommenders_b200 import Env
     c = cases.CASES[name]
     g = cases.load(name)
@@ -87,7 +97,7 @@ def test_batch_builder_bit_exact(name):
 
 
 @pytest.mark.parametrize('name', [n for n, c in cases.CASES.items() if c.get('cached_eval')])
-def test_cached_eval_parity(name):
+def test_cached_eval_parity(name, layout):
     from torch.utils.data import DataLoader
     from legommenders_b200 import DataSet, Env, ops
     c = cases.CASES[name]
