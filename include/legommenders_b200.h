@@ -73,8 +73,10 @@ int lk_colsum(const float* X, float* out, int64_t M, int64_t N, int accumulate, 
  *      lk_split_bf16: fp32 [rows, cols] (pitch ld_in) -> hi/lo [rows, ld_out] (transpose=0) or [cols, ld_out] (transpose=1).
  *      lk_tc_gemm: C[GM,GN] (+)= A·B with both operands K-major (a_mn=b_mn=0: A [GM,GK], B [GN,GK], reduction contiguous)
  *      or both MN-major (a_mn=b_mn=1: A [GK,GM], B [GK,GN]; the weight-gradient case, reduction over token rows). */
+size_t lk_split_bf16_workspace_bytes(int64_t rows, int64_t cols);
+/* colsum (nullable, transpose=0 only): also emit sum over rows of X (the bias gradient rides on the pass that reads dY) */
 int lk_split_bf16(const float* X, int64_t rows, int64_t cols, int64_t ld_in, void* hi, void* lo, int64_t ld_out, int transpose,
-                  cudaStream_t stream);
+                  float* colsum, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t lk_tc_gemm_workspace_bytes(int64_t GM, int64_t GN, int64_t GK);
 int lk_tc_gemm(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo, int64_t ldb, int b_mn,
                float* C, int64_t ldc, int64_t GM, int64_t GN, int64_t GK, const float* bias, const int64_t* rowmask, int act,

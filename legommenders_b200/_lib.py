@@ -35,7 +35,8 @@ SIGNATURES = {
     'lk_linear_bwd_weight_workspace_bytes': ('qqq', 'z'),
     'lk_linear_bwd_weight': ('ppppqqqipzs', 'i'),
     'lk_splitk_reduce': ('ppqqqiis', 'i'),
-    'lk_split_bf16': ('pqqqppqis', 'i'),
+    'lk_split_bf16_workspace_bytes': ('qq', 'z'),
+    'lk_split_bf16': ('pqqqppqippzs', 'i'),
     'lk_tc_gemm_workspace_bytes': ('qqq', 'z'),
     'lk_tc_gemm': ('ppqippqipqqqqppifuipzs', 'i'),
     'lk_colsum_workspace_bytes': ('qq', 'z'),

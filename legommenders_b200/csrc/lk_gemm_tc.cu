@@ -16,6 +16,7 @@
 // the weight-gradient contraction whose reduction runs over token rows) — both through 128-byte-swizzle UMMA descriptors.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "lk_common.cuh"
 #include "../../include/legommenders_b200.h"
@@ -99,6 +100,59 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
 __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// Epilogue of one 128x128 accumulator tile: TMEM -> registers -> bias / activation / dropout / row mask -> global.
+__device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, int acc, int q, int lane, int m0, int n0, int split,
+                                           bool has_k, float inv_keep) {
+  const int row = m0 + q * 32 + lane;
+  const bool row_ok = row < p.GM;
+  float* out;
+  int ldo;
+  if (p.partial) { out = p.partial + (size_t)split * p.GM * p.GN; ldo = p.GN; } else { out = p.C; ldo = p.ldc; }
+  float rm = 1.f;
+  if (!p.partial && p.rowmask && row_ok) rm = p.rowmask[row] > 0 ? 1.f : 0.f;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; c++) {
+    uint32_t v[32];
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int n = n0 + c * 32 + j;
+        if (n >= p.GN) break;
+        float x[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          float t = has_k ? __uint_as_float(v[j + e]) : 0.f;
+          if (!p.partial) {
+            if (p.bias) t += __ldg(p.bias + n + e);
+            if (p.act == 1) t = tanhf(t);
+            else if (p.act == 2) t = fmaxf(t, 0.f);
+            if (p.drop_p > 0.f) t *= dropout_scale(p.seed, (uint64_t)row * p.GN + n + e, p.drop_p, inv_keep);
+            t *= rm;
+          }
+          x[e] = t;
+        }
+        float* o = out + (size_t)row * ldo + n;
+        if (!p.partial && p.accumulate) {
+          const float4 old = *reinterpret_cast<const float4*>(o);
+          x[0] += old.x; x[1] += old.y; x[2] += old.z; x[3] += old.w;
+        }
+        st4(o, make_float4(x[0], x[1], x[2], x[3]));
+      }
+    }
+  }
 }
 
 template <bool A_MN, bool B_MN>
@@ -230,54 +284,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       const bool has_k = kb1 > kb0;
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.GM;
-      float* out;
-      int ldo;
-      if (p.partial) { out = p.partial + (size_t)split * p.GM * p.GN; ldo = p.GN; } else { out = p.C; ldo = p.ldc; }
-      float rm = 1.f;
-      if (!p.partial && p.rowmask && row_ok) rm = p.rowmask[row] > 0 ? 1.f : 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; c++) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int n = n0 + c * 32 + j;
-            if (n >= p.GN) break;
-            float x[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              float t = has_k ? __uint_as_float(v[j + e]) : 0.f;
-              if (!p.partial) {
-                if (p.bias) t += __ldg(p.bias + n + e);
-                if (p.act == 1) t = tanhf(t);
-                else if (p.act == 2) t = fmaxf(t, 0.f);
-                if (p.drop_p > 0.f) t *= dropout_scale(p.seed, (uint64_t)row * p.GN + n + e, p.drop_p, inv_keep);
-                t *= rm;
-              }
-              x[e] = t;
-            }
-            float* o = out + (size_t)row * ldo + n;
-            if (!p.partial && p.accumulate) {
-              const float4 old = *reinterpret_cast<const float4*>(o);
-              x[0] += old.x; x[1] += old.y; x[2] += old.z; x[3] += old.w;
-            }
-            st4(o, make_float4(x[0], x[1], x[2], x[3]));
-          }
-        }
-      }
+      store_tile(p, tmem_base, acc, q, lane, m0, n0, split, has_k, inv_keep);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
@@ -293,29 +300,199 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   }
 }
 
-// fp32 -> (hi, lo) bf16 planes; optional transpose; output pitch ld_out (>= cols, multiple of 8), pad columns zeroed
-__global__ void split_bf16_kernel(const float* __restrict__ X, int64_t rows, int cols, int64_t ld_in, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo, int64_t ld_out) {
-  const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int q = (int)(ld_out >> 2);
-  if (i4 >= rows * q) return;
-  const int64_t r = i4 / q;
-  const int c = (int)(i4 % q) * 4;
-  float x[4] = {0.f, 0.f, 0.f, 0.f};
-  if (c + 3 < cols) {
-    const float4 v = ldg4_stream(X + r * ld_in + c);
-    x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-  } else {
-    for (int e = 0; e < 4; e++) if (c + e < cols) x[e] = X[r * ld_in + c + e];
+// ------------------------------------------------------------------------------------------------------------------
+// Weight-stationary variant for the forward / grad-input contractions (K-major operands, reduction depth <= 320).
+// With K = 256 a 128x128 output tile needs only 3072 MMA cycles but 256 KB of operand tiles; re-streaming both operands per
+// tile makes the kernel L2->SM bandwidth bound (ncu: tensor pipe 8-13% active).  Here a CTA owns ONE 128-column slab of
+// the weight for its whole life — its hi/lo planes for the full reduction depth sit in shared memory (kb x 32 KB) — and
+// only the activation planes are streamed (32 KB per k-block) through the TMA ring while it walks down the M tiles.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int WS_MAX_KB = 5;
+constexpr int A_STAGE_BYTES = 2 * TILE_BYTES;   // A_hi + A_lo for one k-block
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                  const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const Params p, int a_stages) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smemB = smem;                                         // [k_blocks][B_hi 16K | B_lo 16K]
+  uint8_t* smemA = smem + p.k_blocks * 2 * TILE_BYTES;           // [a_stages][A_hi 16K | A_lo 16K]
+  uint64_t* bars = (uint64_t*)(smemA + a_stages * A_STAGE_BYTES);
+  uint64_t* full_bar = bars;                     // [8]
+  uint64_t* empty_bar = bars + 8;                // [8]
+  uint64_t* tfull_bar = bars + 16;               // [ACC_STAGES]
+  uint64_t* tempty_bar = tfull_bar + ACC_STAGES; // [ACC_STAGES]
+  uint64_t* b_bar = tempty_bar + ACC_STAGES;     // weights landed
+  uint32_t* tmem_slot = (uint32_t*)(b_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = max(1, (int)gridDim.x / p.n_tiles);         // CTAs per weight slab
+  const int n_blk = blockIdx.x % p.n_tiles, grp = blockIdx.x / p.n_tiles;
+  const bool active = grp < groups;
+  const int n0 = n_blk * BN;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapAh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapAl) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapBh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapBl) : "memory");
   }
-  __nv_bfloat16 h[4], l[4];
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < a_stages; i++) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    for (int i = 0; i < ACC_STAGES; i++) {
+      mbar_init(smem_u32(&tfull_bar[i]), 1);
+      mbar_init(smem_u32(&tempty_bar[i]), 4);
+    }
+    mbar_init(smem_u32(b_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (active) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const uint32_t bb = smem_u32(b_bar);
+        mbar_expect_tx(bb, p.k_blocks * 2 * TILE_BYTES);
+        for (int kb = 0; kb < p.k_blocks; kb++) {
+          tma_load_2d(smem_u32(smemB + kb * 2 * TILE_BYTES), &mapBh, bb, kb * BK, n0);
+          tma_load_2d(smem_u32(smemB + kb * 2 * TILE_BYTES + TILE_BYTES), &mapBl, bb, kb * BK, n0);
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int mt = grp; mt < p.m_tiles; mt += groups) {
+          for (int kb = 0; kb < p.k_blocks; kb++) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_expect_tx(fb, A_STAGE_BYTES);
+            const uint32_t sa = smem_u32(smemA + stage * A_STAGE_BYTES);
+            tma_load_2d(sa, &mapAh, fb, kb * BK, mt * BM);
+            tma_load_2d(sa + TILE_BYTES, &mapAl, fb, kb * BK, mt * BM);
+            if (++stage == a_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(false, false);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        mbar_wait(smem_u32(b_bar), 0);
+        tc_fence_after();
+        for (int mt = grp; mt < p.m_tiles; mt += groups) {
+          mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kb = 0; kb < p.k_blocks; kb++) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smemA + stage * A_STAGE_BYTES);
+            const uint32_t sb = smem_u32(smemB + kb * 2 * TILE_BYTES);
 #pragma unroll
-  for (int e = 0; e < 4; e++) {
-    h[e] = __float2bfloat16_rn(x[e]);
-    l[e] = __float2bfloat16_rn(x[e] - __bfloat162float(h[e]));
+            for (int k = 0; k < BK / UMMA_K; k++) {
+              const uint64_t ah = make_desc(sa + k * UMMA_K * 2, false);
+              const uint64_t al = make_desc(sa + TILE_BYTES + k * UMMA_K * 2, false);
+              const uint64_t bh = make_desc(sb + k * UMMA_K * 2, false);
+              const uint64_t bl = make_desc(sb + TILE_BYTES + k * UMMA_K * 2, false);
+              umma_bf16(d_tmem, al, bh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(d_tmem, ah, bl, idesc, 1u);
+              umma_bf16(d_tmem, ah, bh, idesc, 1u);
+            }
+            umma_commit(smem_u32(&empty_bar[stage]));
+            if (++stage == a_stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(smem_u32(&tfull_bar[acc]));
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    } else {
+      const int q = warp & 3;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+      for (int mt = grp; mt < p.m_tiles; mt += groups) {
+        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+        tc_fence_after();
+        store_tile(p, tmem_base, acc, q, lane, mt * BM, n0, 0, true, inv_keep);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
   }
-  *reinterpret_cast<uint2*>(hi + r * ld_out + c) = *reinterpret_cast<uint2*>(h);
-  *reinterpret_cast<uint2*>(lo + r * ld_out + c) = *reinterpret_cast<uint2*>(l);
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// fp32 -> (hi, lo) bf16 planes, output pitch ld_out (>= cols, multiple of 8, pad columns zeroed).  A block owns SPLIT_ROWS
+// rows x 256 columns (32 column-threads x 8 elements, 8 row-threads); optionally it also emits per-block column sums of the
+// fp32 input (the bias gradient db = sum_m dY[m,:] rides on the pass that has to read dY anyway).
+constexpr int SPLIT_ROWS = 64;
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ X, int64_t rows, int cols, int64_t ld_in,
+                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t ld_out,
+                                                         float* __restrict__ colsum_part) {
+  __shared__ float red[8][256 + 8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + tx * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * SPLIT_ROWS;
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < ld_out) {
+#pragma unroll 2
+    for (int i = ty; i < SPLIT_ROWS; i += 8) {
+      const int64_t r = r0 + i;
+      if (r >= rows) break;
+      float x[8];
+      if (c + 7 < cols) {
+        const float4 a = ldg4_stream(X + r * ld_in + c), b2 = ldg4_stream(X + r * ld_in + c + 4);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b2.x; x[5] = b2.y; x[6] = b2.z; x[7] = b2.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = (c + e < cols) ? X[r * ld_in + c + e] : 0.f;
+      }
+      __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        h[e] = __float2bfloat16_rn(x[e]);
+        l[e] = __float2bfloat16_rn(x[e] - __bfloat162float(h[e]));
+        cs[e] += x[e];
+      }
+      *reinterpret_cast<uint4*>(hi + r * ld_out + c) = *reinterpret_cast<uint4*>(h);
+      *reinterpret_cast<uint4*>(lo + r * ld_out + c) = *reinterpret_cast<uint4*>(l);
+    }
+  }
+  if (colsum_part) {
+#pragma unroll
+    for (int e = 0; e < 8; e++) red[ty][tx * 8 + e] = cs[e];
+    __syncthreads();
+    const int cc = threadIdx.x;   // 256 threads <-> 256 columns of this block
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += red[i][cc];
+    if (blockIdx.x * 256 + cc < cols) colsum_part[(int64_t)blockIdx.y * cols + blockIdx.x * 256 + cc] = t;
+  }
+}
+
+__global__ void colsum_finish_kernel(const float* __restrict__ part, float* __restrict__ out, int nparts, int cols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int i = 0; i < nparts; i++) s += part[(int64_t)i * cols + c];
+  out[c] = s;
 }
 
 // transposed split through a 32x32 smem tile: out[c, r]
@@ -387,16 +564,28 @@ using namespace lk::tc;
 
 extern "C" {
 
+size_t lk_split_bf16_workspace_bytes(int64_t rows, int64_t cols) {
+  return (size_t)((rows + SPLIT_ROWS - 1) / SPLIT_ROWS) * cols * sizeof(float) + 256;
+}
+
 int lk_split_bf16(const float* X, int64_t rows, int64_t cols, int64_t ld_in, void* hi, void* lo, int64_t ld_out, int transpose,
-                  cudaStream_t st) {
+                  float* colsum, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   LK_REQUIRE(ld_out % 8 == 0, LK_ERR_SHAPE, "lk_split_bf16: output pitch %ld must be a multiple of 8 (16-byte TMA rows)", (long)ld_out);
   if (rows == 0 || cols == 0) return LK_OK;
   if (!transpose) {
     LK_REQUIRE(ld_out >= cols && ld_in % 4 == 0, LK_ERR_SHAPE, "lk_split_bf16: bad pitches");
-    int64_t total = rows * (ld_out / 4);
-    split_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, rows, (int)cols, ld_in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_out);
+    LK_REQUIRE(!colsum || (workspace && workspace_bytes >= lk_split_bf16_workspace_bytes(rows, cols)), LK_ERR_ARG,
+               "lk_split_bf16: workspace too small for the fused column sums");
+    const int nparts = (int)((rows + SPLIT_ROWS - 1) / SPLIT_ROWS);
+    dim3 grid((unsigned)((ld_out + 255) / 256), (unsigned)nparts);
+    split_bf16_kernel<<<grid, 256, 0, st>>>(X, rows, (int)cols, ld_in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_out,
+                                            colsum ? (float*)workspace : nullptr);
+    if (colsum) {
+      colsum_finish_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>((const float*)workspace, colsum, nparts, (int)cols);
+      return check_launch("split_bf16", 2);
+    }
   } else {
-    LK_REQUIRE(ld_out >= rows, LK_ERR_SHAPE, "lk_split_bf16: transposed pitch too small");
+    LK_REQUIRE(ld_out >= rows && !colsum, LK_ERR_SHAPE, "lk_split_bf16: transposed pitch too small / no fused sums when transposing");
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((ld_out + 31) / 32));
     split_bf16_t_kernel<<<grid, dim3(32, 8), 0, st>>>(X, (int)rows, (int)cols, ld_in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_out);
   }
@@ -453,6 +642,22 @@ int lk_tc_gemm(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const 
   }
   int total = p.m_tiles * p.n_tiles * p.splits;
   int grid = total < kNumSMs ? total : kNumSMs;
+  static const bool ws_enabled = getenv("LK_TC_WS") == nullptr || atoi(getenv("LK_TC_WS")) != 0;
+  if (!a_mn && ws_enabled && p.splits == 1 && p.k_blocks <= WS_MAX_KB && p.n_tiles <= kNumSMs && p.m_tiles >= 2 * (kNumSMs / p.n_tiles)) {
+    // weight-stationary: one 128-column weight slab per CTA for its whole life, activations streamed
+    const int b_bytes = p.k_blocks * 2 * TILE_BYTES;
+    int a_stages = (227 * 1024 - 2048 - b_bytes) / A_STAGE_BYTES;
+    if (a_stages > 6) a_stages = 6;
+    const int smem = b_bytes + a_stages * A_STAGE_BYTES + 1024 + 512;
+    static bool ws_attr = false;
+    if (!ws_attr) {
+      cudaFuncSetAttribute(tc_gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      ws_attr = true;
+    }
+    const int groups = kNumSMs / p.n_tiles;
+    tc_gemm_ws_kernel<<<groups * p.n_tiles, NUM_THREADS, smem, st>>>(mAh, mAl, mBh, mBl, p, a_stages);
+    return check_launch("tc_gemm_ws");
+  }
   if (a_mn) tc_gemm_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
   else tc_gemm_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
   rc = check_launch("tc_gemm");

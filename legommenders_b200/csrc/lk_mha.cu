@@ -45,13 +45,13 @@ struct MhaParams {
 
 template <int DH>
 __device__ __forceinline__ float dot_smem(const float (&q)[DH], const float* __restrict__ k) {
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four independent chains: the dot is latency-, not issue-bound
 #pragma unroll
   for (int d = 0; d < DH; d += 4) {
     const float4 kv = *reinterpret_cast<const float4*>(k + d);
-    s = fmaf(q[d], kv.x, s); s = fmaf(q[d + 1], kv.y, s); s = fmaf(q[d + 2], kv.z, s); s = fmaf(q[d + 3], kv.w, s);
+    s0 = fmaf(q[d], kv.x, s0); s1 = fmaf(q[d + 1], kv.y, s1); s2 = fmaf(q[d + 2], kv.z, s2); s3 = fmaf(q[d + 3], kv.w, s3);
   }
-  return s;
+  return (s0 + s1) + (s2 + s3);
 }
 
 // ------------------------------------------------------------------------------------------------ forward

@@ -49,13 +49,22 @@ class Planes:
         self.hi, self.lo, self.rows, self.cols, self.ld = hi, lo, rows, cols, ld
 
 
-def split_planes(x2: torch.Tensor, transpose: bool = False) -> Planes:
+def split_planes(x2: torch.Tensor, transpose: bool = False, colsum: bool = False):
+    """-> Planes, or (Planes, column sums of x2) when colsum=True (bias gradient fused into the split pass)."""
     rows, cols = x2.shape
     orows, ocols = (cols, rows) if transpose else (rows, cols)
     ld = (ocols + 7) // 8 * 8
     buf = torch.empty((2, orows, ld), dtype=torch.bfloat16, device=x2.device)
-    call('lk_split_bf16', ptr(x2), rows, cols, x2.stride(0), ptr(buf[0]), ptr(buf[1]), ld, int(transpose))
-    return Planes(buf[0], buf[1], orows, ocols, ld)
+    cs = ws = None
+    nbytes = 0
+    if colsum:
+        cs = torch.empty((cols,), dtype=torch.float32, device=x2.device)
+        nbytes = query('lk_split_bf16_workspace_bytes', rows, cols)
+        ws = workspace(nbytes, x2.device, 'colsum')
+    call('lk_split_bf16', ptr(x2), rows, cols, x2.stride(0), ptr(buf[0]), ptr(buf[1]), ld, int(transpose), ptr(cs), ptr(ws),
+         ws.numel() if ws is not None else 0)
+    planes = Planes(buf[0], buf[1], orows, ocols, ld)
+    return (planes, cs) if colsum else planes
 
 
 _wplanes = {}
@@ -122,15 +131,17 @@ def linear_bwd_data_raw(dy2, w, out=None, accumulate=False, dyp=None):
     return dx
 
 
-def linear_bwd_weight_raw(dy2, x2, want_bias=True, dyp=None, xp=None):
+def linear_bwd_weight_raw(dy2, x2, want_bias=True, dyp=None, xp=None, db=None):
     """dW = dYᵀ·X (contraction over the M token rows: both operands MN-major), db = column sums of dY."""
     M, N = dy2.shape
     K = x2.shape[1] if x2 is not None else xp.cols
     if tc_ok(M, N, K):
-        dyp = dyp if dyp is not None else split_planes(dy2)
+        if dyp is None:
+            dyp, db = split_planes(dy2, colsum=True) if want_bias else (split_planes(dy2), None)
         xp = xp if xp is not None else split_planes(x2)
         dw = tc_gemm(dyp, xp, True, N, K, M)
-        db = colsum_raw(dy2) if want_bias else None
+        if want_bias and db is None:
+            db = colsum_raw(dy2)
         return dw, db
     if x2 is None:
         raise RuntimeError('linear_bwd_weight_raw: fp32 input required for the SIMT path')
@@ -185,11 +196,13 @@ class _Linear(Function):
         dx = dw = db = None
         M, N = dy2.shape
         K = w.shape[1]
-        dyp = split_planes(dy2) if (tc_ok(M, K, N) or tc_ok(M, N, K)) else None
+        dyp = dbias = None
+        if tc_ok(M, K, N) or tc_ok(M, N, K):
+            dyp, dbias = split_planes(dy2, colsum=True) if ctx.has_b else (split_planes(dy2), None)
         if ctx.needs_input_grad[0]:
             dx = linear_bwd_data_raw(dy2, w, dyp=dyp).view(*dy.shape[:-1], K)
         if ctx.needs_input_grad[1] or (ctx.has_b and ctx.needs_input_grad[2]):
-            dw, db = linear_bwd_weight_raw(dy2, x2, want_bias=ctx.has_b, dyp=dyp, xp=ctx.xp)
+            dw, db = linear_bwd_weight_raw(dy2, x2, want_bias=ctx.has_b, dyp=dyp, xp=ctx.xp, db=dbias)
         ctx.xp = None
         return dx, dw, db, None, None, None, None
 
@@ -367,8 +380,10 @@ class _AdditiveAttention(Function):
         call('lk_additive_pool_bwd', ptr(x2), ptr(hid), ptr(w2), ptr(alpha), ptr(cu), ptr(_f32(dout)), ptr(dx), ptr(dpre), ptr(dw2p),
              N, S, D, A, 0)
         dw2 = colsum_raw(dw2p).view(1, A)
-        dpp = split_planes(dpre) if (tc_ok(rows, D, A) or tc_ok(rows, A, D)) else None
-        dw1, db1 = linear_bwd_weight_raw(dpre, x2, dyp=dpp, xp=ctx.xp)
+        dpp = db1 = None
+        if tc_ok(rows, D, A) or tc_ok(rows, A, D):
+            dpp, db1 = split_planes(dpre, colsum=True)
+        dw1, db1 = linear_bwd_weight_raw(dpre, x2, dyp=dpp, xp=ctx.xp, db=db1)
         linear_bwd_data_raw(dpre, w1, out=dx, accumulate=True, dyp=dpp)
         ctx.xp = None
         return dx.view(xshape), None, None, None, dw1, db1, dw2

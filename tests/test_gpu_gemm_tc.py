@@ -17,7 +17,7 @@ def rel(a, b):
     return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
 
 
-@pytest.mark.parametrize('rows,cols', [(5, 300), (129, 256), (1000, 64), (3, 4)])
+@pytest.mark.parametrize('rows,cols', [(5, 300), (129, 256), (1000, 64), (3, 4), (4100, 768)])
 def test_split_planes(ops, rows, cols):
     g = torch.Generator().manual_seed(rows + cols)
     x = torch.randn(rows, cols, generator=g) * 3
@@ -32,10 +32,13 @@ def test_split_planes(ops, rows, cols):
     assert torch.equal(t.hi.float().cpu()[:, :rows], hi[:, :cols].t())
     assert torch.equal(t.lo.float().cpu()[:, :rows], lo[:, :cols].t())
     assert (t.hi.float().cpu()[:, rows:] == 0).all()
+    p2, cs = ops.split_planes(x.cuda(), colsum=True)
+    assert torch.equal(p2.hi, p.hi) and torch.equal(p2.lo, p.lo)
+    assert (cs.double().cpu() - x.double().sum(0)).abs().max().item() <= 1e-5 * max(1.0, x.abs().sum(0).max().item())
 
 
 @pytest.mark.parametrize('M,N,K', [(128, 128, 64), (128, 128, 256), (300, 256, 256), (1000, 768, 256), (257, 64, 300),
-                                   (4000, 256, 300), (513, 32, 64), (20000, 256, 256), (256, 256, 4096)])
+                                   (4000, 256, 300), (513, 32, 64), (20000, 256, 256), (256, 256, 4096), (40000, 768, 256), (40000, 256, 300), (38000, 128, 64)])
 def test_tc_gemm_k_major(ops, M, N, K):
     g = torch.Generator().manual_seed(M + N + K)
     a = torch.randn(M, K, generator=g)
