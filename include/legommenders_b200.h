@@ -78,6 +78,8 @@ size_t lk_split_bf16_workspace_bytes(int64_t rows, int64_t cols);
 int lk_split_bf16(const float* X, int64_t rows, int64_t cols, int64_t ld_in, void* hi, void* lo, int64_t ld_out, int transpose,
                   float* colsum, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t lk_tc_gemm_workspace_bytes(int64_t GM, int64_t GN, int64_t GK);
+/* tuning switch (default 0): use the weight-stationary kernel for K-major contractions with reduction depth <= 320 */
+void lk_tc_set_weight_stationary(int enabled);
 int lk_tc_gemm(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo, int64_t ldb, int b_mn,
                float* C, int64_t ldc, int64_t GM, int64_t GN, int64_t GK, const float* bias, const int64_t* rowmask, int act,
                float drop_p, uint64_t seed, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);

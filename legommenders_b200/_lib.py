@@ -38,6 +38,7 @@ SIGNATURES = {
     'lk_split_bf16_workspace_bytes': ('qq', 'z'),
     'lk_split_bf16': ('pqqqppqippzs', 'i'),
     'lk_tc_gemm_workspace_bytes': ('qqq', 'z'),
+    'lk_tc_set_weight_stationary': ('i', 'v'),
     'lk_tc_gemm': ('ppqippqipqqqqppifuipzs', 'i'),
     'lk_colsum_workspace_bytes': ('qq', 'z'),
     'lk_colsum': ('ppqqipzs', 'i'),
@@ -82,7 +83,7 @@ def load() -> ctypes.CDLL:
         for name, (args, res) in SIGNATURES.items():
             fn = getattr(lib, name)   # AttributeError if the header and the library disagree
             fn.argtypes = [_T[a] for a in args]
-            fn.restype = ctypes.c_char_p if res == 'c' else _T[res]
+            fn.restype = ctypes.c_char_p if res == 'c' else (None if res == 'v' else _T[res])
         _lib = lib
     return _lib
 

@@ -28,8 +28,8 @@ constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3, UMMA_K = 16, ACC_STAGES =
 constexpr int TILE_BYTES = BM * BK * 2;        // one plane of one operand: 16 KiB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi, A_lo, B_hi, B_lo
 constexpr int TMEM_COLS = ACC_STAGES * BN;     // 256 fp32 columns
-constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 64 + 8 * 32;   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8 * 32 * 20 * 4 /*epilogue staging*/;
 
 struct Params {
   float* C;                 // [GM, ldc] (or split partials [splits, GM, GN] when partial != null)
@@ -102,56 +102,66 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-// Epilogue of one 128x128 accumulator tile: TMEM -> registers -> bias / activation / dropout / row mask -> global.
-__device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, int acc, int q, int lane, int m0, int n0, int split,
-                                           bool has_k, float inv_keep) {
+// Epilogue of one 128x128 accumulator tile by 8 warps: warp (q, half) owns TMEM lanes 32q..32q+31 and columns
+// 64*half..64*half+63.  Per 16-column chunk: tcgen05.ld (row = lane) -> bias / activation / dropout / row mask in registers
+// -> transpose through a warp-private shared tile -> 64-byte-contiguous row segments to global (a warp store covers 8 rows).
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_LD = 20;                                   // floats per staged row (16 + 4 pad: conflict-free float4 stores)
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_LD * 4;   // 20 KiB
+
+__device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, int acc, int q, int half, int lane, int m0, int n0,
+                                           int split, bool has_k, float inv_keep, float* stage) {
   const int row = m0 + q * 32 + lane;
   const bool row_ok = row < p.GM;
   float* out;
   int ldo;
   if (p.partial) { out = p.partial + (size_t)split * p.GM * p.GN; ldo = p.GN; } else { out = p.C; ldo = p.ldc; }
+  const bool fused = p.partial == nullptr;
   float rm = 1.f;
-  if (!p.partial && p.rowmask && row_ok) rm = p.rowmask[row] > 0 ? 1.f : 0.f;
+  if (fused && p.rowmask && row_ok) rm = p.rowmask[row] > 0 ? 1.f : 0.f;
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; c++) {
-    uint32_t v[32];
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+  for (int c = 0; c < 4; c++) {
+    const int nc0 = n0 + half * 64 + c * 16;
+    if (nc0 >= p.GN) break;                                  // warp-uniform
+    uint32_t v[16];
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * 64 + c * 16);
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
+    float bj = 0.f;
+    if (fused && p.bias && lane < 16 && nc0 + lane < p.GN) bj = __ldg(p.bias + nc0 + lane);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (row_ok) {
+    float x[16];
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int n = n0 + c * 32 + j;
-        if (n >= p.GN) break;
-        float x[4];
+    for (int j = 0; j < 16; j++) {
+      float t = has_k ? __uint_as_float(v[j]) : 0.f;
+      if (fused) {
+        t += __shfl_sync(0xffffffffu, bj, j);
+        if (p.act == 1) t = tanhf(t);
+        else if (p.act == 2) t = fmaxf(t, 0.f);
+        if (p.drop_p > 0.f) t *= dropout_scale(p.seed, (uint64_t)row * p.GN + nc0 + j, p.drop_p, inv_keep);
+        t *= rm;
+      }
+      x[j] = t;
+    }
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          float t = has_k ? __uint_as_float(v[j + e]) : 0.f;
-          if (!p.partial) {
-            if (p.bias) t += __ldg(p.bias + n + e);
-            if (p.act == 1) t = tanhf(t);
-            else if (p.act == 2) t = fmaxf(t, 0.f);
-            if (p.drop_p > 0.f) t *= dropout_scale(p.seed, (uint64_t)row * p.GN + n + e, p.drop_p, inv_keep);
-            t *= rm;
-          }
-          x[e] = t;
-        }
-        float* o = out + (size_t)row * ldo + n;
-        if (!p.partial && p.accumulate) {
-          const float4 old = *reinterpret_cast<const float4*>(o);
-          x[0] += old.x; x[1] += old.y; x[2] += old.z; x[3] += old.w;
-        }
-        st4(o, make_float4(x[0], x[1], x[2], x[3]));
+    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+      const int r = it * 8 + (lane >> 2), c4 = (lane & 3) * 4;
+      const int grow = m0 + q * 32 + r, n = nc0 + c4;
+      if (grow < p.GM && n < p.GN) {
+        float4 val = *reinterpret_cast<const float4*>(stage + r * EPI_LD + c4);
+        float* o = out + (size_t)grow * ldo + n;
+        if (fused && p.accumulate) f4_add(val, *reinterpret_cast<const float4*>(o));
+        st4(o, val);
       }
     }
+    __syncwarp();
   }
 }
 
@@ -184,7 +194,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     }
     for (int i = 0; i < ACC_STAGES; i++) {
       mbar_init(smem_u32(&tfull_bar[i]), 1);
-      mbar_init(smem_u32(&tempty_bar[i]), 4);   // one arrive per epilogue warp
+      mbar_init(smem_u32(&tempty_bar[i]), EPI_WARPS);   // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -271,8 +281,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       }
     }
   } else {
-    // ------------------------------------------------ epilogue (warps 2..5) ----------------------------------------
+    // ------------------------------------------------ epilogue (warps 2..9) ----------------------------------------
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // which 64-column half of the tile
+    float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * 32 * EPI_LD;
     int acc = 0;
     uint32_t acc_phase = 0;
     const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
@@ -284,7 +296,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       const bool has_k = kb1 > kb0;
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
-      store_tile(p, tmem_base, acc, q, lane, m0, n0, split, has_k, inv_keep);
+      store_tile(p, tmem_base, acc, q, half, lane, m0, n0, split, has_k, inv_keep, stage);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
@@ -344,7 +356,7 @@ tc_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_consta
     }
     for (int i = 0; i < ACC_STAGES; i++) {
       mbar_init(smem_u32(&tfull_bar[i]), 1);
-      mbar_init(smem_u32(&tempty_bar[i]), 4);
+      mbar_init(smem_u32(&tempty_bar[i]), EPI_WARPS);
     }
     mbar_init(smem_u32(b_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -415,14 +427,15 @@ tc_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_consta
         }
       }
     } else {
-      const int q = warp & 3;
+      const int q = warp & 3, half = (warp - 2) >> 2;
+      float* stage = reinterpret_cast<float*>(smemA + a_stages * A_STAGE_BYTES + 512) + (warp - 2) * 32 * EPI_LD;
       int acc = 0;
       uint32_t acc_phase = 0;
       const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
       for (int mt = grp; mt < p.m_tiles; mt += groups) {
         mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
         tc_fence_after();
-        store_tile(p, tmem_base, acc, q, lane, mt * BM, n0, 0, true, inv_keep);
+        store_tile(p, tmem_base, acc, q, half, lane, mt * BM, n0, 0, true, inv_keep, stage);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
@@ -547,6 +560,8 @@ static int make_map(CUtensorMap* m, const void* base, int64_t inner, int64_t out
   return LK_OK;
 }
 
+static int g_ws_enabled = 0;   // measured: no gain over the streaming kernel once the epilogue was fixed (profiles/r1_03)
+
 static int pick_splits(int64_t GM, int64_t GN, int64_t GK) {
   int64_t tiles = ((GM + BM - 1) / BM) * ((GN + BN - 1) / BN);
   int64_t kb = (GK + BK - 1) / BK;
@@ -591,6 +606,8 @@ int lk_split_bf16(const float* X, int64_t rows, int64_t cols, int64_t ld_in, voi
   }
   return check_launch("split_bf16");
 }
+
+void lk_tc_set_weight_stationary(int enabled) { g_ws_enabled = enabled; }
 
 size_t lk_tc_gemm_workspace_bytes(int64_t GM, int64_t GN, int64_t GK) {
   int s = pick_splits(GM, GN, GK);
@@ -642,13 +659,12 @@ int lk_tc_gemm(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const 
   }
   int total = p.m_tiles * p.n_tiles * p.splits;
   int grid = total < kNumSMs ? total : kNumSMs;
-  static const bool ws_enabled = getenv("LK_TC_WS") == nullptr || atoi(getenv("LK_TC_WS")) != 0;
-  if (!a_mn && ws_enabled && p.splits == 1 && p.k_blocks <= WS_MAX_KB && p.n_tiles <= kNumSMs && p.m_tiles >= 2 * (kNumSMs / p.n_tiles)) {
+  if (!a_mn && g_ws_enabled && p.splits == 1 && p.k_blocks <= WS_MAX_KB && p.n_tiles <= kNumSMs && p.m_tiles >= 2 * (kNumSMs / p.n_tiles)) {
     // weight-stationary: one 128-column weight slab per CTA for its whole life, activations streamed
     const int b_bytes = p.k_blocks * 2 * TILE_BYTES;
-    int a_stages = (227 * 1024 - 2048 - b_bytes) / A_STAGE_BYTES;
+    int a_stages = (227 * 1024 - 2048 - EPI_STAGE_BYTES - b_bytes) / A_STAGE_BYTES;
     if (a_stages > 6) a_stages = 6;
-    const int smem = b_bytes + a_stages * A_STAGE_BYTES + 1024 + 512;
+    const int smem = b_bytes + a_stages * A_STAGE_BYTES + 1024 + 512 + EPI_STAGE_BYTES;
     static bool ws_attr = false;
     if (!ws_attr) {
       cudaFuncSetAttribute(tc_gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
