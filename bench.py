@@ -207,28 +207,30 @@ def main():
             torch.cuda.synchronize()
 
     def timed(fn, k):
-        """K steps bracketed by barrier + synchronize; device time by CUDA events; max over ranks."""
+        """K steps bracketed by barrier + synchronize; device time by CUDA events; max over ranks.
+        Also returns the per-step device times (an event after every step) so that a hiccup shows up as max >> median."""
         sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(k + 1)]
         w0 = time.time()
-        e0.record()
+        evs[0].record()
         for i in range(k):
             fn(i)
-        e1.record()
+            evs[i + 1].record()
         sync_all()
         w1 = time.time()
-        ms = e0.elapsed_time(e1)
+        ms = evs[0].elapsed_time(evs[k])
+        per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(k))
         if world_size > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = t.item()
-        return ms, w0, w1
+        return ms, w0, w1, dict(median=per[len(per) // 2], min=per[0], max=per[-1])
 
-    for i in range(max(args.warmup, 3)):
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # started before the warm-up: its start-up is not timed
+    for i in range(max(args.warmup, 3, POOL)):
         step(devb[i % POOL])
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = _lib.load().lk_launch_count()
-    ms, w0, w1 = timed(lambda i: step(devb[i % POOL]), args.steps)
+    ms, w0, w1, per_step = timed(lambda i: step(devb[i % POOL]), args.steps)
     launches = int(_lib.load().lk_launch_count() - l0)
     clocks = sampler.stop(w0, w1) if sampler else None
     value = world_size * args.batch * args.steps / (ms / 1000.0)
@@ -240,7 +242,7 @@ def main():
 
     for i in range(2):
         e2e_step(i)
-    ms_e2e, _, _ = timed(e2e_step, args.steps)
+    ms_e2e, _, _, per_step_e2e = timed(e2e_step, args.steps)
     e2e_value = world_size * args.batch * args.steps / (ms_e2e / 1000.0)
 
     # per-entry-point device time over two extra steps (CUDA events around every C-ABI call on the launching stream)
@@ -263,12 +265,12 @@ def main():
                              + ('; the kernel executes 3 bf16 MMAs per algorithmic product to hold fp32 parity, so the tensor pipe runs at 3x this rate' if tc else ''))
 
     line = dict(metric='NRMS train impressions/s', value=value, unit='impressions/s', n_gpus=world_size, steps=args.steps,
-                warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                warmup=args.warmup, ms_per_step=ms / args.steps, ms_per_step_dist=per_step, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', impl='b200',
                 config=dict(base_cfg, l2='per-step working set (~1 GB of activations) exceeds the 126 MB L2; batches rotate through a pool of 8'),
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit='impressions/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
-                         ms_per_step=ms_e2e / args.steps),
+                         ms_per_step=ms_e2e / args.steps, ms_per_step_dist=per_step_e2e),
                 gpu_launches=launches, roofline=roof, kernel_ms_share=shares)
 
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:

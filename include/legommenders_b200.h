@@ -36,6 +36,9 @@ unsigned long long lk_launch_count(void);
 /* out[m,:] (+)= valid(m) ? table[ids[m],:] : 0, valid = mask ? mask[m]>0 : ids[m]>-1 */
 int lk_gather_rows(const int64_t* ids, const int64_t* mask, const float* table, float* out, int64_t M, int64_t E,
                    int accumulate, cudaStream_t stream);
+/* gather straight into split-bf16 planes (A operand of the projection GEMM): hi/lo [M, ld], rows with ids<0 are zero */
+int lk_gather_split_bf16(const int64_t* ids, const float* table, void* hi, void* lo, int64_t M, int64_t E, int64_t ld,
+                         cudaStream_t stream);
 /* gather + masked pooling over S tokens (model/operators/pooling_operator.py:46-56): mode 0 mean, 1 max, 2 sum */
 int lk_gather_pool(const int64_t* ids, const int64_t* mask, const float* table, float* out, int64_t N, int64_t S, int64_t E,
                    int mode, cudaStream_t stream);
@@ -137,6 +140,17 @@ int lk_dot_bce_bwd(const float* U, const float* V, const float* y, const float* 
 int lk_cached_scores(const float* U, const float* I, const int64_t* uid, const int64_t* iid, float* out, int64_t R, int64_t D,
                      cudaStream_t stream);
 int lk_index_rows(const float* table, const int64_t* ids, float* out, int64_t R, int64_t D, cudaStream_t stream);
+
+/* ---- native training-step driver: the whole Legommender.forward + backward of the NRMS configuration
+ *      (model/legommender.py:219-263 with config/model/nrms.yaml) over packed rows in ONE call; see csrc/lk_nrms_step.cu.
+ *      offsets[22]: element offsets into params/grads (order documented at the definition). */
+size_t lk_nrms_arena_bytes(int64_t T_max, int64_t N_max, int64_t B, int64_t D, int64_t A, int64_t E, int64_t H);
+int lk_nrms_fwd_bwd(const int64_t* title_ids, const int64_t* cat_ids, const int64_t* special_ids, const int32_t* cu_items,
+                    int64_t n_items, int64_t T, int64_t S_max, const int32_t* cu_users, int64_t B, int64_t C, int64_t H_max,
+                    const float* glove_table, const float* params, float* grads, const int64_t* offsets, int64_t D, int64_t heads,
+                    int64_t A, int64_t E, int64_t n_cats, int64_t n_special, float drop_embed, float drop_attn, uint64_t seed,
+                    float* loss_out, float* scores_out, void* arena, size_t arena_bytes, cudaStream_t stream);
+int lk_fill_f32(float* p, float value, int64_t n, cudaStream_t stream);
 
 /* ---- optimiser — base_lego.py:198-204 (torch.optim.Adam defaults), one launch over a flat parameter buffer */
 int lk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

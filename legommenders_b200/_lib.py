@@ -26,6 +26,7 @@ SIGNATURES = {
     'lk_launch_count': ('', 'u'),
     'lk_gather_rows': ('ppppqqis', 'i'),
     'lk_gather_pool': ('ppppqqqis', 'i'),
+    'lk_gather_split_bf16': ('ppppqqqs', 'i'),
     'lk_scatter_add_workspace_bytes': ('qqq', 'z'),
     'lk_scatter_add_sorted': ('ppppqpqqqipzs', 'i'),
     'lk_linear_fwd': ('pppppqqqiifus', 'i'),
@@ -61,6 +62,9 @@ SIGNATURES = {
     'lk_cached_scores': ('pppppqqs', 'i'),
     'lk_index_rows': ('pppqqs', 'i'),
     'lk_adam_step': ('ppppqffffqfs', 'i'),
+    'lk_fill_f32': ('pfqs', 'i'),
+    'lk_nrms_arena_bytes': ('qqqqqqq', 'z'),
+    'lk_nrms_fwd_bwd': ('ppppqqqpqqqpppp' + 'qqqqqq' + 'ffu' + 'pppzs', 'i'),
 }
 
 _lib = None

@@ -8,6 +8,7 @@
 // Backward for trainable tables is a sorted-index segmented scatter-add (no atomics, deterministic):
 //   radix sort (id, position) -> run-length encode -> fixed-size partial sums -> per-id ordered reduction.
 #include <cub/cub.cuh>
+#include <cuda_bf16.h>
 
 #include "lk_common.cuh"
 #include "../../include/legommenders_b200.h"
@@ -39,6 +40,33 @@ __global__ void __launch_bounds__(GW * 32) gather_rows_kernel(const int64_t* __r
       }
     } else if (!accumulate) {
       for (int c = lane; c < E4; c += 32) st4(o + c * 4, f4_zero());
+    }
+  }
+}
+
+// gather straight into split-bf16 planes (the A operand of the projection GEMM): row m of hi/lo = split(table[ids[m]]) or 0
+__global__ void __launch_bounds__(GW * 32) gather_split_kernel(const int64_t* __restrict__ ids, const float* __restrict__ table,
+                                                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                               int64_t M, int E, int ld) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * GW + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * GW;
+  const int L4 = ld >> 2;
+  for (int64_t m = warp; m < M; m += nwarps) {
+    const int64_t id = ids[m];
+    const float* src = table + id * (int64_t)E;
+    for (int c = lane; c < L4; c += 32) {
+      float4 v = f4_zero();
+      if (id > -1 && c * 4 < E) v = ldg4(src + c * 4);
+      __align__(8) __nv_bfloat16 h[4], l[4];
+      const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        h[e] = __float2bfloat16_rn(x[e]);
+        l[e] = __float2bfloat16_rn(x[e] - __bfloat162float(h[e]));
+      }
+      *reinterpret_cast<uint2*>(hi + m * ld + c * 4) = *reinterpret_cast<uint2*>(h);
+      *reinterpret_cast<uint2*>(lo + m * ld + c * 4) = *reinterpret_cast<uint2*>(l);
     }
   }
 }
@@ -217,6 +245,15 @@ int lk_gather_rows(const int64_t* ids, const int64_t* mask, const float* table, 
   if (blocks > (int64_t)kNumSMs * 64) blocks = (int64_t)kNumSMs * 64;
   gather_rows_kernel<<<(unsigned)blocks, GW * 32, 0, st>>>(ids, mask, table, out, M, (int)E, accumulate);
   return check_launch("gather_rows");
+}
+
+int lk_gather_split_bf16(const int64_t* ids, const float* table, void* hi, void* lo, int64_t M, int64_t E, int64_t ld, cudaStream_t st) {
+  LK_REQUIRE(E % 4 == 0 && ld % 8 == 0 && ld >= E, LK_ERR_SHAPE, "lk_gather_split_bf16: E=%ld must be a multiple of 4, ld=%ld of 8", (long)E, (long)ld);
+  if (M == 0) return LK_OK;
+  int64_t blocks = (M + GW - 1) / GW;
+  if (blocks > (int64_t)kNumSMs * 64) blocks = (int64_t)kNumSMs * 64;
+  gather_split_kernel<<<(unsigned)blocks, GW * 32, 0, st>>>(ids, table, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, M, (int)E, (int)ld);
+  return check_launch("gather_split");
 }
 
 int lk_gather_pool(const int64_t* ids, const int64_t* mask, const float* table, float* out, int64_t N, int64_t S, int64_t E,

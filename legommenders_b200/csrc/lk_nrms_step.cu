@@ -1,0 +1,271 @@
+// Native NRMS training-step driver: ONE C-ABI call enqueues the whole forward + backward of
+// Legommender.forward (model/legommender.py:219-263) for the NRMS configuration (config/model/nrms.yaml:
+// AttentionOperator item + user encoders, ConcatInputer, DotPredictor, CrossEntropy with label 0) over PACKED rows.
+//
+// Why: with the kernels at a few tens of microseconds each, a Python/autograd-driven step is bound by the host (~25-40 us
+// per launch).  This driver issues the same kernels in the same order from C++ (~120 launches, ~2-3 us each), owns no
+// memory (the caller passes an arena), never synchronises, and writes every parameter gradient into a flat gradient
+// buffer at caller-given offsets so that data-parallel training is one NCCL allreduce + one Adam launch afterwards.
+//
+// Row layout (see packing.py): item tokens are packed [T] with int32 offsets cu_items[n_items+1]; the first B*C items are
+// the candidates, the rest are the valid history items user by user, so their encodings are directly the user encoder's
+// packed token rows with offsets cu_users[B+1].
+#include <cuda_bf16.h>
+
+#include "lk_common.cuh"
+#include "../../include/legommenders_b200.h"
+
+namespace lk {
+namespace nrms {
+
+struct Arena {
+  char* base;
+  size_t cap, off;
+  bool ok;
+  void* take(size_t bytes) {
+    size_t a = (off + 255) & ~(size_t)255;
+    if (a + bytes > cap) { ok = false; return base; }
+    off = a + bytes;
+    return base + a;
+  }
+  float* f32(size_t n) { return (float*)take(n * 4); }
+};
+
+struct PlaneBuf {
+  __nv_bfloat16 *hi, *lo;
+  int64_t rows, cols, ld;
+};
+
+static inline int64_t r8(int64_t x) { return (x + 7) / 8 * 8; }
+
+struct Ctx {
+  Arena a;
+  cudaStream_t st;
+  void* ws;          // shared scratch for split-K partials / scatter / colsum
+  size_t ws_bytes;
+  int rc;
+};
+
+#define STEP(expr)                 \
+  do {                             \
+    if (c.rc == 0) c.rc = (expr);  \
+  } while (0)
+
+static PlaneBuf alloc_planes(Ctx& c, int64_t rows, int64_t cols) {
+  PlaneBuf p;
+  p.rows = rows; p.cols = cols; p.ld = r8(cols);
+  p.hi = (__nv_bfloat16*)c.a.take((size_t)rows * p.ld * 2);
+  p.lo = (__nv_bfloat16*)c.a.take((size_t)rows * p.ld * 2);
+  return p;
+}
+// planes of X [rows, cols]; optional column sums into `colsum`
+static PlaneBuf split(Ctx& c, const float* X, int64_t rows, int64_t cols, float* colsum = nullptr) {
+  PlaneBuf p = alloc_planes(c, rows, cols);
+  STEP(lk_split_bf16(X, rows, cols, cols, p.hi, p.lo, p.ld, 0, colsum, c.ws, c.ws_bytes, c.st));
+  return p;
+}
+static PlaneBuf split_t(Ctx& c, const float* X, int64_t rows, int64_t cols) {   // planes of X^T: [cols, rows]
+  PlaneBuf p = alloc_planes(c, cols, rows);
+  STEP(lk_split_bf16(X, rows, cols, cols, p.hi, p.lo, p.ld, 1, nullptr, nullptr, 0, c.st));
+  return p;
+}
+// Y[M,N] = epilogue(A[M,K] · B[N,K]^T)
+static void gemm_nt(Ctx& c, const PlaneBuf& A, const PlaneBuf& B, float* Y, int64_t M, int64_t N, int64_t K, const float* bias,
+                    const int64_t* rowmask, int act, float drop_p, uint64_t seed, int accumulate) {
+  STEP(lk_tc_gemm(A.hi, A.lo, A.ld, 0, B.hi, B.lo, B.ld, 0, Y, N, M, N, K, bias, rowmask, act, drop_p, seed, accumulate, c.ws, c.ws_bytes,
+                  c.st));
+}
+// dW[N,K] = dY[T,N]^T · X[T,K]
+static void gemm_wgrad(Ctx& c, const PlaneBuf& dY, const PlaneBuf& X, float* dW, int64_t T, int64_t N, int64_t K) {
+  STEP(lk_tc_gemm(dY.hi, dY.lo, dY.ld, 1, X.hi, X.lo, X.ld, 1, dW, K, N, K, T, nullptr, nullptr, 0, 0.f, 0, 0, c.ws, c.ws_bytes, c.st));
+}
+
+struct EncWeights {   // one AttentionOperator
+  const float *in_w, *in_b, *out_w, *out_b, *lin_w, *lin_b, *w1, *b1, *w2;
+  float *g_in_w, *g_in_b, *g_out_w, *g_out_b, *g_lin_w, *g_lin_b, *g_w1, *g_b1, *g_w2;
+};
+struct EncPlanes { PlaneBuf in_w, in_wT, out_w, out_wT, lin_w, lin_wT, w1, w1T; };
+struct EncSaved {
+  PlaneBuf xp, ctxp, outp, linp;
+  float *qkv, *lse, *lin, *hid, *alpha, *rep;
+  const int32_t* cu;
+  int64_t T, N, S;
+  uint64_t seed;
+};
+
+static EncPlanes weight_planes(Ctx& c, const EncWeights& w, int64_t D, int64_t A, bool need_in_wT) {
+  EncPlanes p;
+  p.in_w = split(c, w.in_w, 3 * D, D);
+  if (need_in_wT) p.in_wT = split_t(c, w.in_w, 3 * D, D);
+  p.out_w = split(c, w.out_w, D, D);  p.out_wT = split_t(c, w.out_w, D, D);
+  p.lin_w = split(c, w.lin_w, D, D);  p.lin_wT = split_t(c, w.lin_w, D, D);
+  p.w1 = split(c, w.w1, A, D);        p.w1T = split_t(c, w.w1, A, D);
+  return p;
+}
+
+// attention_operator.py:46-59 over packed rows: xp = planes of the input rows [T,D]
+static void enc_fwd(Ctx& c, EncSaved& s, const EncWeights& w, const EncPlanes& wp, int64_t D, int64_t H, int64_t A, float drop_attn) {
+  const int64_t T = s.T, N = s.N;
+  s.qkv = c.a.f32(T * 3 * D);
+  gemm_nt(c, s.xp, wp.in_w, s.qkv, T, 3 * D, D, w.in_b, nullptr, 0, 0.f, 0, 0);
+  float* ctx = c.a.f32(T * D);
+  s.lse = c.a.f32(T * H);
+  STEP(lk_mha_fwd(s.qkv, nullptr, s.cu, ctx, s.lse, N, s.S, D, H, drop_attn, s.seed, c.st));
+  s.ctxp = split(c, ctx, T, D);
+  float* out = c.a.f32(T * D);
+  gemm_nt(c, s.ctxp, wp.out_w, out, T, D, D, w.out_b, nullptr, 0, 0.f, 0, 0);
+  s.outp = split(c, out, T, D);
+  s.lin = c.a.f32(T * D);
+  gemm_nt(c, s.outp, wp.lin_w, s.lin, T, D, D, w.lin_b, nullptr, 0, 0.f, 0, 0);
+  s.linp = split(c, s.lin, T, D);
+  s.hid = c.a.f32(T * A);
+  gemm_nt(c, s.linp, wp.w1, s.hid, T, A, D, w.b1, nullptr, 1 /*tanh*/, 0.f, 0, 0);
+  s.alpha = c.a.f32(T);
+  s.rep = c.a.f32(N * D);
+  STEP(lk_additive_pool_fwd(s.lin, s.hid, w.w2, nullptr, s.cu, s.rep, s.alpha, N, s.S, D, A, c.st));
+}
+
+// backward of enc_fwd: drep [N,D] -> dX [T,D] (or nothing when dX == null); parameter gradients into w.g_*
+static void enc_bwd(Ctx& c, const EncSaved& s, const EncWeights& w, const EncPlanes& wp, int64_t D, int64_t H, int64_t A, float drop_attn,
+                    const float* drep, float* dX) {
+  const int64_t T = s.T, N = s.N;
+  const size_t mark = c.a.off;
+  float* dlin = c.a.f32(T * D);
+  float* dpre = c.a.f32(T * A);
+  float* dw2p = c.a.f32(N * A);
+  STEP(lk_additive_pool_bwd(s.lin, s.hid, w.w2, s.alpha, s.cu, drep, dlin, dpre, dw2p, N, s.S, D, A, 0, c.st));
+  STEP(lk_colsum(dw2p, w.g_w2, N, A, 0, c.ws, c.ws_bytes, c.st));
+  PlaneBuf dprep = split(c, dpre, T, A, w.g_b1);
+  gemm_wgrad(c, dprep, s.linp, w.g_w1, T, A, D);
+  gemm_nt(c, dprep, wp.w1T, dlin, T, D, A, nullptr, nullptr, 0, 0.f, 0, 1 /*accumulate onto alpha*drep*/);
+  PlaneBuf dlinp = split(c, dlin, T, D, w.g_lin_b);
+  gemm_wgrad(c, dlinp, s.outp, w.g_lin_w, T, D, D);
+  float* dout = dpre;   // reuse [T,A>=?]: only when A >= D; otherwise take fresh
+  if (A < D) dout = c.a.f32(T * D);
+  gemm_nt(c, dlinp, wp.lin_wT, dout, T, D, D, nullptr, nullptr, 0, 0.f, 0, 0);
+  PlaneBuf doutp = split(c, dout, T, D, w.g_out_b);
+  gemm_wgrad(c, doutp, s.ctxp, w.g_out_w, T, D, D);
+  float* dctx = dlin;   // dlin is dead after its split
+  gemm_nt(c, doutp, wp.out_wT, dctx, T, D, D, nullptr, nullptr, 0, 0.f, 0, 0);
+  float* dqkv = c.a.f32(T * 3 * D);
+  STEP(lk_mha_bwd(s.qkv, nullptr, s.cu, s.lse, dctx, dqkv, N, s.S, D, H, drop_attn, s.seed, c.st));
+  PlaneBuf dqkvp = split(c, dqkv, T, 3 * D, w.g_in_b);
+  gemm_wgrad(c, dqkvp, s.xp, w.g_in_w, T, 3 * D, D);
+  if (dX) gemm_nt(c, dqkvp, wp.in_wT, dX, T, D, 3 * D, nullptr, nullptr, 0, 0.f, 0, 0);
+  c.a.off = mark;   // all temporaries of this backward are dead (stream order keeps reuse safe)
+}
+
+}  // namespace nrms
+}  // namespace lk
+
+using namespace lk;
+using namespace lk::nrms;
+
+// shared scratch: the largest of the split-reduction partials, scatter-add and column-sum workspaces of one step
+static size_t scratch_bytes(int64_t T, int64_t N, int64_t D, int64_t A, int64_t E) {
+  size_t m = 0;
+  auto up = [&](size_t v) { if (v > m) m = v; };
+  up(lk_tc_gemm_workspace_bytes(3 * D, D, T));
+  up(lk_tc_gemm_workspace_bytes(D, D, T));
+  up(lk_tc_gemm_workspace_bytes(A, D, T));
+  up(lk_tc_gemm_workspace_bytes(D, E, T));
+  up(lk_scatter_add_workspace_bytes(T, 64, D));
+  up(lk_split_bf16_workspace_bytes(T, 3 * D));
+  up(lk_colsum_workspace_bytes(N, A));
+  return m + (1 << 20);
+}
+
+extern "C" {
+
+size_t lk_nrms_arena_bytes(int64_t T_max, int64_t N_max, int64_t B, int64_t D, int64_t A, int64_t E, int64_t H) {
+  // forward-saved + backward temporaries per token row (floats), see enc_fwd / enc_bwd; generous upper bound
+  size_t per_row = (size_t)(2 * r8(E) / 2 + 14 * D + 3 * A + H + 8) * 4 + 64;
+  size_t per_item = (size_t)(6 * D + 2 * A) * 4;
+  size_t weights = (size_t)(2 * (2 * 3 * D * D + 6 * D * D + 2 * A * D) + 2 * D * r8(E)) * 4 + (1 << 20);
+  size_t ws = scratch_bytes(T_max, N_max, D, A, E);
+  // user side rows are item rows of the history part: bounded by N_max rows
+  return (size_t)(T_max + 2 * N_max) * per_row + (size_t)(N_max + B) * per_item + weights + ws + (8 << 20);
+}
+
+// offsets[]: element offsets into params / grads for, in order:
+//   0 glove.linear.weight [D,E]   1 glove.linear.bias [D]   2 category.weight [n_cats,D]   3 special.weight [n_special,D]
+//   4..12  item_op: in_proj_weight, in_proj_bias, out_proj.weight, out_proj.bias, linear.weight, linear.bias,
+//                   additive.encoder.0.weight, additive.encoder.0.bias, additive.encoder.2.weight
+//   13..21 user_op: same nine
+int lk_nrms_fwd_bwd(const int64_t* title_ids, const int64_t* cat_ids, const int64_t* special_ids, const int32_t* cu_items,
+                    int64_t n_items, int64_t T, int64_t S_max, const int32_t* cu_users, int64_t B, int64_t C, int64_t H_max,
+                    const float* glove_table, const float* params, float* grads, const int64_t* offsets, int64_t D, int64_t heads,
+                    int64_t A, int64_t E, int64_t n_cats, int64_t n_special, float drop_embed, float drop_attn, uint64_t seed,
+                    float* loss_out, float* scores_out, void* arena, size_t arena_bytes, cudaStream_t st) {
+  LK_REQUIRE(n_items >= B * C && B > 0 && C > 0, LK_ERR_ARG, "lk_nrms_fwd_bwd: the first B*C items must be the candidates");
+  LK_REQUIRE(D % 8 == 0 && A % 8 == 0 && E % 4 == 0 && D % heads == 0, LK_ERR_SHAPE, "lk_nrms_fwd_bwd: unsupported dims");
+  Ctx c;
+  c.a = Arena{(char*)arena, arena_bytes, 0, true};
+  c.st = st;
+  c.rc = 0;
+  c.ws_bytes = scratch_bytes(T > 0 ? T : 1, n_items, D, A, E);
+  c.ws = c.a.take(c.ws_bytes);
+  LK_REQUIRE(c.a.ok, LK_ERR_ARG, "lk_nrms_fwd_bwd: arena too small");
+
+  auto P = [&](int i) { return params + offsets[i]; };
+  auto G = [&](int i) { return grads + offsets[i]; };
+  EncWeights wi{P(4), P(5), P(6), P(7), P(8), P(9), P(10), P(11), P(12), G(4), G(5), G(6), G(7), G(8), G(9), G(10), G(11), G(12)};
+  EncWeights wu{P(13), P(14), P(15), P(16), P(17), P(18), P(19), P(20), P(21),
+                G(13), G(14), G(15), G(16), G(17), G(18), G(19), G(20), G(21)};
+  const uint64_t s_embed = seed * 4 + 0, s_item = seed * 4 + 1, s_user = seed * 4 + 2;
+
+  // ---- weights -> split-bf16 planes (parameters change every step) ------------------------------------------------
+  EncPlanes pi = weight_planes(c, wi, D, A, true);
+  EncPlanes pu = weight_planes(c, wu, D, A, true);
+  PlaneBuf pg = split(c, P(0), D, E);
+
+  // ---- embedding stage (concat_inputer.py:92-114 + embedding_hub.py:95-96) -------------------------------------------
+  int64_t* valid = (int64_t*)c.a.take((size_t)T * 8);
+  STEP(lk_valid_mask(title_ids, valid, T, st));
+  PlaneBuf gp = alloc_planes(c, T, E);
+  STEP(lk_gather_split_bf16(title_ids, glove_table, gp.hi, gp.lo, T, E, gp.ld, st));
+  float* x = c.a.f32(T * D);
+  gemm_nt(c, gp, pg, x, T, D, E, P(1), valid, 0, drop_embed, s_embed, 0);
+  STEP(lk_gather_rows(cat_ids, nullptr, P(2), x, T, D, 1, st));
+  STEP(lk_gather_rows(special_ids, nullptr, P(3), x, T, D, 1, st));
+
+  // ---- item encoder over all packed items, user encoder over the packed history encodings ---------------------------------
+  EncSaved si;
+  si.T = T; si.N = n_items; si.S = S_max; si.cu = cu_items; si.seed = s_item;
+  si.xp = split(c, x, T, D);
+  enc_fwd(c, si, wi, pi, D, heads, A, drop_attn);
+
+  const int64_t Tu = n_items - B * C;
+  EncSaved su;
+  su.T = Tu; su.N = B; su.S = H_max; su.cu = cu_users; su.seed = s_user;
+  su.xp = split(c, si.rep + B * C * D, Tu, D);
+  enc_fwd(c, su, wu, pu, D, heads, A, drop_attn);
+
+  // ---- DotPredictor + CrossEntropy(label 0) (legommender.py:252-254, 268-283) ----------------------------------------------
+  float* scores = scores_out ? scores_out : c.a.f32(B * C);
+  float* probs = c.a.f32(B * C);
+  float* rowloss = c.a.f32(B);
+  STEP(lk_dot_ce_fwd(su.rep, si.rep, scores, probs, rowloss, loss_out, B, C, D, st));
+
+  // ---- backward ---------------------------------------------------------------------------------------------------------
+  float* one = c.a.f32(1);
+  STEP(lk_fill_f32(one, 1.0f, 1, st));
+  float* drep = c.a.f32(n_items * D);
+  float* duser = c.a.f32(B * D);
+  STEP(lk_dot_ce_bwd(su.rep, si.rep, probs, one, duser, drep, B, C, D, st));          // dV -> drep[0 : B*C]
+  enc_bwd(c, su, wu, pu, D, heads, A, drop_attn, duser, drep + B * C * D);             // dX_u -> drep[B*C :]
+  float* dx = c.a.f32(T * D);
+  enc_bwd(c, si, wi, pi, D, heads, A, drop_attn, drep, dx);
+
+  // embedding tables: sorted segmented scatter-add; GloVe projection: dP = dx * dropout * valid
+  STEP(lk_scatter_add_sorted(cat_ids, nullptr, dx, nullptr, 1, G(2), T, n_cats, D, 0, c.ws, c.ws_bytes, st));
+  STEP(lk_scatter_add_sorted(special_ids, nullptr, dx, nullptr, 1, G(3), T, n_special, D, 0, c.ws, c.ws_bytes, st));
+  STEP(lk_act_bwd(dx, nullptr, valid, dx, T, D, 0, drop_embed, s_embed, st));
+  PlaneBuf dpp = split(c, dx, T, D, G(1));
+  gemm_wgrad(c, dpp, gp, G(0), T, D, E);
+
+  LK_REQUIRE(c.a.ok, LK_ERR_ARG, "lk_nrms_fwd_bwd: arena too small (%zu bytes given)", arena_bytes);
+  return c.rc;
+}
+
+}  // extern "C"

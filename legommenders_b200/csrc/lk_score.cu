@@ -160,6 +160,11 @@ __global__ void __launch_bounds__(SW * 32) index_rows_kernel(const float* __rest
   }
 }
 
+__global__ void fill_kernel(float* __restrict__ p, float v, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             int64_t n, float lr_over_bc1, float b1, float b2, float eps, float inv_sqrt_bc2, float grad_scale) {
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -264,6 +269,12 @@ int lk_index_rows(const float* table, const int64_t* ids, float* out, int64_t R,
   if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
   index_rows_kernel<<<(unsigned)blocks, SW * 32, 0, st>>>(table, ids, out, R, (int)D);
   return check_launch("index_rows");
+}
+
+int lk_fill_f32(float* p, float value, int64_t n, cudaStream_t st) {
+  if (n == 0) return LK_OK;
+  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, value, n);
+  return check_launch("fill");
 }
 
 int lk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,

@@ -54,3 +54,111 @@ class FlatAdam:
         ops.adam_step(self.flat, self.grad, self.m, self.v, self.step_count, lr=self.lr if lr is None else lr,
                       beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, grad_scale=1.0 / self.world)
         ops.invalidate_weight_planes()   # the kernel updated the parameters behind torch's version counters
+
+
+class NativeNRMSStep:
+    """Training step of the NRMS configuration through the native driver `lk_nrms_fwd_bwd` (csrc/lk_nrms_step.cu):
+    host packing -> one C-ABI call for forward+backward -> (allreduce) -> one Adam launch.  Same kernels and the same
+    mathematics as the autograd path in legommender.py; it only removes the per-launch Python/autograd cost."""
+
+    ENC = ['multi_head_attention.in_proj_weight', 'multi_head_attention.in_proj_bias', 'multi_head_attention.out_proj.weight',
+           'multi_head_attention.out_proj.bias', 'linear.weight', 'linear.bias', 'additive_attention.encoder.0.weight',
+           'additive_attention.encoder.0.bias', 'additive_attention.encoder.2.weight']
+
+    def __init__(self, model, opt: FlatAdam):
+        import numpy as np
+        from . import _lib
+        from .embedding_hub import Table, Transformation
+        from .inputer.concat_inputer import ConcatInputer
+        from .operators.attention_operator import AttentionOperator
+        cfgm = model.config
+        if not (isinstance(model.item_op, AttentionOperator) and isinstance(model.user_op, AttentionOperator)
+                and isinstance(model.item_op.inputer, ConcatInputer) and model.use_neg_sampling and cfgm.use_item_content):
+            raise ValueError('NativeNRMSStep needs the NRMS configuration (Attention item/user operators, negative sampling)')
+        inp = model.item_op.inputer
+        if len(inp.inputs) != 2 or not inp.use_sep_token:
+            raise ValueError('NativeNRMSStep expects item inputs [title, category] with SEP tokens')
+        self.title_col, self.cat_col, self.special_col = inp.inputs[0], inp.inputs[1], inp.vocab.name
+        tv = inp.ut.meta.features[self.title_col].tokenizer.vocab.name
+        cv = inp.ut.meta.features[self.cat_col].tokenizer.vocab.name
+        ttab, ctab, stab = model.eh(tv), model.eh(cv), model.eh(self.special_col)
+        if not (isinstance(ttab, Transformation) and isinstance(ctab, Table) and isinstance(stab, Table)):
+            raise ValueError('NativeNRMSStep expects a projected (pretrained) title table and plain category / special tables')
+        if ttab.embedding.weight.requires_grad:
+            raise ValueError('NativeNRMSStep expects the pretrained title table to be frozen')
+        self.model, self.opt = model, opt
+        self.glove = ttab.embedding.weight
+        mha = model.item_op.multi_head_attention
+        self.D, self.heads = mha.embed_dim, mha.num_heads
+        self.A = model.item_op.additive_attention.hidden_size
+        self.E = self.glove.shape[1]
+        self.n_cats, self.n_special = ctab.weight.shape[0], stab.weight.shape[0]
+        self.drop_embed, self.drop_attn = float(ttab.p), float(mha.dropout)
+        if model.user_op.multi_head_attention.num_heads != self.heads or model.user_op.multi_head_attention.dropout != mha.dropout:
+            raise ValueError('NativeNRMSStep expects identical head count / dropout in both encoders')
+        named = dict(model.named_parameters())
+        names = [f'embedding_vocab_table.{tv}.linear.weight', f'embedding_vocab_table.{tv}.linear.bias',
+                 f'embedding_vocab_table.{cv}.weight', f'embedding_vocab_table.{self.special_col}.weight']
+        names += [f'item_op.{n}' for n in self.ENC] + [f'user_op.{n}' for n in self.ENC]
+        base = opt.flat.data_ptr()
+        offs = []
+        for n in names:
+            p = named[n]
+            off = p.data_ptr() - base
+            if off < 0 or off % 4 or off // 4 + p.numel() > opt.flat.numel():
+                raise ValueError(f'{n} does not live in the flat parameter buffer')
+            offs.append(off // 4)
+        if len(named) - 1 != len(names):   # every trainable parameter must be covered (the frozen table is the only other one)
+            extra = set(k for k, v in named.items() if v.requires_grad) - set(names)
+            if extra:
+                raise ValueError(f'parameters not handled by the native step: {sorted(extra)}')
+        self.offsets = np.asarray(offs, dtype=np.int64)
+        self._lib = _lib
+        self.arena = None
+        self.loss = torch.zeros((), dtype=torch.float32, device=opt.flat.device)
+        self.calls = 0
+
+    def _ensure_arena(self, T, N, B):
+        need = self._lib.query('lk_nrms_arena_bytes', T, N, B, self.D, self.A, self.E, self.heads)
+        if self.arena is None or self.arena.numel() < need:
+            self.arena = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.opt.flat.device)
+
+    def pack(self, batch):
+        """Host-side integer bookkeeping (packing.py); cached on device-resident batches."""
+        from .packing import pack_offsets, pack_tokens
+        meta = batch.get('__lk_packed__')
+        if meta is None:
+            cm = self.model.cm
+            cand, hist = batch[cm.item_col], batch[cm.history_col]
+            B, C, S = cand['attention_mask'].shape
+            H = hist['attention_mask'].shape[1]
+            clicks = batch[cm.mask_col]
+            ids = {c: torch.cat([cand['input_ids'][c].reshape(B * C, S), hist['input_ids'][c].reshape(B * H, S)])
+                   for c in cand['input_ids']}
+            mask = torch.cat([cand['attention_mask'].reshape(B * C, S), hist['attention_mask'].reshape(B * H, S)])
+            valid = torch.cat([torch.ones(B * C, dtype=clicks.dtype, device=clicks.device), clicks.reshape(-1)])
+            pk = pack_tokens(ids, mask, valid, keep_empty=False)
+            cu_u, max_u = pack_offsets(clicks)
+            meta = (pk, cu_u, max_u, B, C)
+            if mask.is_cuda:
+                batch['__lk_packed__'] = meta
+        return meta
+
+    def fwd_bwd(self, batch, training=True):
+        """Enqueue forward + backward; gradients land in opt.grad, the loss (device scalar) is returned."""
+        from ._lib import call, ptr
+        pk, cu_u, max_u, B, C = self.pack(batch)
+        self._ensure_arena(pk.rows, pk.n, B)
+        self.calls += 1
+        seed = (torch.initial_seed() * 1000003 + self.calls) & ((1 << 60) - 1)
+        de, da = (self.drop_embed, self.drop_attn) if training else (0.0, 0.0)
+        call('lk_nrms_fwd_bwd', ptr(pk.ids[self.title_col]), ptr(pk.ids[self.cat_col]), ptr(pk.ids[self.special_col]), ptr(pk.cu),
+             pk.n, pk.rows, pk.max_len, ptr(cu_u), B, C, max_u, ptr(self.glove), ptr(self.opt.flat), ptr(self.opt.grad),
+             self.offsets.ctypes.data, self.D, self.heads, self.A, self.E, self.n_cats, self.n_special, float(de), float(da), int(seed),
+             ptr(self.loss), None, ptr(self.arena), self.arena.numel())
+        return self.loss
+
+    def step(self, batch, lr=None):
+        loss = self.fwd_bwd(batch, training=True)
+        self.opt.step(lr)
+        return loss
