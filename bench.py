@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--batch', type=int, default=64, help='impressions per GPU per step')
     ap.add_argument('--small', action='store_true', help='tiny world (debug only; not a valid bench line)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--autograd', action='store_true', help='drive the kernels through torch.autograd instead of the native step driver')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     return ap.parse_args()
 
@@ -144,7 +145,8 @@ def main():
     workload_name = 'NRMS train step, synthetic MIND-small shape (65,238 items, 400k x 300 GloVe-shaped table, title 30, history 50, 1+4 candidates, hidden 256)'
     base_cfg = dict(workload=workload_name, batch_per_gpu=args.batch, global_batch=args.batch * max(world_size, 1),
                     items_per_step_per_gpu=args.batch * (1 + NEG + WORKLOAD['hist_len']), dropout=DROPOUT,
-                    parallelism=f'dp{world_size}' if world_size > 1 else 'single')
+                    parallelism=f'dp{world_size}' if world_size > 1 else 'single',
+                    driver='autograd' if args.autograd else 'native (lk_nrms_fwd_bwd)')
 
     # ---------------- reference arm: CPU only, rank 0 only ----------------------------------------------------
     if args.impl == 'reference':
@@ -175,7 +177,7 @@ def main():
         dist.barrier()
     from legommenders_b200 import Env, _lib, builder
     from legommenders_b200.batching import BatchBuilder, tree_bytes, tree_to_device
-    from legommenders_b200.trainer import FlatAdam
+    from legommenders_b200.trainer import FlatAdam, NativeNRMSStep
 
     torch.manual_seed(2023)
     world = build_world(args.small)
@@ -193,7 +195,13 @@ def main():
     devb = [tree_to_device(b, dev, non_blocking=False) for b in host]
     h2d = tree_bytes(host[0])
 
+    native = None if args.autograd else NativeNRMSStep(model, opt)
+
     def step(batch):
+        """One training step.  Default: the native driver (ONE C-ABI call enqueues forward+backward, then allreduce + Adam);
+        --autograd: the same kernels driven by torch.autograd through the plugin surface (model(batch) / loss.backward())."""
+        if native is not None:
+            return native.step(batch)          # every gradient slot is overwritten by the driver: no zero_grad needed
         opt.zero_grad()
         loss = model(batch=batch)
         loss.backward()
@@ -248,11 +256,18 @@ def main():
     # per-entry-point device time over two extra steps (CUDA events around every C-ABI call on the launching stream)
     roof, shares = None, None
     if rank == 0:
-        prof = _lib.profile_begin()
-        for i in range(2):
-            step(devb[i % POOL])
-        torch.cuda.synchronize()
-        shares, gemm = _lib.profile_end(prof)
+        if native is not None:
+            _lib.native_profile_begin()
+            for i in range(2):
+                step(devb[i % POOL])
+            torch.cuda.synchronize()
+            shares, gemm = _lib.native_profile_end()
+        else:
+            prof = _lib.profile_begin()
+            for i in range(2):
+                step(devb[i % POOL])
+            torch.cuda.synchronize()
+            shares, gemm = _lib.profile_end(prof)
         pk = peaks()
         if gemm['ms'] > 0:
             ach = gemm['flops'] / (gemm['ms'] / 1e3) / 1e12
@@ -261,6 +276,7 @@ def main():
                         else 'gemm_simt_kernel (fp32 FFMA)', achieved=ach, peak=pk['tensor'],
                         unit='TFLOP/s', frac=ach / pk['tensor'], traffic=None, peak_source=pk['which'],
                         share_of_step=gemm['ms'] / max(sum(shares.values()), 1e-9), launches=gemm['calls'],
+                        per_shape=gemm.get('per_shape'),
                         note='achieved = algorithmic flops (2*M*N*K per call, counted once) / CUDA-event time of the calls in a live step'
                              + ('; the kernel executes 3 bf16 MMAs per algorithmic product to hold fp32 parity, so the tensor pipe runs at 3x this rate' if tc else ''))
 

@@ -31,6 +31,12 @@ int lk_device_ok(void);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long lk_launch_count(void);
 
+/* per-call device timing inside the native step drivers: enable(1) clears and starts recording one CUDA-event pair per
+ * sub-call; collect() synchronises the events and aggregates by entry-point name -> number of distinct names written
+ * (names: cap strings of name_stride bytes; ms/flops/calls: cap entries).  flops = algorithmic 2*M*N*K of dense contractions. */
+void lk_profile_enable(int on);
+int lk_profile_collect(char* names, int name_stride, float* ms, double* flops, int* calls, int cap);
+
 /* ---- (1) EmbeddingHub token gather — model/inputer/concat_inputer.py:105-113, simple_inputer.py:51-64,
  *      loader/embedding_hub.py:378-385 (aten::embedding + mask multiply + add) ------------------------- */
 /* out[m,:] (+)= valid(m) ? table[ids[m],:] : 0, valid = mask ? mask[m]>0 : ids[m]>-1 */
@@ -140,6 +146,16 @@ int lk_dot_bce_bwd(const float* U, const float* V, const float* y, const float* 
 int lk_cached_scores(const float* U, const float* I, const int64_t* uid, const int64_t* iid, float* out, int64_t R, int64_t D,
                      cudaStream_t stream);
 int lk_index_rows(const float* table, const int64_t* ids, float* out, int64_t R, int64_t D, cudaStream_t stream);
+
+/* ---- group metrics of the evaluation phase — utils/metrics.py:88-160, 223-235, 313-369 (MetricPool.calculate with GAUC, MRR,
+ *      NDCG@k).  groups: any int64 key (user id); rows of a group need not be contiguous.  ks: HOST array of nk <= 8 nDCG
+ *      cut-offs; disc_prefix: DEVICE fp64 table, disc_prefix[p] = sum_{q<p} 1/log2(q+2), n_disc >= max(k)+1 entries.
+ *      out (device, 3+nk doubles): mean GAUC, mean MRR, mean NDCG@ks[0..], number of groups.  per_group (nullable, device
+ *      [(2+nk), R] floats, first `number of groups` entries of each row valid, groups in ascending key order). */
+size_t lk_group_metrics_workspace_bytes(int64_t R, int nk);
+int lk_group_metrics(const float* scores, const int64_t* labels, const int64_t* groups, int64_t R, const int32_t* ks, int nk,
+                     const double* disc_prefix, int64_t n_disc, double* out, float* per_group, void* workspace,
+                     size_t workspace_bytes, cudaStream_t stream);
 
 /* ---- native training-step driver: the whole Legommender.forward + backward of the NRMS configuration
  *      (model/legommender.py:219-263 with config/model/nrms.yaml) over packed rows in ONE call; see csrc/lk_nrms_step.cu.

@@ -10,7 +10,8 @@ from .embedding_hub import EmbeddingHub
 from .lego_config import LegoConfig
 from .legommender import Legommender
 from .resampler import Resampler, DataSet
-from . import operators, predictors, ops
+from . import operators, predictors, ops, evaluate, sharding
+from .metrics import MetricPool
 
 __all__ = ['Env', 'ColumnMap', 'EmbeddingHub', 'LegoConfig', 'Legommender', 'Resampler', 'DataSet', 'operators',
-           'predictors', 'ops']
+           'predictors', 'ops', 'evaluate', 'sharding', 'MetricPool']

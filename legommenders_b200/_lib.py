@@ -24,6 +24,8 @@ SIGNATURES = {
     'lk_last_error': ('', 'c'),
     'lk_device_ok': ('', 'i'),
     'lk_launch_count': ('', 'u'),
+    'lk_profile_enable': ('i', 'v'),
+    'lk_profile_collect': ('pipppi', 'i'),
     'lk_gather_rows': ('ppppqqis', 'i'),
     'lk_gather_pool': ('ppppqqqis', 'i'),
     'lk_gather_split_bf16': ('ppppqqqs', 'i'),
@@ -61,6 +63,8 @@ SIGNATURES = {
     'lk_dot_bce_bwd': ('ppppppppqqs', 'i'),
     'lk_cached_scores': ('pppppqqs', 'i'),
     'lk_index_rows': ('pppqqs', 'i'),
+    'lk_group_metrics_workspace_bytes': ('qi', 'z'),
+    'lk_group_metrics': ('pppqpipqpppzs', 'i'),
     'lk_adam_step': ('ppppqffffqfs', 'i'),
     'lk_fill_f32': ('pfqs', 'i'),
     'lk_nrms_arena_bytes': ('qqqqqqq', 'z'),
@@ -154,6 +158,37 @@ def profile_end(records):
             g['calls'] += 1
     gemm = max(per.values(), key=lambda g: g['ms']) if per else dict(ms=0.0, flops=0, calls=0, name=None)
     return {k: round(v, 4) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])}, gemm
+
+
+def native_profile_begin():
+    """Start per-sub-call CUDA-event timing inside the native step drivers (lk_profile_enable)."""
+    load().lk_profile_enable(1)
+
+
+def native_profile_end():
+    """-> ({sub-call: total ms}, {'ms','flops','calls','name'} of the slowest dense-contraction entry point)."""
+    lib = load()
+    cap, stride = 64, 40
+    names = ctypes.create_string_buffer(cap * stride)
+    ms = (ctypes.c_float * cap)()
+    flops = (ctypes.c_double * cap)()
+    calls = (ctypes.c_int * cap)()
+    n = lib.lk_profile_collect(ctypes.cast(names, ctypes.c_void_p), stride, ctypes.cast(ms, ctypes.c_void_p),
+                               ctypes.cast(flops, ctypes.c_void_p), ctypes.cast(calls, ctypes.c_void_p), cap)
+    lib.lk_profile_enable(0)
+    if n < 0:
+        raise RuntimeError(f'lk_profile_collect failed: {lib.lk_last_error().decode()}')
+    shares, gemms = {}, []
+    for i in range(n):
+        name = names.raw[i * stride:(i + 1) * stride].split(b'\0', 1)[0].decode()
+        shares[name] = round(float(ms[i]), 4)
+        if flops[i] > 0:
+            gemms.append(dict(ms=float(ms[i]), flops=float(flops[i]), calls=int(calls[i]), name=name))
+    # every dense contraction of the driver goes through lk_tc_gemm (labelled per shape): aggregate them
+    gemm = dict(ms=sum(g['ms'] for g in gemms), flops=sum(g['flops'] for g in gemms), calls=sum(g['calls'] for g in gemms),
+                name='lk_tc_gemm' if gemms else None, per_shape={g['name']: dict(ms=round(g['ms'], 4), calls=g['calls'],
+                tflops=round(g['flops'] / max(g['ms'], 1e-9) / 1e9, 1)) for g in gemms})
+    return dict(sorted(shares.items(), key=lambda kv: -kv[1])), gemm
 
 
 def query(name: str, *args) -> int:

@@ -83,14 +83,19 @@ class UserCacher(BaseCacher):
     def __init__(self, placeholder, **kwargs):
         super().__init__(**kwargs)
         self.placeholder = placeholder
+        self.rows = None    # user-sharded evaluation (sharding.py): only these positions of `contents` are encoded
 
     def _cache(self, contents):
         out = self.placeholder.to(Env.device)
-        n = len(contents)
+        todo = list(range(len(contents))) if self.rows is None else [int(i) for i in self.rows]
         with torch.no_grad():
-            for s in range(0, n, self.page_size):
-                rows = [contents[i] for i in range(s, min(s + self.page_size, n))]
-                out[s:s + len(rows)] = self.operator(batch=stack_trees(rows))
+            for s in range(0, len(todo), self.page_size):
+                page = todo[s:s + self.page_size]
+                rep = self.operator(batch=stack_trees([contents[i] for i in page]))
+                if self.rows is None:
+                    out[page[0]:page[0] + len(page)] = rep
+                else:
+                    out[torch.as_tensor(page, device=out.device)] = rep
         return out
 
 

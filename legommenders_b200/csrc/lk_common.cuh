@@ -13,6 +13,9 @@ namespace lk {
 
 void set_error(const char* fmt, ...);
 void count_launches(int n);   // kernels launched by this library (reported by lk_launch_count)
+bool prof_enabled();          // lk_profile_enable(1): native drivers bracket every sub-call with CUDA events
+void prof_begin(const char* expr, double flops, cudaStream_t st);
+void prof_end(cudaStream_t st);
 
 inline int check_launch(const char* what, int n = 1) {
   count_launches(n);

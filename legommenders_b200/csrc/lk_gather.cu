@@ -196,6 +196,61 @@ __global__ void __launch_bounds__(GW * 32) run_reduce_kernel(const int* __restri
   st4(o, acc);
 }
 
+// ------------------------------------------------------------------------------------------------
+// small tables (V <= 64 rows: category / special-token tables): no sort.  A block owns SM_CHUNK consecutive positions;
+// SM_LANES row-lanes walk them in order, each into its own shared [V][E] accumulator; the lanes are then summed in fixed
+// order into partial[block][V][E] and a second kernel reduces the blocks in fixed order -> deterministic, no atomics.
+// ------------------------------------------------------------------------------------------------
+constexpr int SM_MAX_V = 64, SM_CHUNK = 512, SM_LANES = 4;
+
+__global__ void __launch_bounds__(256) scatter_small_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
+                                                            const float* __restrict__ src, const float* __restrict__ scale,
+                                                            int row_div, int64_t P, int V, int E, float* __restrict__ partial) {
+  extern __shared__ __align__(16) float acc_s[];   // [SM_LANES][V][E]
+  const int E4 = E >> 2;
+  const int cols = blockDim.x / SM_LANES;          // column threads per row-lane
+  const int rl = threadIdx.x / cols, ct = threadIdx.x - rl * cols;
+  float* mine = acc_s + (size_t)rl * V * E;
+  for (int i = ct; i < V * E4; i += cols) reinterpret_cast<float4*>(mine)[i] = f4_zero();
+  __syncthreads();
+  const int64_t p0 = (int64_t)blockIdx.x * SM_CHUNK;
+  const int64_t p1 = p0 + SM_CHUNK < P ? p0 + SM_CHUNK : P;
+  for (int64_t p = p0 + rl; p < p1; p += SM_LANES) {
+    const int64_t id = ids[p];
+    const bool valid = mask ? (mask[p] > 0) : (id > -1);
+    if (!valid) continue;
+    const float sc = scale ? scale[p] : 1.f;
+    const float* s = src + (p / row_div) * (int64_t)E;
+    float* a = mine + (size_t)id * E;
+    for (int c = ct; c < E4; c += cols) {
+      float4 v = ldg4(s + c * 4);
+      float4 o = *reinterpret_cast<float4*>(a + c * 4);
+      f4_fma(o, sc, v);
+      *reinterpret_cast<float4*>(a + c * 4) = o;
+    }
+  }
+  __syncthreads();
+  float* out = partial + (size_t)blockIdx.x * V * E;
+  for (int i = threadIdx.x; i < V * E4; i += blockDim.x) {
+    float4 t = reinterpret_cast<const float4*>(acc_s)[i];
+#pragma unroll
+    for (int l = 1; l < SM_LANES; l++) f4_add(t, reinterpret_cast<const float4*>(acc_s + (size_t)l * V * E)[i]);
+    reinterpret_cast<float4*>(out)[i] = t;
+  }
+}
+
+__global__ void scatter_small_finish_kernel(const float* __restrict__ partial, float* __restrict__ dtable, int nblk, int VE4,
+                                            int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= VE4) return;
+  float4 t = accumulate ? reinterpret_cast<const float4*>(dtable)[i] : f4_zero();
+  for (int b = 0; b < nblk; b++) f4_add(t, ldg4_stream(partial + ((size_t)b * VE4 + i) * 4));
+  reinterpret_cast<float4*>(dtable)[i] = t;
+}
+
+static bool small_table(int64_t V, int64_t E) { return V <= SM_MAX_V && (size_t)SM_LANES * V * E * 4 <= 96 * 1024; }
+static size_t small_ws_bytes(int64_t P, int64_t V, int64_t E) { return (size_t)((P + SM_CHUNK - 1) / SM_CHUNK) * V * E * 4 + 256; }
+
 struct ScatterWs {
   int *keys, *vals, *skeys, *svals, *run_key, *run_len, *run_off, *npart, *part_off, *num_runs;
   float* partial;
@@ -269,6 +324,7 @@ int lk_gather_pool(const int64_t* ids, const int64_t* mask, const float* table, 
 }
 
 size_t lk_scatter_add_workspace_bytes(int64_t P, int64_t V, int64_t E) {
+  if (small_table(V, E)) return small_ws_bytes(P, V, E);
   ScatterWs w;
   return carve(w, nullptr, P, V, (int)E) + 256;
 }
@@ -279,6 +335,16 @@ int lk_scatter_add_sorted(const int64_t* ids, const int64_t* mask, const float* 
   LK_REQUIRE(E % 4 == 0, LK_ERR_SHAPE, "lk_scatter_add_sorted: row width %ld must be a multiple of 4 floats", (long)E);
   LK_REQUIRE(P < (1LL << 31) && V < (1LL << 30), LK_ERR_SHAPE, "lk_scatter_add_sorted: P or V too large for 32-bit keys");
   LK_REQUIRE(workspace_bytes >= lk_scatter_add_workspace_bytes(P, V, E), LK_ERR_ARG, "lk_scatter_add_sorted: workspace too small");
+  if (small_table(V, E) && P > 0) {
+    const int nblk = (int)((P + SM_CHUNK - 1) / SM_CHUNK);
+    const size_t smem = (size_t)SM_LANES * V * E * 4;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(scatter_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+    scatter_small_kernel<<<nblk, 256, smem, st>>>(ids, mask, src, scale, (int)row_div, P, (int)V, (int)E, (float*)workspace);
+    const int VE4 = (int)(V * E / 4);
+    scatter_small_finish_kernel<<<(VE4 + 127) / 128, 128, 0, st>>>((const float*)workspace, dtable, nblk, VE4, accumulate);
+    return check_launch("scatter_add_small", 2);
+  }
   if (!accumulate) cudaMemsetAsync(dtable, 0, (size_t)V * E * sizeof(float), st);
   if (P == 0) return LK_OK;
   ScatterWs w;

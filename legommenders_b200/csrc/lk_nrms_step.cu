@@ -22,9 +22,11 @@ struct Arena {
   char* base;
   size_t cap, off;
   bool ok;
+  size_t high;   // high-water mark (the sizing pass runs the same allocation sequence with no memory behind it)
   void* take(size_t bytes) {
     size_t a = (off + 255) & ~(size_t)255;
-    if (a + bytes > cap) { ok = false; return base; }
+    if (a + bytes > high) high = a + bytes;
+    if (a + bytes > cap) { ok = false; off = a + bytes; return base; }
     off = a + bytes;
     return base + a;
   }
@@ -44,12 +46,19 @@ struct Ctx {
   void* ws;          // shared scratch for split-K partials / scatter / colsum
   size_t ws_bytes;
   int rc;
+  bool dry;          // sizing pass: walk the allocations, launch nothing
 };
 
-#define STEP(expr)                 \
-  do {                             \
-    if (c.rc == 0) c.rc = (expr);  \
+#define STEP_L(label, expr, flops)                              \
+  do {                                                          \
+    if (c.rc == 0 && !c.dry) {                                  \
+      const bool prof_ = prof_enabled();                        \
+      if (prof_) prof_begin(label, (double)(flops), c.st);      \
+      c.rc = (expr);                                            \
+      if (prof_) prof_end(c.st);                                \
+    }                                                           \
   } while (0)
+#define STEP(expr) STEP_L(#expr, expr, 0)
 
 static PlaneBuf alloc_planes(Ctx& c, int64_t rows, int64_t cols) {
   PlaneBuf p;
@@ -72,12 +81,17 @@ static PlaneBuf split_t(Ctx& c, const float* X, int64_t rows, int64_t cols) {   
 // Y[M,N] = epilogue(A[M,K] · B[N,K]^T)
 static void gemm_nt(Ctx& c, const PlaneBuf& A, const PlaneBuf& B, float* Y, int64_t M, int64_t N, int64_t K, const float* bias,
                     const int64_t* rowmask, int act, float drop_p, uint64_t seed, int accumulate) {
-  STEP(lk_tc_gemm(A.hi, A.lo, A.ld, 0, B.hi, B.lo, B.ld, 0, Y, N, M, N, K, bias, rowmask, act, drop_p, seed, accumulate, c.ws, c.ws_bytes,
-                  c.st));
+  char label[40];
+  snprintf(label, sizeof(label), "gemm_nt %ldx%ldx%ld", (long)M, (long)N, (long)K);
+  STEP_L(label, lk_tc_gemm(A.hi, A.lo, A.ld, 0, B.hi, B.lo, B.ld, 0, Y, N, M, N, K, bias, rowmask, act, drop_p, seed, accumulate, c.ws,
+                           c.ws_bytes, c.st), 2.0 * M * N * K);
 }
 // dW[N,K] = dY[T,N]^T · X[T,K]
 static void gemm_wgrad(Ctx& c, const PlaneBuf& dY, const PlaneBuf& X, float* dW, int64_t T, int64_t N, int64_t K) {
-  STEP(lk_tc_gemm(dY.hi, dY.lo, dY.ld, 1, X.hi, X.lo, X.ld, 1, dW, K, N, K, T, nullptr, nullptr, 0, 0.f, 0, 0, c.ws, c.ws_bytes, c.st));
+  char label[40];
+  snprintf(label, sizeof(label), "gemm_wgrad %ldx%ldx%ld", (long)N, (long)K, (long)T);
+  STEP_L(label, lk_tc_gemm(dY.hi, dY.lo, dY.ld, 1, X.hi, X.lo, X.ld, 1, dW, K, N, K, T, nullptr, nullptr, 0, 0.f, 0, 0, c.ws, c.ws_bytes,
+                           c.st), 2.0 * T * N * K);
 }
 
 struct EncWeights {   // one AttentionOperator
@@ -170,42 +184,24 @@ static size_t scratch_bytes(int64_t T, int64_t N, int64_t D, int64_t A, int64_t 
   up(lk_tc_gemm_workspace_bytes(A, D, T));
   up(lk_tc_gemm_workspace_bytes(D, E, T));
   up(lk_scatter_add_workspace_bytes(T, 64, D));
+  up(lk_scatter_add_workspace_bytes(T, 24, D));   // the small-table path's block partials grow with V (category / special tables)
   up(lk_split_bf16_workspace_bytes(T, 3 * D));
   up(lk_colsum_workspace_bytes(N, A));
   return m + (1 << 20);
 }
 
-extern "C" {
-
-size_t lk_nrms_arena_bytes(int64_t T_max, int64_t N_max, int64_t B, int64_t D, int64_t A, int64_t E, int64_t H) {
-  // forward-saved + backward temporaries per token row (floats), see enc_fwd / enc_bwd; generous upper bound
-  size_t per_row = (size_t)(2 * r8(E) / 2 + 14 * D + 3 * A + H + 8) * 4 + 64;
-  size_t per_item = (size_t)(6 * D + 2 * A) * 4;
-  size_t weights = (size_t)(2 * (2 * 3 * D * D + 6 * D * D + 2 * A * D) + 2 * D * r8(E)) * 4 + (1 << 20);
-  size_t ws = scratch_bytes(T_max, N_max, D, A, E);
-  // user side rows are item rows of the history part: bounded by N_max rows
-  return (size_t)(T_max + 2 * N_max) * per_row + (size_t)(N_max + B) * per_item + weights + ws + (8 << 20);
-}
-
-// offsets[]: element offsets into params / grads for, in order:
-//   0 glove.linear.weight [D,E]   1 glove.linear.bias [D]   2 category.weight [n_cats,D]   3 special.weight [n_special,D]
-//   4..12  item_op: in_proj_weight, in_proj_bias, out_proj.weight, out_proj.bias, linear.weight, linear.bias,
-//                   additive.encoder.0.weight, additive.encoder.0.bias, additive.encoder.2.weight
-//   13..21 user_op: same nine
-int lk_nrms_fwd_bwd(const int64_t* title_ids, const int64_t* cat_ids, const int64_t* special_ids, const int32_t* cu_items,
-                    int64_t n_items, int64_t T, int64_t S_max, const int32_t* cu_users, int64_t B, int64_t C, int64_t H_max,
-                    const float* glove_table, const float* params, float* grads, const int64_t* offsets, int64_t D, int64_t heads,
-                    int64_t A, int64_t E, int64_t n_cats, int64_t n_special, float drop_embed, float drop_attn, uint64_t seed,
-                    float* loss_out, float* scores_out, void* arena, size_t arena_bytes, cudaStream_t st) {
-  LK_REQUIRE(n_items >= B * C && B > 0 && C > 0, LK_ERR_ARG, "lk_nrms_fwd_bwd: the first B*C items must be the candidates");
-  LK_REQUIRE(D % 8 == 0 && A % 8 == 0 && E % 4 == 0 && D % heads == 0, LK_ERR_SHAPE, "lk_nrms_fwd_bwd: unsupported dims");
+static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const int64_t* cat_ids, const int64_t* special_ids,
+                    const int32_t* cu_items, int64_t n_items, int64_t T, int64_t S_max, const int32_t* cu_users, int64_t B, int64_t C,
+                    int64_t H_max, const float* glove_table, const float* params, float* grads, const int64_t* offsets, int64_t D,
+                    int64_t heads, int64_t A, int64_t E, int64_t n_cats, int64_t n_special, float drop_embed, float drop_attn,
+                    uint64_t seed, float* loss_out, float* scores_out, void* arena, size_t arena_bytes, cudaStream_t st) {
   Ctx c;
-  c.a = Arena{(char*)arena, arena_bytes, 0, true};
+  c.a = Arena{(char*)arena, arena_bytes, 0, true, 0};
   c.st = st;
   c.rc = 0;
+  c.dry = dry;
   c.ws_bytes = scratch_bytes(T > 0 ? T : 1, n_items, D, A, E);
   c.ws = c.a.take(c.ws_bytes);
-  LK_REQUIRE(c.a.ok, LK_ERR_ARG, "lk_nrms_fwd_bwd: arena too small");
 
   auto P = [&](int i) { return params + offsets[i]; };
   auto G = [&](int i) { return grads + offsets[i]; };
@@ -264,8 +260,37 @@ int lk_nrms_fwd_bwd(const int64_t* title_ids, const int64_t* cat_ids, const int6
   PlaneBuf dpp = split(c, dx, T, D, G(1));
   gemm_wgrad(c, dpp, gp, G(0), T, D, E);
 
-  LK_REQUIRE(c.a.ok, LK_ERR_ARG, "lk_nrms_fwd_bwd: arena too small (%zu bytes given)", arena_bytes);
+  if (high_out) *high_out = c.a.high;
+  LK_REQUIRE(c.a.ok, LK_ERR_ARG, "lk_nrms_fwd_bwd: arena too small (%zu bytes given, %zu needed)", arena_bytes, c.a.high);
   return c.rc;
+}
+
+extern "C" {
+
+// exact: the sizing pass walks the same allocation sequence as a real step (no launches, no memory behind the arena)
+size_t lk_nrms_arena_bytes(int64_t T_max, int64_t N_max, int64_t B, int64_t D, int64_t A, int64_t E, int64_t H) {
+  static const int64_t zeros[22] = {0};
+  size_t high = 0;
+  nrms_run(true, &high, nullptr, nullptr, nullptr, nullptr, N_max + B, T_max, 1, nullptr, B, 1, 1, nullptr, nullptr, nullptr, zeros, D, H, A,
+           E, 64, 64, 0.f, 0.f, 0, nullptr, nullptr, nullptr, ~(size_t)0 >> 1, nullptr);
+  return high + 4096;
+}
+
+// offsets[]: element offsets into params / grads for, in order:
+//   0 glove.linear.weight [D,E]   1 glove.linear.bias [D]   2 category.weight [n_cats,D]   3 special.weight [n_special,D]
+//   4..12  item_op: in_proj_weight, in_proj_bias, out_proj.weight, out_proj.bias, linear.weight, linear.bias,
+//                   additive.encoder.0.weight, additive.encoder.0.bias, additive.encoder.2.weight
+//   13..21 user_op: same nine
+int lk_nrms_fwd_bwd(const int64_t* title_ids, const int64_t* cat_ids, const int64_t* special_ids, const int32_t* cu_items,
+                    int64_t n_items, int64_t T, int64_t S_max, const int32_t* cu_users, int64_t B, int64_t C, int64_t H_max,
+                    const float* glove_table, const float* params, float* grads, const int64_t* offsets, int64_t D, int64_t heads,
+                    int64_t A, int64_t E, int64_t n_cats, int64_t n_special, float drop_embed, float drop_attn, uint64_t seed,
+                    float* loss_out, float* scores_out, void* arena, size_t arena_bytes, cudaStream_t st) {
+  LK_REQUIRE(n_items >= B * C && B > 0 && C > 0, LK_ERR_ARG, "lk_nrms_fwd_bwd: the first B*C items must be the candidates");
+  LK_REQUIRE(D % 8 == 0 && A % 8 == 0 && E % 4 == 0 && D % heads == 0, LK_ERR_SHAPE, "lk_nrms_fwd_bwd: unsupported dims");
+  return nrms_run(false, nullptr, title_ids, cat_ids, special_ids, cu_items, n_items, T, S_max, cu_users, B, C, H_max, glove_table, params,
+                  grads, offsets, D, heads, A, E, n_cats, n_special, drop_embed, drop_attn, seed, loss_out, scores_out, arena,
+                  arena_bytes, st);
 }
 
 }  // extern "C"

@@ -207,3 +207,62 @@ def test_native_step_driver_parity(name):
     for _ in range(25):
         losses.append(native.step(copy.deepcopy(batch)).item())
     assert all(np.isfinite(losses)) and np.mean(losses[-5:]) < np.mean(losses[:5])
+
+
+# ------------------------------------------------------------------------------------------------ evaluation on the device
+@pytest.mark.parametrize('R,G,ties', [(2000, 60, True), (5000, 400, False), (64, 1, True), (70000, 2500, True)])
+def test_group_metrics_kernel_matches_oracle(R, G, ties):
+    """lk_group_metrics (GAUC / MRR / nDCG@k with sklearn tie semantics) against the oracle's restatement of
+    utils/metrics.py; groups are interleaved (rows of a group are not contiguous) and scores contain ties."""
+    from legommenders_b200 import Env
+    from legommenders_b200.metrics import MetricPool
+    Env.use_cuda(0)
+    rng = np.random.default_rng(R + G)
+    groups = rng.integers(0, G, size=R).astype(np.int64) * 7 - 3          # arbitrary (also negative) keys
+    scores = rng.standard_normal(R).astype(np.float32)
+    if ties:
+        scores = np.round(scores * 2) / 2                                   # heavy ties
+    labels = (rng.random(R) < 0.3).astype(np.int64)
+    for g in np.unique(groups):                                             # both classes in every group (SURVEY §8c)
+        idx = np.flatnonzero(groups == g)
+        if len(idx) < 2:
+            groups[idx] = groups[0]
+    for g in np.unique(groups):
+        idx = np.flatnonzero(groups == g)
+        labels[idx[0]], labels[idx[-1]] = 1, 0
+    names = ['GAUC', 'MRR', 'NDCG@1', 'NDCG@5', 'NDCG@10']
+    ref = O.metric_pool(scores, labels, groups, names)
+    pool = MetricPool.parse(names)
+    got = pool.calculate(torch.from_numpy(scores), torch.from_numpy(labels), torch.from_numpy(groups), per_group=True)
+    assert pool.n_groups == len(np.unique(groups))
+    for k in names:
+        assert abs(got[k] - ref[k]) <= 2e-6, (k, got[k], ref[k])
+    # per-group values, group by group (ascending key order = pandas groupby order)
+    keys = np.unique(groups)
+    pg = pool.per_group.cpu().numpy()
+    for gi in rng.choice(len(keys), size=min(20, len(keys)), replace=False):
+        idx = np.flatnonzero(groups == keys[gi])
+        assert abs(pg[0, gi] - O.auc(scores[idx], labels[idx])) <= 1e-6
+        assert abs(pg[1, gi] - O.mrr(scores[idx], labels[idx])) <= 1e-6
+        assert abs(pg[4, gi] - O.ndcg(scores[idx], labels[idx], 10)) <= 1e-6
+
+
+@pytest.mark.parametrize('name', ['nrms_small', 'naml_small'])
+def test_evaluate_matches_golden_metrics(name):
+    """evaluate.py: caches -> one-kernel scoring -> one-kernel metrics; equal to the reference's metrics at 4 decimals."""
+    from legommenders_b200 import DataSet, Env, evaluate
+    c = cases.CASES[name]
+    g = cases.load(name)
+    world, llm = cases.make_world(c)
+    model, resampler, cfg = build(c, world, llm)
+    Env.test()
+    model.eval()
+    evaluate.build_caches(model, resampler.item_cache, DataSet(world.fast_table(), resampler))
+    vals, scores, rows = evaluate.evaluate(model, torch.from_numpy(world.eval_users), torch.from_numpy(world.eval_items),
+                                           torch.from_numpy(g['eval_labels']))
+    assert rows is None
+    assert helpers.normwise(scores.cpu().numpy(), g['eval_scores']) <= TOL
+    for (k, v), ref in zip(vals.items(), g['metrics']):
+        assert round(v, 4) == round(float(ref), 4), k
+    model.cacher.clean()
+    Env.train()
