@@ -139,6 +139,9 @@ def cpu_reference(world, batches, budget_s=None, steps=None, warmup=1):
 
 def main():
     args = parse()
+    if os.environ.get('LK_BENCH_WATCHDOG'):      # debugging aid: dump every thread's stack if the run exceeds N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ['LK_BENCH_WATCHDOG']), exit=True)
     rank = int(os.environ.get('RANK', 0))
     world_size = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))

@@ -87,8 +87,32 @@ size_t lk_split_bf16_workspace_bytes(int64_t rows, int64_t cols);
 int lk_split_bf16(const float* X, int64_t rows, int64_t cols, int64_t ld_in, void* hi, void* lo, int64_t ld_out, int transpose,
                   float* colsum, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t lk_tc_gemm_workspace_bytes(int64_t GM, int64_t GN, int64_t GK);
-/* tuning switch (default 0): use the weight-stationary kernel for K-major contractions with reduction depth <= 320 */
-void lk_tc_set_weight_stationary(int enabled);
+/* Fused epilogue of lk_tc_gemm_ex, applied in this order to every result element r[m,n] of A·B:
+ *   r += bias[n];  r = act(r);  r *= dropout(seed, m*GN+n);  r *= rowmask(m);  r += add_tab0[add_ids0[m], n] (+ add_tab1 ...)  where id > -1;
+ *   r += C[m,n] when accumulate;  then r is stored to C (unless store_c_off), to the split-bf16 planes out_hi/out_lo (the next
+ *   contraction's operand, produced without an extra pass) and summed over m into colsum[n] (bias gradients). */
+typedef struct lk_gemm_epilogue {
+  const float* bias;          /* [GN] */
+  const int64_t* rowmask;     /* [GM]; keep row when > 0, or when > -1 if rowmask_is_ids (the row's token id) */
+  int rowmask_is_ids;
+  int act;                    /* 0 none, 1 tanh, 2 relu */
+  float drop_p;
+  uint64_t seed;
+  int accumulate;             /* r += C */
+  int store_c_off;            /* 1: do not store r to C (C only read for accumulate, or null) */
+  const int64_t* add_ids0;    /* [GM] */
+  const float* add_tab0;      /* [*, GN] */
+  const int64_t* add_ids1;
+  const float* add_tab1;
+  void* out_hi;               /* bf16 [GM, ld_planes] */
+  void* out_lo;
+  int64_t ld_planes;
+  float* colsum;              /* [GN] */
+} lk_gemm_epilogue;
+/* a_mn/b_mn: operand stored [rows, k] (0, K-major) or [k, rows] (1, MN-major); (1,0) is not instantiated */
+int lk_tc_gemm_ex(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo, int64_t ldb, int b_mn,
+                  float* C, int64_t ldc, int64_t GM, int64_t GN, int64_t GK, const lk_gemm_epilogue* ep, void* workspace,
+                  size_t workspace_bytes, cudaStream_t stream);
 int lk_tc_gemm(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo, int64_t ldb, int b_mn,
                float* C, int64_t ldc, int64_t GM, int64_t GN, int64_t GK, const float* bias, const int64_t* rowmask, int act,
                float drop_p, uint64_t seed, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -110,11 +134,16 @@ int lk_conv1d_bwd_weight(const float* dY, const float* X, float* dWr, float* db,
  * reference computes and masks away; results on valid positions are identical. */
 
 /* ---- (2) NRMS multi-head self-attention core — nn.MultiheadAttention, attention_operator.py:49-55.
- *      qkv [rows,3D], ctx [rows,D], lse [rows,H]; head dim D/H in {8,16,32,64} ---------------------------------- */
-int lk_mha_fwd(const float* qkv, const int64_t* mask, const int32_t* cu, float* ctx, float* lse, int64_t N, int64_t S, int64_t D,
-               int64_t H, float drop_p, uint64_t seed, cudaStream_t stream);
-int lk_mha_bwd(const float* qkv, const int64_t* mask, const int32_t* cu, const float* lse, const float* dctx, float* dqkv, int64_t N,
+ *      qkv [rows,3D], ctx [rows,D], lse [rows,H]; head dim D/H in {8,16,32,64}.
+ *      Forward: ctx as fp32 and/or as split-bf16 planes ctx_hi/ctx_lo [rows, D] (either may be null).
+ *      Backward: needs the forward's fp32 ctx (D_i = dO_i·O_i) and lse; dqkv as fp32 and/or planes dq_hi/dq_lo [rows, 3D];
+ *      colsum_part (nullable) [N, 3D]: per-sequence column sums of dqkv (in_proj bias gradient = their sum over N).
+ *      Plane / column-sum outputs of the backward need S*H <= 416. ------------------------------------------------------- */
+int lk_mha_fwd(const float* qkv, const int64_t* mask, const int32_t* cu, float* ctx, void* ctx_hi, void* ctx_lo, float* lse, int64_t N,
                int64_t S, int64_t D, int64_t H, float drop_p, uint64_t seed, cudaStream_t stream);
+int lk_mha_bwd(const float* qkv, const int64_t* mask, const int32_t* cu, const float* ctx, const float* lse, const float* dctx,
+               float* dqkv, void* dq_hi, void* dq_lo, float* colsum_part, int64_t N, int64_t S, int64_t D, int64_t H, float drop_p,
+               uint64_t seed, cudaStream_t stream);
 
 /* ---- (3) AdditiveAttention pooling — model/common/attention.py:31-38.  X [rows,D], Hd = tanh(W1 x + b1) [rows,A] ------ */
 int lk_additive_pool_fwd(const float* X, const float* Hd, const float* w2, const int64_t* mask, const int32_t* cu, float* out,

@@ -41,7 +41,7 @@ SIGNATURES = {
     'lk_split_bf16_workspace_bytes': ('qq', 'z'),
     'lk_split_bf16': ('pqqqppqippzs', 'i'),
     'lk_tc_gemm_workspace_bytes': ('qqq', 'z'),
-    'lk_tc_set_weight_stationary': ('i', 'v'),
+    'lk_tc_gemm_ex': ('ppqippqipqqqqppzs', 'i'),
     'lk_tc_gemm': ('ppqippqipqqqqppifuipzs', 'i'),
     'lk_colsum_workspace_bytes': ('qq', 'z'),
     'lk_colsum': ('ppqqipzs', 'i'),
@@ -49,8 +49,8 @@ SIGNATURES = {
     'lk_conv1d_bwd_data': ('pppqqqqiis', 'i'),
     'lk_conv1d_bwd_weight_workspace_bytes': ('qqqi', 'z'),
     'lk_conv1d_bwd_weight': ('ppppqqqqiipzs', 'i'),
-    'lk_mha_fwd': ('pppppqqqqfus', 'i'),
-    'lk_mha_bwd': ('ppppppqqqqfus', 'i'),
+    'lk_mha_fwd': ('pppppppqqqqfus', 'i'),
+    'lk_mha_bwd': ('ppppppppppqqqqfus', 'i'),
     'lk_additive_pool_fwd': ('pppppppqqqqs', 'i'),
     'lk_additive_pool_bwd': ('pppppppppqqqqis', 'i'),
     'lk_masked_pool': ('pppqqqis', 'i'),

@@ -26,7 +26,7 @@ bool prof_enabled() { return g_prof; }
 void prof_begin(const char* expr, double flops, cudaStream_t st) {
   ProfRec r;
   size_t n = 0;
-  while (expr[n] && expr[n] != '(' && n + 1 < sizeof(r.name))   // entry-point name, or a caller-made label { r.name[n] = expr[n]; n++; }
+  while (expr[n] && expr[n] != '(' && n + 1 < sizeof(r.name)) { r.name[n] = expr[n]; n++; }   // entry-point name or caller-made label
   r.name[n] = 0;
   r.flops = flops;
   cudaEventCreate(&r.e0);

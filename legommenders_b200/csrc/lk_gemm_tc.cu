@@ -29,7 +29,9 @@ constexpr int TILE_BYTES = BM * BK * 2;        // one plane of one operand: 16 K
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi, A_lo, B_hi, B_lo
 constexpr int TMEM_COLS = ACC_STAGES * BN;     // 256 fp32 columns
 constexpr int NUM_THREADS = 64 + 8 * 32;   // TMA warp, MMA warp, 8 epilogue warps
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8 * 32 * 20 * 4 /*epilogue staging*/;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_LD = 20;                 // floats per staged epilogue row (16 + 4 pad: conflict-free float4 stores)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 32 * EPI_LD * 4 /*epilogue staging*/;
 
 struct Params {
   float* C;                 // [GM, ldc] (or split partials [splits, GM, GN] when partial != null)
@@ -38,9 +40,17 @@ struct Params {
   int m_tiles, n_tiles, k_blocks, splits, kb_per_split;
   const float* bias;        // [GN] or null
   const int64_t* rowmask;   // [GM] or null
+  int rowmask_is_ids;       // 0: keep row when rowmask > 0;  1: rowmask holds ids, keep row when id > -1
   int act, accumulate;
+  int store_c;              // 0: C is only read (accumulate) — the result leaves as planes / column sums
   float drop_p;
   unsigned long long seed;
+  // fused producers of the NEXT contraction's operands (all optional)
+  const int64_t* add_ids[2];   // [GM] row addends: result[row,:] += add_tab[i][add_ids[i][row], :] where the id is > -1
+  const float* add_tab[2];     // [*, GN]
+  __nv_bfloat16 *out_hi, *out_lo;   // split-bf16 image of the result, pitch ld_planes
+  int ld_planes;
+  float* colsum_part;          // [m_tiles*4, GN] per-(tile, lane-quarter) column sums of the result rows < GM
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -105,9 +115,6 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
 // Epilogue of one 128x128 accumulator tile by 8 warps: warp (q, half) owns TMEM lanes 32q..32q+31 and columns
 // 64*half..64*half+63.  Per 16-column chunk: tcgen05.ld (row = lane) -> bias / activation / dropout / row mask in registers
 // -> transpose through a warp-private shared tile -> 64-byte-contiguous row segments to global (a warp store covers 8 rows).
-constexpr int EPI_WARPS = 8;
-constexpr int EPI_LD = 20;                                   // floats per staged row (16 + 4 pad: conflict-free float4 stores)
-constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_LD * 4;   // 20 KiB
 
 __device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, int acc, int q, int half, int lane, int m0, int n0,
                                            int split, bool has_k, float inv_keep, float* stage) {
@@ -115,10 +122,16 @@ __device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, 
   const bool row_ok = row < p.GM;
   float* out;
   int ldo;
-  if (p.partial) { out = p.partial + (size_t)split * p.GM * p.GN; ldo = p.GN; } else { out = p.C; ldo = p.ldc; }
+  if (p.partial) { out = p.partial + (size_t)split * p.GM * p.GN; ldo = p.GN; } else { out = p.C; ldo = p.ldc; }   // C may be null (planes only)
   const bool fused = p.partial == nullptr;
   float rm = 1.f;
-  if (fused && p.rowmask && row_ok) rm = p.rowmask[row] > 0 ? 1.f : 0.f;
+  if (fused && p.rowmask && row_ok) rm = p.rowmask[row] > (p.rowmask_is_ids ? -1 : 0) ? 1.f : 0.f;
+  const float* add0 = nullptr;
+  const float* add1 = nullptr;
+  if (fused && row_ok) {
+    if (p.add_ids[0]) { const int64_t id = p.add_ids[0][row]; if (id > -1) add0 = p.add_tab[0] + id * (int64_t)p.GN; }
+    if (p.add_ids[1]) { const int64_t id = p.add_ids[1][row]; if (id > -1) add1 = p.add_tab[1] + id * (int64_t)p.GN; }
+  }
 #pragma unroll 1
   for (int c = 0; c < 4; c++) {
     const int nc0 = n0 + half * 64 + c * 16;
@@ -147,19 +160,53 @@ __device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, 
       }
       x[j] = t;
     }
+    if (add0) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        if (nc0 + j < p.GN) { const float4 a = ldg4(add0 + nc0 + j); x[j] += a.x; x[j + 1] += a.y; x[j + 2] += a.z; x[j + 3] += a.w; }
+    }
+    if (add1) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        if (nc0 + j < p.GN) { const float4 a = ldg4(add1 + nc0 + j); x[j] += a.x; x[j + 1] += a.y; x[j + 2] += a.z; x[j + 3] += a.w; }
+    }
 #pragma unroll
     for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
     __syncwarp();
+    float4 cs = f4_zero();
+    const int c4 = (lane & 3) * 4, n = nc0 + c4;
 #pragma unroll
     for (int it = 0; it < 4; it++) {
-      const int r = it * 8 + (lane >> 2), c4 = (lane & 3) * 4;
-      const int grow = m0 + q * 32 + r, n = nc0 + c4;
+      const int r = it * 8 + (lane >> 2);
+      const int grow = m0 + q * 32 + r;
       if (grow < p.GM && n < p.GN) {
         float4 val = *reinterpret_cast<const float4*>(stage + r * EPI_LD + c4);
-        float* o = out + (size_t)grow * ldo + n;
-        if (fused && p.accumulate) f4_add(val, *reinterpret_cast<const float4*>(o));
-        st4(o, val);
+        if (out) {
+          float* o = out + (size_t)grow * ldo + n;
+          if (fused && p.accumulate) f4_add(val, *reinterpret_cast<const float4*>(o));
+          if (!fused || p.store_c) st4(o, val);
+        }
+        if (fused && p.out_hi) {
+          __align__(8) __nv_bfloat16 h[4], l[4];
+          const float xv[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            h[e] = __float2bfloat16_rn(xv[e]);
+            l[e] = __float2bfloat16_rn(xv[e] - __bfloat162float(h[e]));
+          }
+          *reinterpret_cast<uint2*>(p.out_hi + (size_t)grow * p.ld_planes + n) = *reinterpret_cast<uint2*>(h);
+          *reinterpret_cast<uint2*>(p.out_lo + (size_t)grow * p.ld_planes + n) = *reinterpret_cast<uint2*>(l);
+        }
+        f4_add(cs, val);
       }
+    }
+    if (fused && p.colsum_part) {     // warp-uniform branch
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+      }
+      if (lane < 4 && n < p.GN) st4(p.colsum_part + ((size_t)(m0 / BM) * 4 + q) * p.GN + n, cs);
     }
     __syncwarp();
   }
@@ -312,146 +359,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Weight-stationary variant for the forward / grad-input contractions (K-major operands, reduction depth <= 320).
-// With K = 256 a 128x128 output tile needs only 3072 MMA cycles but 256 KB of operand tiles; re-streaming both operands per
-// tile makes the kernel L2->SM bandwidth bound (ncu: tensor pipe 8-13% active).  Here a CTA owns ONE 128-column slab of
-// the weight for its whole life — its hi/lo planes for the full reduction depth sit in shared memory (kb x 32 KB) — and
-// only the activation planes are streamed (32 KB per k-block) through the TMA ring while it walks down the M tiles.
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int WS_MAX_KB = 5;
-constexpr int A_STAGE_BYTES = 2 * TILE_BYTES;   // A_hi + A_lo for one k-block
-
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
-                  const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const Params p, int a_stages) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* smemB = smem;                                         // [k_blocks][B_hi 16K | B_lo 16K]
-  uint8_t* smemA = smem + p.k_blocks * 2 * TILE_BYTES;           // [a_stages][A_hi 16K | A_lo 16K]
-  uint64_t* bars = (uint64_t*)(smemA + a_stages * A_STAGE_BYTES);
-  uint64_t* full_bar = bars;                     // [8]
-  uint64_t* empty_bar = bars + 8;                // [8]
-  uint64_t* tfull_bar = bars + 16;               // [ACC_STAGES]
-  uint64_t* tempty_bar = tfull_bar + ACC_STAGES; // [ACC_STAGES]
-  uint64_t* b_bar = tempty_bar + ACC_STAGES;     // weights landed
-  uint32_t* tmem_slot = (uint32_t*)(b_bar + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int groups = max(1, (int)gridDim.x / p.n_tiles);         // CTAs per weight slab
-  const int n_blk = blockIdx.x % p.n_tiles, grp = blockIdx.x / p.n_tiles;
-  const bool active = grp < groups;
-  const int n0 = n_blk * BN;
-
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapAh) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapAl) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapBh) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapBl) : "memory");
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < a_stages; i++) {
-      mbar_init(smem_u32(&full_bar[i]), 1);
-      mbar_init(smem_u32(&empty_bar[i]), 1);
-    }
-    for (int i = 0; i < ACC_STAGES; i++) {
-      mbar_init(smem_u32(&tfull_bar[i]), 1);
-      mbar_init(smem_u32(&tempty_bar[i]), EPI_WARPS);
-    }
-    mbar_init(smem_u32(b_bar), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (active) {
-    if (warp == 0) {
-      if (lane == 0) {
-        const uint32_t bb = smem_u32(b_bar);
-        mbar_expect_tx(bb, p.k_blocks * 2 * TILE_BYTES);
-        for (int kb = 0; kb < p.k_blocks; kb++) {
-          tma_load_2d(smem_u32(smemB + kb * 2 * TILE_BYTES), &mapBh, bb, kb * BK, n0);
-          tma_load_2d(smem_u32(smemB + kb * 2 * TILE_BYTES + TILE_BYTES), &mapBl, bb, kb * BK, n0);
-        }
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int mt = grp; mt < p.m_tiles; mt += groups) {
-          for (int kb = 0; kb < p.k_blocks; kb++) {
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-            const uint32_t fb = smem_u32(&full_bar[stage]);
-            mbar_expect_tx(fb, A_STAGE_BYTES);
-            const uint32_t sa = smem_u32(smemA + stage * A_STAGE_BYTES);
-            tma_load_2d(sa, &mapAh, fb, kb * BK, mt * BM);
-            tma_load_2d(sa + TILE_BYTES, &mapAl, fb, kb * BK, mt * BM);
-            if (++stage == a_stages) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc(false, false);
-        int stage = 0, acc = 0;
-        uint32_t phase = 0, acc_phase = 0;
-        mbar_wait(smem_u32(b_bar), 0);
-        tc_fence_after();
-        for (int mt = grp; mt < p.m_tiles; mt += groups) {
-          mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * BN;
-          for (int kb = 0; kb < p.k_blocks; kb++) {
-            mbar_wait(smem_u32(&full_bar[stage]), phase);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smemA + stage * A_STAGE_BYTES);
-            const uint32_t sb = smem_u32(smemB + kb * 2 * TILE_BYTES);
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; k++) {
-              const uint64_t ah = make_desc(sa + k * UMMA_K * 2, false);
-              const uint64_t al = make_desc(sa + TILE_BYTES + k * UMMA_K * 2, false);
-              const uint64_t bh = make_desc(sb + k * UMMA_K * 2, false);
-              const uint64_t bl = make_desc(sb + TILE_BYTES + k * UMMA_K * 2, false);
-              umma_bf16(d_tmem, al, bh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              umma_bf16(d_tmem, ah, bl, idesc, 1u);
-              umma_bf16(d_tmem, ah, bh, idesc, 1u);
-            }
-            umma_commit(smem_u32(&empty_bar[stage]));
-            if (++stage == a_stages) { stage = 0; phase ^= 1; }
-          }
-          umma_commit(smem_u32(&tfull_bar[acc]));
-          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-        }
-      }
-    } else {
-      const int q = warp & 3, half = (warp - 2) >> 2;
-      float* stage = reinterpret_cast<float*>(smemA + a_stages * A_STAGE_BYTES + 512) + (warp - 2) * 32 * EPI_LD;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-      for (int mt = grp; mt < p.m_tiles; mt += groups) {
-        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
-        tc_fence_after();
-        store_tile(p, tmem_base, acc, q, half, lane, mt * BM, n0, 0, true, inv_keep, stage);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
-  }
-}
-
 // fp32 -> (hi, lo) bf16 planes, output pitch ld_out (>= cols, multiple of 8, pad columns zeroed).  A block owns SPLIT_ROWS
 // rows x 256 columns (32 column-threads x 8 elements, 8 row-threads); optionally it also emits per-block column sums of the
 // fp32 input (the bias gradient db = sum_m dY[m,:] rides on the pass that has to read dY anyway).
@@ -508,6 +415,24 @@ __global__ void colsum_finish_kernel(const float* __restrict__ part, float* __re
   out[c] = s;
 }
 
+// out[c] = sum_i part[i, c] in a fixed order: 32 part-lanes x 32 columns per block, then an ordered shared-memory reduction
+__global__ void __launch_bounds__(1024) colsum_finish2_kernel(const float* __restrict__ part, float* __restrict__ out, int nparts, int cols) {
+  __shared__ float red[32][33];
+  const int cx = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s = 0.f;
+  if (c < cols)
+    for (int i = pl; i < nparts; i += 32) s += part[(int64_t)i * cols + c];
+  red[pl][cx] = s;
+  __syncthreads();
+  if (pl == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i++) t += red[i][cx];
+    out[c] = t;
+  }
+}
+
 // transposed split through a 32x32 smem tile: out[c, r]
 __global__ void split_bf16_t_kernel(const float* __restrict__ X, int rows, int cols, int64_t ld_in, __nv_bfloat16* __restrict__ hi,
                                     __nv_bfloat16* __restrict__ lo, int64_t ld_out) {
@@ -560,8 +485,6 @@ static int make_map(CUtensorMap* m, const void* base, int64_t inner, int64_t out
   return LK_OK;
 }
 
-static int g_ws_enabled = 0;   // measured: no gain over the streaming kernel once the epilogue was fixed (profiles/r1_03)
-
 static int pick_splits(int64_t GM, int64_t GN, int64_t GK) {
   int64_t tiles = ((GM + BM - 1) / BM) * ((GN + BN - 1) / BN);
   int64_t kb = (GK + BK - 1) / BK;
@@ -607,31 +530,38 @@ int lk_split_bf16(const float* X, int64_t rows, int64_t cols, int64_t ld_in, voi
   return check_launch("split_bf16");
 }
 
-void lk_tc_set_weight_stationary(int enabled) { g_ws_enabled = enabled; }
-
 size_t lk_tc_gemm_workspace_bytes(int64_t GM, int64_t GN, int64_t GK) {
   int s = pick_splits(GM, GN, GK);
-  return s > 1 ? (size_t)s * GM * GN * sizeof(float) + 256 : 256;
+  const size_t colsum = (size_t)((GM + BM - 1) / BM) * 4 * GN * sizeof(float);   // per-(tile, quarter) column-sum partials
+  return (s > 1 ? (size_t)s * GM * GN * sizeof(float) : colsum) + 256;
 }
 
-int lk_tc_gemm(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo, int64_t ldb, int b_mn,
-               float* C, int64_t ldc, int64_t GM, int64_t GN, int64_t GK, const float* bias, const int64_t* rowmask, int act,
-               float drop_p, uint64_t seed, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+int lk_tc_gemm_ex(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo, int64_t ldb, int b_mn,
+                  float* C, int64_t ldc, int64_t GM, int64_t GN, int64_t GK, const lk_gemm_epilogue* ep, void* workspace,
+                  size_t workspace_bytes, cudaStream_t st) {
+  static const lk_gemm_epilogue none = {};
+  if (!ep) ep = &none;
   LK_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 && GN % 4 == 0, LK_ERR_SHAPE, "lk_tc_gemm: pitches must be 16-byte multiples");
-  LK_REQUIRE(a_mn == b_mn, LK_ERR_ARG, "lk_tc_gemm: mixed operand majors are not instantiated");
-  LK_REQUIRE(((uintptr_t)A_hi | (uintptr_t)A_lo | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C) % 16 == 0, LK_ERR_ARG,
-             "lk_tc_gemm: operands must be 16-byte aligned");
+  LK_REQUIRE(!(a_mn && !b_mn), LK_ERR_ARG, "lk_tc_gemm: MN-major A with K-major B is not instantiated");
+  LK_REQUIRE(((uintptr_t)A_hi | (uintptr_t)A_lo | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C | (uintptr_t)ep->out_hi |
+              (uintptr_t)ep->out_lo) % 16 == 0, LK_ERR_ARG, "lk_tc_gemm: operands must be 16-byte aligned");
+  LK_REQUIRE(C || ep->out_hi || ep->colsum, LK_ERR_ARG, "lk_tc_gemm: no output requested");
+  LK_REQUIRE(!ep->out_hi || (ep->out_lo && ep->ld_planes % 8 == 0 && ep->ld_planes >= GN), LK_ERR_ARG, "lk_tc_gemm: bad output planes");
+  LK_REQUIRE(!ep->accumulate || C, LK_ERR_ARG, "lk_tc_gemm: accumulate needs C");
   if (GM == 0 || GN == 0) return LK_OK;
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
-  if (a_mn) {   // A stored [GK, GM] (GM contiguous), B stored [GK, GN]
+  if (a_mn) {   // A stored [GK, GM] (GM contiguous)
     if ((rc = make_map(&mAh, A_hi, GM, GK, lda, 64))) return rc;
     if ((rc = make_map(&mAl, A_lo, GM, GK, lda, 64))) return rc;
-    if ((rc = make_map(&mBh, B_hi, GN, GK, ldb, 64))) return rc;
-    if ((rc = make_map(&mBl, B_lo, GN, GK, ldb, 64))) return rc;
-  } else {      // A stored [GM, GK] (GK contiguous), B stored [GN, GK]
+  } else {      // A stored [GM, GK] (GK contiguous)
     if ((rc = make_map(&mAh, A_hi, GK, GM, lda, BM))) return rc;
     if ((rc = make_map(&mAl, A_lo, GK, GM, lda, BM))) return rc;
+  }
+  if (b_mn) {   // B stored [GK, GN] (GN contiguous)
+    if ((rc = make_map(&mBh, B_hi, GN, GK, ldb, 64))) return rc;
+    if ((rc = make_map(&mBl, B_lo, GN, GK, ldb, 64))) return rc;
+  } else {      // B stored [GN, GK] (GK contiguous)
     if ((rc = make_map(&mBh, B_hi, GK, GN, ldb, BN))) return rc;
     if ((rc = make_map(&mBl, B_lo, GK, GN, ldb, BN))) return rc;
   }
@@ -644,42 +574,52 @@ int lk_tc_gemm(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const 
   p.kb_per_split = (p.k_blocks + p.splits - 1) / p.splits;
   p.splits = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
   p.partial = nullptr;
+  const bool plain = !ep->bias && !ep->rowmask && ep->act == 0 && ep->drop_p == 0.f && !ep->add_ids0 && !ep->add_ids1 && !ep->out_hi &&
+                     !ep->colsum;
   if (p.splits > 1) {
     LK_REQUIRE(workspace && workspace_bytes >= (size_t)p.splits * GM * GN * sizeof(float), LK_ERR_ARG, "lk_tc_gemm: workspace too small");
-    LK_REQUIRE(!bias && !rowmask && act == 0 && drop_p == 0.f, LK_ERR_ARG, "lk_tc_gemm: split reduction has no fused epilogue");
+    LK_REQUIRE(plain && C, LK_ERR_ARG, "lk_tc_gemm: split reduction has no fused epilogue");
     p.partial = (float*)workspace;
   }
-  p.bias = bias; p.rowmask = rowmask; p.act = act; p.accumulate = accumulate; p.drop_p = drop_p; p.seed = (unsigned long long)seed;
+  p.bias = ep->bias; p.rowmask = ep->rowmask; p.rowmask_is_ids = ep->rowmask_is_ids; p.act = ep->act; p.accumulate = ep->accumulate;
+  p.store_c = (C && !ep->store_c_off) ? 1 : 0;
+  p.drop_p = ep->drop_p; p.seed = (unsigned long long)ep->seed;
+  p.add_ids[0] = ep->add_ids0; p.add_tab[0] = ep->add_tab0; p.add_ids[1] = ep->add_ids1; p.add_tab[1] = ep->add_tab1;
+  p.out_hi = (__nv_bfloat16*)ep->out_hi; p.out_lo = (__nv_bfloat16*)ep->out_lo; p.ld_planes = (int)ep->ld_planes;
+  p.colsum_part = nullptr;
+  if (ep->colsum) {
+    LK_REQUIRE(workspace && workspace_bytes >= (size_t)p.m_tiles * 4 * GN * sizeof(float), LK_ERR_ARG, "lk_tc_gemm: workspace too small for column sums");
+    p.colsum_part = (float*)workspace;
+  }
 
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(tc_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     attr_set = true;
   }
   int total = p.m_tiles * p.n_tiles * p.splits;
   int grid = total < kNumSMs ? total : kNumSMs;
-  if (!a_mn && g_ws_enabled && p.splits == 1 && p.k_blocks <= WS_MAX_KB && p.n_tiles <= kNumSMs && p.m_tiles >= 2 * (kNumSMs / p.n_tiles)) {
-    // weight-stationary: one 128-column weight slab per CTA for its whole life, activations streamed
-    const int b_bytes = p.k_blocks * 2 * TILE_BYTES;
-    int a_stages = (227 * 1024 - 2048 - EPI_STAGE_BYTES - b_bytes) / A_STAGE_BYTES;
-    if (a_stages > 6) a_stages = 6;
-    const int smem = b_bytes + a_stages * A_STAGE_BYTES + 1024 + 512 + EPI_STAGE_BYTES;
-    static bool ws_attr = false;
-    if (!ws_attr) {
-      cudaFuncSetAttribute(tc_gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      ws_attr = true;
-    }
-    const int groups = kNumSMs / p.n_tiles;
-    tc_gemm_ws_kernel<<<groups * p.n_tiles, NUM_THREADS, smem, st>>>(mAh, mAl, mBh, mBl, p, a_stages);
-    return check_launch("tc_gemm_ws");
-  }
   if (a_mn) tc_gemm_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
+  else if (b_mn) tc_gemm_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
   else tc_gemm_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
   rc = check_launch("tc_gemm");
   if (rc) return rc;
-  if (p.splits > 1) return lk_splitk_reduce(p.partial, C, GM, GN, ldc, p.splits, accumulate, st);
+  if (p.splits > 1) return lk_splitk_reduce(p.partial, C, GM, GN, ldc, p.splits, ep->accumulate, st);
+  if (ep->colsum) {
+    colsum_finish2_kernel<<<(unsigned)((GN + 31) / 32), 1024, 0, st>>>(p.colsum_part, ep->colsum, p.m_tiles * 4, (int)GN);
+    return check_launch("tc_gemm_colsum");
+  }
   return LK_OK;
+}
+
+int lk_tc_gemm(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo, int64_t ldb, int b_mn,
+               float* C, int64_t ldc, int64_t GM, int64_t GN, int64_t GK, const float* bias, const int64_t* rowmask, int act,
+               float drop_p, uint64_t seed, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  lk_gemm_epilogue ep = {};
+  ep.bias = bias; ep.rowmask = rowmask; ep.act = act; ep.drop_p = drop_p; ep.seed = seed; ep.accumulate = accumulate;
+  return lk_tc_gemm_ex(A_hi, A_lo, lda, a_mn, B_hi, B_lo, ldb, b_mn, C, ldc, GM, GN, GK, &ep, workspace, workspace_bytes, st);
 }
 
 }  // extern "C"

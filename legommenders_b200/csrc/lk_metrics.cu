@@ -55,7 +55,7 @@ static size_t metric_carve(MetricWs& w, void* base, int64_t R) {
 __global__ void metric_keys_kernel(const int64_t* __restrict__ groups, long long* __restrict__ keys, int* __restrict__ vals, int64_t R) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R) return;
-  keys[i] = (long long)groups[i] ^ (long long)0x8000000000000000LL;   // order-preserving map of signed ids onto unsigned radix order
+  keys[i] = (long long)groups[i];   // cub's radix sort orders signed keys correctly (ascending, like pandas groupby)
   vals[i] = (int)i;
 }
 

@@ -5,16 +5,27 @@
 // logits = (q·dh^-0.5)·kᵀ, -inf on padded keys, softmax over keys, dropout(p) on the probabilities in
 // training, ctx = probs·v.
 //
-// Sequences are short (<= 33 item tokens, <= 50 history items) and there are thousands of them, so ONE CTA owns
-// ONE sequence with all its heads: the K and V tiles [L, D] are staged in shared memory with coalesced loads and
-// every thread owns one (head, query) pair — its q row and its output accumulator live in registers, keys are
-// walked with warp-broadcast 16-byte shared loads, and the softmax needs no cross-lane traffic at all.
-// The backward recomputes probabilities from the saved row log-sum-exp (no [N,H,S,S] tensor is ever stored):
-// phase A (thread = head,query) produces D_i and dQ, phase B (thread = head,key) produces dK and dV.
+// Shape of the problem: thousands of short sequences (<= 33 item tokens, <= 50/100 history items), head dim 32.  The tiles
+// are far too small for tcgen05 and fp32 parity rules out single-pass tensor-core math, so this is an fp32 CUDA-core
+// kernel whose limiter is the shared-memory return path (128 B/clk/SM: one operand word per lane per FMA if nothing is
+// reused).  The work split is therefore chosen to cut shared-memory words per FMA by R (2 for head dim 32: with one shuffle
+// step per dot product the instruction issue rate and the shared-memory return path are then about equally loaded):
+//   * one CTA owns one sequence and a group of HG heads (HG*DH = 128 columns); two [L, 128] tiles sit in shared memory;
+//   * R adjacent lanes (a "quad") share a group of R rows of one head; each lane owns a W = DH/R wide slice of the head
+//     dimension for ALL R rows, so one W-float shared load feeds R*W FMAs; partial dot products are completed with
+//     log2(R) xor-shuffles inside the quad.
+//   forward     quad = R queries:  one pass over the keys with an online softmax (K/V tiles)
+//   backward A  quad = R queries:  p_ij from the saved log-sum-exp, dS_ij = p_ij (dP_ij - D_i) with D_i = dO_i·O_i, dQ_i
+//   backward B  quad = R keys:     dV_j, dK_j in one pass over the queries (Q/dO tiles re-staged in the same memory)
+// Probabilities are never stored; exp is ex2.approx on log2(e)-prescaled logits (rel. error 2^-22).  Results leave through a
+// shared tile: coalesced stores, optional split-bf16 plane output (ctx and dqkv only feed tensor-core contractions) and
+// deterministic per-sequence column sums of dqkv (the in_proj bias gradient).
 //
 // Two sequence layouts are served: dense [N, S, *] with a key-validity mask (the reference's padded layout) and
 // packed rows with cumulative offsets `cu` (padding-free execution: pad tokens and pad history slots, which the
 // reference computes and then masks away, are never touched).
+#include <cuda_bf16.h>
+
 #include "lk_common.cuh"
 #include "../../include/legommenders_b200.h"
 
@@ -32,246 +43,438 @@ __device__ __forceinline__ void seq_range(const SeqView& v, int64_t n, int64_t& 
 }
 
 struct MhaParams {
-  const float* qkv;      // [rows, 3D]
-  float* ctx;            // [rows, D]
-  float* lse;            // [rows, H]
-  const float* dctx;     // bwd: [rows, D]
-  float* dqkv;           // bwd: [rows, 3D]
+  const float* qkv;                 // [rows, 3D]
+  float* ctx;                       // [rows, D] fp32 (fwd: written; bwd: read for D_i = dO·O)
+  __nv_bfloat16 *ctx_hi, *ctx_lo;   // fwd: optional split-bf16 image of ctx, pitch D
+  float* lse;                       // [rows, H]  natural-log log-sum-exp of the scaled logits
+  const float* dctx;                // bwd: [rows, D]
+  float* dqkv;                      // bwd: [rows, 3D] fp32 (nullable when planes are requested)
+  __nv_bfloat16 *dq_hi, *dq_lo;     // bwd: optional split-bf16 image of dqkv, pitch 3D
+  float* colsum_part;               // bwd: optional [N, 3D] per-sequence column sums of dqkv
   SeqView seq;
-  int D, H;
+  int D, H, HG;                     // HG heads per CTA
   float scale, drop_p;
+  uint32_t drop_thr;                // keep iff (hash >> 8) >= drop_thr, drop_thr = p * 2^24
   unsigned long long seed;
 };
 
-template <int DH>
-__device__ __forceinline__ float dot_smem(const float (&q)[DH], const float* __restrict__ k) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four independent chains: the dot is latency-, not issue-bound
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+constexpr int MHA_THREADS = 256;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// attention dropout: keep bit of probability (row, head, key j) = one 64-bit hash per (row, head), a 32-bit finaliser per key
+__device__ __forceinline__ uint32_t attn_hash_base(unsigned long long seed, uint64_t row_head) {
+  return mix32(seed * 0x9E3779B97F4A7C15ULL + row_head);
+}
+__device__ __forceinline__ bool attn_keep(uint32_t hb, int j, uint32_t thr) {
+  uint32_t x = hb ^ ((uint32_t)(j + 1) * 0x9E3779B9u);
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return (x >> 8) >= thr;
+}
+
+template <int R>
+__device__ __forceinline__ float quad_sum(float v) {
+  if (R >= 2) v += __shfl_xor_sync(0xffffffffu, v, 1);
+  if (R >= 4) v += __shfl_xor_sync(0xffffffffu, v, 2);
+  if (R >= 8) v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+
+template <int W>
+__device__ __forceinline__ void lds_slice(float (&v)[W], const float* __restrict__ src) {
 #pragma unroll
-  for (int d = 0; d < DH; d += 4) {
-    const float4 kv = *reinterpret_cast<const float4*>(k + d);
-    s0 = fmaf(q[d], kv.x, s0); s1 = fmaf(q[d + 1], kv.y, s1); s2 = fmaf(q[d + 2], kv.z, s2); s3 = fmaf(q[d + 3], kv.w, s3);
+  for (int w = 0; w < W; w += 4) {
+    const float4 x = *reinterpret_cast<const float4*>(src + w);
+    v[w] = x.x; v[w + 1] = x.y; v[w + 2] = x.z; v[w + 3] = x.w;
   }
-  return (s0 + s1) + (s2 + s3);
+}
+template <int W>
+__device__ __forceinline__ void ldg_slice(float (&v)[W], const float* __restrict__ src, float s) {
+#pragma unroll
+  for (int w = 0; w < W; w += 4) {
+    const float4 x = ldg4(src + w);
+    v[w] = x.x * s; v[w + 1] = x.y * s; v[w + 2] = x.z * s; v[w + 3] = x.w * s;
+  }
+}
+template <int W>
+__device__ __forceinline__ float dot_slice(const float (&a)[W], const float (&b)[W]) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int w = 0; w < W; w += 2) { s0 = fmaf(a[w], b[w], s0); s1 = fmaf(a[w + 1], b[w + 1], s1); }
+  return s0 + s1;
+}
+template <int W>
+__device__ __forceinline__ void sts_slice(float* __restrict__ dst, const float (&v)[W], float s) {
+#pragma unroll
+  for (int w = 0; w < W; w += 4) *reinterpret_cast<float4*>(dst + w) = make_float4(v[w] * s, v[w + 1] * s, v[w + 2] * s, v[w + 3] * s);
+}
+
+// Shared tiles are [S][TP] with TP = TW + 4 (TW = HG*DH columns of this CTA): rows stay 16-byte aligned and the row-per-lane
+// writes of the result tiles spread over the banks.
+__device__ __forceinline__ void stage_tile(float* T, const float* __restrict__ src, int64_t ld, int L, int TW) {
+  const int C4 = TW >> 2, TP = TW + 4;
+  for (int idx = threadIdx.x; idx < L * C4; idx += blockDim.x) {
+    const int t = idx / C4, c = (idx - t * C4) * 4;
+    cp_async16(T + t * TP + c, src + (int64_t)t * ld + c);
+  }
+}
+
+// write a result tile to global rows (pitch ld, in elements) as fp32 and/or split-bf16 planes, 16 bytes per thread, coalesced;
+// optionally its column sums (fixed row order -> deterministic)
+__device__ __forceinline__ void flush_tile(const float* __restrict__ T, int L, int TW, float* __restrict__ f32, __nv_bfloat16* __restrict__ hi,
+                                           __nv_bfloat16* __restrict__ lo, int64_t ld, float* __restrict__ colsum) {
+  const int C4 = TW >> 2, TP = TW + 4;
+  for (int idx = threadIdx.x; idx < L * C4; idx += blockDim.x) {
+    const int t = idx / C4, c = (idx - t * C4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(T + t * TP + c);
+    if (f32) st4(f32 + (int64_t)t * ld + c, v);
+    if (hi) {
+      __align__(8) __nv_bfloat16 h[4], l[4];
+      const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        h[e] = __float2bfloat16_rn(x[e]);
+        l[e] = __float2bfloat16_rn(x[e] - __bfloat162float(h[e]));
+      }
+      *reinterpret_cast<uint2*>(hi + (int64_t)t * ld + c) = *reinterpret_cast<uint2*>(h);
+      *reinterpret_cast<uint2*>(lo + (int64_t)t * ld + c) = *reinterpret_cast<uint2*>(l);
+    }
+  }
+  if (colsum) {
+    for (int c = threadIdx.x; c < TW; c += blockDim.x) {
+      float s = 0.f;
+      for (int t = 0; t < L; t++) s += T[t * TP + c];
+      colsum[c] = s;
+    }
+  }
+}
+
+// decomposition of a work item: (local head, row group, slice)
+struct Item { int hl, g, ds; bool active; };
+template <int R>
+__device__ __forceinline__ Item item_of(int w, int G, int items) {
+  Item it;
+  it.active = w < items;
+  const int wc = it.active ? w : 0;
+  it.ds = wc % R;
+  const int t = wc / R;
+  it.g = t % G;
+  it.hl = t / G;
+  return it;
+}
+// keep bits of this quad's R (row, key) pairs: lane ds computed `mine`; returns the R bits of the quad
+template <int R>
+__device__ __forceinline__ uint32_t quad_bits(bool mine) {
+  const uint32_t b = __ballot_sync(0xffffffffu, mine);
+  return (b >> ((threadIdx.x & 31) & ~(R - 1))) & ((1u << R) - 1u);
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int DH>
-__global__ void __launch_bounds__(512) mha_fwd_seq_kernel(MhaParams p) {
+template <int DH, int R>
+__global__ void __maxnreg__(DH <= 32 ? 96 : 168) mha_fwd_seq_kernel(MhaParams p) {   // 4 CTAs of 160 threads per SM at head dim 32
+  constexpr int W = DH / R;
   extern __shared__ __align__(16) float smem[];
   const int64_t n = blockIdx.x;
   int64_t row0; int L;
   seq_range(p.seq, n, row0, L);
   if (L == 0) return;
-  const int D = p.D, H = p.H;
-  float* Ks = smem;                       // [L][D]
-  float* Vs = Ks + (size_t)p.seq.S * D;   // [L][D]
-  float* valid = Vs + (size_t)p.seq.S * D;   // [L] 1/0
+  const int D = p.D, H = p.H, S = p.seq.S, HG = p.HG, TW = HG * DH, TP = TW + 4;
+  const int h0 = blockIdx.y * HG, c0 = h0 * DH;          // first head / first column of this CTA
+  float* Ks = smem;                        // [S][TP]
+  float* Vs = Ks + (size_t)S * TP;
+  float* Os = Vs + (size_t)S * TP;         // result tile
+  float* valid = Os + (size_t)S * TP;      // [S]
 
   const float* base = p.qkv + row0 * 3 * (int64_t)D;
-  for (int idx = threadIdx.x; idx < L * (D / 4); idx += blockDim.x) {
-    const int t = idx / (D / 4), c = (idx - t * (D / 4)) * 4;
-    const float* r = base + (int64_t)t * 3 * D + c;
-    *reinterpret_cast<float4*>(Ks + t * D + c) = ldg4(r + D);
-    *reinterpret_cast<float4*>(Vs + t * D + c) = ldg4(r + 2 * D);
-  }
+  stage_tile(Ks, base + D + c0, 3 * D, L, TW);
+  stage_tile(Vs, base + 2 * D + c0, 3 * D, L, TW);
   for (int t = threadIdx.x; t < L; t += blockDim.x)
-    valid[t] = (p.seq.cu || !p.seq.mask || p.seq.mask[n * p.seq.S + t] > 0) ? 1.f : 0.f;
+    valid[t] = (p.seq.cu || !p.seq.mask || p.seq.mask[n * S + t] > 0) ? 1.f : 0.f;
+  cp_async_wait_all();
   __syncthreads();
 
   const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-  for (int w = threadIdx.x; w < L * H; w += blockDim.x) {
-    const int h = w / L, i = w - h * L;
-    float q[DH], acc[DH];
-    const float* qr = base + (int64_t)i * 3 * D + h * DH;
+  const int G = (L + R - 1) / R, items = HG * G * R;
+  for (int w0 = 0; w0 < items; w0 += blockDim.x) {
+    const Item it = item_of<R>(w0 + threadIdx.x, G, items);
+    const int h = h0 + it.hl, col = it.hl * DH + it.ds * W;
+    float q[R][W], acc[R][W], m[R], l[R];
 #pragma unroll
-    for (int d = 0; d < DH; d += 4) {
-      const float4 v = ldg4(qr + d);
-      q[d] = v.x * p.scale; q[d + 1] = v.y * p.scale; q[d + 2] = v.z * p.scale; q[d + 3] = v.w * p.scale;
-      acc[d] = acc[d + 1] = acc[d + 2] = acc[d + 3] = 0.f;
+    for (int r = 0; r < R; r++) {
+      const int i = min(it.g * R + r, L - 1);
+      ldg_slice<W>(q[r], base + (int64_t)i * 3 * D + c0 + col, p.scale * kLog2e);
+      m[r] = -INFINITY; l[r] = 0.f;
+#pragma unroll
+      for (int w = 0; w < W; w++) acc[r][w] = 0.f;
     }
-    const float* kh = Ks + h * DH;
-    const float* vh = Vs + h * DH;
-    float mx = -INFINITY;
-    for (int j = 0; j < L; j++)
-      if (valid[j] != 0.f) mx = fmaxf(mx, dot_smem<DH>(q, kh + j * D));
-    float l = 0.f;
-    const uint64_t didx = (((uint64_t)(row0 + i)) * H + h) * (uint64_t)p.seq.S;
+    const int my_i = min(it.g * R + it.ds, L - 1);
+    const uint32_t hb = attn_hash_base(p.seed, (uint64_t)(row0 + my_i) * H + h);
     for (int j = 0; j < L; j++) {
-      if (valid[j] == 0.f) continue;
-      float pr = expf(dot_smem<DH>(q, kh + j * D) - mx);
-      l += pr;
-      if (p.drop_p > 0.f) pr *= dropout_scale(p.seed, didx + j, p.drop_p, inv_keep);
-      const float* vr = vh + j * D;
+      if (valid[j] == 0.f) continue;                      // CTA-uniform
+      float kv[W], s[R];
+      lds_slice<W>(kv, Ks + j * TP + col);
 #pragma unroll
-      for (int d = 0; d < DH; d += 4) {
-        const float4 vv = *reinterpret_cast<const float4*>(vr + d);
-        acc[d] = fmaf(pr, vv.x, acc[d]); acc[d + 1] = fmaf(pr, vv.y, acc[d + 1]);
-        acc[d + 2] = fmaf(pr, vv.z, acc[d + 2]); acc[d + 3] = fmaf(pr, vv.w, acc[d + 3]);
+      for (int r = 0; r < R; r++) s[r] = quad_sum<R>(dot_slice<W>(q[r], kv));
+      uint32_t bits = (1u << R) - 1u;
+      if (p.drop_p > 0.f) bits = quad_bits<R>(attn_keep(hb, j, p.drop_thr));
+      lds_slice<W>(kv, Vs + j * TP + col);
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        if (s[r] > m[r]) {                                // rescale the running sums (rare after the first keys)
+          const float c = ex2(m[r] - s[r]);               // 2^-inf = 0 on the first valid key
+          l[r] *= c;
+#pragma unroll
+          for (int w = 0; w < W; w++) acc[r][w] *= c;
+          m[r] = s[r];
+        }
+        float pr = ex2(s[r] - m[r]);
+        l[r] += pr;
+        pr = ((bits >> r) & 1u) ? pr * inv_keep : 0.f;
+#pragma unroll
+        for (int w = 0; w < W; w++) acc[r][w] = fmaf(pr, kv[w], acc[r][w]);
       }
     }
-    // all keys masked: mx = -inf, l = 0 -> 0 * inf = NaN, as torch's softmax over an all -inf row
-    const float inv = 1.f / l;
-    float* o = p.ctx + (row0 + i) * (int64_t)D + h * DH;
+    // all keys masked: l = 0 -> 0 * inf = NaN, as torch's softmax over an all -inf row
 #pragma unroll
-    for (int d = 0; d < DH; d += 4) st4(o + d, make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv));
-    p.lse[(row0 + i) * H + h] = mx + logf(l);
+    for (int r = 0; r < R; r++) {
+      const int i = it.g * R + r;
+      if (it.active && i < L) {
+        sts_slice<W>(Os + i * TP + col, acc[r], 1.f / l[r]);
+        if (r == it.ds) p.lse[(row0 + i) * H + h] = (m[r] + log2f(l[r])) * kLn2;
+      }
+    }
   }
+  __syncthreads();
+  const int64_t off = row0 * (int64_t)D + c0;
+  flush_tile(Os, L, TW, p.ctx ? p.ctx + off : nullptr, p.ctx_hi ? p.ctx_hi + off : nullptr, p.ctx_lo ? p.ctx_lo + off : nullptr, D, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-template <int DH>
-__global__ void __launch_bounds__(416) mha_bwd_seq_kernel(MhaParams p) {
+// A: quad = R queries   p_ij = 2^(s2_ij - lse2_i);  dP_ij = (dO_i·v_j) keep_ij;  D_i = dO_i·O_i;  dS_ij = p_ij (dP_ij - D_i)
+//                       dQ_i = scale Σ_j dS_ij k_j
+// B: quad = R keys      dV_j = Σ_i p_ij keep_ij dO_i;   dK_j = scale Σ_i dS_ij q_i
+template <int DH, int R>
+__global__ void __maxnreg__(DH <= 32 ? 200 : 255) mha_bwd_seq_kernel(MhaParams p) {  // 2 CTAs of 160 threads per SM at head dim 32
+  constexpr int W = DH / R;
   extern __shared__ __align__(16) float smem[];
   const int64_t n = blockIdx.x;
   int64_t row0; int L;
   seq_range(p.seq, n, row0, L);
   if (L == 0) return;
-  const int D = p.D, H = p.H, S = p.seq.S;
-  float* Qs = smem;                        // [L][D] raw q
-  float* Ks = Qs + (size_t)S * D;
-  float* Vs = Ks + (size_t)S * D;
-  float* Gs = Vs + (size_t)S * D;          // dctx
-  float* lse_s = Gs + (size_t)S * D;       // [H][S]
-  float* Di_s = lse_s + (size_t)H * S;     // [H][S]
-  float* valid = Di_s + (size_t)H * S;     // [S]
+  const int D = p.D, H = p.H, S = p.seq.S, HG = p.HG, TW = HG * DH, TP = TW + 4;
+  const int h0 = blockIdx.y * HG, c0 = h0 * DH;
+  float* T0 = smem;                        // A: K     B: Q
+  float* T1 = T0 + (size_t)S * TP;         // A: V     B: dO
+  float* U0 = T1 + (size_t)S * TP;         // A: dQ out   B: dK out
+  float* U1 = U0 + (size_t)S * TP;         //             B: dV out
+  float* lse_s = U1 + (size_t)S * TP;      // [HG][S]  log2-domain log-sum-exp
+  float* Di_s = lse_s + (size_t)HG * S;    // [HG][S]
+  uint32_t* hb_s = reinterpret_cast<uint32_t*>(Di_s + (size_t)HG * S);   // [HG][S] dropout hash of (row, head)
+  float* valid = reinterpret_cast<float*>(hb_s + (size_t)HG * S);        // [S]
 
   const float* base = p.qkv + row0 * 3 * (int64_t)D;
   const float* gbase = p.dctx + row0 * (int64_t)D;
-  for (int idx = threadIdx.x; idx < L * (D / 4); idx += blockDim.x) {
-    const int t = idx / (D / 4), c = (idx - t * (D / 4)) * 4;
-    const float* r = base + (int64_t)t * 3 * D + c;
-    *reinterpret_cast<float4*>(Qs + t * D + c) = ldg4(r);
-    *reinterpret_cast<float4*>(Ks + t * D + c) = ldg4(r + D);
-    *reinterpret_cast<float4*>(Vs + t * D + c) = ldg4(r + 2 * D);
-    *reinterpret_cast<float4*>(Gs + t * D + c) = ldg4(gbase + (int64_t)t * D + c);
-  }
-  for (int w = threadIdx.x; w < L * H; w += blockDim.x) {
-    const int h = w / L, i = w - h * L;
-    lse_s[h * S + i] = p.lse[(row0 + i) * H + h];
+  const float* obase = p.ctx + row0 * (int64_t)D;
+  stage_tile(T0, base + D + c0, 3 * D, L, TW);
+  stage_tile(T1, base + 2 * D + c0, 3 * D, L, TW);
+  for (int w = threadIdx.x; w < HG * L; w += blockDim.x) {
+    const int hl = w / L, i = w - hl * L;
+    lse_s[hl * S + i] = p.lse[(row0 + i) * H + h0 + hl] * kLog2e;
+    hb_s[hl * S + i] = attn_hash_base(p.seed, (uint64_t)(row0 + i) * H + h0 + hl);
   }
   for (int t = threadIdx.x; t < L; t += blockDim.x)
     valid[t] = (p.seq.cu || !p.seq.mask || p.seq.mask[n * S + t] > 0) ? 1.f : 0.f;
+  cp_async_wait_all();
   __syncthreads();
 
   const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-  float* dbase = p.dqkv + row0 * 3 * (int64_t)D;
+  const int G = (L + R - 1) / R, items = HG * G * R;
+  float* dbase = p.dqkv ? p.dqkv + row0 * 3 * (int64_t)D + c0 : nullptr;
+  __nv_bfloat16* hbase = p.dq_hi ? p.dq_hi + row0 * 3 * (int64_t)D + c0 : nullptr;
+  __nv_bfloat16* lbase = p.dq_lo ? p.dq_lo + row0 * 3 * (int64_t)D + c0 : nullptr;
+  float* csum = p.colsum_part ? p.colsum_part + n * 3 * (int64_t)D + c0 : nullptr;
 
-  // ---- phase A: thread = (head, query): D_i = sum_j p_ij dP_ij ; dQ_i = scale * sum_j p_ij (dP_ij - D_i) K_j
-  for (int w = threadIdx.x; w < L * H; w += blockDim.x) {
-    const int h = w / L, i = w - h * L;
-    float q[DH], g[DH], dq[DH];
+  // ---- phase A ---------------------------------------------------------------------------------------------------
+  for (int w0 = 0; w0 < items; w0 += blockDim.x) {
+    const Item it = item_of<R>(w0 + threadIdx.x, G, items);
+    const int col = it.hl * DH + it.ds * W;
+    float q[R][W], g[R][W], dq[R][W], Di[R], lse2[R];
 #pragma unroll
-    for (int d = 0; d < DH; d++) {
-      q[d] = Qs[i * D + h * DH + d] * p.scale;
-      g[d] = Gs[i * D + h * DH + d];
-      dq[d] = 0.f;
+    for (int r = 0; r < R; r++) {
+      const int i = min(it.g * R + r, L - 1);
+      float o[W];
+      ldg_slice<W>(q[r], base + (int64_t)i * 3 * D + c0 + col, p.scale * kLog2e);
+      ldg_slice<W>(g[r], gbase + (int64_t)i * D + c0 + col, 1.f);
+      ldg_slice<W>(o, obase + (int64_t)i * D + c0 + col, 1.f);
+      Di[r] = quad_sum<R>(dot_slice<W>(g[r], o));
+      lse2[r] = lse_s[it.hl * S + i];
+#pragma unroll
+      for (int w = 0; w < W; w++) dq[r][w] = 0.f;
     }
-    const float lse_i = lse_s[h * S + i];
-    const float* kh = Ks + h * DH;
-    const float* vh = Vs + h * DH;
-    const uint64_t didx = (((uint64_t)(row0 + i)) * H + h) * (uint64_t)S;
-    float Di = 0.f;
+#pragma unroll
+    for (int r = 0; r < R; r++) {                       // lane ds publishes row ds (static register indexing)
+      const int i = it.g * R + r;
+      if (r == it.ds && it.active && i < L) Di_s[it.hl * S + i] = Di[r];
+    }
+    const uint32_t hb = hb_s[it.hl * S + min(it.g * R + it.ds, L - 1)];
     for (int j = 0; j < L; j++) {
       if (valid[j] == 0.f) continue;
-      const float pr = expf(dot_smem<DH>(q, kh + j * D) - lse_i);
-      float dP = dot_smem<DH>(g, vh + j * D);
-      if (p.drop_p > 0.f) dP *= dropout_scale(p.seed, didx + j, p.drop_p, inv_keep);
-      Di = fmaf(pr, dP, Di);
-    }
-    Di_s[h * S + i] = Di;
-    for (int j = 0; j < L; j++) {
-      if (valid[j] == 0.f) continue;
-      const float* kr = kh + j * D;
-      const float pr = expf(dot_smem<DH>(q, kr) - lse_i);
-      float dP = dot_smem<DH>(g, vh + j * D);
-      if (p.drop_p > 0.f) dP *= dropout_scale(p.seed, didx + j, p.drop_p, inv_keep);
-      const float dS = pr * (dP - Di);
+      float kv[W], vv[W], ps[R], pd[R];
+      lds_slice<W>(kv, T0 + j * TP + col);
+      lds_slice<W>(vv, T1 + j * TP + col);
 #pragma unroll
-      for (int d = 0; d < DH; d += 4) {
-        const float4 kv = *reinterpret_cast<const float4*>(kr + d);
-        dq[d] = fmaf(dS, kv.x, dq[d]); dq[d + 1] = fmaf(dS, kv.y, dq[d + 1]);
-        dq[d + 2] = fmaf(dS, kv.z, dq[d + 2]); dq[d + 3] = fmaf(dS, kv.w, dq[d + 3]);
+      for (int r = 0; r < R; r++) {
+        ps[r] = quad_sum<R>(dot_slice<W>(q[r], kv));
+        pd[r] = quad_sum<R>(dot_slice<W>(g[r], vv));
+      }
+      uint32_t bits = (1u << R) - 1u;
+      if (p.drop_p > 0.f) bits = quad_bits<R>(attn_keep(hb, j, p.drop_thr));
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const float pr = ex2(ps[r] - lse2[r]);
+        const float dP = ((bits >> r) & 1u) ? pd[r] * inv_keep : 0.f;
+        const float dS = pr * (dP - Di[r]);
+#pragma unroll
+        for (int w = 0; w < W; w++) dq[r][w] = fmaf(dS, kv[w], dq[r][w]);
       }
     }
-    float* o = dbase + (int64_t)i * 3 * D + h * DH;
 #pragma unroll
-    for (int d = 0; d < DH; d += 4)
-      st4(o + d, make_float4(dq[d] * p.scale, dq[d + 1] * p.scale, dq[d + 2] * p.scale, dq[d + 3] * p.scale));
+    for (int r = 0; r < R; r++) {
+      const int i = it.g * R + r;
+      if (it.active && i < L) sts_slice<W>(U0 + i * TP + col, dq[r], p.scale);
+    }
   }
   __syncthreads();
-
-  // ---- phase B: thread = (head, key), two register-light passes:
-  //      B1: dV_j = sum_i (p_ij * drop_ij) dO_i        B2: dK_j = scale * sum_i p_ij (dP_ij - D_i) q_i
-  for (int w = threadIdx.x; w < L * H; w += blockDim.x) {
-    const int h = w / L, j = w - h * L;
-    float k[DH], acc[DH];
+  flush_tile(U0, L, TW, dbase, hbase, lbase, 3 * D, csum);
+  // ---- phase B: re-stage Q and dO over K and V ---------------------------------------------------------------------
+  stage_tile(T0, base + c0, 3 * D, L, TW);
+  stage_tile(T1, gbase + c0, D, L, TW);
+  cp_async_wait_all();
+  __syncthreads();
+  for (int w0 = 0; w0 < items; w0 += blockDim.x) {
+    const Item it = item_of<R>(w0 + threadIdx.x, G, items);
+    const int col = it.hl * DH + it.ds * W;
+    float k[R][W], v[R][W], dk[R][W], dv[R][W];
+    uint32_t kvalid = 0;
 #pragma unroll
-    for (int d = 0; d < DH; d++) { k[d] = Ks[j * D + h * DH + d] * p.scale; acc[d] = 0.f; }
-    const float* qh = Qs + h * DH;
-    const float* gh = Gs + h * DH;
-    const bool ok = valid[j] != 0.f;
-    if (ok) {
-      for (int i = 0; i < L; i++) {
-        const float* gr = gh + i * D;
-        float pd = expf(dot_smem<DH>(k, qh + i * D) - lse_s[h * S + i]);
-        if (p.drop_p > 0.f) pd *= dropout_scale(p.seed, (((uint64_t)(row0 + i)) * H + h) * (uint64_t)S + j, p.drop_p, inv_keep);
+    for (int r = 0; r < R; r++) {
+      const int j = it.g * R + r, jc = min(j, L - 1);
+      ldg_slice<W>(k[r], base + (int64_t)jc * 3 * D + D + c0 + col, p.scale * kLog2e);
+      ldg_slice<W>(v[r], base + (int64_t)jc * 3 * D + 2 * D + c0 + col, 1.f);
+      if (j < L && valid[jc] != 0.f) kvalid |= 1u << r;
 #pragma unroll
-        for (int d = 0; d < DH; d += 4) {
-          const float4 gv = *reinterpret_cast<const float4*>(gr + d);
-          acc[d] = fmaf(pd, gv.x, acc[d]); acc[d + 1] = fmaf(pd, gv.y, acc[d + 1]);
-          acc[d + 2] = fmaf(pd, gv.z, acc[d + 2]); acc[d + 3] = fmaf(pd, gv.w, acc[d + 3]);
+      for (int w = 0; w < W; w++) { dk[r][w] = 0.f; dv[r][w] = 0.f; }
+    }
+    const int my_j = it.g * R + it.ds;
+    const float* lse_h = lse_s + it.hl * S;
+    const float* Di_h = Di_s + it.hl * S;
+    const uint32_t* hb_h = hb_s + it.hl * S;
+    for (int i = 0; i < L; i++) {
+      float qv[W], gv[W], ps[R], pd[R];
+      lds_slice<W>(qv, T0 + i * TP + col);
+      lds_slice<W>(gv, T1 + i * TP + col);
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        ps[r] = quad_sum<R>(dot_slice<W>(k[r], qv));
+        pd[r] = quad_sum<R>(dot_slice<W>(v[r], gv));
+      }
+      uint32_t bits = (1u << R) - 1u;
+      if (p.drop_p > 0.f) bits = quad_bits<R>(attn_keep(hb_h[i], my_j, p.drop_thr));
+      bits &= kvalid;
+      const float lse_i = lse_h[i], Di = Di_h[i];
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const float pr = ((kvalid >> r) & 1u) ? ex2(ps[r] - lse_i) : 0.f;
+        const bool kept = (bits >> r) & 1u;
+        const float pk = kept ? pr * inv_keep : 0.f;               // p * keep
+        const float dS = pr * ((kept ? pd[r] * inv_keep : 0.f) - Di);
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+          dv[r][w] = fmaf(pk, gv[w], dv[r][w]);
+          dk[r][w] = fmaf(dS, qv[w], dk[r][w]);
         }
       }
     }
-    float* o = dbase + (int64_t)j * 3 * D + h * DH;
+    // dK carries q's prescale (scale*log2e is on k here, so dk accumulated raw q): dK = scale * Σ dS q
 #pragma unroll
-    for (int d = 0; d < DH; d += 4) st4(o + 2 * D + d, make_float4(acc[d], acc[d + 1], acc[d + 2], acc[d + 3]));
-
-    float v[DH];
-#pragma unroll
-    for (int d = 0; d < DH; d++) { v[d] = Vs[j * D + h * DH + d]; acc[d] = 0.f; }
-    if (ok) {
-      for (int i = 0; i < L; i++) {
-        const float* qr = qh + i * D;
-        const float pr = expf(dot_smem<DH>(k, qr) - lse_s[h * S + i]);
-        float dP = dot_smem<DH>(v, gh + i * D);
-        if (p.drop_p > 0.f) dP *= dropout_scale(p.seed, (((uint64_t)(row0 + i)) * H + h) * (uint64_t)S + j, p.drop_p, inv_keep);
-        const float dS = pr * (dP - Di_s[h * S + i]) * p.scale;
-#pragma unroll
-        for (int d = 0; d < DH; d += 4) {
-          const float4 qv = *reinterpret_cast<const float4*>(qr + d);
-          acc[d] = fmaf(dS, qv.x, acc[d]); acc[d + 1] = fmaf(dS, qv.y, acc[d + 1]);
-          acc[d + 2] = fmaf(dS, qv.z, acc[d + 2]); acc[d + 3] = fmaf(dS, qv.w, acc[d + 3]);
-        }
+    for (int r = 0; r < R; r++) {
+      const int j = it.g * R + r;
+      if (it.active && j < L) {
+        sts_slice<W>(U0 + j * TP + col, dk[r], p.scale);
+        sts_slice<W>(U1 + j * TP + col, dv[r], 1.f);
       }
     }
-#pragma unroll
-    for (int d = 0; d < DH; d += 4) st4(o + D + d, make_float4(acc[d], acc[d + 1], acc[d + 2], acc[d + 3]));
   }
+  __syncthreads();
+  flush_tile(U0, L, TW, dbase ? dbase + D : nullptr, hbase ? hbase + D : nullptr, lbase ? lbase + D : nullptr, 3 * D, csum ? csum + D : nullptr);
+  flush_tile(U1, L, TW, dbase ? dbase + 2 * D : nullptr, hbase ? hbase + 2 * D : nullptr, lbase ? lbase + 2 * D : nullptr, 3 * D,
+             csum ? csum + 2 * D : nullptr);
 }
 
-template <int DH>
-static int launch_fwd(const MhaParams& p, int64_t N, int threads, cudaStream_t st) {
-  size_t smem = ((size_t)2 * p.seq.S * p.D + p.seq.S) * sizeof(float);
-  LK_REQUIRE(smem <= 227 * 1024, LK_ERR_SHAPE, "lk_mha_fwd: K/V tiles (%zu B) do not fit shared memory", smem);
+// heads per CTA: the largest divisor of H with HG*DH <= 128 columns
+static int pick_hg(int H, int dh) {
+  int hg = 128 / dh;
+  if (hg < 1) hg = 1;
+  if (hg > H) hg = H;
+  while (H % hg) hg--;
+  return hg;
+}
+static int pick_threads(int64_t S, int hg, int R) {
+  int64_t t = (int64_t)hg * ((S + R - 1) / R) * R;
+  t = (t + 31) / 32 * 32;
+  // registers are granted to a CTA in units of 4 warps: a 160-thread CTA pays for 256.  When the longest sequences overshoot
+  // 128 threads by one warp, run 128 threads and let those (rare) sequences take a second round.
+  if (t > 128 && t <= 160) t = 128;
+  return (int)(t < 64 ? 64 : (t > MHA_THREADS ? MHA_THREADS : t));
+}
+
+template <int DH, int R>
+static int launch_fwd(MhaParams p, int64_t N, cudaStream_t st) {
+  p.HG = pick_hg(p.H, DH);
+  const int TP = p.HG * DH + 4;
+  size_t smem = ((size_t)3 * p.seq.S * TP + p.seq.S) * sizeof(float);
+  LK_REQUIRE(smem <= 227 * 1024, LK_ERR_SHAPE, "lk_mha_fwd: tiles (%zu B) do not fit shared memory", smem);
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(mha_fwd_seq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
-  mha_fwd_seq_kernel<DH><<<(unsigned)N, threads, smem, st>>>(p);
+  if (!attr) {
+    cudaFuncSetAttribute(mha_fwd_seq_kernel<DH, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(mha_fwd_seq_kernel<DH, R>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr = true;
+  }
+  dim3 grid((unsigned)N, (unsigned)(p.H / p.HG));
+  mha_fwd_seq_kernel<DH, R><<<grid, pick_threads(p.seq.S, p.HG, R), smem, st>>>(p);
   return check_launch("mha_fwd");
 }
-template <int DH>
-static int launch_bwd(const MhaParams& p, int64_t N, int threads, cudaStream_t st) {
-  size_t smem = ((size_t)4 * p.seq.S * p.D + 2 * (size_t)p.H * p.seq.S + p.seq.S) * sizeof(float);
+template <int DH, int R>
+static int launch_bwd(MhaParams p, int64_t N, cudaStream_t st) {
+  p.HG = pick_hg(p.H, DH);
+  const int TP = p.HG * DH + 4;
+  size_t smem = ((size_t)4 * p.seq.S * TP + 3 * (size_t)p.HG * p.seq.S + p.seq.S) * sizeof(float);
   LK_REQUIRE(smem <= 227 * 1024, LK_ERR_SHAPE, "lk_mha_bwd: tiles (%zu B) do not fit shared memory", smem);
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(mha_bwd_seq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
-  mha_bwd_seq_kernel<DH><<<(unsigned)N, threads, smem, st>>>(p);
+  if (!attr) {
+    cudaFuncSetAttribute(mha_bwd_seq_kernel<DH, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(mha_bwd_seq_kernel<DH, R>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr = true;
+  }
+  dim3 grid((unsigned)N, (unsigned)(p.H / p.HG));
+  mha_bwd_seq_kernel<DH, R><<<grid, pick_threads(p.seq.S, p.HG, R), smem, st>>>(p);
   return check_launch("mha_bwd");
 }
 
-static int pick_threads(int64_t S, int64_t H) {
-  int64_t t = (S * H + 31) / 32 * 32;
-  return (int)(t < 64 ? 64 : (t > 416 ? 416 : t));
+static void set_dropout(MhaParams& p, float drop_p, uint64_t seed) {
+  p.drop_p = drop_p;
+  p.seed = (unsigned long long)seed;
+  double t = (double)drop_p * 16777216.0;
+  p.drop_thr = t <= 0.0 ? 0u : (t >= 16777216.0 ? 16777216u : (uint32_t)t);
 }
 
 }  // namespace lk
@@ -280,35 +483,47 @@ using namespace lk;
 
 extern "C" {
 
-int lk_mha_fwd(const float* qkv, const int64_t* mask, const int32_t* cu, float* ctx, float* lse, int64_t N, int64_t S, int64_t D,
-               int64_t H, float drop_p, uint64_t seed, cudaStream_t st) {
+int lk_mha_fwd(const float* qkv, const int64_t* mask, const int32_t* cu, float* ctx, void* ctx_hi, void* ctx_lo, float* lse, int64_t N,
+               int64_t S, int64_t D, int64_t H, float drop_p, uint64_t seed, cudaStream_t st) {
   LK_REQUIRE(H > 0 && D % H == 0 && D % 4 == 0, LK_ERR_SHAPE, "lk_mha_fwd: D=%ld not divisible by heads=%ld", (long)D, (long)H);
+  LK_REQUIRE(ctx || ctx_hi, LK_ERR_ARG, "lk_mha_fwd: no output requested");
+  LK_REQUIRE(!ctx_hi || ctx_lo, LK_ERR_ARG, "lk_mha_fwd: both output planes are needed");
   if (N == 0 || S == 0) return LK_OK;
   const int dh = (int)(D / H);
-  MhaParams p{qkv, ctx, lse, nullptr, nullptr, {cu, mask, (int)S}, (int)D, (int)H, 1.0f / sqrtf((float)dh), drop_p, (unsigned long long)seed};
-  const int threads = pick_threads(S, H);
+  MhaParams p{};
+  p.qkv = qkv; p.ctx = ctx; p.ctx_hi = (__nv_bfloat16*)ctx_hi; p.ctx_lo = (__nv_bfloat16*)ctx_lo; p.lse = lse;
+  p.seq = SeqView{cu, mask, (int)S};
+  p.D = (int)D; p.H = (int)H; p.scale = 1.0f / sqrtf((float)dh);
+  set_dropout(p, drop_p, seed);
   switch (dh) {
-    case 8: return launch_fwd<8>(p, N, threads, st);
-    case 16: return launch_fwd<16>(p, N, threads, st);
-    case 32: return launch_fwd<32>(p, N, threads, st);
-    case 64: return launch_fwd<64>(p, N, threads, st);
+    case 8: return launch_fwd<8, 2>(p, N, st);
+    case 16: return launch_fwd<16, 2>(p, N, st);
+    case 32: return launch_fwd<32, 2>(p, N, st);
+    case 64: return launch_fwd<64, 4>(p, N, st);
   }
   LK_REQUIRE(false, LK_ERR_SHAPE, "lk_mha_fwd: head dim %d not in {8,16,32,64}", dh);
 }
 
-int lk_mha_bwd(const float* qkv, const int64_t* mask, const int32_t* cu, const float* lse, const float* dctx, float* dqkv, int64_t N,
-               int64_t S, int64_t D, int64_t H, float drop_p, uint64_t seed, cudaStream_t st) {
+int lk_mha_bwd(const float* qkv, const int64_t* mask, const int32_t* cu, const float* ctx, const float* lse, const float* dctx,
+               float* dqkv, void* dq_hi, void* dq_lo, float* colsum_part, int64_t N, int64_t S, int64_t D, int64_t H, float drop_p,
+               uint64_t seed, cudaStream_t st) {
   LK_REQUIRE(H > 0 && D % H == 0 && D % 4 == 0, LK_ERR_SHAPE, "lk_mha_bwd: D=%ld not divisible by heads=%ld", (long)D, (long)H);
+  LK_REQUIRE(dqkv || dq_hi, LK_ERR_ARG, "lk_mha_bwd: no output requested");
+  LK_REQUIRE(!dq_hi || dq_lo, LK_ERR_ARG, "lk_mha_bwd: both output planes are needed");
+  LK_REQUIRE(ctx && lse && dctx, LK_ERR_ARG, "lk_mha_bwd: the forward's ctx and lse are needed (D_i = dO·O)");
   if (N == 0 || S == 0) return LK_OK;
   const int dh = (int)(D / H);
-  MhaParams p{qkv, nullptr, const_cast<float*>(lse), dctx, dqkv, {cu, mask, (int)S}, (int)D, (int)H, 1.0f / sqrtf((float)dh), drop_p,
-              (unsigned long long)seed};
-  const int threads = pick_threads(S, H);
+  MhaParams p{};
+  p.qkv = qkv; p.ctx = const_cast<float*>(ctx); p.lse = const_cast<float*>(lse); p.dctx = dctx; p.dqkv = dqkv;
+  p.dq_hi = (__nv_bfloat16*)dq_hi; p.dq_lo = (__nv_bfloat16*)dq_lo; p.colsum_part = colsum_part;
+  p.seq = SeqView{cu, mask, (int)S};
+  p.D = (int)D; p.H = (int)H; p.scale = 1.0f / sqrtf((float)dh);
+  set_dropout(p, drop_p, seed);
   switch (dh) {
-    case 8: return launch_bwd<8>(p, N, threads, st);
-    case 16: return launch_bwd<16>(p, N, threads, st);
-    case 32: return launch_bwd<32>(p, N, threads, st);
-    case 64: return launch_bwd<64>(p, N, threads, st);
+    case 8: return launch_bwd<8, 2>(p, N, st);
+    case 16: return launch_bwd<16, 2>(p, N, st);
+    case 32: return launch_bwd<32, 2>(p, N, st);
+    case 64: return launch_bwd<64, 4>(p, N, st);
   }
   LK_REQUIRE(false, LK_ERR_SHAPE, "lk_mha_bwd: head dim %d not in {8,16,32,64}", dh);
 }

@@ -73,18 +73,13 @@ static PlaneBuf split(Ctx& c, const float* X, int64_t rows, int64_t cols, float*
   STEP(lk_split_bf16(X, rows, cols, cols, p.hi, p.lo, p.ld, 0, colsum, c.ws, c.ws_bytes, c.st));
   return p;
 }
-static PlaneBuf split_t(Ctx& c, const float* X, int64_t rows, int64_t cols) {   // planes of X^T: [cols, rows]
-  PlaneBuf p = alloc_planes(c, cols, rows);
-  STEP(lk_split_bf16(X, rows, cols, cols, p.hi, p.lo, p.ld, 1, nullptr, nullptr, 0, c.st));
-  return p;
-}
-// Y[M,N] = epilogue(A[M,K] · B[N,K]^T)
-static void gemm_nt(Ctx& c, const PlaneBuf& A, const PlaneBuf& B, float* Y, int64_t M, int64_t N, int64_t K, const float* bias,
-                    const int64_t* rowmask, int act, float drop_p, uint64_t seed, int accumulate) {
+// General fused contraction: Y = epilogue(A · op(B)).  b_mn = 0: B stored [N,K] (forward); b_mn = 1: B stored [K,N] — the SAME planes of a
+// weight W [out,in] serve Y = X·Wᵀ (b_mn = 0, N = out) and dX = dY·W (b_mn = 1, K = out, N = in), so no transposed copies exist.
+static void gemm(Ctx& c, const char* what, const PlaneBuf& A, const PlaneBuf& B, int b_mn, float* Y, int64_t M, int64_t N, int64_t K,
+                 const lk_gemm_epilogue& ep) {
   char label[40];
-  snprintf(label, sizeof(label), "gemm_nt %ldx%ldx%ld", (long)M, (long)N, (long)K);
-  STEP_L(label, lk_tc_gemm(A.hi, A.lo, A.ld, 0, B.hi, B.lo, B.ld, 0, Y, N, M, N, K, bias, rowmask, act, drop_p, seed, accumulate, c.ws,
-                           c.ws_bytes, c.st), 2.0 * M * N * K);
+  snprintf(label, sizeof(label), "gemm_%s %ldx%ldx%ld", what, (long)M, (long)N, (long)K);
+  STEP_L(label, lk_tc_gemm_ex(A.hi, A.lo, A.ld, 0, B.hi, B.lo, B.ld, b_mn, Y, N, M, N, K, &ep, c.ws, c.ws_bytes, c.st), 2.0 * M * N * K);
 }
 // dW[N,K] = dY[T,N]^T · X[T,K]
 static void gemm_wgrad(Ctx& c, const PlaneBuf& dY, const PlaneBuf& X, float* dW, int64_t T, int64_t N, int64_t K) {
@@ -93,47 +88,55 @@ static void gemm_wgrad(Ctx& c, const PlaneBuf& dY, const PlaneBuf& X, float* dW,
   STEP_L(label, lk_tc_gemm(dY.hi, dY.lo, dY.ld, 1, X.hi, X.lo, X.ld, 1, dW, K, N, K, T, nullptr, nullptr, 0, 0.f, 0, 0, c.ws, c.ws_bytes,
                            c.st), 2.0 * T * N * K);
 }
+static lk_gemm_epilogue ep_planes(const PlaneBuf& out, const float* bias = nullptr, float* colsum = nullptr) {
+  lk_gemm_epilogue ep = {};
+  ep.bias = bias; ep.out_hi = out.hi; ep.out_lo = out.lo; ep.ld_planes = out.ld; ep.colsum = colsum;
+  return ep;
+}
 
 struct EncWeights {   // one AttentionOperator
   const float *in_w, *in_b, *out_w, *out_b, *lin_w, *lin_b, *w1, *b1, *w2;
   float *g_in_w, *g_in_b, *g_out_w, *g_out_b, *g_lin_w, *g_lin_b, *g_w1, *g_b1, *g_w2;
 };
-struct EncPlanes { PlaneBuf in_w, in_wT, out_w, out_wT, lin_w, lin_wT, w1, w1T; };
+struct EncPlanes { PlaneBuf in_w, out_w, lin_w, w1; };
 struct EncSaved {
   PlaneBuf xp, ctxp, outp, linp;
-  float *qkv, *lse, *lin, *hid, *alpha, *rep;
+  float *qkv, *ctx, *lse, *lin, *hid, *alpha, *rep;
   const int32_t* cu;
   int64_t T, N, S;
   uint64_t seed;
 };
 
-static EncPlanes weight_planes(Ctx& c, const EncWeights& w, int64_t D, int64_t A, bool need_in_wT) {
+static EncPlanes weight_planes(Ctx& c, const EncWeights& w, int64_t D, int64_t A) {
   EncPlanes p;
   p.in_w = split(c, w.in_w, 3 * D, D);
-  if (need_in_wT) p.in_wT = split_t(c, w.in_w, 3 * D, D);
-  p.out_w = split(c, w.out_w, D, D);  p.out_wT = split_t(c, w.out_w, D, D);
-  p.lin_w = split(c, w.lin_w, D, D);  p.lin_wT = split_t(c, w.lin_w, D, D);
-  p.w1 = split(c, w.w1, A, D);        p.w1T = split_t(c, w.w1, A, D);
+  p.out_w = split(c, w.out_w, D, D);
+  p.lin_w = split(c, w.lin_w, D, D);
+  p.w1 = split(c, w.w1, A, D);
   return p;
 }
 
-// attention_operator.py:46-59 over packed rows: xp = planes of the input rows [T,D]
+// attention_operator.py:46-59 over packed rows: s.xp = planes of the input rows [T,D].  Tensors that only feed the next
+// contraction (ctx, out) leave their producer as split-bf16 planes; fp32 copies exist only where a SIMT kernel reads them.
 static void enc_fwd(Ctx& c, EncSaved& s, const EncWeights& w, const EncPlanes& wp, int64_t D, int64_t H, int64_t A, float drop_attn) {
   const int64_t T = s.T, N = s.N;
   s.qkv = c.a.f32(T * 3 * D);
-  gemm_nt(c, s.xp, wp.in_w, s.qkv, T, 3 * D, D, w.in_b, nullptr, 0, 0.f, 0, 0);
-  float* ctx = c.a.f32(T * D);
+  lk_gemm_epilogue ep = {};
+  ep.bias = w.in_b;
+  gemm(c, "qkv", s.xp, wp.in_w, 0, s.qkv, T, 3 * D, D, ep);
+  s.ctx = c.a.f32(T * D);                      // fp32 ctx is kept for the backward's D_i = dO·O
+  s.ctxp = alloc_planes(c, T, D);
   s.lse = c.a.f32(T * H);
-  STEP(lk_mha_fwd(s.qkv, nullptr, s.cu, ctx, s.lse, N, s.S, D, H, drop_attn, s.seed, c.st));
-  s.ctxp = split(c, ctx, T, D);
-  float* out = c.a.f32(T * D);
-  gemm_nt(c, s.ctxp, wp.out_w, out, T, D, D, w.out_b, nullptr, 0, 0.f, 0, 0);
-  s.outp = split(c, out, T, D);
+  STEP(lk_mha_fwd(s.qkv, nullptr, s.cu, s.ctx, s.ctxp.hi, s.ctxp.lo, s.lse, N, s.S, D, H, drop_attn, s.seed, c.st));
+  s.outp = alloc_planes(c, T, D);
+  gemm(c, "out", s.ctxp, wp.out_w, 0, nullptr, T, D, D, ep_planes(s.outp, w.out_b));
   s.lin = c.a.f32(T * D);
-  gemm_nt(c, s.outp, wp.lin_w, s.lin, T, D, D, w.lin_b, nullptr, 0, 0.f, 0, 0);
-  s.linp = split(c, s.lin, T, D);
+  s.linp = alloc_planes(c, T, D);
+  gemm(c, "lin", s.outp, wp.lin_w, 0, s.lin, T, D, D, ep_planes(s.linp, w.lin_b));
   s.hid = c.a.f32(T * A);
-  gemm_nt(c, s.linp, wp.w1, s.hid, T, A, D, w.b1, nullptr, 1 /*tanh*/, 0.f, 0, 0);
+  ep = {};
+  ep.bias = w.b1; ep.act = 1 /*tanh*/;
+  gemm(c, "w1", s.linp, wp.w1, 0, s.hid, T, A, D, ep);
   s.alpha = c.a.f32(T);
   s.rep = c.a.f32(N * D);
   STEP(lk_additive_pool_fwd(s.lin, s.hid, w.w2, nullptr, s.cu, s.rep, s.alpha, N, s.S, D, A, c.st));
@@ -151,21 +154,24 @@ static void enc_bwd(Ctx& c, const EncSaved& s, const EncWeights& w, const EncPla
   STEP(lk_colsum(dw2p, w.g_w2, N, A, 0, c.ws, c.ws_bytes, c.st));
   PlaneBuf dprep = split(c, dpre, T, A, w.g_b1);
   gemm_wgrad(c, dprep, s.linp, w.g_w1, T, A, D);
-  gemm_nt(c, dprep, wp.w1T, dlin, T, D, A, nullptr, nullptr, 0, 0.f, 0, 1 /*accumulate onto alpha*drep*/);
-  PlaneBuf dlinp = split(c, dlin, T, D, w.g_lin_b);
+  // dlin = alpha*drep (already in dlin) + dpre·W1 -> only its planes and column sums are needed downstream
+  PlaneBuf dlinp = alloc_planes(c, T, D);
+  lk_gemm_epilogue ep = ep_planes(dlinp, nullptr, w.g_lin_b);
+  ep.accumulate = 1; ep.store_c_off = 1;
+  gemm(c, "dlin", dprep, wp.w1, 1, dlin, T, D, A, ep);
   gemm_wgrad(c, dlinp, s.outp, w.g_lin_w, T, D, D);
-  float* dout = dpre;   // reuse [T,A>=?]: only when A >= D; otherwise take fresh
-  if (A < D) dout = c.a.f32(T * D);
-  gemm_nt(c, dlinp, wp.lin_wT, dout, T, D, D, nullptr, nullptr, 0, 0.f, 0, 0);
-  PlaneBuf doutp = split(c, dout, T, D, w.g_out_b);
+  PlaneBuf doutp = alloc_planes(c, T, D);
+  gemm(c, "dout", dlinp, wp.lin_w, 1, nullptr, T, D, D, ep_planes(doutp, nullptr, w.g_out_b));
   gemm_wgrad(c, doutp, s.ctxp, w.g_out_w, T, D, D);
-  float* dctx = dlin;   // dlin is dead after its split
-  gemm_nt(c, doutp, wp.out_wT, dctx, T, D, D, nullptr, nullptr, 0, 0.f, 0, 0);
-  float* dqkv = c.a.f32(T * 3 * D);
-  STEP(lk_mha_bwd(s.qkv, nullptr, s.cu, s.lse, dctx, dqkv, N, s.S, D, H, drop_attn, s.seed, c.st));
-  PlaneBuf dqkvp = split(c, dqkv, T, 3 * D, w.g_in_b);
+  float* dctx = dlin;   // dlin is dead once its planes exist
+  ep = {};
+  gemm(c, "dctx", doutp, wp.out_w, 1, dctx, T, D, D, ep);
+  PlaneBuf dqkvp = alloc_planes(c, T, 3 * D);
+  float* binp = c.a.f32(N * 3 * D);            // per-sequence column sums of dqkv
+  STEP(lk_mha_bwd(s.qkv, nullptr, s.cu, s.ctx, s.lse, dctx, nullptr, dqkvp.hi, dqkvp.lo, binp, N, s.S, D, H, drop_attn, s.seed, c.st));
+  STEP(lk_colsum(binp, w.g_in_b, N, 3 * D, 0, c.ws, c.ws_bytes, c.st));
   gemm_wgrad(c, dqkvp, s.xp, w.g_in_w, T, 3 * D, D);
-  if (dX) gemm_nt(c, dqkvp, wp.in_wT, dX, T, D, 3 * D, nullptr, nullptr, 0, 0.f, 0, 0);
+  if (dX) gemm(c, "dx", dqkvp, wp.in_w, 1, dX, T, D, 3 * D, ep);
   c.a.off = mark;   // all temporaries of this backward are dead (stream order keeps reuse safe)
 }
 
@@ -187,6 +193,9 @@ static size_t scratch_bytes(int64_t T, int64_t N, int64_t D, int64_t A, int64_t 
   up(lk_scatter_add_workspace_bytes(T, 24, D));   // the small-table path's block partials grow with V (category / special tables)
   up(lk_split_bf16_workspace_bytes(T, 3 * D));
   up(lk_colsum_workspace_bytes(N, A));
+  up(lk_colsum_workspace_bytes(N, 3 * D));
+  up(lk_tc_gemm_workspace_bytes(T, 3 * D, D));     // column-sum partials of the fused epilogues
+  up(lk_tc_gemm_workspace_bytes(T, D, 3 * D));
   return m + (1 << 20);
 }
 
@@ -211,24 +220,26 @@ static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const 
   const uint64_t s_embed = seed * 4 + 0, s_item = seed * 4 + 1, s_user = seed * 4 + 2;
 
   // ---- weights -> split-bf16 planes (parameters change every step) ------------------------------------------------
-  EncPlanes pi = weight_planes(c, wi, D, A, true);
-  EncPlanes pu = weight_planes(c, wu, D, A, true);
+  EncPlanes pi = weight_planes(c, wi, D, A);
+  EncPlanes pu = weight_planes(c, wu, D, A);
   PlaneBuf pg = split(c, P(0), D, E);
 
   // ---- embedding stage (concat_inputer.py:92-114 + embedding_hub.py:95-96) -------------------------------------------
-  int64_t* valid = (int64_t*)c.a.take((size_t)T * 8);
-  STEP(lk_valid_mask(title_ids, valid, T, st));
+  // x[t] = valid(title)·dropout(W·glove[title] + b) + category[cat] + special[sp]  — one contraction whose epilogue applies the row
+  // mask (title id > -1), adds the two small-table rows and writes x directly as the item encoder's operand planes
   PlaneBuf gp = alloc_planes(c, T, E);
   STEP(lk_gather_split_bf16(title_ids, glove_table, gp.hi, gp.lo, T, E, gp.ld, st));
-  float* x = c.a.f32(T * D);
-  gemm_nt(c, gp, pg, x, T, D, E, P(1), valid, 0, drop_embed, s_embed, 0);
-  STEP(lk_gather_rows(cat_ids, nullptr, P(2), x, T, D, 1, st));
-  STEP(lk_gather_rows(special_ids, nullptr, P(3), x, T, D, 1, st));
 
   // ---- item encoder over all packed items, user encoder over the packed history encodings ---------------------------------
   EncSaved si;
   si.T = T; si.N = n_items; si.S = S_max; si.cu = cu_items; si.seed = s_item;
-  si.xp = split(c, x, T, D);
+  si.xp = alloc_planes(c, T, D);
+  {
+    lk_gemm_epilogue ep = ep_planes(si.xp, P(1));
+    ep.rowmask = title_ids; ep.rowmask_is_ids = 1; ep.drop_p = drop_embed; ep.seed = s_embed;
+    ep.add_ids0 = cat_ids; ep.add_tab0 = P(2); ep.add_ids1 = special_ids; ep.add_tab1 = P(3);
+    gemm(c, "embed", gp, pg, 0, nullptr, T, D, E, ep);
+  }
   enc_fwd(c, si, wi, pi, D, heads, A, drop_attn);
 
   const int64_t Tu = n_items - B * C;
@@ -256,6 +267,8 @@ static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const 
   // embedding tables: sorted segmented scatter-add; GloVe projection: dP = dx * dropout * valid
   STEP(lk_scatter_add_sorted(cat_ids, nullptr, dx, nullptr, 1, G(2), T, n_cats, D, 0, c.ws, c.ws_bytes, st));
   STEP(lk_scatter_add_sorted(special_ids, nullptr, dx, nullptr, 1, G(3), T, n_special, D, 0, c.ws, c.ws_bytes, st));
+  int64_t* valid = (int64_t*)c.a.take((size_t)T * 8);
+  STEP(lk_valid_mask(title_ids, valid, T, st));
   STEP(lk_act_bwd(dx, nullptr, valid, dx, T, D, 0, drop_embed, s_embed, st));
   PlaneBuf dpp = split(c, dx, T, D, G(1));
   gemm_wgrad(c, dpp, gp, G(0), T, D, E);

@@ -5,6 +5,7 @@ no torch math runs on the hot path.  Each op cites the reference call site it re
 """
 from __future__ import annotations
 
+import ctypes
 import os
 import weakref
 
@@ -103,6 +104,48 @@ def tc_gemm(A: Planes, B: Planes, mn_major: bool, GM, GN, GK, out=None, bias=Non
     call('lk_tc_gemm', ptr(A.hi), ptr(A.lo), A.ld, int(mn_major), ptr(B.hi), ptr(B.lo), B.ld, int(mn_major), ptr(y), y.stride(0),
          GM, GN, GK, ptr(bias), ptr(rowmask), act, float(drop_p), int(seed), int(accumulate), ptr(ws), ws.numel())
     return y
+
+
+class GemmEpilogue(ctypes.Structure):
+    """struct lk_gemm_epilogue (include/legommenders_b200.h)"""
+    _fields_ = [('bias', ctypes.c_void_p), ('rowmask', ctypes.c_void_p), ('rowmask_is_ids', ctypes.c_int), ('act', ctypes.c_int),
+                ('drop_p', ctypes.c_float), ('seed', ctypes.c_uint64), ('accumulate', ctypes.c_int), ('store_c_off', ctypes.c_int),
+                ('add_ids0', ctypes.c_void_p), ('add_tab0', ctypes.c_void_p), ('add_ids1', ctypes.c_void_p), ('add_tab1', ctypes.c_void_p),
+                ('out_hi', ctypes.c_void_p), ('out_lo', ctypes.c_void_p), ('ld_planes', ctypes.c_int64), ('colsum', ctypes.c_void_p)]
+
+
+def tc_gemm_ex(A: Planes, B: Planes, GM, GN, GK, b_mn=False, a_mn=False, out=None, store_c=True, bias=None, rowmask=None,
+               rowmask_is_ids=False, act=0, drop_p=0.0, seed=0, accumulate=False, add0=None, add1=None, want_planes=False,
+               want_colsum=False):
+    """lk_tc_gemm_ex: the contraction with its fused epilogue (row addends from small tables, split-bf16 plane output, column
+    sums).  add0/add1 = (ids int64 [GM], table fp32 [*, GN]).  Returns (C or None, Planes or None, colsum or None)."""
+    dev = A.hi.device
+    y = out
+    if y is None and store_c:
+        y = torch.empty((GM, GN), dtype=torch.float32, device=dev)
+    ep = GemmEpilogue()
+    keep = [bias, rowmask, add0, add1]
+    ep.bias, ep.rowmask, ep.rowmask_is_ids, ep.act = ptr(bias), ptr(rowmask), int(rowmask_is_ids), act
+    ep.drop_p, ep.seed, ep.accumulate, ep.store_c_off = float(drop_p), int(seed), int(accumulate), int(not store_c)
+    if add0 is not None:
+        ep.add_ids0, ep.add_tab0 = ptr(add0[0]), ptr(add0[1])
+    if add1 is not None:
+        ep.add_ids1, ep.add_tab1 = ptr(add1[0]), ptr(add1[1])
+    planes = cs = None
+    if want_planes:
+        ld = (GN + 7) // 8 * 8
+        buf = torch.zeros((2, GM, ld), dtype=torch.bfloat16, device=dev)
+        planes = Planes(buf[0], buf[1], GM, GN, ld)
+        ep.out_hi, ep.out_lo, ep.ld_planes = ptr(buf[0]), ptr(buf[1]), ld
+    if want_colsum:
+        cs = torch.empty((GN,), dtype=torch.float32, device=dev)
+        ep.colsum = ptr(cs)
+    nbytes = query('lk_tc_gemm_workspace_bytes', GM, GN, GK)
+    ws = workspace(nbytes, dev, 'tc')
+    call('lk_tc_gemm_ex', ptr(A.hi), ptr(A.lo), A.ld, int(a_mn), ptr(B.hi), ptr(B.lo), B.ld, int(b_mn), ptr(y),
+         y.stride(0) if y is not None else GN, GM, GN, GK, ctypes.addressof(ep), ptr(ws), ws.numel())
+    del keep
+    return y, planes, cs
 
 
 def linear_fwd_raw(x2, w, b, rowmask, act, out=None, accumulate=False, drop_p=0.0, seed=0, xp=None):
@@ -323,17 +366,18 @@ class _MHACore(Function):
             N, S, rows = cu.numel() - 1, int(max_len), qkv.shape[0]
         out = torch.empty((*qkv.shape[:-1], D), dtype=torch.float32, device=qkv.device)
         lse = torch.empty((rows, heads), dtype=torch.float32, device=qkv.device)
-        call('lk_mha_fwd', ptr(qkv), ptr(mask), ptr(cu), ptr(out), ptr(lse), N, S, D, heads, float(drop_p), int(seed))
-        ctx.save_for_backward(qkv, mask, cu, lse)
+        call('lk_mha_fwd', ptr(qkv), ptr(mask), ptr(cu), ptr(out), None, None, ptr(lse), N, S, D, heads, float(drop_p), int(seed))
+        ctx.save_for_backward(qkv, mask, cu, lse, out)
         ctx.dims = (N, S, D, heads, drop_p, seed)
         return out
 
     @staticmethod
     def backward(ctx, dctx):
-        qkv, mask, cu, lse = ctx.saved_tensors
+        qkv, mask, cu, lse, out = ctx.saved_tensors
         N, S, D, heads, drop_p, seed = ctx.dims
         dqkv = torch.empty_like(qkv)
-        call('lk_mha_bwd', ptr(qkv), ptr(mask), ptr(cu), ptr(lse), ptr(_f32(dctx)), ptr(dqkv), N, S, D, heads, float(drop_p), int(seed))
+        call('lk_mha_bwd', ptr(qkv), ptr(mask), ptr(cu), ptr(out), ptr(lse), ptr(_f32(dctx)), ptr(dqkv), None, None, None, N, S, D, heads,
+             float(drop_p), int(seed))
         return dqkv, None, None, None, None, None, None
 
 

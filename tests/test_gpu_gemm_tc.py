@@ -79,3 +79,48 @@ def test_tc_gemm_mn_major_weight_gradient(ops, T, N, K):
     assert rel(dw, ref) <= 3e-5
     dw2 = ops.tc_gemm(dyp, xp, True, N, K, T)
     assert torch.equal(dw, dw2)
+
+
+@pytest.mark.parametrize('M,N,K', [(700, 256, 300), (40000, 256, 256), (130, 768, 256)])
+def test_tc_gemm_fused_producer_epilogue(ops, M, N, K):
+    """lk_tc_gemm_ex: row mask from token ids, small-table row addends, plane output without an fp32 store, column sums,
+    accumulate-without-store — the fusions the native NRMS step relies on."""
+    g = torch.Generator().manual_seed(M + N)
+    a, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / 16
+    bias = torch.randn(N, generator=g)
+    tok = torch.randint(-1, 50, (M,), generator=g)                       # -1 = not a title token
+    tab0, tab1 = torch.randn(18, N, generator=g), torch.randn(3, N, generator=g)
+    id0 = torch.where(torch.rand(M, generator=g) < 0.1, torch.randint(0, 18, (M,), generator=g), torch.full((M,), -1))
+    id1 = torch.where(torch.rand(M, generator=g) < 0.2, torch.randint(0, 3, (M,), generator=g), torch.full((M,), -1))
+    ap, bp = ops.split_planes(a.cuda()), ops.split_planes(b.cuda())
+    ref = (a.double() @ b.double().t() + bias.double()) * (tok > -1).double().unsqueeze(-1)
+    ref = ref + torch.where((id0 > -1).unsqueeze(-1), tab0.double()[id0.clamp(min=0)], torch.zeros((), dtype=torch.float64))
+    ref = ref + torch.where((id1 > -1).unsqueeze(-1), tab1.double()[id1.clamp(min=0)], torch.zeros((), dtype=torch.float64))
+    y, planes, cs = ops.tc_gemm_ex(ap, bp, M, N, K, bias=bias.cuda(), rowmask=tok.cuda(), rowmask_is_ids=True,
+                                   add0=(id0.cuda(), tab0.cuda()), add1=(id1.cuda(), tab1.cuda()), want_planes=True, want_colsum=True)
+    assert rel(y, ref) <= 3e-5
+    assert torch.equal(planes.hi.float().cpu()[:, :N], y.cpu().bfloat16().float())          # planes are the split of what was stored
+    assert torch.equal(planes.lo.float().cpu()[:, :N], (y.cpu() - y.cpu().bfloat16().float()).bfloat16().float())
+    assert (cs.double().cpu() - y.double().cpu().sum(0)).abs().max().item() <= 2e-5 * max(1.0, y.abs().sum(0).max().item())
+    # planes only (no fp32 result at all), and accumulate onto C without storing C
+    y2, planes2, _ = ops.tc_gemm_ex(ap, bp, M, N, K, bias=bias.cuda(), store_c=False, want_planes=True)
+    assert y2 is None
+    full = a.double() @ b.double().t() + bias.double()
+    assert rel(planes2.hi.float()[:, :N] + planes2.lo.float()[:, :N], full) <= 3e-5
+    base = torch.randn(M, N, generator=g)
+    c = base.clone().cuda()
+    _, planes3, cs3 = ops.tc_gemm_ex(ap, bp, M, N, K, out=c, store_c=False, accumulate=True, want_planes=True, want_colsum=True)
+    assert torch.equal(c.cpu(), base)                                                        # C untouched
+    tot = base.double() + a.double() @ b.double().t()
+    assert rel(planes3.hi.float()[:, :N] + planes3.lo.float()[:, :N], tot) <= 3e-5
+    assert (cs3.double().cpu() - tot.sum(0)).abs().max().item() <= 3e-5 * max(1.0, tot.abs().sum(0).max().item())
+
+
+@pytest.mark.parametrize('M,N,K', [(300, 256, 256), (40000, 256, 768), (5000, 300, 256), (129, 64, 32)])
+def test_tc_gemm_input_gradient_with_untransposed_weight(ops, M, N, K):
+    """dX[M,N] = dY[M,K] · W[K,N] with W's own (row-major [K,N]) planes as an MN-major B operand: no transposed weight copies."""
+    g = torch.Generator().manual_seed(M + K)
+    dy = torch.randn(M, K, generator=g)
+    w = torch.randn(K, N, generator=g) / K ** 0.5
+    y, _, _ = ops.tc_gemm_ex(ops.split_planes(dy.cuda()), ops.split_planes(w.cuda()), M, N, K, b_mn=True)
+    assert rel(y, dy.double() @ w.double()) <= 3e-5

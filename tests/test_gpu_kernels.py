@@ -183,7 +183,8 @@ def test_conv1d_relu_mask(ops, N_, S, Cin, Cout):
 
 
 # ------------------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize('N_,S,D,H', [(11, 33, 256, 8), (4, 50, 256, 8), (7, 12, 64, 8), (3, 70, 64, 2), (2, 1, 32, 4)])
+@pytest.mark.parametrize('N_,S,D,H', [(11, 33, 256, 8), (4, 50, 256, 8), (7, 12, 64, 8), (3, 70, 64, 2), (2, 1, 32, 4), (3, 100, 256, 8),
+                                       (5, 9, 128, 2), (4, 31, 64, 4)])
 def test_mha_core(ops, N_, S, D, H):
     g = torch.Generator().manual_seed(S + D)
     x = torch.randn(N_, S, D, generator=g)
@@ -397,6 +398,48 @@ def test_dropout_statistics_and_backward(ops):
     assert rel(xg.grad, ref) <= 1e-5
     y2 = ops.linear(xg.detach(), wg.detach(), None, drop_p=p, seed=99).cpu()
     assert not torch.equal(y2 != 0, kept)                          # a different seed gives a different mask
+
+
+def test_attention_dropout_mask_is_shared_by_forward_and_backward(ops):
+    """q = 0 makes every probability 1/L, v_j = e_j exposes the dropout mask in ctx; the backward (phase A: dQ through dP and
+    D_i, phase B: dV) must use exactly that mask."""
+    N_, S, D, H, p = 6, 24, 256, 8, 0.25
+    dh = D // H
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.zeros(N_, S, 3 * D)
+    k = torch.randn(N_, S, D, generator=g)
+    qkv[..., D:2 * D] = k
+    v = torch.zeros(N_, S, H, dh)
+    for j in range(S):
+        v[:, j, :, j] = 1.0
+    qkv[..., 2 * D:] = v.reshape(N_, S, D)
+    mask = torch.ones(N_, S, dtype=torch.int64)
+    dctx = torch.randn(N_, S, D, generator=g)
+    x = dev(qkv).requires_grad_(True)
+    c = ops.mha_core(x, dev(mask), H, drop_p=p, seed=77)
+    c.backward(dev(dctx))
+    cc = c.detach().cpu().view(N_, S, H, dh)[..., :S]                  # [n, i, h, j] = keep_ij / ((1-p) L)
+    keep = cc.permute(0, 2, 1, 3) * S                                  # [n, h, i, j] in {0, 1/(1-p)}
+    kept = keep != 0
+    assert abs(kept.float().mean().item() - (1 - p)) < 0.02
+    assert torch.allclose(keep[kept], torch.full_like(keep[kept], 1 / (1 - p)), rtol=1e-5)
+    P = torch.full((N_, H, S, S), 1.0 / S, dtype=torch.float64)
+    Pd = P * keep.double()
+    dO = dctx.double().view(N_, S, H, dh).permute(0, 2, 1, 3)          # [n,h,i,d]
+    V = v.double().permute(0, 2, 1, 3)                                 # [n,h,j,d]
+    K = k.double().view(N_, S, H, dh).permute(0, 2, 1, 3)
+    dV = Pd.transpose(-1, -2) @ dO
+    dPd = (dO @ V.transpose(-1, -2)) * keep.double()
+    Di = (Pd * (dO @ V.transpose(-1, -2))).sum(-1, keepdim=True)
+    dS = P * (dPd - Di)
+    dQ = (dS @ K) * dh ** -0.5
+    gq = x.grad.cpu().double()
+    got_dq = gq[..., :D].view(N_, S, H, dh).permute(0, 2, 1, 3)
+    got_dv = gq[..., 2 * D:].view(N_, S, H, dh).permute(0, 2, 1, 3)
+    assert rel(got_dv, dV) <= 1e-5
+    assert rel(got_dq, dQ) <= 1e-5
+    c2 = ops.mha_core(x.detach(), dev(mask), H, drop_p=p, seed=78).cpu()
+    assert not torch.equal(c2 != 0, c.detach().cpu() != 0)              # another seed, another mask
 
 
 def test_error_reporting(ops):
