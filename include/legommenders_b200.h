@@ -55,6 +55,14 @@ int lk_scatter_add_sorted(const int64_t* ids, const int64_t* mask, const float* 
                           float* dtable, int64_t P, int64_t V, int64_t E, int accumulate, void* workspace,
                           size_t workspace_bytes, cudaStream_t stream);
 
+/* backward of the whole ConcatInputer embedding stage (concat_inputer.py:105-113 + embedding_hub.py:95-96) in one pass over
+ * dx [T,D]:  dP = dx·dropout(seed)·(title id > -1) as split-bf16 planes [T, ld] (operand of the projection weight gradient),
+ * g_bias [D] = column sums of dP, g_cat [n_cats, D] / g_special [n_special, D] = per-id sums of dx.  Deterministic. */
+size_t lk_concat_embed_bwd_workspace_bytes(int64_t T, int64_t D, int64_t n_cats, int64_t n_special);
+int lk_concat_embed_bwd(const float* dx, const int64_t* title_ids, const int64_t* cat_ids, const int64_t* special_ids, int64_t T,
+                        int64_t D, int64_t n_cats, int64_t n_special, float drop_p, uint64_t seed, void* dp_hi, void* dp_lo, int64_t ld,
+                        float* g_bias, float* g_cat, float* g_special, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 /* ---- dense contractions — nn.Linear (loader/embedding_hub.py:95-96, model/operators/attention_operator.py:56,
  *      cnn_operator.py:62, model/common/attention.py:17-19), MHA in/out projections (attention_operator.py:32-37)
  *      act: 0 none, 1 tanh, 2 relu; rowmask (nullable) zeroes rows with mask<=0 after the activation */
@@ -189,7 +197,8 @@ int lk_group_metrics(const float* scores, const int64_t* labels, const int64_t* 
 /* ---- native training-step driver: the whole Legommender.forward + backward of the NRMS configuration
  *      (model/legommender.py:219-263 with config/model/nrms.yaml) over packed rows in ONE call; see csrc/lk_nrms_step.cu.
  *      offsets[22]: element offsets into params/grads (order documented at the definition). */
-size_t lk_nrms_arena_bytes(int64_t T_max, int64_t N_max, int64_t B, int64_t D, int64_t A, int64_t E, int64_t H);
+size_t lk_nrms_arena_bytes(int64_t T_max, int64_t N_max, int64_t B, int64_t D, int64_t A, int64_t E, int64_t H, int64_t n_cats,
+                           int64_t n_special);
 int lk_nrms_fwd_bwd(const int64_t* title_ids, const int64_t* cat_ids, const int64_t* special_ids, const int32_t* cu_items,
                     int64_t n_items, int64_t T, int64_t S_max, const int32_t* cu_users, int64_t B, int64_t C, int64_t H_max,
                     const float* glove_table, const float* params, float* grads, const int64_t* offsets, int64_t D, int64_t heads,

@@ -31,6 +31,8 @@ SIGNATURES = {
     'lk_gather_split_bf16': ('ppppqqqs', 'i'),
     'lk_scatter_add_workspace_bytes': ('qqq', 'z'),
     'lk_scatter_add_sorted': ('ppppqpqqqipzs', 'i'),
+    'lk_concat_embed_bwd_workspace_bytes': ('qqqq', 'z'),
+    'lk_concat_embed_bwd': ('ppppqqqqfuppqppppzs', 'i'),
     'lk_linear_fwd': ('pppppqqqiifus', 'i'),
     'lk_act_bwd': ('ppppqqifus', 'i'),
     'lk_valid_mask': ('ppqs', 'i'),
@@ -67,7 +69,7 @@ SIGNATURES = {
     'lk_group_metrics': ('pppqpipqpppzs', 'i'),
     'lk_adam_step': ('ppppqffffqfs', 'i'),
     'lk_fill_f32': ('pfqs', 'i'),
-    'lk_nrms_arena_bytes': ('qqqqqqq', 'z'),
+    'lk_nrms_arena_bytes': ('qqqqqqqqq', 'z'),
     'lk_nrms_fwd_bwd': ('ppppqqqpqqqpppp' + 'qqqqqq' + 'ffu' + 'pppzs', 'i'),
 }
 
@@ -110,6 +112,8 @@ _profile = None   # when a list: (name, flops, start_event, stop_event) per C-AB
 
 # algorithmic flops of the dense-contraction entry points, from their (M, N, K) arguments
 _FLOPS = {
+    'lk_concat_embed_bwd_workspace_bytes': ('qqqq', 'z'),
+    'lk_concat_embed_bwd': ('ppppqqqqfuppqppppzs', 'i'),
     'lk_linear_fwd': lambda a: 2 * a[5] * a[6] * a[7],
     'lk_linear_bwd_data': lambda a: 2 * a[3] * a[4] * a[5],
     'lk_linear_bwd_weight': lambda a: 2 * a[4] * a[5] * a[6],

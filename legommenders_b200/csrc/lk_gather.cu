@@ -251,6 +251,94 @@ __global__ void scatter_small_finish_kernel(const float* __restrict__ partial, f
 static bool small_table(int64_t V, int64_t E) { return V <= SM_MAX_V && (size_t)SM_LANES * V * E * 4 <= 96 * 1024; }
 static size_t small_ws_bytes(int64_t P, int64_t V, int64_t E) { return (size_t)((P + SM_CHUNK - 1) / SM_CHUNK) * V * E * 4 + 256; }
 
+// ------------------------------------------------------------------------------------------------
+// backward of the ConcatInputer embedding stage in ONE pass over dx (concat_inputer.py:105-113 + embedding_hub.py:95-96):
+//   x[t] = valid(title[t]) · dropout(W·glove[title[t]] + b) + cat_table[cat[t]] + special_table[sp[t]]
+//   => dP[t]   = dx[t] · dropout · valid     -> split-bf16 planes (operand of the projection's weight gradient) + column sums (db)
+//      dcat[c] = Σ_{t: cat[t]=c} dx[t],   dspecial likewise              (deterministic: block partials, fixed-order finish)
+// A block owns EB_ROWS consecutive rows; EB_LANES row-lanes walk them in order with private shared accumulators.
+// ------------------------------------------------------------------------------------------------
+constexpr int EB_ROWS = 128, EB_LANES = 4;
+
+__global__ void __launch_bounds__(256) concat_embed_bwd_kernel(const float* __restrict__ dx, const int64_t* __restrict__ title,
+                                                               const int64_t* __restrict__ cat, const int64_t* __restrict__ special,
+                                                               int64_t T, int D, int Vc, int Vs, float drop_p, unsigned long long seed,
+                                                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld,
+                                                               float* __restrict__ part) {
+  extern __shared__ __align__(16) float sm[];           // [EB_LANES][1 + Vc + Vs][D]
+  __shared__ int s_title[EB_ROWS], s_cat[EB_ROWS], s_sp[EB_ROWS];
+  const int D4 = D >> 2, NT = 1 + Vc + Vs;
+  const int cols = blockDim.x / EB_LANES;
+  const int rl = threadIdx.x / cols, ct = threadIdx.x - rl * cols;
+  const int64_t r0 = (int64_t)blockIdx.x * EB_ROWS;
+  const int nrows = (int)((T - r0) < EB_ROWS ? (T - r0) : EB_ROWS);
+  for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
+    s_title[i] = title[r0 + i] > -1 ? 1 : 0;
+    s_cat[i] = (int)cat[r0 + i];
+    s_sp[i] = (int)special[r0 + i];
+  }
+  float* mine = sm + (size_t)rl * NT * D;
+  for (int i = ct; i < NT * D4; i += cols) reinterpret_cast<float4*>(mine)[i] = f4_zero();
+  __syncthreads();
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (int i = rl; i < nrows; i += EB_LANES) {
+    const int64_t row = r0 + i;
+    const bool tv = s_title[i] != 0;
+    const int ci = s_cat[i], si = s_sp[i];
+    for (int c = ct; c < D4; c += cols) {
+      const float4 g = ldg4_stream(dx + row * D + c * 4);
+      float4 m = f4_zero();
+      if (tv) {
+        m = g;
+        if (drop_p > 0.f) {
+          const uint64_t e = (uint64_t)row * D + c * 4;
+          m.x *= dropout_scale(seed, e, drop_p, inv_keep); m.y *= dropout_scale(seed, e + 1, drop_p, inv_keep);
+          m.z *= dropout_scale(seed, e + 2, drop_p, inv_keep); m.w *= dropout_scale(seed, e + 3, drop_p, inv_keep);
+        }
+        f4_add(*reinterpret_cast<float4*>(mine + c * 4), m);
+      }
+      __align__(8) __nv_bfloat16 h[4], l[4];
+      const float xv[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        h[e] = __float2bfloat16_rn(xv[e]);
+        l[e] = __float2bfloat16_rn(xv[e] - __bfloat162float(h[e]));
+      }
+      *reinterpret_cast<uint2*>(hi + row * ld + c * 4) = *reinterpret_cast<uint2*>(h);
+      *reinterpret_cast<uint2*>(lo + row * ld + c * 4) = *reinterpret_cast<uint2*>(l);
+      if (ci > -1) f4_add(*reinterpret_cast<float4*>(mine + (size_t)(1 + ci) * D + c * 4), g);
+      if (si > -1) f4_add(*reinterpret_cast<float4*>(mine + (size_t)(1 + Vc + si) * D + c * 4), g);
+    }
+  }
+  __syncthreads();
+  float* out = part + (size_t)blockIdx.x * NT * D;
+  for (int i = threadIdx.x; i < NT * D4; i += blockDim.x) {
+    float4 t = reinterpret_cast<const float4*>(sm)[i];
+#pragma unroll
+    for (int l2 = 1; l2 < EB_LANES; l2++) f4_add(t, reinterpret_cast<const float4*>(sm + (size_t)l2 * NT * D)[i]);
+    reinterpret_cast<float4*>(out)[i] = t;
+  }
+}
+
+// out[c] = Σ_b part[b, c] in a fixed order: 32 part-lanes x 32 columns per block, then an ordered shared-memory reduction
+__global__ void __launch_bounds__(1024) partial_finish_kernel(const float* __restrict__ part, int nparts, int64_t stride, int cols,
+                                                              float* __restrict__ out) {
+  __shared__ float red[32][33];
+  const int cx = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s = 0.f;
+  if (c < cols)
+    for (int i = pl; i < nparts; i += 32) s += part[(int64_t)i * stride + c];
+  red[pl][cx] = s;
+  __syncthreads();
+  if (pl == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i++) t += red[i][cx];
+    out[c] = t;
+  }
+}
+
 struct ScatterWs {
   int *keys, *vals, *skeys, *svals, *run_key, *run_len, *run_off, *npart, *part_off, *num_runs;
   float* partial;
@@ -321,6 +409,36 @@ int lk_gather_pool(const int64_t* ids, const int64_t* mask, const float* table, 
   else if (mode == 1) gather_pool_kernel<1><<<grid, GW * 32, 0, st>>>(ids, mask, table, out, N, (int)S, (int)E);
   else gather_pool_kernel<2><<<grid, GW * 32, 0, st>>>(ids, mask, table, out, N, (int)S, (int)E);
   return check_launch("gather_pool");
+}
+
+size_t lk_concat_embed_bwd_workspace_bytes(int64_t T, int64_t D, int64_t n_cats, int64_t n_special) {
+  return (size_t)((T + EB_ROWS - 1) / EB_ROWS) * (1 + n_cats + n_special) * D * sizeof(float) + 256;
+}
+
+int lk_concat_embed_bwd(const float* dx, const int64_t* title_ids, const int64_t* cat_ids, const int64_t* special_ids, int64_t T,
+                        int64_t D, int64_t n_cats, int64_t n_special, float drop_p, uint64_t seed, void* dp_hi, void* dp_lo, int64_t ld,
+                        float* g_bias, float* g_cat, float* g_special, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const int NT = (int)(1 + n_cats + n_special);
+  const size_t smem = (size_t)EB_LANES * NT * D * sizeof(float);
+  LK_REQUIRE(D % 4 == 0 && ld % 8 == 0 && ld >= D && D / 4 <= 64, LK_ERR_SHAPE, "lk_concat_embed_bwd: D=%ld must be a multiple of 4 and <= 256, ld a multiple of 8", (long)D);
+  LK_REQUIRE(smem <= 200 * 1024, LK_ERR_SHAPE, "lk_concat_embed_bwd: tables with %d rows do not fit the shared accumulators", NT - 1);
+  LK_REQUIRE(workspace && workspace_bytes >= lk_concat_embed_bwd_workspace_bytes(T, D, n_cats, n_special), LK_ERR_ARG,
+             "lk_concat_embed_bwd: workspace too small");
+  const int nblk = (int)((T + EB_ROWS - 1) / EB_ROWS);
+  if (T > 0) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(concat_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    concat_embed_bwd_kernel<<<nblk, 256, smem, st>>>(dx, title_ids, cat_ids, special_ids, T, (int)D, (int)n_cats, (int)n_special, drop_p,
+                                                     (unsigned long long)seed, (__nv_bfloat16*)dp_hi, (__nv_bfloat16*)dp_lo, (int)ld,
+                                                     (float*)workspace);
+  }
+  const float* part = (const float*)workspace;
+  const int64_t stride = (int64_t)NT * D;
+  partial_finish_kernel<<<(unsigned)((D + 31) / 32), 1024, 0, st>>>(part, nblk, stride, (int)D, g_bias);
+  partial_finish_kernel<<<(unsigned)((n_cats * D + 31) / 32), 1024, 0, st>>>(part + D, nblk, stride, (int)(n_cats * D), g_cat);
+  partial_finish_kernel<<<(unsigned)((n_special * D + 31) / 32), 1024, 0, st>>>(part + (1 + n_cats) * D, nblk, stride, (int)(n_special * D),
+                                                                                g_special);
+  return check_launch("concat_embed_bwd", 4);
 }
 
 size_t lk_scatter_add_workspace_bytes(int64_t P, int64_t V, int64_t E) {

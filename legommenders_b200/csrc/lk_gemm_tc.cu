@@ -112,6 +112,19 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// (hi, lo) bf16 planes of four floats: two packed cvt.rn.bf16x2 per plane; hi's fp32 image is its bits shifted up
+__device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
+  uint32_t h01, h23, l01, l23;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h01) : "f"(v.y), "f"(v.x));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h23) : "f"(v.w), "f"(v.z));
+  const float r0 = v.x - __uint_as_float(h01 << 16), r1 = v.y - __uint_as_float(h01 & 0xffff0000u);
+  const float r2 = v.z - __uint_as_float(h23 << 16), r3 = v.w - __uint_as_float(h23 & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l01) : "f"(r1), "f"(r0));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l23) : "f"(r3), "f"(r2));
+  hi = make_uint2(h01, h23);
+  lo = make_uint2(l01, l23);
+}
+
 // Epilogue of one 128x128 accumulator tile by 8 warps: warp (q, half) owns TMEM lanes 32q..32q+31 and columns
 // 64*half..64*half+63.  Per 16-column chunk: tcgen05.ld (row = lane) -> bias / activation / dropout / row mask in registers
 // -> transpose through a warp-private shared tile -> 64-byte-contiguous row segments to global (a warp store covers 8 rows).
@@ -132,33 +145,52 @@ __device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, 
     if (p.add_ids[0]) { const int64_t id = p.add_ids[0][row]; if (id > -1) add0 = p.add_tab[0] + id * (int64_t)p.GN; }
     if (p.add_ids[1]) { const int64_t id = p.add_ids[1][row]; if (id > -1) add1 = p.add_tab[1] + id * (int64_t)p.GN; }
   }
-#pragma unroll 1
-  for (int c = 0; c < 4; c++) {
-    const int nc0 = n0 + half * 64 + c * 16;
-    if (nc0 >= p.GN) break;                                  // warp-uniform
-    uint32_t v[16];
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * 64 + c * 16);
+  // the TMEM load of chunk c+1 is in flight while chunk c is processed and stored
+  uint32_t v[16];
+  const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * 64);
+  auto tmem_ld16 = [&](int c) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-    float bj = 0.f;
-    if (fused && p.bias && lane < 16 && nc0 + lane < p.GN) bj = __ldg(p.bias + nc0 + lane);
+        : "r"(taddr0 + (uint32_t)(c * 16)));
+  };
+  if (n0 + half * 64 < p.GN) tmem_ld16(0);
+#pragma unroll 1
+  for (int c = 0; c < 4; c++) {
+    const int nc0 = n0 + half * 64 + c * 16;
+    if (nc0 >= p.GN) break;                                  // warp-uniform
+    float4 bb[4];
+    if (fused && p.bias) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) bb[j] = (nc0 + 4 * j < p.GN) ? ldg4(p.bias + nc0 + 4 * j) : f4_zero();
+    }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     float x[16];
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      float t = has_k ? __uint_as_float(v[j]) : 0.f;
-      if (fused) {
-        t += __shfl_sync(0xffffffffu, bj, j);
-        if (p.act == 1) t = tanhf(t);
-        else if (p.act == 2) t = fmaxf(t, 0.f);
-        if (p.drop_p > 0.f) t *= dropout_scale(p.seed, (uint64_t)row * p.GN + nc0 + j, p.drop_p, inv_keep);
-        t *= rm;
+    for (int j = 0; j < 16; j++) x[j] = has_k ? __uint_as_float(v[j]) : 0.f;
+    if (c + 1 < 4 && nc0 + 16 < p.GN) tmem_ld16(c + 1);
+    if (fused) {    // every branch below is warp-uniform and sits OUTSIDE the per-element loops
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) { x[4 * j] += bb[j].x; x[4 * j + 1] += bb[j].y; x[4 * j + 2] += bb[j].z; x[4 * j + 3] += bb[j].w; }
       }
-      x[j] = t;
+      if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) x[j] = tanhf(x[j]);
+      } else if (p.act == 2) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) x[j] = fmaxf(x[j], 0.f);
+      }
+      if (p.drop_p > 0.f) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) x[j] *= dropout_scale(p.seed, (uint64_t)row * p.GN + nc0 + j, p.drop_p, inv_keep);
+      }
+      if (p.rowmask) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) x[j] *= rm;
+      }
     }
     if (add0) {
 #pragma unroll
@@ -174,6 +206,7 @@ __device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, 
     for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
     __syncwarp();
     float4 cs = f4_zero();
+    const bool want_cs = fused && p.colsum_part != nullptr;
     const int c4 = (lane & 3) * 4, n = nc0 + c4;
 #pragma unroll
     for (int it = 0; it < 4; it++) {
@@ -187,20 +220,15 @@ __device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, 
           if (!fused || p.store_c) st4(o, val);
         }
         if (fused && p.out_hi) {
-          __align__(8) __nv_bfloat16 h[4], l[4];
-          const float xv[4] = {val.x, val.y, val.z, val.w};
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            h[e] = __float2bfloat16_rn(xv[e]);
-            l[e] = __float2bfloat16_rn(xv[e] - __bfloat162float(h[e]));
-          }
-          *reinterpret_cast<uint2*>(p.out_hi + (size_t)grow * p.ld_planes + n) = *reinterpret_cast<uint2*>(h);
-          *reinterpret_cast<uint2*>(p.out_lo + (size_t)grow * p.ld_planes + n) = *reinterpret_cast<uint2*>(l);
+          uint2 h, l;
+          split4(val, h, l);
+          *reinterpret_cast<uint2*>(p.out_hi + (size_t)grow * p.ld_planes + n) = h;
+          *reinterpret_cast<uint2*>(p.out_lo + (size_t)grow * p.ld_planes + n) = l;
         }
-        f4_add(cs, val);
+        if (want_cs) f4_add(cs, val);
       }
     }
-    if (fused && p.colsum_part) {     // warp-uniform branch
+    if (want_cs) {     // warp-uniform branch
 #pragma unroll
       for (int o = 4; o < 32; o <<= 1) {
         cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);

@@ -182,7 +182,7 @@ using namespace lk;
 using namespace lk::nrms;
 
 // shared scratch: the largest of the split-reduction partials, scatter-add and column-sum workspaces of one step
-static size_t scratch_bytes(int64_t T, int64_t N, int64_t D, int64_t A, int64_t E) {
+static size_t scratch_bytes(int64_t T, int64_t N, int64_t D, int64_t A, int64_t E, int64_t n_cats, int64_t n_special) {
   size_t m = 0;
   auto up = [&](size_t v) { if (v > m) m = v; };
   up(lk_tc_gemm_workspace_bytes(3 * D, D, T));
@@ -194,6 +194,7 @@ static size_t scratch_bytes(int64_t T, int64_t N, int64_t D, int64_t A, int64_t 
   up(lk_split_bf16_workspace_bytes(T, 3 * D));
   up(lk_colsum_workspace_bytes(N, A));
   up(lk_colsum_workspace_bytes(N, 3 * D));
+  up(lk_concat_embed_bwd_workspace_bytes(T, D, n_cats, n_special));
   up(lk_tc_gemm_workspace_bytes(T, 3 * D, D));     // column-sum partials of the fused epilogues
   up(lk_tc_gemm_workspace_bytes(T, D, 3 * D));
   return m + (1 << 20);
@@ -209,7 +210,7 @@ static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const 
   c.st = st;
   c.rc = 0;
   c.dry = dry;
-  c.ws_bytes = scratch_bytes(T > 0 ? T : 1, n_items, D, A, E);
+  c.ws_bytes = scratch_bytes(T > 0 ? T : 1, n_items, D, A, E, n_cats, n_special);
   c.ws = c.a.take(c.ws_bytes);
 
   auto P = [&](int i) { return params + offsets[i]; };
@@ -264,13 +265,10 @@ static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const 
   float* dx = c.a.f32(T * D);
   enc_bwd(c, si, wi, pi, D, heads, A, drop_attn, drep, dx);
 
-  // embedding tables: sorted segmented scatter-add; GloVe projection: dP = dx * dropout * valid
-  STEP(lk_scatter_add_sorted(cat_ids, nullptr, dx, nullptr, 1, G(2), T, n_cats, D, 0, c.ws, c.ws_bytes, st));
-  STEP(lk_scatter_add_sorted(special_ids, nullptr, dx, nullptr, 1, G(3), T, n_special, D, 0, c.ws, c.ws_bytes, st));
-  int64_t* valid = (int64_t*)c.a.take((size_t)T * 8);
-  STEP(lk_valid_mask(title_ids, valid, T, st));
-  STEP(lk_act_bwd(dx, nullptr, valid, dx, T, D, 0, drop_embed, s_embed, st));
-  PlaneBuf dpp = split(c, dx, T, D, G(1));
+  // embedding stage backward in one pass over dx: small-table gradients, dP planes, bias gradient
+  PlaneBuf dpp = alloc_planes(c, T, D);
+  STEP(lk_concat_embed_bwd(dx, title_ids, cat_ids, special_ids, T, D, n_cats, n_special, drop_embed, s_embed, dpp.hi, dpp.lo, dpp.ld, G(1),
+                           G(2), G(3), c.ws, c.ws_bytes, st));
   gemm_wgrad(c, dpp, gp, G(0), T, D, E);
 
   if (high_out) *high_out = c.a.high;
@@ -281,11 +279,12 @@ static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const 
 extern "C" {
 
 // exact: the sizing pass walks the same allocation sequence as a real step (no launches, no memory behind the arena)
-size_t lk_nrms_arena_bytes(int64_t T_max, int64_t N_max, int64_t B, int64_t D, int64_t A, int64_t E, int64_t H) {
+size_t lk_nrms_arena_bytes(int64_t T_max, int64_t N_max, int64_t B, int64_t D, int64_t A, int64_t E, int64_t H, int64_t n_cats,
+                           int64_t n_special) {
   static const int64_t zeros[22] = {0};
   size_t high = 0;
   nrms_run(true, &high, nullptr, nullptr, nullptr, nullptr, N_max + B, T_max, 1, nullptr, B, 1, 1, nullptr, nullptr, nullptr, zeros, D, H, A,
-           E, 64, 64, 0.f, 0.f, 0, nullptr, nullptr, nullptr, ~(size_t)0 >> 1, nullptr);
+           E, n_cats, n_special, 0.f, 0.f, 0, nullptr, nullptr, nullptr, ~(size_t)0 >> 1, nullptr);
   return high + 4096;
 }
 

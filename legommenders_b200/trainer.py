@@ -119,9 +119,13 @@ class NativeNRMSStep:
         self.calls = 0
 
     def _ensure_arena(self, T, N, B):
-        need = self._lib.query('lk_nrms_arena_bytes', T, N, B, self.D, self.A, self.E, self.heads)
-        if self.arena is None or self.arena.numel() < need:
-            self.arena = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.opt.flat.device)
+        """Grow-only arena sized by the driver's own sizing pass, with 20% head-room so that it is queried rarely."""
+        cap = getattr(self, '_cap', None)
+        if self.arena is None or T > cap[0] or N > cap[1] or B > cap[2]:
+            cap = (int(T * 1.2) + 64, int(N * 1.2) + 8, B)
+            need = self._lib.query('lk_nrms_arena_bytes', cap[0], cap[1], B, self.D, self.A, self.E, self.heads, self.n_cats, self.n_special)
+            self.arena = torch.empty(int(need), dtype=torch.uint8, device=self.opt.flat.device)
+            self._cap = cap
 
     def pack(self, batch):
         """Host-side integer bookkeeping (packing.py); cached on device-resident batches."""

@@ -442,6 +442,39 @@ def test_attention_dropout_mask_is_shared_by_forward_and_backward(ops):
     assert not torch.equal(c2 != 0, c.detach().cpu() != 0)              # another seed, another mask
 
 
+@pytest.mark.parametrize('drop_p', [0.0, 0.2])
+def test_concat_embed_backward_one_pass(ops, drop_p):
+    """lk_concat_embed_bwd against the separate kernels it fuses (lk_act_bwd for dropout·valid with the same seed/indexing,
+    index_add for the small tables): planes, bias gradient, category and special-token gradients."""
+    from legommenders_b200._lib import call, ptr, query, workspace
+    T, D, Vc, Vs, seed = 5000, 256, 18, 3, 4242
+    g = torch.Generator().manual_seed(8)
+    dx = torch.randn(T, D, generator=g)
+    kind = torch.randint(0, 10, (T,), generator=g)
+    title = torch.where(kind < 7, torch.randint(0, 1000, (T,), generator=g), torch.full((T,), -1))
+    cat = torch.where(kind == 7, torch.randint(0, Vc, (T,), generator=g), torch.full((T,), -1))
+    sp = torch.where(kind >= 8, torch.randint(0, Vs, (T,), generator=g), torch.full((T,), -1))
+    dxd = dev(dx)
+    valid = ops.valid_mask(dev(title))
+    ref_dp = ops.act_bwd_raw(dxd, None, valid, 0, drop_p, seed).cpu()
+    ref_cat = torch.zeros(Vc, D, dtype=torch.float64).index_add_(0, cat[cat > -1], dx[cat > -1].double())
+    ref_sp = torch.zeros(Vs, D, dtype=torch.float64).index_add_(0, sp[sp > -1], dx[sp > -1].double())
+    hi = torch.zeros(T, D, dtype=torch.bfloat16, device='cuda')
+    lo = torch.zeros_like(hi)
+    gb, gc, gs = (torch.empty(n, device='cuda') for n in (D, Vc * D, Vs * D))
+    ws = workspace(query('lk_concat_embed_bwd_workspace_bytes', T, D, Vc, Vs), dxd.device, 'embed')
+    td, cd, sd = dev(title), dev(cat), dev(sp)       # keep the device copies alive across the call
+    call('lk_concat_embed_bwd', ptr(dxd), ptr(td), ptr(cd), ptr(sd), T, D, Vc, Vs, float(drop_p), seed, ptr(hi), ptr(lo),
+         D, ptr(gb), ptr(gc), ptr(gs), ptr(ws), ws.numel())
+    assert torch.equal(hi.float().cpu(), ref_dp.bfloat16().float())
+    assert torch.equal(lo.float().cpu(), (ref_dp - ref_dp.bfloat16().float()).bfloat16().float())
+    assert rel(gb, ref_dp.double().sum(0)) <= 1e-5
+    assert rel(gc.view(Vc, D), ref_cat) <= 1e-5
+    assert rel(gs.view(Vs, D), ref_sp) <= 1e-5
+    if drop_p:
+        assert abs((ref_dp[title > -1] != 0).float().mean().item() - (1 - drop_p)) < 0.01
+
+
 def test_error_reporting(ops):
     with pytest.raises(RuntimeError, match='multiple'):
         ops.gather_add(None, dev(torch.zeros(3, dtype=torch.long)), None, dev(torch.randn(4, 6)))
