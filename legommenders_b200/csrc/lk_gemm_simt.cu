@@ -210,13 +210,25 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* _
 }
 
 // Column sums of a row-major [M,N] matrix, deterministic two-stage (db = sum_m dY[m,:]).
-__global__ void colsum_stage1(const float* __restrict__ X, float* __restrict__ part, int M, int N, int rows_per_block) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+// block = 32 columns x 8 row-lanes over `rows_per_block` rows; the row-lanes are combined in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) colsum_stage1(const float* __restrict__ X, float* __restrict__ part, int M, int N, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
   float s = 0.f;
-  for (int r = r0; r < r1; r++) s += __ldg(X + (size_t)r * N + n);
-  part[(size_t)blockIdx.y * N + n] = s;
+  if (n < N) {
+#pragma unroll 4
+    for (int r = r0 + ty; r < r1; r += 8) s += __ldg(X + (size_t)r * N + n);
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += red[i][tx];
+    part[(size_t)blockIdx.y * N + n] = t;
+  }
 }
 __global__ void colsum_stage2(const float* __restrict__ part, float* __restrict__ out, int nparts, int N, int accumulate) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -344,8 +356,8 @@ int lk_linear_bwd_weight(const float* dY, const float* X, float* dW, float* db, 
     float* part = ws + (size_t)splits * N * K;
     int rpb = 512;
     int nparts = (int)((M + rpb - 1) / rpb);
-    dim3 g1((unsigned)((N + 127) / 128), nparts);
-    colsum_stage1<<<g1, 128, 0, st>>>(dY, part, (int)M, (int)N, rpb);
+    dim3 g1((unsigned)((N + 31) / 32), nparts);
+    colsum_stage1<<<g1, 256, 0, st>>>(dY, part, (int)M, (int)N, rpb);
     colsum_stage2<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(part, db, nparts, (int)N, accumulate);
     rc = check_launch("colsum", 2);
   }
@@ -386,8 +398,8 @@ int lk_colsum(const float* X, float* out, int64_t M, int64_t N, int accumulate, 
   }
   int rpb = 512;
   int nparts = (int)((M + rpb - 1) / rpb);
-  dim3 g1((unsigned)((N + 127) / 128), nparts);
-  colsum_stage1<<<g1, 128, 0, st>>>(X, (float*)workspace, (int)M, (int)N, rpb);
+  dim3 g1((unsigned)((N + 31) / 32), nparts);
+  colsum_stage1<<<g1, 256, 0, st>>>(X, (float*)workspace, (int)M, (int)N, rpb);
   colsum_stage2<<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const float*)workspace, out, nparts, (int)N, accumulate);
   return check_launch("colsum", 2);
 }
@@ -449,8 +461,8 @@ int lk_conv1d_bwd_weight(const float* dY, const float* X, float* dWr, float* db,
     float* part = ws + (size_t)splits * Cout * Kw;
     int rpb = 512;
     int nparts = (int)((rows + rpb - 1) / rpb);
-    dim3 g1((unsigned)((Cout + 127) / 128), nparts);
-    colsum_stage1<<<g1, 128, 0, st>>>(dY, part, (int)rows, (int)Cout, rpb);
+    dim3 g1((unsigned)((Cout + 31) / 32), nparts);
+    colsum_stage1<<<g1, 256, 0, st>>>(dY, part, (int)rows, (int)Cout, rpb);
     colsum_stage2<<<(unsigned)((Cout + 127) / 128), 128, 0, st>>>(part, db, nparts, (int)Cout, accumulate);
     rc = check_launch("colsum", 2);
   }

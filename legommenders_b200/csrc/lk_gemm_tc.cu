@@ -28,10 +28,13 @@ constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3, UMMA_K = 16, ACC_STAGES =
 constexpr int TILE_BYTES = BM * BK * 2;        // one plane of one operand: 16 KiB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi, A_lo, B_hi, B_lo
 constexpr int TMEM_COLS = ACC_STAGES * BN;     // 256 fp32 columns
-constexpr int NUM_THREADS = 64 + 8 * 32;   // TMA warp, MMA warp, 8 epilogue warps
-constexpr int EPI_WARPS = 8;
-constexpr int EPI_LD = 20;                 // floats per staged epilogue row (16 + 4 pad: conflict-free float4 stores)
+constexpr int EPI_WARPS = 16;              // warp (q, cg): TMEM lanes 32q..32q+31, columns 32cg..32cg+31 of the tile
+constexpr int EPI_CHUNKS = BN / (EPI_WARPS / 4) / 16;   // 16-column chunks per warp
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;   // TMA warp, MMA warp, epilogue warps
+constexpr int EPI_LD = 16;                 // staged epilogue rows are unpadded; an XOR swizzle of the 16-byte column keeps both
+                                           // the row-per-lane writes and the 4-lanes-per-row reads free of bank conflicts
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 32 * EPI_LD * 4 /*epilogue staging*/;
+static_assert(SMEM_BYTES <= 227 * 1024, "tc_gemm shared memory budget");
 
 struct Params {
   float* C;                 // [GM, ldc] (or split partials [splits, GM, GN] when partial != null)
@@ -125,11 +128,11 @@ __device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
   lo = make_uint2(l01, l23);
 }
 
-// Epilogue of one 128x128 accumulator tile by 8 warps: warp (q, half) owns TMEM lanes 32q..32q+31 and columns
-// 64*half..64*half+63.  Per 16-column chunk: tcgen05.ld (row = lane) -> bias / activation / dropout / row mask in registers
+// Epilogue of one 128x128 accumulator tile by 16 warps: warp (q, cg) owns TMEM lanes 32q..32q+31 and columns
+// 32*cg..32*cg+31.  Per 16-column chunk: tcgen05.ld (row = lane) -> bias / activation / dropout / row mask in registers
 // -> transpose through a warp-private shared tile -> 64-byte-contiguous row segments to global (a warp store covers 8 rows).
 
-__device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, int acc, int q, int half, int lane, int m0, int n0,
+__device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, int acc, int q, int cg, int lane, int m0, int n0,
                                            int split, bool has_k, float inv_keep, float* stage) {
   const int row = m0 + q * 32 + lane;
   const bool row_ok = row < p.GM;
@@ -147,7 +150,7 @@ __device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, 
   }
   // the TMEM load of chunk c+1 is in flight while chunk c is processed and stored
   uint32_t v[16];
-  const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * 64);
+  const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cg * (16 * EPI_CHUNKS));
   auto tmem_ld16 = [&](int c) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -156,10 +159,10 @@ __device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, 
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr0 + (uint32_t)(c * 16)));
   };
-  if (n0 + half * 64 < p.GN) tmem_ld16(0);
+  if (n0 + cg * (16 * EPI_CHUNKS) < p.GN) tmem_ld16(0);
 #pragma unroll 1
-  for (int c = 0; c < 4; c++) {
-    const int nc0 = n0 + half * 64 + c * 16;
+  for (int c = 0; c < EPI_CHUNKS; c++) {
+    const int nc0 = n0 + cg * (16 * EPI_CHUNKS) + c * 16;
     if (nc0 >= p.GN) break;                                  // warp-uniform
     float4 bb[4];
     if (fused && p.bias) {
@@ -170,7 +173,7 @@ __device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, 
     float x[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) x[j] = has_k ? __uint_as_float(v[j]) : 0.f;
-    if (c + 1 < 4 && nc0 + 16 < p.GN) tmem_ld16(c + 1);
+    if (c + 1 < EPI_CHUNKS && nc0 + 16 < p.GN) tmem_ld16(c + 1);
     if (fused) {    // every branch below is warp-uniform and sits OUTSIDE the per-element loops
       if (p.bias) {
 #pragma unroll
@@ -203,7 +206,8 @@ __device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, 
         if (nc0 + j < p.GN) { const float4 a = ldg4(add1 + nc0 + j); x[j] += a.x; x[j + 1] += a.y; x[j + 2] += a.z; x[j + 3] += a.w; }
     }
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+    for (int j = 0; j < 16; j += 4)
+      *reinterpret_cast<float4*>(stage + lane * EPI_LD + (((j >> 2) ^ ((lane >> 1) & 3)) << 2)) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
     __syncwarp();
     float4 cs = f4_zero();
     const bool want_cs = fused && p.colsum_part != nullptr;
@@ -213,7 +217,7 @@ __device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, 
       const int r = it * 8 + (lane >> 2);
       const int grow = m0 + q * 32 + r;
       if (grow < p.GM && n < p.GN) {
-        float4 val = *reinterpret_cast<const float4*>(stage + r * EPI_LD + c4);
+        float4 val = *reinterpret_cast<const float4*>(stage + r * EPI_LD + ((((lane & 3)) ^ ((r >> 1) & 3)) << 2));
         if (out) {
           float* o = out + (size_t)grow * ldo + n;
           if (fused && p.accumulate) f4_add(val, *reinterpret_cast<const float4*>(o));
@@ -358,7 +362,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   } else {
     // ------------------------------------------------ epilogue (warps 2..9) ----------------------------------------
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;       // which 64-column half of the tile
+    const int cg = (warp - 2) >> 2;         // which column group of the tile
     float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * 32 * EPI_LD;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -371,7 +375,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       const bool has_k = kb1 > kb0;
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
-      store_tile(p, tmem_base, acc, q, half, lane, m0, n0, split, has_k, inv_keep, stage);
+      store_tile(p, tmem_base, acc, q, cg, lane, m0, n0, split, has_k, inv_keep, stage);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
