@@ -262,8 +262,11 @@ __global__ void __maxnreg__(DH <= 32 ? 96 : 168) mha_fwd_seq_kernel(MhaParams p)
 // A: quad = R queries   p_ij = 2^(s2_ij - lse2_i);  dP_ij = (dO_i·v_j) keep_ij;  D_i = dO_i·O_i;  dS_ij = p_ij (dP_ij - D_i)
 //                       dQ_i = scale Σ_j dS_ij k_j
 // B: quad = R keys      dV_j = Σ_i p_ij keep_ij dO_i;   dK_j = scale Σ_i dS_ij q_i
-template <int DH, int R>
-__global__ void __maxnreg__(DH <= 32 ? 200 : 255) mha_bwd_seq_kernel(MhaParams p) {  // 2 CTAs of 160 threads per SM at head dim 32
+// SP = true: phase A leaves Pd = p∘keep and dS in shared memory ([HG][L][LP] each) and phase B is two plain axpys per pair
+// (160 instead of 224 FMAs per pair, one exp and one hash per pair); SP = false recomputes them in phase B (long sequences
+// whose L x L matrices do not fit shared memory).
+template <int DH, int R, bool SP>
+__global__ void __maxnreg__(DH <= 32 ? (SP ? 168 : 200) : 255) mha_bwd_seq_kernel(MhaParams p) {
   constexpr int W = DH / R;
   extern __shared__ __align__(16) float smem[];
   const int64_t n = blockIdx.x;
@@ -280,6 +283,9 @@ __global__ void __maxnreg__(DH <= 32 ? 200 : 255) mha_bwd_seq_kernel(MhaParams p
   float* Di_s = lse_s + (size_t)HG * S;    // [HG][S]
   uint32_t* hb_s = reinterpret_cast<uint32_t*>(Di_s + (size_t)HG * S);   // [HG][S] dropout hash of (row, head)
   float* valid = reinterpret_cast<float*>(hb_s + (size_t)HG * S);        // [S]
+  const int LP = (S + 1) & ~1;                                           // even row pitch: phase B reads key pairs as float2
+  float* Pd_s = valid + ((S + 3) & ~3);                                  // SP: [HG][S][LP]  p * keep
+  float* dS_s = Pd_s + (SP ? (size_t)HG * S * LP : 0);                   // SP: [HG][S][LP]  dS * scale
 
   const float* base = p.qkv + row0 * 3 * (int64_t)D;
   const float* gbase = p.dctx + row0 * (int64_t)D;
@@ -341,10 +347,16 @@ __global__ void __maxnreg__(DH <= 32 ? 200 : 255) mha_bwd_seq_kernel(MhaParams p
 #pragma unroll
       for (int r = 0; r < R; r++) {
         const float pr = ex2(ps[r] - lse2[r]);
-        const float dP = ((bits >> r) & 1u) ? pd[r] * inv_keep : 0.f;
+        const bool kept = (bits >> r) & 1u;
+        const float dP = kept ? pd[r] * inv_keep : 0.f;
         const float dS = pr * (dP - Di[r]);
 #pragma unroll
         for (int w = 0; w < W; w++) dq[r][w] = fmaf(dS, kv[w], dq[r][w]);
+        if (SP && r == it.ds && it.active) {              // lane ds publishes row ds of the quad
+          const int i = min(it.g * R + r, L - 1);
+          Pd_s[((size_t)it.hl * S + i) * LP + j] = kept ? pr * inv_keep : 0.f;
+          dS_s[((size_t)it.hl * S + i) * LP + j] = dS * p.scale;
+        }
       }
     }
 #pragma unroll
@@ -360,57 +372,105 @@ __global__ void __maxnreg__(DH <= 32 ? 200 : 255) mha_bwd_seq_kernel(MhaParams p
   stage_tile(T1, gbase + c0, D, L, TW);
   cp_async_wait_all();
   __syncthreads();
-  for (int w0 = 0; w0 < items; w0 += blockDim.x) {
-    const Item it = item_of<R>(w0 + threadIdx.x, G, items);
-    const int col = it.hl * DH + it.ds * W;
-    float k[R][W], v[R][W], dk[R][W], dv[R][W];
-    uint32_t kvalid = 0;
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      const int j = it.g * R + r, jc = min(j, L - 1);
-      ldg_slice<W>(k[r], base + (int64_t)jc * 3 * D + D + c0 + col, p.scale * kLog2e);
-      ldg_slice<W>(v[r], base + (int64_t)jc * 3 * D + 2 * D + c0 + col, 1.f);
-      if (j < L && valid[jc] != 0.f) kvalid |= 1u << r;
-#pragma unroll
-      for (int w = 0; w < W; w++) { dk[r][w] = 0.f; dv[r][w] = 0.f; }
-    }
-    const int my_j = it.g * R + it.ds;
-    const float* lse_h = lse_s + it.hl * S;
-    const float* Di_h = Di_s + it.hl * S;
-    const uint32_t* hb_h = hb_s + it.hl * S;
-    for (int i = 0; i < L; i++) {
-      float qv[W], gv[W], ps[R], pd[R];
-      lds_slice<W>(qv, T0 + i * TP + col);
-      lds_slice<W>(gv, T1 + i * TP + col);
+  if (SP) {
+    // phase A skipped masked keys: their columns of Pd / dS were never written, and rows of a quad beyond L were clamped
+    for (int w0 = 0; w0 < items; w0 += blockDim.x) {
+      const Item it = item_of<R>(w0 + threadIdx.x, G, items);
+      const int col = it.hl * DH + it.ds * W;
+      float dk[R][W], dv[R][W];
+      bool kok[R];
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        ps[r] = quad_sum<R>(dot_slice<W>(k[r], qv));
-        pd[r] = quad_sum<R>(dot_slice<W>(v[r], gv));
+        const int j = it.g * R + r;
+        kok[r] = j < L && valid[min(j, L - 1)] != 0.f;
+#pragma unroll
+        for (int w = 0; w < W; w++) { dk[r][w] = 0.f; dv[r][w] = 0.f; }
       }
-      uint32_t bits = (1u << R) - 1u;
-      if (p.drop_p > 0.f) bits = quad_bits<R>(attn_keep(hb_h[i], my_j, p.drop_thr));
-      bits &= kvalid;
-      const float lse_i = lse_h[i], Di = Di_h[i];
+      const float* pd_h = Pd_s + (size_t)it.hl * S * LP + it.g * R;
+      const float* ds_h = dS_s + (size_t)it.hl * S * LP + it.g * R;
+      for (int i = 0; i < L; i++) {
+        float qv[W], gv[W], pk[R], dsv[R];
+        lds_slice<W>(qv, T0 + i * TP + col);
+        lds_slice<W>(gv, T1 + i * TP + col);
+        if (R == 2) {
+          const float2 a = *reinterpret_cast<const float2*>(pd_h + (size_t)i * LP), b = *reinterpret_cast<const float2*>(ds_h + (size_t)i * LP);
+          pk[0] = a.x; pk[R - 1] = a.y; dsv[0] = b.x; dsv[R - 1] = b.y;
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; r++) { pk[r] = pd_h[(size_t)i * LP + r]; dsv[r] = ds_h[(size_t)i * LP + r]; }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const float a = kok[r] ? pk[r] : 0.f, b = kok[r] ? dsv[r] : 0.f;
+#pragma unroll
+          for (int w = 0; w < W; w++) {
+            dv[r][w] = fmaf(a, gv[w], dv[r][w]);
+            dk[r][w] = fmaf(b, qv[w], dk[r][w]);
+          }
+        }
+      }
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        const float pr = ((kvalid >> r) & 1u) ? ex2(ps[r] - lse_i) : 0.f;
-        const bool kept = (bits >> r) & 1u;
-        const float pk = kept ? pr * inv_keep : 0.f;               // p * keep
-        const float dS = pr * ((kept ? pd[r] * inv_keep : 0.f) - Di);
-#pragma unroll
-        for (int w = 0; w < W; w++) {
-          dv[r][w] = fmaf(pk, gv[w], dv[r][w]);
-          dk[r][w] = fmaf(dS, qv[w], dk[r][w]);
+        const int j = it.g * R + r;
+        if (it.active && j < L) {
+          sts_slice<W>(U0 + j * TP + col, dk[r], 1.f);      // dS_s already carries the scale
+          sts_slice<W>(U1 + j * TP + col, dv[r], 1.f);
         }
       }
     }
-    // dK carries q's prescale (scale*log2e is on k here, so dk accumulated raw q): dK = scale * Σ dS q
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      const int j = it.g * R + r;
-      if (it.active && j < L) {
-        sts_slice<W>(U0 + j * TP + col, dk[r], p.scale);
-        sts_slice<W>(U1 + j * TP + col, dv[r], 1.f);
+  } else {
+    for (int w0 = 0; w0 < items; w0 += blockDim.x) {
+      const Item it = item_of<R>(w0 + threadIdx.x, G, items);
+      const int col = it.hl * DH + it.ds * W;
+      float k[R][W], v[R][W], dk[R][W], dv[R][W];
+      uint32_t kvalid = 0;
+  #pragma unroll
+      for (int r = 0; r < R; r++) {
+        const int j = it.g * R + r, jc = min(j, L - 1);
+        ldg_slice<W>(k[r], base + (int64_t)jc * 3 * D + D + c0 + col, p.scale * kLog2e);
+        ldg_slice<W>(v[r], base + (int64_t)jc * 3 * D + 2 * D + c0 + col, 1.f);
+        if (j < L && valid[jc] != 0.f) kvalid |= 1u << r;
+  #pragma unroll
+        for (int w = 0; w < W; w++) { dk[r][w] = 0.f; dv[r][w] = 0.f; }
+      }
+      const int my_j = it.g * R + it.ds;
+      const float* lse_h = lse_s + it.hl * S;
+      const float* Di_h = Di_s + it.hl * S;
+      const uint32_t* hb_h = hb_s + it.hl * S;
+      for (int i = 0; i < L; i++) {
+        float qv[W], gv[W], ps[R], pd[R];
+        lds_slice<W>(qv, T0 + i * TP + col);
+        lds_slice<W>(gv, T1 + i * TP + col);
+  #pragma unroll
+        for (int r = 0; r < R; r++) {
+          ps[r] = quad_sum<R>(dot_slice<W>(k[r], qv));
+          pd[r] = quad_sum<R>(dot_slice<W>(v[r], gv));
+        }
+        uint32_t bits = (1u << R) - 1u;
+        if (p.drop_p > 0.f) bits = quad_bits<R>(attn_keep(hb_h[i], my_j, p.drop_thr));
+        bits &= kvalid;
+        const float lse_i = lse_h[i], Di = Di_h[i];
+  #pragma unroll
+        for (int r = 0; r < R; r++) {
+          const float pr = ((kvalid >> r) & 1u) ? ex2(ps[r] - lse_i) : 0.f;
+          const bool kept = (bits >> r) & 1u;
+          const float pk = kept ? pr * inv_keep : 0.f;               // p * keep
+          const float dS = pr * ((kept ? pd[r] * inv_keep : 0.f) - Di);
+  #pragma unroll
+          for (int w = 0; w < W; w++) {
+            dv[r][w] = fmaf(pk, gv[w], dv[r][w]);
+            dk[r][w] = fmaf(dS, qv[w], dk[r][w]);
+          }
+        }
+      }
+      // dK carries q's prescale (scale*log2e is on k here, so dk accumulated raw q): dK = scale * Σ dS q
+  #pragma unroll
+      for (int r = 0; r < R; r++) {
+        const int j = it.g * R + r;
+        if (it.active && j < L) {
+          sts_slice<W>(U0 + j * TP + col, dk[r], p.scale);
+          sts_slice<W>(U1 + j * TP + col, dv[r], 1.f);
+        }
       }
     }
   }
@@ -453,21 +513,27 @@ static int launch_fwd(MhaParams p, int64_t N, cudaStream_t st) {
   mha_fwd_seq_kernel<DH, R><<<grid, pick_threads(p.seq.S, p.HG, R), smem, st>>>(p);
   return check_launch("mha_fwd");
 }
-template <int DH, int R>
-static int launch_bwd(MhaParams p, int64_t N, cudaStream_t st) {
-  p.HG = pick_hg(p.H, DH);
-  const int TP = p.HG * DH + 4;
-  size_t smem = ((size_t)4 * p.seq.S * TP + 3 * (size_t)p.HG * p.seq.S + p.seq.S) * sizeof(float);
-  LK_REQUIRE(smem <= 227 * 1024, LK_ERR_SHAPE, "lk_mha_bwd: tiles (%zu B) do not fit shared memory", smem);
+template <int DH, int R, bool SP>
+static int launch_bwd_sp(const MhaParams& p, int64_t N, size_t smem, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(mha_bwd_seq_kernel<DH, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(mha_bwd_seq_kernel<DH, R>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(mha_bwd_seq_kernel<DH, R, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(mha_bwd_seq_kernel<DH, R, SP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr = true;
   }
   dim3 grid((unsigned)N, (unsigned)(p.H / p.HG));
-  mha_bwd_seq_kernel<DH, R><<<grid, pick_threads(p.seq.S, p.HG, R), smem, st>>>(p);
+  mha_bwd_seq_kernel<DH, R, SP><<<grid, pick_threads(p.seq.S, p.HG, R), smem, st>>>(p);
   return check_launch("mha_bwd");
+}
+template <int DH, int R>
+static int launch_bwd(MhaParams p, int64_t N, cudaStream_t st) {
+  p.HG = pick_hg(p.H, DH);
+  const int TP = p.HG * DH + 4, S = p.seq.S, LP = (S + 1) & ~1;
+  const size_t base = ((size_t)4 * S * TP + 3 * (size_t)p.HG * S + ((S + 3) & ~3)) * sizeof(float);
+  const size_t with_p = base + (size_t)2 * p.HG * S * LP * sizeof(float);
+  if (with_p <= 227 * 1024) return launch_bwd_sp<DH, R, true>(p, N, with_p, st);
+  LK_REQUIRE(base <= 227 * 1024, LK_ERR_SHAPE, "lk_mha_bwd: tiles (%zu B) do not fit shared memory", base);
+  return launch_bwd_sp<DH, R, false>(p, N, base, st);
 }
 
 static void set_dropout(MhaParams& p, float drop_p, uint64_t seed) {
