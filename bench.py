@@ -41,6 +41,7 @@ def parse():
     ap.add_argument('--batch', type=int, default=64, help='impressions per GPU per step')
     ap.add_argument('--small', action='store_true', help='tiny world (debug only; not a valid bench line)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the cached-eval / gather HBM lines')
     ap.add_argument('--autograd', action='store_true', help='drive the kernels through torch.autograd instead of the native step driver')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     return ap.parse_args()
@@ -246,14 +247,33 @@ def main():
     clocks = sampler.stop(w0, w1) if sampler else None
     value = world_size * args.batch * args.steps / (ms / 1000.0)
 
-    # e2e: host (pinned) batch -> H2D -> step -> D2H loss read, every step
-    def e2e_step(i):
+    # e2e: host (pinned) batch -> H2D -> step -> D2H loss read, every step.
+    #   wire : the reference's collated batch (int64 [B,55,S] trees, 3.7 MB) copied up, packed on the device
+    #   ids  : the product's data path (batching.DeviceBatcher): item-id list + offsets copied up (~50 KB), token ids expanded on the
+    #          device from the resident per-item token tables; same packed rows, bit for bit
+    def e2e_wire_step(i):
         b = tree_to_device(host[i % POOL], dev, non_blocking=True)
         return step(b).item()
 
     for i in range(2):
-        e2e_step(i)
-    ms_e2e, _, _, per_step_e2e = timed(e2e_step, args.steps)
+        e2e_wire_step(i)
+    ms_wire, _, _, per_step_wire = timed(e2e_wire_step, args.steps)
+    e2e_wire = dict(value=world_size * args.batch * args.steps / (ms_wire / 1000.0), unit='impressions/s', h2d_bytes_per_step=h2d,
+                    d2h_bytes_per_step=4, ms_per_step=ms_wire / args.steps, ms_per_step_dist=per_step_wire)
+    if native is not None:
+        from legommenders_b200.batching import DeviceBatcher
+        dbat = DeviceBatcher(resampler, world, dev, neg_count=NEG, seed=2000 + rank)
+        hostb = [dbat.host_batch(rng.integers(0, world.n_train, size=args.batch)) for _ in range(POOL)]
+        h2d_ids = DeviceBatcher.h2d_bytes(hostb[0])
+
+        def e2e_step(i):
+            return step(dbat.to_device(hostb[i % POOL])).item()
+
+        for i in range(3):
+            e2e_step(i)
+        ms_e2e, _, _, per_step_e2e = timed(e2e_step, args.steps)
+    else:
+        ms_e2e, per_step_e2e, h2d_ids = ms_wire, per_step_wire, h2d
     e2e_value = world_size * args.batch * args.steps / (ms_e2e / 1000.0)
 
     # per-entry-point device time over two extra steps (CUDA events around every C-ABI call on the launching stream)
@@ -288,10 +308,15 @@ def main():
                 dtype='f32', data='synthetic', impl='b200',
                 config=dict(base_cfg, l2='per-step working set (~1 GB of activations) exceeds the 126 MB L2; batches rotate through a pool of 8'),
                 clocks=clocks,
-                e2e=dict(value=e2e_value, unit='impressions/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
-                         ms_per_step=ms_e2e / args.steps, ms_per_step_dist=per_step_e2e),
+                e2e=dict(value=e2e_value, unit='impressions/s', h2d_bytes_per_step=h2d_ids, d2h_bytes_per_step=4,
+                         ms_per_step=ms_e2e / args.steps, ms_per_step_dist=per_step_e2e,
+                         path='id-only host batch -> H2D -> lk_pack_item_tokens -> lk_nrms_fwd_bwd -> allreduce -> Adam -> D2H loss'
+                         if native is not None else 'wire-format batch'),
+                e2e_wire_format=e2e_wire,
                 gpu_launches=launches, roofline=roof, kernel_ms_share=shares)
 
+    if rank == 0 and world_size == 1 and not args.small and not args.no_extra:
+        line['extra'] = hbm_bound_lines(dev, world, peaks()['hbm'])
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         hb = [{k: v for k, v in b.items()} for b in host[:4]]
         r = cpu_reference(world, hb, budget_s=args.cpu_seconds)
@@ -302,6 +327,65 @@ def main():
     if world_size > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def hbm_bound_lines(dev, world, hbm_peak):
+    """The HBM-bound pieces of the metric (BASELINE.json: cached-eval scores/s, gather HBM GB/s), each timed alone with CUDA events
+    (5 repetitions after 2 warm-ups, inputs resident, a 256 MB write between repetitions to flush L2) and set against the measured
+    copy bandwidth.  Algorithmic bytes per unit as in DESIGN.md §4."""
+    from legommenders_b200 import ops
+    from legommenders_b200.metrics import MetricPool
+    g = torch.Generator(device='cpu').manual_seed(5)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def time_it(fn, reps=5):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    out = {}
+    # (5) cached evaluation at MIND-small validation shape: every impression row against the two caches
+    D = HIDDEN
+    U = torch.randn(world.n_users, D, generator=g).to(dev)
+    I = torch.randn(world.n_items, D, generator=g).to(dev)
+    R = int(len(world.eval_users))
+    uid, iid = torch.from_numpy(world.eval_users).to(dev), torch.from_numpy(world.eval_items).to(dev)
+    lab = torch.from_numpy(world.eval_click).to(dev)
+    sc = torch.empty(R, dtype=torch.float32, device=dev)
+    ms = time_it(lambda: ops.cached_scores(U, I, uid, iid, out=sc))
+    by = R * (2 * D * 4 + 2 * 8 + 4)
+    out['cached_eval'] = dict(rows=R, ms=ms, scores_per_s=R / ms * 1e3, algorithmic_GBps=by / ms / 1e6, hbm_frac=by / ms / 1e6 / hbm_peak,
+                              bytes_per_score=2 * D * 4 + 20, note='caches 67 MB + 94 MB: partly L2-resident, so >1.0 is possible')
+    pool = MetricPool.parse(['GAUC', 'MRR', 'NDCG@1', 'NDCG@5', 'NDCG@10'])
+    ms_m = time_it(lambda: pool.calculate(sc, lab, uid), reps=3)
+    out['group_metrics'] = dict(rows=R, groups=pool.n_groups, ms=ms_m, rows_per_s=R / ms_m * 1e3,
+                                note='GAUC, MRR, NDCG@1/5/10 incl. the sort by group key and the D2H of the 5 means')
+    # (1) gather + masked mean pooling: MIND-small items over the 400k x 300 table, then a 4M-row table (config 4 size, HBM-resident)
+    E = world.embed_dim
+    ids = torch.from_numpy(world.item_title_matrix()).to(dev)                     # [N_items, 30], -1 padded
+    table = torch.from_numpy(world.word_table).to(dev)
+    N, S = ids.shape
+    real = int((ids > -1).sum().item())
+    ms = time_it(lambda: ops.gather_pool(ids, None, table))
+    by = real * E * 4 + N * S * 8 + N * E * 4
+    out['gather_pool_mind_small'] = dict(items=N, real_tokens=real, ms=ms, algorithmic_GBps=by / ms / 1e6, hbm_frac=by / ms / 1e6 / hbm_peak,
+                                         note='Zipf token ids: the hot rows live in L2')
+    big = torch.empty((4_000_000, E), dtype=torch.float32, device=dev).normal_(0, 0.4)
+    ids_b = torch.randint(0, big.shape[0], (N * 4, S), generator=g).to(dev)
+    ids_b[:, 24:] = -1
+    real = int((ids_b > -1).sum().item())
+    ms = time_it(lambda: ops.gather_pool(ids_b, None, big))
+    by = real * E * 4 + ids_b.numel() * 8 + ids_b.shape[0] * E * 4
+    out['gather_pool_4M_rows'] = dict(items=ids_b.shape[0], real_tokens=real, ms=ms, algorithmic_GBps=by / ms / 1e6,
+                                      hbm_frac=by / ms / 1e6 / hbm_peak, note='4.8 GB table, uniform ids: HBM-resident rows of 1200 B')
+    return out
 
 
 def host_batches_cpu(world, batch, n):

@@ -55,6 +55,12 @@ int lk_scatter_add_sorted(const int64_t* ids, const int64_t* mask, const float* 
                           float* dtable, int64_t P, int64_t V, int64_t E, int accumulate, void* workspace,
                           size_t workspace_bytes, cudaStream_t stream);
 
+/* packed token ids of an item list from device-resident per-item token tables [N_items, S] (the Resampler's item cache,
+ * loader/resampler.py:113-126): out_c[cu[n] + t] = table_c[items[n], t], t < cu[n+1]-cu[n].  tables / outs: HOST arrays of ncols (<= 4)
+ * device pointers; items int64 [n], cu int32 [n+1] on the device. */
+int lk_pack_item_tokens(const int64_t* const* tables, int64_t* const* outs, int ncols, const int64_t* items, const int32_t* cu, int64_t n,
+                        int64_t S, cudaStream_t stream);
+
 /* backward of the whole ConcatInputer embedding stage (concat_inputer.py:105-113 + embedding_hub.py:95-96) in one pass over
  * dx [T,D]:  dP = dx·dropout(seed)·(title id > -1) as split-bf16 planes [T, ld] (operand of the projection weight gradient),
  * g_bias [D] = column sums of dP, g_cat [n_cats, D] / g_special [n_special, D] = per-id sums of dx.  Deterministic. */

@@ -31,6 +31,7 @@ SIGNATURES = {
     'lk_gather_split_bf16': ('ppppqqqs', 'i'),
     'lk_scatter_add_workspace_bytes': ('qqq', 'z'),
     'lk_scatter_add_sorted': ('ppppqpqqqipzs', 'i'),
+    'lk_pack_item_tokens': ('ppippqqs', 'i'),
     'lk_concat_embed_bwd_workspace_bytes': ('qqqq', 'z'),
     'lk_concat_embed_bwd': ('ppppqqqqfuppqppppzs', 'i'),
     'lk_linear_fwd': ('pppppqqqiifus', 'i'),
@@ -112,6 +113,7 @@ _profile = None   # when a list: (name, flops, start_event, stop_event) per C-AB
 
 # algorithmic flops of the dense-contraction entry points, from their (M, N, K) arguments
 _FLOPS = {
+    'lk_pack_item_tokens': ('ppippqqs', 'i'),
     'lk_concat_embed_bwd_workspace_bytes': ('qqqq', 'z'),
     'lk_concat_embed_bwd': ('ppppqqqqfuppqppppzs', 'i'),
     'lk_linear_fwd': lambda a: 2 * a[5] * a[6] * a[7],

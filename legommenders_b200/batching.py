@@ -79,3 +79,66 @@ def tree_bytes(tree) -> int:
     if isinstance(tree, dict):
         return sum(tree_bytes(v) for v in tree.values())
     return tree.numel() * tree.element_size()
+
+
+class DeviceBatcher:
+    """Id-only training batches.  The per-item token layouts (`Resampler.item_cache`, built once by the inputer,
+    loader/resampler.py:113-126) live on the DEVICE as `[N_items, S]` tables; a training batch crosses PCIe as the item-id list of its
+    candidates + valid history items and two int32 offset vectors (~50 KB instead of the 3.7 MB of `[B, 55, S]` int64 trees), and
+    `lk_pack_item_tokens` expands it straight into the packed rows the native step consumes.  The packed ids are bit-identical to
+    `packing.pack_tokens` applied to the Resampler / BatchBuilder batch of the same candidates (tests/test_gpu_model.py).
+    Layout of the item list: the B*C candidates first ([pos, negatives...] per impression), then the valid history items user by
+    user (history right-padding with item 0 is never materialised)."""
+
+    def __init__(self, resampler, world, device, neg_count: int = 4, seed: int = 0):
+        from ._lib import load
+        self.world, self.device, self.neg_count = world, device, neg_count
+        self.sampler = BatchBuilder.__new__(BatchBuilder)          # reuse the candidate sampler only
+        self.sampler.world, self.sampler.neg_count, self.sampler.neg_lists = world, neg_count, world.negs
+        self.sampler.rng = np.random.default_rng(seed)
+        trees = stack_trees(resampler.item_cache)
+        self.cols = list(trees['input_ids'].keys())
+        mask = trees['attention_mask']
+        if isinstance(mask, dict):
+            raise ValueError('DeviceBatcher needs a single-sequence inputer (ConcatInputer)')
+        self.S = mask.shape[1]
+        self.item_len = mask.sum(dim=1).numpy().astype(np.int64)                    # host: offsets are host arithmetic
+        self.tables = [trees['input_ids'][c].to(device).contiguous() for c in self.cols]
+        self.hist = [np.asarray(h, dtype=np.int64) for h in world.histories]
+        self._lib = load()
+
+    def host_batch(self, rows: np.ndarray) -> dict:
+        """Pinned host buffers of one batch: item list, item offsets, user offsets (all that is copied per step)."""
+        users, pos = self.world.train_users[rows], self.world.train_pos[rows]
+        cand = self.sampler.sample_candidates(users, pos)
+        hists = [self.hist[int(u)] for u in users]
+        items = np.concatenate([cand.reshape(-1)] + hists)
+        lens = self.item_len[items]
+        cu = np.zeros(len(items) + 1, dtype=np.int32)
+        np.cumsum(lens, out=cu[1:])
+        cu_u = np.zeros(len(users) + 1, dtype=np.int32)
+        np.cumsum([len(h) for h in hists], out=cu_u[1:])
+        pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
+        return dict(items=pin(torch.from_numpy(items)), cu=pin(torch.from_numpy(cu)), cu_users=pin(torch.from_numpy(cu_u)),
+                    n=len(items), rows=int(cu[-1]), max_len=int(lens.max()), max_hist=int(max(len(h) for h in hists)),
+                    B=len(users), C=cand.shape[1], user_id=torch.from_numpy(users))
+
+    def to_device(self, hb: dict) -> dict:
+        """H2D of the id lists + one kernel -> a batch the native step accepts (carries its packed rows)."""
+        import ctypes
+        from ._lib import call
+        from .packing import Packed
+        dev = self.device
+        items = hb['items'].to(dev, non_blocking=True)
+        cu = hb['cu'].to(dev, non_blocking=True)
+        cu_u = hb['cu_users'].to(dev, non_blocking=True)
+        outs = [torch.empty(hb['rows'], dtype=torch.int64, device=dev) for _ in self.cols]
+        tp = (ctypes.c_void_p * len(self.cols))(*[t.data_ptr() for t in self.tables])
+        op = (ctypes.c_void_p * len(self.cols))(*[t.data_ptr() for t in outs])
+        call('lk_pack_item_tokens', ctypes.addressof(tp), ctypes.addressof(op), len(self.cols), items.data_ptr(), cu.data_ptr(), hb['n'], self.S)
+        pk = Packed(OrderedDict(zip(self.cols, outs)), cu, hb['n'], hb['rows'], hb['max_len'])
+        return {'__lk_packed__': (pk, cu_u, hb['max_hist'], hb['B'], hb['C']), '__keep__': (items,)}
+
+    @staticmethod
+    def h2d_bytes(hb: dict) -> int:
+        return sum(hb[k].numel() * hb[k].element_size() for k in ('items', 'cu', 'cu_users'))

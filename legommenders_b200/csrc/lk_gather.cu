@@ -339,6 +339,27 @@ __global__ void __launch_bounds__(1024) partial_finish_kernel(const float* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// packed token ids of a list of items from device-resident per-item token tables (the Resampler's per-item cache,
+// loader/resampler.py:113-126, kept on the device so that a training batch crosses PCIe as item ids, not as [B, 55, S] trees)
+//   out_c[cu[n] + t] = table_c[item[n], t]   for t < cu[n+1] - cu[n]      (valid tokens are left-packed, concat_inputer.py:58-87)
+// ------------------------------------------------------------------------------------------------
+struct PackCols { const int64_t* table[4]; int64_t* out[4]; int ncols; };
+
+__global__ void __launch_bounds__(256) pack_item_tokens_kernel(PackCols pc, const int64_t* __restrict__ items, const int* __restrict__ cu,
+                                                               int64_t n, int S) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= n) return;
+  const int64_t id = items[w];
+  const int r0 = cu[w], L = cu[w + 1] - r0;
+  for (int c = 0; c < pc.ncols; c++) {
+    const int64_t* src = pc.table[c] + id * S;
+    int64_t* dst = pc.out[c] + r0;
+    for (int t = lane; t < L; t += 32) dst[t] = src[t];
+  }
+}
+
 struct ScatterWs {
   int *keys, *vals, *skeys, *svals, *run_key, *run_len, *run_off, *npart, *part_off, *num_runs;
   float* partial;
@@ -409,6 +430,17 @@ int lk_gather_pool(const int64_t* ids, const int64_t* mask, const float* table, 
   else if (mode == 1) gather_pool_kernel<1><<<grid, GW * 32, 0, st>>>(ids, mask, table, out, N, (int)S, (int)E);
   else gather_pool_kernel<2><<<grid, GW * 32, 0, st>>>(ids, mask, table, out, N, (int)S, (int)E);
   return check_launch("gather_pool");
+}
+
+int lk_pack_item_tokens(const int64_t* const* tables, int64_t* const* outs, int ncols, const int64_t* items, const int32_t* cu, int64_t n,
+                        int64_t S, cudaStream_t st) {
+  LK_REQUIRE(ncols >= 1 && ncols <= 4, LK_ERR_ARG, "lk_pack_item_tokens: 1..4 token columns");
+  if (n == 0) return LK_OK;
+  PackCols pc;
+  pc.ncols = ncols;
+  for (int c = 0; c < 4; c++) { pc.table[c] = c < ncols ? tables[c] : nullptr; pc.out[c] = c < ncols ? outs[c] : nullptr; }
+  pack_item_tokens_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(pc, items, cu, n, (int)S);
+  return check_launch("pack_item_tokens");
 }
 
 size_t lk_concat_embed_bwd_workspace_bytes(int64_t T, int64_t D, int64_t n_cats, int64_t n_special) {

@@ -122,8 +122,9 @@ __device__ __forceinline__ void sts_slice(float* __restrict__ dst, const float (
 // writes of the result tiles spread over the banks.
 __device__ __forceinline__ void stage_tile(float* T, const float* __restrict__ src, int64_t ld, int L, int TW) {
   const int C4 = TW >> 2, TP = TW + 4;
+  const int sh = (C4 & (C4 - 1)) == 0 ? 31 - __clz(C4) : -1;       // power-of-two tile widths: shifts instead of divisions
   for (int idx = threadIdx.x; idx < L * C4; idx += blockDim.x) {
-    const int t = idx / C4, c = (idx - t * C4) * 4;
+    const int t = sh >= 0 ? idx >> sh : idx / C4, c = (idx - t * C4) * 4;
     cp_async16(T + t * TP + c, src + (int64_t)t * ld + c);
   }
 }
@@ -133,8 +134,9 @@ __device__ __forceinline__ void stage_tile(float* T, const float* __restrict__ s
 __device__ __forceinline__ void flush_tile(const float* __restrict__ T, int L, int TW, float* __restrict__ f32, __nv_bfloat16* __restrict__ hi,
                                            __nv_bfloat16* __restrict__ lo, int64_t ld, float* __restrict__ colsum) {
   const int C4 = TW >> 2, TP = TW + 4;
+  const int sh = (C4 & (C4 - 1)) == 0 ? 31 - __clz(C4) : -1;
   for (int idx = threadIdx.x; idx < L * C4; idx += blockDim.x) {
-    const int t = idx / C4, c = (idx - t * C4) * 4;
+    const int t = sh >= 0 ? idx >> sh : idx / C4, c = (idx - t * C4) * 4;
     const float4 v = *reinterpret_cast<const float4*>(T + t * TP + c);
     if (f32) st4(f32 + (int64_t)t * ld + c, v);
     if (hi) {
@@ -354,8 +356,8 @@ __global__ void __maxnreg__(DH <= 32 ? (SP ? 168 : 200) : 255) mha_bwd_seq_kerne
         for (int w = 0; w < W; w++) dq[r][w] = fmaf(dS, kv[w], dq[r][w]);
         if (SP && r == it.ds && it.active) {              // lane ds publishes row ds of the quad
           const int i = min(it.g * R + r, L - 1);
-          Pd_s[((size_t)it.hl * S + i) * LP + j] = kept ? pr * inv_keep : 0.f;
-          dS_s[((size_t)it.hl * S + i) * LP + j] = dS * p.scale;
+          Pd_s[(it.hl * S + i) * LP + j] = kept ? pr * inv_keep : 0.f;
+          dS_s[(it.hl * S + i) * LP + j] = dS * p.scale;
         }
       }
     }
@@ -386,18 +388,21 @@ __global__ void __maxnreg__(DH <= 32 ? (SP ? 168 : 200) : 255) mha_bwd_seq_kerne
 #pragma unroll
         for (int w = 0; w < W; w++) { dk[r][w] = 0.f; dv[r][w] = 0.f; }
       }
-      const float* pd_h = Pd_s + (size_t)it.hl * S * LP + it.g * R;
-      const float* ds_h = dS_s + (size_t)it.hl * S * LP + it.g * R;
-      for (int i = 0; i < L; i++) {
+      const float* pd_h = Pd_s + (it.hl * S * LP + it.g * R);
+      const float* ds_h = dS_s + (it.hl * S * LP + it.g * R);
+      const float* qp = T0 + col;
+      const float* gp = T1 + col;
+#pragma unroll 2
+      for (int i = 0; i < L; i++, pd_h += LP, ds_h += LP, qp += TP, gp += TP) {
         float qv[W], gv[W], pk[R], dsv[R];
-        lds_slice<W>(qv, T0 + i * TP + col);
-        lds_slice<W>(gv, T1 + i * TP + col);
+        lds_slice<W>(qv, qp);
+        lds_slice<W>(gv, gp);
         if (R == 2) {
-          const float2 a = *reinterpret_cast<const float2*>(pd_h + (size_t)i * LP), b = *reinterpret_cast<const float2*>(ds_h + (size_t)i * LP);
+          const float2 a = *reinterpret_cast<const float2*>(pd_h), b = *reinterpret_cast<const float2*>(ds_h);
           pk[0] = a.x; pk[R - 1] = a.y; dsv[0] = b.x; dsv[R - 1] = b.y;
         } else {
 #pragma unroll
-          for (int r = 0; r < R; r++) { pk[r] = pd_h[(size_t)i * LP + r]; dsv[r] = ds_h[(size_t)i * LP + r]; }
+          for (int r = 0; r < R; r++) { pk[r] = pd_h[r]; dsv[r] = ds_h[r]; }
         }
 #pragma unroll
         for (int r = 0; r < R; r++) {

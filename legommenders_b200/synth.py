@@ -142,6 +142,13 @@ class MindWorld:
         self.index_v = Vocab('index', max(n_train, len(self.eval_users), n_users))
         self.click_v = Vocab('click', 2)
 
+    def item_title_matrix(self) -> np.ndarray:
+        """[n_items, title_len] int64 token ids, right-padded with -1 (SimpleInputer layout of the title column)."""
+        m = np.full((self.n_items, self.title_len), -1, dtype=np.int64)
+        for i, t in enumerate(self.titles):
+            m[i, :len(t)] = t
+        return m
+
     # UniTok-shaped views ---------------------------------------------------------------------
     def item_table(self) -> Table:
         feats = [Feature('item_id', self.item_v), Feature(self.title_col, self.word_v, self.title_len),

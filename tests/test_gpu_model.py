@@ -266,3 +266,32 @@ def test_evaluate_matches_golden_metrics(name):
         assert round(v, 4) == round(float(ref), 4), k
     model.cacher.clean()
     Env.train()
+
+
+def test_device_batcher_packs_bit_exact():
+    """Id-only batches (DeviceBatcher + lk_pack_item_tokens) give exactly the packed rows that packing.pack_tokens derives from the
+    wire-format batch of the same candidates, and the native step computes the same loss from either."""
+    from legommenders_b200 import Env
+    from legommenders_b200.batching import BatchBuilder, DeviceBatcher, tree_to_device
+    from legommenders_b200.trainer import FlatAdam, NativeNRMSStep
+    c = cases.CASES['nrms_small']
+    world, llm = cases.make_world(c)
+    model, resampler, cfg = build(c, world, llm)
+    Env.train()
+    rows = np.arange(16) % world.n_train
+    wire = BatchBuilder(resampler, world, neg_count=4, seed=5).train_batch(rows)
+    dbat = DeviceBatcher(resampler, world, Env.device, neg_count=4, seed=5)
+    hb = dbat.host_batch(rows)
+    idb = dbat.to_device(hb)
+    opt = FlatAdam(model, lr=1e-3)
+    native = NativeNRMSStep(model, opt)
+    pk_w, cu_u_w, max_u_w, B_w, C_w = native.pack(tree_to_device(wire, Env.device))
+    pk_i, cu_u_i, max_u_i, B_i, C_i = native.pack(idb)
+    assert (pk_w.n, pk_w.rows, pk_w.max_len, max_u_w, B_w, C_w) == (pk_i.n, pk_i.rows, pk_i.max_len, max_u_i, B_i, C_i)
+    assert torch.equal(pk_w.cu.cpu(), pk_i.cu.cpu()) and torch.equal(cu_u_w.cpu(), cu_u_i.cpu())
+    for col in pk_w.ids:
+        assert torch.equal(pk_w.ids[col].cpu(), pk_i.ids[col].cpu()), col
+    l1 = native.fwd_bwd(tree_to_device(wire, Env.device), training=False).item()
+    l2 = native.fwd_bwd(idb, training=False).item()
+    assert l1 == l2
+    assert DeviceBatcher.h2d_bytes(hb) < 0.05 * sum(v.numel() * 8 for v in wire['history']['input_ids'].values())
