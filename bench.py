@@ -316,7 +316,7 @@ def main():
                 gpu_launches=launches, roofline=roof, kernel_ms_share=shares)
 
     if rank == 0 and world_size == 1 and not args.small and not args.no_extra:
-        line['extra'] = hbm_bound_lines(dev, world, peaks()['hbm'])
+        line['extra'] = hbm_bound_lines(dev, world, peaks()['hbm'], model=model, resampler=resampler, tensor_peak=peaks()['tensor'])
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         hb = [{k: v for k, v in b.items()} for b in host[:4]]
         r = cpu_reference(world, hb, budget_s=args.cpu_seconds)
@@ -329,7 +329,7 @@ def main():
         dist.destroy_process_group()
 
 
-def hbm_bound_lines(dev, world, hbm_peak):
+def hbm_bound_lines(dev, world, hbm_peak, model=None, resampler=None, tensor_peak=1400.0):
     """The HBM-bound pieces of the metric (BASELINE.json: cached-eval scores/s, gather HBM GB/s), each timed alone with CUDA events
     (5 repetitions after 2 warm-ups, inputs resident, a 256 MB write between repetitions to flush L2) and set against the measured
     copy bandwidth.  Algorithmic bytes per unit as in DESIGN.md §4."""
@@ -351,6 +351,18 @@ def hbm_bound_lines(dev, world, hbm_peak):
         return sorted(ts)[len(ts) // 2]
 
     out = {}
+
+    def guarded(name):
+        """Each extra line is independent: a failure is recorded under its own key and the others still run."""
+        def deco(fn):
+            try:
+                fn()
+            except Exception as e:   # noqa: BLE001
+                out[name] = dict(error=f'{type(e).__name__}: {e}'[:300])
+            torch.cuda.synchronize()
+            return fn
+        return deco
+
     # (5) cached evaluation at MIND-small validation shape: every impression row against the two caches
     D = HIDDEN
     U = torch.randn(world.n_users, D, generator=g).to(dev)
@@ -385,6 +397,82 @@ def hbm_bound_lines(dev, world, hbm_peak):
     by = real * E * 4 + ids_b.numel() * 8 + ids_b.shape[0] * E * 4
     out['gather_pool_4M_rows'] = dict(items=ids_b.shape[0], real_tokens=real, ms=ms, algorithmic_GBps=by / ms / 1e6,
                                       hbm_frac=by / ms / 1e6 / hbm_peak, note='4.8 GB table, uniform ids: HBM-resident rows of 1200 B')
+    del big, ids_b, table, ids
+
+    # (5, end to end) config 3 through the public evaluate() call: pinned host ids -> H2D -> lk_cached_scores -> lk_group_metrics ->
+    # D2H of the metric means, every repetition.  The two caches are attached to the model's cacher the way ReprCacher leaves them.
+    @guarded('cached_eval_e2e')
+    def _():
+        from legommenders_b200 import evaluate as ev
+        cacher = model.cacher
+        cacher.item.repr, cacher.user.repr = I, U
+        cacher.item.cached = cacher.user.cached = True
+        hu, hi_, hl = (torch.from_numpy(a).pin_memory() for a in (world.eval_users, world.eval_items, world.eval_click))
+        res = {}
+
+        def run():
+            res['m'] = ev.evaluate(model, hu, hi_, hl)[0]
+        ms_e = time_it(run, reps=3)
+        cacher.item.repr = cacher.user.repr = None
+        cacher.item.cached = cacher.user.cached = False
+        out['cached_eval_e2e'] = dict(rows=R, ms=ms_e, scores_per_s=R / ms_e * 1e3, h2d_bytes=int(4 * 8 * R), d2h_bytes=5 * 8,
+                                      metrics={k: round(float(v), 4) for k, v in res['m'].items()},
+                                      note='evaluate(): H2D of user/item/label ids, scoring, GAUC/MRR/NDCG@1,5,10, D2H of the means')
+
+    # (a15) item-representation cache build through the cacher contract (positional content list, pages of cache_page_size)
+    @guarded('item_cache_build')
+    def _():
+        from legommenders_b200 import Env
+        Env.test(); model.eval()
+        contents = resampler.item_cache
+        model.cacher.item.cache(contents[:2048])
+        torch.cuda.synchronize()
+        t0 = time.time()
+        model.cacher.item.cache(contents)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        model.cacher.clean()
+        Env.train(); model.train()
+        out['item_cache_build'] = dict(items=len(contents), seconds=dt, items_per_s=len(contents) / dt,
+                                       note='ItemCacher.cache(resampler.item_cache): host stacking of per-item id rows (Python) + packed NRMS item encoder per page, wall clock')
+
+    # (2) LLM-embedding item path (config 5): frozen [1M, 4096] item table -> tensor-core projection to 256-d, then the catalog
+    # scoring sweep of 4096 users against the 1M projected items.  The frozen table is held as split-bf16 planes (same bytes as fp32).
+    @guarded('llm_item_path')
+    def _():
+        n_llm, E_llm, U_sw = 1_000_000, 4096, 4096
+        tab = torch.empty((n_llm, E_llm), dtype=torch.float32, device=dev).normal_(0, 1)
+        W = torch.empty((D, E_llm), dtype=torch.float32, device=dev).normal_(0, 0.02)
+        bias = torch.zeros(D, dtype=torch.float32, device=dev)
+        ops.split_planes(tab[:4096])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); tp = ops.split_planes(tab); e1.record()
+        torch.cuda.synchronize()
+        ms_split = e0.elapsed_time(e1)
+        ref_rows = torch.arange(0, n_llm, n_llm // 64, device=dev)[:64]
+        ref = (tab[ref_rows].double() @ W.double().t()).float()
+        del tab
+        Wp = ops.split_planes(W)
+        rep = torch.empty((n_llm, D), dtype=torch.float32, device=dev)
+        ms_p = time_it(lambda: ops.tc_gemm(tp, Wp, False, n_llm, D, E_llm, out=rep, bias=bias), reps=3)
+        err = float((rep[ref_rows] - ref).abs().max() / ref.abs().max())
+        fl = 2.0 * n_llm * D * E_llm
+        by_p = n_llm * E_llm * 4 + n_llm * D * 4
+        del tp
+        Ip = ops.split_planes(rep)
+        Up = ops.split_planes(torch.randn(U_sw, D, generator=g).to(dev))
+        sc2 = torch.empty((U_sw, n_llm), dtype=torch.float32, device=dev)
+        ms_s = time_it(lambda: ops.tc_gemm(Up, Ip, False, U_sw, n_llm, D, out=sc2), reps=3)
+        by_s = U_sw * n_llm * 4 + n_llm * D * 4
+        out['llm_item_path'] = dict(
+            items=n_llm, embed_dim=E_llm, users=U_sw,
+            split_ms=ms_split, split_GBps=2 * n_llm * E_llm * 4 / ms_split / 1e6,
+            projection=dict(ms=ms_p, items_per_s=n_llm / ms_p * 1e3, tflops=fl / ms_p / 1e9, tensor_frac=fl / ms_p / 1e9 / tensor_peak,
+                            pipe_tensor_frac=3 * fl / ms_p / 1e9 / tensor_peak, algorithmic_GBps=by_p / ms_p / 1e6,
+                            hbm_frac=by_p / ms_p / 1e6 / hbm_peak, max_rel_err_vs_fp64=err),
+            scoring_sweep=dict(ms=ms_s, scores_per_s=U_sw * n_llm / ms_s * 1e3, tflops=fl / ms_s / 1e9, tensor_frac=fl / ms_s / 1e9 / tensor_peak,
+                               algorithmic_GBps=by_s / ms_s / 1e6, hbm_frac=by_s / ms_s / 1e6 / hbm_peak),
+            note='lk_tc_gemm (tcgen05 split-bf16 x3): the pipe executes 3 MMAs per algorithmic product; the sweep writes 16.8 GB of fp32 scores')
     return out
 
 

@@ -100,6 +100,16 @@ size_t lk_split_bf16_workspace_bytes(int64_t rows, int64_t cols);
 /* colsum (nullable, transpose=0 only): also emit sum over rows of X (the bias gradient rides on the pass that reads dY) */
 int lk_split_bf16(const float* X, int64_t rows, int64_t cols, int64_t ld_in, void* hi, void* lo, int64_t ld_out, int transpose,
                   float* colsum, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* several (weight) matrices in ONE launch: the parameters change every optimiser step, so their operand planes are rebuilt per
+ * step — nine 7-us launches become one.  At most LK_SPLIT_MAX_SEGS segments; pad columns of the planes are zeroed. */
+#define LK_SPLIT_MAX_SEGS 16
+typedef struct lk_split_seg {
+  const float* X;             /* fp32 [rows, cols], pitch ld_in */
+  void* hi;                   /* bf16 [rows, ld_out] */
+  void* lo;
+  int64_t rows, cols, ld_in, ld_out;
+} lk_split_seg;
+int lk_split_bf16_multi(const lk_split_seg* segs, int n_segs, cudaStream_t stream);
 size_t lk_tc_gemm_workspace_bytes(int64_t GM, int64_t GN, int64_t GK);
 /* Fused epilogue of lk_tc_gemm_ex, applied in this order to every result element r[m,n] of A·B:
  *   r += bias[n];  r = act(r);  r *= dropout(seed, m*GN+n);  r *= rowmask(m);  r += add_tab0[add_ids0[m], n] (+ add_tab1 ...)  where id > -1;

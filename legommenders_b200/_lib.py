@@ -43,6 +43,7 @@ SIGNATURES = {
     'lk_splitk_reduce': ('ppqqqiis', 'i'),
     'lk_split_bf16_workspace_bytes': ('qq', 'z'),
     'lk_split_bf16': ('pqqqppqippzs', 'i'),
+    'lk_split_bf16_multi': ('pis', 'i'),
     'lk_tc_gemm_workspace_bytes': ('qqq', 'z'),
     'lk_tc_gemm_ex': ('ppqippqipqqqqppzs', 'i'),
     'lk_tc_gemm': ('ppqippqipqqqqppifuipzs', 'i'),
@@ -113,9 +114,6 @@ _profile = None   # when a list: (name, flops, start_event, stop_event) per C-AB
 
 # algorithmic flops of the dense-contraction entry points, from their (M, N, K) arguments
 _FLOPS = {
-    'lk_pack_item_tokens': ('ppippqqs', 'i'),
-    'lk_concat_embed_bwd_workspace_bytes': ('qqqq', 'z'),
-    'lk_concat_embed_bwd': ('ppppqqqqfuppqppppzs', 'i'),
     'lk_linear_fwd': lambda a: 2 * a[5] * a[6] * a[7],
     'lk_linear_bwd_data': lambda a: 2 * a[3] * a[4] * a[5],
     'lk_linear_bwd_weight': lambda a: 2 * a[4] * a[5] * a[6],

@@ -1,5 +1,6 @@
 // Library-level entry points: version, per-thread error string, device check.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -14,6 +15,10 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("LK_PDL"); return !(e && e[0] == '0'); }();
+  return on;
 }
 static unsigned long long g_launches = 0;
 void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }

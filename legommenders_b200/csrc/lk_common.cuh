@@ -37,6 +37,38 @@ inline int check_launch(const char* what, int n = 1) {
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// A training step is ~80 short kernels in one stream; without PDL every boundary pays launch latency + grid ramp-up after
+// the predecessor has fully drained.  Every kernel of this library starts with pdl_prologue(): it lets the NEXT kernel in
+// the stream be scheduled as soon as this grid's last CTA is resident (griddepcontrol.launch_dependents), and then blocks
+// until the PREVIOUS grid has completed and its memory is visible (griddepcontrol.wait) before touching global memory.
+// Every kernel waits on its immediate predecessor before doing anything, so stream order is preserved transitively
+// (reads after writes and buffer reuse alike); only launch latency and CTA scheduling overlap.  LK_PDL=0 turns it off.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_trigger();
+  pdl_wait();
+}
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through cudaGetLastError in check_launch
+}
+#define LK_LAUNCH(kernel, grid, block, smem, st, ...) \
+  lk::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), st, ##__VA_ARGS__)
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

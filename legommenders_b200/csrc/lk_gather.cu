@@ -23,6 +23,7 @@ constexpr int GW = 8;  // warps per block in the gather kernels
 __global__ void __launch_bounds__(GW * 32) gather_rows_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
                                                               const float* __restrict__ table, float* __restrict__ out,
                                                               int64_t M, int E, int accumulate) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * GW + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * GW;
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(GW * 32) gather_rows_kernel(const int64_t* __r
 __global__ void __launch_bounds__(GW * 32) gather_split_kernel(const int64_t* __restrict__ ids, const float* __restrict__ table,
                                                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                                                int64_t M, int E, int ld) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * GW + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * GW;
@@ -78,6 +80,7 @@ template <int MODE>  // 0 mean, 1 max, 2 sum
 __global__ void __launch_bounds__(GW * 32) gather_pool_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
                                                               const float* __restrict__ table, float* __restrict__ out,
                                                               int64_t N, int S, int E) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t n = (int64_t)blockIdx.x * GW + (threadIdx.x >> 5);
   const int c = (blockIdx.y * 32 + lane) * 4;
@@ -128,6 +131,7 @@ constexpr int SEG = 32;  // rows per partial sum
 
 __global__ void make_keys_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask, int* __restrict__ keys,
                                  int* __restrict__ vals, int64_t P, int V) {
+  pdl_prologue();
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   int64_t id = ids[p];
@@ -138,6 +142,7 @@ __global__ void make_keys_kernel(const int64_t* __restrict__ ids, const int64_t*
 
 __global__ void partial_counts_kernel(const int* __restrict__ run_len, const int* __restrict__ num_runs, int* __restrict__ npart,
                                       int cap) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cap) return;
   npart[i] = (i < *num_runs) ? (run_len[i] + SEG - 1) / SEG : 0;
@@ -149,6 +154,7 @@ __global__ void __launch_bounds__(GW * 32) partial_sums_kernel(const int* __rest
                                                                const int* __restrict__ num_runs, const float* __restrict__ src,
                                                                const float* __restrict__ scale, int row_div, int E,
                                                                float* __restrict__ partial, int max_partials) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * GW + (threadIdx.x >> 5);
   const int R = *num_runs;
@@ -180,6 +186,7 @@ __global__ void __launch_bounds__(GW * 32) run_reduce_kernel(const int* __restri
                                                              const int* __restrict__ part_off, const int* __restrict__ num_runs,
                                                              const float* __restrict__ partial, float* __restrict__ dtable, int V,
                                                              int E, int accumulate, int max_runs) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * GW + (threadIdx.x >> 5);
   if (r >= max_runs || r >= *num_runs) return;
@@ -206,6 +213,7 @@ constexpr int SM_MAX_V = 64, SM_CHUNK = 512, SM_LANES = 4;
 __global__ void __launch_bounds__(256) scatter_small_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
                                                             const float* __restrict__ src, const float* __restrict__ scale,
                                                             int row_div, int64_t P, int V, int E, float* __restrict__ partial) {
+  pdl_prologue();
   extern __shared__ __align__(16) float acc_s[];   // [SM_LANES][V][E]
   const int E4 = E >> 2;
   const int cols = blockDim.x / SM_LANES;          // column threads per row-lane
@@ -241,6 +249,7 @@ __global__ void __launch_bounds__(256) scatter_small_kernel(const int64_t* __res
 
 __global__ void scatter_small_finish_kernel(const float* __restrict__ partial, float* __restrict__ dtable, int nblk, int VE4,
                                             int accumulate) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= VE4) return;
   float4 t = accumulate ? reinterpret_cast<const float4*>(dtable)[i] : f4_zero();
@@ -265,6 +274,7 @@ __global__ void __launch_bounds__(256) concat_embed_bwd_kernel(const float* __re
                                                                int64_t T, int D, int Vc, int Vs, float drop_p, unsigned long long seed,
                                                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld,
                                                                float* __restrict__ part) {
+  pdl_prologue();
   extern __shared__ __align__(16) float sm[];           // [EB_LANES][1 + Vc + Vs][D]
   __shared__ int s_title[EB_ROWS], s_cat[EB_ROWS], s_sp[EB_ROWS];
   const int D4 = D >> 2, NT = 1 + Vc + Vs;
@@ -323,6 +333,7 @@ __global__ void __launch_bounds__(256) concat_embed_bwd_kernel(const float* __re
 // out[c] = Σ_b part[b, c] in a fixed order: 32 part-lanes x 32 columns per block, then an ordered shared-memory reduction
 __global__ void __launch_bounds__(1024) partial_finish_kernel(const float* __restrict__ part, int nparts, int64_t stride, int cols,
                                                               float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float red[32][33];
   const int cx = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -348,6 +359,7 @@ struct PackCols { const int64_t* table[4]; int64_t* out[4]; int ncols; };
 
 __global__ void __launch_bounds__(256) pack_item_tokens_kernel(PackCols pc, const int64_t* __restrict__ items, const int* __restrict__ cu,
                                                                int64_t n, int S) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= n) return;
@@ -407,7 +419,7 @@ int lk_gather_rows(const int64_t* ids, const int64_t* mask, const float* table, 
   if (M == 0) return LK_OK;
   int64_t blocks = (M + GW - 1) / GW;
   if (blocks > (int64_t)kNumSMs * 64) blocks = (int64_t)kNumSMs * 64;
-  gather_rows_kernel<<<(unsigned)blocks, GW * 32, 0, st>>>(ids, mask, table, out, M, (int)E, accumulate);
+  LK_LAUNCH((gather_rows_kernel), (unsigned)blocks, GW * 32, 0, st, ids, mask, table, out, M, (int)E, accumulate);
   return check_launch("gather_rows");
 }
 
@@ -416,7 +428,7 @@ int lk_gather_split_bf16(const int64_t* ids, const float* table, void* hi, void*
   if (M == 0) return LK_OK;
   int64_t blocks = (M + GW - 1) / GW;
   if (blocks > (int64_t)kNumSMs * 64) blocks = (int64_t)kNumSMs * 64;
-  gather_split_kernel<<<(unsigned)blocks, GW * 32, 0, st>>>(ids, table, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, M, (int)E, (int)ld);
+  LK_LAUNCH((gather_split_kernel), (unsigned)blocks, GW * 32, 0, st, ids, table, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, M, (int)E, (int)ld);
   return check_launch("gather_split");
 }
 
@@ -426,9 +438,9 @@ int lk_gather_pool(const int64_t* ids, const int64_t* mask, const float* table, 
   LK_REQUIRE(mode >= 0 && mode <= 2, LK_ERR_ARG, "lk_gather_pool: mode must be 0 (mean), 1 (max) or 2 (sum)");
   if (N == 0) return LK_OK;
   dim3 grid((unsigned)((N + GW - 1) / GW), (unsigned)((E + 127) / 128));
-  if (mode == 0) gather_pool_kernel<0><<<grid, GW * 32, 0, st>>>(ids, mask, table, out, N, (int)S, (int)E);
-  else if (mode == 1) gather_pool_kernel<1><<<grid, GW * 32, 0, st>>>(ids, mask, table, out, N, (int)S, (int)E);
-  else gather_pool_kernel<2><<<grid, GW * 32, 0, st>>>(ids, mask, table, out, N, (int)S, (int)E);
+  if (mode == 0) LK_LAUNCH((gather_pool_kernel<0>), grid, GW * 32, 0, st, ids, mask, table, out, N, (int)S, (int)E);
+  else if (mode == 1) LK_LAUNCH((gather_pool_kernel<1>), grid, GW * 32, 0, st, ids, mask, table, out, N, (int)S, (int)E);
+  else LK_LAUNCH((gather_pool_kernel<2>), grid, GW * 32, 0, st, ids, mask, table, out, N, (int)S, (int)E);
   return check_launch("gather_pool");
 }
 
@@ -439,7 +451,7 @@ int lk_pack_item_tokens(const int64_t* const* tables, int64_t* const* outs, int 
   PackCols pc;
   pc.ncols = ncols;
   for (int c = 0; c < 4; c++) { pc.table[c] = c < ncols ? tables[c] : nullptr; pc.out[c] = c < ncols ? outs[c] : nullptr; }
-  pack_item_tokens_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(pc, items, cu, n, (int)S);
+  LK_LAUNCH((pack_item_tokens_kernel), (unsigned)((n + 7) / 8), 256, 0, st, pc, items, cu, n, (int)S);
   return check_launch("pack_item_tokens");
 }
 
@@ -460,15 +472,15 @@ int lk_concat_embed_bwd(const float* dx, const int64_t* title_ids, const int64_t
   if (T > 0) {
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(concat_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-    concat_embed_bwd_kernel<<<nblk, 256, smem, st>>>(dx, title_ids, cat_ids, special_ids, T, (int)D, (int)n_cats, (int)n_special, drop_p,
+    LK_LAUNCH((concat_embed_bwd_kernel), nblk, 256, smem, st, dx, title_ids, cat_ids, special_ids, T, (int)D, (int)n_cats, (int)n_special, drop_p,
                                                      (unsigned long long)seed, (__nv_bfloat16*)dp_hi, (__nv_bfloat16*)dp_lo, (int)ld,
                                                      (float*)workspace);
   }
   const float* part = (const float*)workspace;
   const int64_t stride = (int64_t)NT * D;
-  partial_finish_kernel<<<(unsigned)((D + 31) / 32), 1024, 0, st>>>(part, nblk, stride, (int)D, g_bias);
-  partial_finish_kernel<<<(unsigned)((n_cats * D + 31) / 32), 1024, 0, st>>>(part + D, nblk, stride, (int)(n_cats * D), g_cat);
-  partial_finish_kernel<<<(unsigned)((n_special * D + 31) / 32), 1024, 0, st>>>(part + (1 + n_cats) * D, nblk, stride, (int)(n_special * D),
+  LK_LAUNCH((partial_finish_kernel), (unsigned)((D + 31) / 32), 1024, 0, st, part, nblk, stride, (int)D, g_bias);
+  LK_LAUNCH((partial_finish_kernel), (unsigned)((n_cats * D + 31) / 32), 1024, 0, st, part + D, nblk, stride, (int)(n_cats * D), g_cat);
+  LK_LAUNCH((partial_finish_kernel), (unsigned)((n_special * D + 31) / 32), 1024, 0, st, part + (1 + n_cats) * D, nblk, stride, (int)(n_special * D),
                                                                                 g_special);
   return check_launch("concat_embed_bwd", 4);
 }
@@ -490,9 +502,9 @@ int lk_scatter_add_sorted(const int64_t* ids, const int64_t* mask, const float* 
     const size_t smem = (size_t)SM_LANES * V * E * 4;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(scatter_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
-    scatter_small_kernel<<<nblk, 256, smem, st>>>(ids, mask, src, scale, (int)row_div, P, (int)V, (int)E, (float*)workspace);
+    LK_LAUNCH((scatter_small_kernel), nblk, 256, smem, st, ids, mask, src, scale, (int)row_div, P, (int)V, (int)E, (float*)workspace);
     const int VE4 = (int)(V * E / 4);
-    scatter_small_finish_kernel<<<(VE4 + 127) / 128, 128, 0, st>>>((const float*)workspace, dtable, nblk, VE4, accumulate);
+    LK_LAUNCH((scatter_small_finish_kernel), (VE4 + 127) / 128, 128, 0, st, (const float*)workspace, dtable, nblk, VE4, accumulate);
     return check_launch("scatter_add_small", 2);
   }
   if (!accumulate) cudaMemsetAsync(dtable, 0, (size_t)V * E * sizeof(float), st);
@@ -500,7 +512,7 @@ int lk_scatter_add_sorted(const int64_t* ids, const int64_t* mask, const float* 
   ScatterWs w;
   carve(w, workspace, P, V, (int)E);
   const int cap = run_cap(P, V);
-  make_keys_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(ids, mask, w.keys, w.vals, P, (int)V);
+  LK_LAUNCH((make_keys_kernel), (unsigned)((P + 255) / 256), 256, 0, st, ids, mask, w.keys, w.vals, P, (int)V);
   int end_bit = 1;
   while ((1LL << end_bit) <= V) end_bit++;
   size_t cb = w.cub_bytes;
@@ -509,15 +521,15 @@ int lk_scatter_add_sorted(const int64_t* ids, const int64_t* mask, const float* 
   cub::DeviceRunLengthEncode::Encode(w.cub, cb, w.skeys, w.run_key, w.run_len, w.num_runs, (int)P, st);
   cb = w.cub_bytes;
   cub::DeviceScan::ExclusiveSum(w.cub, cb, w.run_len, w.run_off, cap, st);
-  partial_counts_kernel<<<(cap + 255) / 256, 256, 0, st>>>(w.run_len, w.num_runs, w.npart, cap);
+  LK_LAUNCH((partial_counts_kernel), (cap + 255) / 256, 256, 0, st, w.run_len, w.num_runs, w.npart, cap);
   cb = w.cub_bytes;
   cub::DeviceScan::ExclusiveSum(w.cub, cb, w.npart, w.part_off, cap, st);
   const int maxp = (int)partial_cap(P, V);
   dim3 g1((maxp + GW - 1) / GW, (unsigned)((E + 127) / 128));
-  partial_sums_kernel<<<g1, GW * 32, 0, st>>>(w.svals, w.run_off, w.run_len, w.part_off, w.num_runs, src, scale, (int)row_div, (int)E,
+  LK_LAUNCH((partial_sums_kernel), g1, GW * 32, 0, st, w.svals, w.run_off, w.run_len, w.part_off, w.num_runs, src, scale, (int)row_div, (int)E,
                                             w.partial, maxp);
   dim3 g2((cap + GW - 1) / GW, (unsigned)((E + 127) / 128));
-  run_reduce_kernel<<<g2, GW * 32, 0, st>>>(w.run_key, w.run_len, w.part_off, w.num_runs, w.partial, dtable, (int)V, (int)E, 1, cap);
+  LK_LAUNCH((run_reduce_kernel), g2, GW * 32, 0, st, w.run_key, w.run_len, w.part_off, w.num_runs, w.partial, dtable, (int)V, (int)E, 1, cap);
   return check_launch("scatter_add_sorted", 4);
 }
 

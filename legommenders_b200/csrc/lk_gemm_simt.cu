@@ -49,6 +49,7 @@ __device__ __forceinline__ float4 load_rowmajor4(const float* base, int ld, int 
 
 template <bool AK, bool BKM, bool CONV_A, bool CONV_B>
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmParams p) {
+  pdl_prologue();
   __shared__ __align__(16) float As[2][BK][BM + SPAD];
   __shared__ __align__(16) float Bs[2][BK][BN + SPAD];
 
@@ -194,24 +195,43 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmParams p) {
   }
 }
 
-// Deterministic split-K reduction: C[m,n] (+)= sum_z partial[z,m,n]  (fixed z order)
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C, int M, int N, int ldc,
-                                     int splits, int accumulate) {
-  size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t total4 = (size_t)M * N / 4;
-  if (i4 >= total4) return;
-  size_t e = i4 * 4;
-  int m = (int)(e / N), n = (int)(e % N);
+// Deterministic split-K reduction: C[m,n] (+)= sum_z partial[z,m,n].  A block owns 64 float4 outputs; its four z-lanes each sum
+// every fourth partial (loads in flight in parallel) and are combined in a fixed order, so the result does not depend on timing.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C, int M, int N, int ldc,
+                                                            int splits, int accumulate) {
+  pdl_prologue();
+  __shared__ float4 red[3][64];
+  const int q = threadIdx.x & 63, zl = threadIdx.x >> 6;
+  const size_t i4 = (size_t)blockIdx.x * 64 + q;
+  const size_t total4 = (size_t)M * N / 4, MN = (size_t)M * N;
+  const bool ok = i4 < total4;
+  const size_t e = i4 * 4;
   float4 s = f4_zero();
-  for (int z = 0; z < splits; z++) f4_add(s, ldg4_stream(partial + (size_t)z * M * N + e));
-  float* o = C + (size_t)m * ldc + n;
-  if (accumulate) f4_add(s, *reinterpret_cast<const float4*>(o));
-  st4(o, s);
+  if (ok) {
+    int z = zl;
+#pragma unroll 1
+    for (; z + 12 < splits; z += 16) {
+      const float4 a = ldg4_stream(partial + (size_t)z * MN + e), b = ldg4_stream(partial + (size_t)(z + 4) * MN + e);
+      const float4 c = ldg4_stream(partial + (size_t)(z + 8) * MN + e), d = ldg4_stream(partial + (size_t)(z + 12) * MN + e);
+      f4_add(s, a); f4_add(s, b); f4_add(s, c); f4_add(s, d);
+    }
+    for (; z < splits; z += 4) f4_add(s, ldg4_stream(partial + (size_t)z * MN + e));
+  }
+  if (zl > 0) red[zl - 1][q] = s;
+  __syncthreads();
+  if (zl == 0 && ok) {
+    f4_add(s, red[0][q]); f4_add(s, red[1][q]); f4_add(s, red[2][q]);
+    const int m = (int)(e / N), n = (int)(e % N);
+    float* o = C + (size_t)m * ldc + n;
+    if (accumulate) f4_add(s, *reinterpret_cast<const float4*>(o));
+    st4(o, s);
+  }
 }
 
 // Column sums of a row-major [M,N] matrix, deterministic two-stage (db = sum_m dY[m,:]).
 // block = 32 columns x 8 row-lanes over `rows_per_block` rows; the row-lanes are combined in a fixed order (deterministic)
 __global__ void __launch_bounds__(256) colsum_stage1(const float* __restrict__ X, float* __restrict__ part, int M, int N, int rows_per_block) {
+  pdl_prologue();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
@@ -231,6 +251,7 @@ __global__ void __launch_bounds__(256) colsum_stage1(const float* __restrict__ X
   }
 }
 __global__ void colsum_stage2(const float* __restrict__ part, float* __restrict__ out, int nparts, int N, int accumulate) {
+  pdl_prologue();
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
@@ -241,6 +262,7 @@ __global__ void colsum_stage2(const float* __restrict__ part, float* __restrict_
 // dPre = dY * act'(Y) * dropout_scale * rowmask   (Y is the saved epilogue OUTPUT, i.e. after act/dropout/mask)
 __global__ void act_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ Y, const int64_t* __restrict__ rowmask,
                                float* __restrict__ dPre, int64_t M, int N, int act, float drop_p, unsigned long long seed) {
+  pdl_prologue();
   int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int N4 = N >> 2;
   if (i4 >= M * N4) return;
@@ -275,6 +297,7 @@ __global__ void act_bwd_kernel(const float* __restrict__ dY, const float* __rest
 }
 
 __global__ void valid_mask_kernel(const int64_t* __restrict__ ids, int64_t* __restrict__ out, int64_t n) {
+  pdl_prologue();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = ids[i] > -1 ? 1 : 0;
 }
@@ -282,7 +305,7 @@ __global__ void valid_mask_kernel(const int64_t* __restrict__ ids, int64_t* __re
 template <bool AK, bool BKM, bool CA, bool CB>
 static int launch(const GemmParams& p, int splits, cudaStream_t st) {
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
-  gemm_simt_kernel<AK, BKM, CA, CB><<<grid, NT, 0, st>>>(p);
+  LK_LAUNCH((gemm_simt_kernel<AK, BKM, CA, CB>), grid, NT, 0, st, p);
   return check_launch("gemm_simt");
 }
 
@@ -348,7 +371,7 @@ int lk_linear_bwd_weight(const float* dY, const float* X, float* dW, float* db, 
   if (rc) return rc;
   if (splits > 1) {
     size_t total4 = (size_t)N * K / 4;
-    splitk_reduce_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(ws, dW, (int)N, (int)K, (int)K, splits, accumulate);
+    LK_LAUNCH((splitk_reduce_kernel), (unsigned)((total4 + 63) / 64), 256, 0, st, ws, dW, (int)N, (int)K, (int)K, splits, accumulate);
     rc = check_launch("splitk_reduce");
     if (rc) return rc;
   }
@@ -357,8 +380,8 @@ int lk_linear_bwd_weight(const float* dY, const float* X, float* dW, float* db, 
     int rpb = 512;
     int nparts = (int)((M + rpb - 1) / rpb);
     dim3 g1((unsigned)((N + 31) / 32), nparts);
-    colsum_stage1<<<g1, 256, 0, st>>>(dY, part, (int)M, (int)N, rpb);
-    colsum_stage2<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(part, db, nparts, (int)N, accumulate);
+    LK_LAUNCH((colsum_stage1), g1, 256, 0, st, dY, part, (int)M, (int)N, rpb);
+    LK_LAUNCH((colsum_stage2), (unsigned)((N + 127) / 128), 128, 0, st, part, db, nparts, (int)N, accumulate);
     rc = check_launch("colsum", 2);
   }
   return rc;
@@ -369,13 +392,13 @@ int lk_act_bwd(const float* dY, const float* Y, const int64_t* rowmask, float* d
   LK_REQUIRE(N % 4 == 0, LK_ERR_SHAPE, "lk_act_bwd: N=%ld must be a multiple of 4", (long)N);
   if (M == 0) return LK_OK;
   int64_t total = M * (N / 4);
-  act_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dY, Y, rowmask, dPre, M, (int)N, act, drop_p, (unsigned long long)seed);
+  LK_LAUNCH((act_bwd_kernel), (unsigned)((total + 255) / 256), 256, 0, st, dY, Y, rowmask, dPre, M, (int)N, act, drop_p, (unsigned long long)seed);
   return check_launch("act_bwd");
 }
 
 int lk_valid_mask(const int64_t* ids, int64_t* out, int64_t n, cudaStream_t st) {
   if (n == 0) return LK_OK;
-  valid_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ids, out, n);
+  LK_LAUNCH((valid_mask_kernel), (unsigned)((n + 255) / 256), 256, 0, st, ids, out, n);
   return check_launch("valid_mask");
 }
 
@@ -383,7 +406,7 @@ int lk_splitk_reduce(const float* partial, float* C, int64_t M, int64_t N, int64
   LK_REQUIRE(N % 4 == 0 && ldc % 4 == 0, LK_ERR_SHAPE, "lk_splitk_reduce: N and ldc must be multiples of 4");
   size_t total4 = (size_t)M * N / 4;
   if (total4 == 0) return LK_OK;
-  splitk_reduce_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(partial, C, (int)M, (int)N, (int)ldc, splits, accumulate);
+  LK_LAUNCH((splitk_reduce_kernel), (unsigned)((total4 + 63) / 64), 256, 0, st, partial, C, (int)M, (int)N, (int)ldc, splits, accumulate);
   return check_launch("splitk_reduce");
 }
 
@@ -399,8 +422,8 @@ int lk_colsum(const float* X, float* out, int64_t M, int64_t N, int accumulate, 
   int rpb = 512;
   int nparts = (int)((M + rpb - 1) / rpb);
   dim3 g1((unsigned)((N + 31) / 32), nparts);
-  colsum_stage1<<<g1, 256, 0, st>>>(X, (float*)workspace, (int)M, (int)N, rpb);
-  colsum_stage2<<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const float*)workspace, out, nparts, (int)N, accumulate);
+  LK_LAUNCH((colsum_stage1), g1, 256, 0, st, X, (float*)workspace, (int)M, (int)N, rpb);
+  LK_LAUNCH((colsum_stage2), (unsigned)((N + 127) / 128), 128, 0, st, (const float*)workspace, out, nparts, (int)N, accumulate);
   return check_launch("colsum", 2);
 }
 
@@ -453,7 +476,7 @@ int lk_conv1d_bwd_weight(const float* dY, const float* X, float* dWr, float* db,
   if (rc) return rc;
   if (splits > 1) {
     size_t total4 = (size_t)Cout * Kw / 4;
-    splitk_reduce_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(ws, dWr, (int)Cout, Kw, Kw, splits, accumulate);
+    LK_LAUNCH((splitk_reduce_kernel), (unsigned)((total4 + 63) / 64), 256, 0, st, ws, dWr, (int)Cout, Kw, Kw, splits, accumulate);
     rc = check_launch("splitk_reduce");
     if (rc) return rc;
   }
@@ -462,8 +485,8 @@ int lk_conv1d_bwd_weight(const float* dY, const float* X, float* dWr, float* db,
     int rpb = 512;
     int nparts = (int)((rows + rpb - 1) / rpb);
     dim3 g1((unsigned)((Cout + 31) / 32), nparts);
-    colsum_stage1<<<g1, 256, 0, st>>>(dY, part, (int)rows, (int)Cout, rpb);
-    colsum_stage2<<<(unsigned)((Cout + 127) / 128), 128, 0, st>>>(part, db, nparts, (int)Cout, accumulate);
+    LK_LAUNCH((colsum_stage1), g1, 256, 0, st, dY, part, (int)rows, (int)Cout, rpb);
+    LK_LAUNCH((colsum_stage2), (unsigned)((Cout + 127) / 128), 128, 0, st, part, db, nparts, (int)Cout, accumulate);
     rc = check_launch("colsum", 2);
   }
   return rc;

@@ -248,6 +248,7 @@ template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const Params p) {
+  pdl_trigger();   // the wait comes after the CTA set-up below (barriers, TMEM allocation, descriptor prefetch touch no global data)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024-byte alignment
   uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
@@ -285,6 +286,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // the previous kernel in the stream has completed: operands may be read, outputs overwritten
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer ------------------------------------------------
@@ -398,6 +400,7 @@ constexpr int SPLIT_ROWS = 64;
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ X, int64_t rows, int cols, int64_t ld_in,
                                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t ld_out,
                                                          float* __restrict__ colsum_part) {
+  pdl_prologue();
   __shared__ float red[8][256 + 8];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 256 + tx * 8;
@@ -439,16 +442,39 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
   }
 }
 
-__global__ void colsum_finish_kernel(const float* __restrict__ part, float* __restrict__ out, int nparts, int cols) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  float s = 0.f;
-  for (int i = 0; i < nparts; i++) s += part[(int64_t)i * cols + c];
-  out[c] = s;
+// several matrices in one launch (blockIdx.y = segment): each thread converts 8 contiguous columns of one row
+struct SplitSegs { lk_split_seg seg[LK_SPLIT_MAX_SEGS]; };
+__global__ void __launch_bounds__(256) split_bf16_multi_kernel(const SplitSegs segs) {
+  pdl_prologue();
+  const lk_split_seg& g = segs.seg[blockIdx.y];
+  const int64_t chunks = g.ld_out >> 3, total = g.rows * chunks;
+  __nv_bfloat16* hi = (__nv_bfloat16*)g.hi;
+  __nv_bfloat16* lo = (__nv_bfloat16*)g.lo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / chunks;
+    const int c = (int)(i - r * chunks) * 8;
+    float x[8];
+    if (c + 7 < g.cols) {
+      const float4 a = ldg4(g.X + r * g.ld_in + c), b2 = ldg4(g.X + r * g.ld_in + c + 4);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b2.x; x[5] = b2.y; x[6] = b2.z; x[7] = b2.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; e++) x[e] = (c + e < g.cols) ? g.X[r * g.ld_in + c + e] : 0.f;
+    }
+    __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      h[e] = __float2bfloat16_rn(x[e]);
+      l[e] = __float2bfloat16_rn(x[e] - __bfloat162float(h[e]));
+    }
+    *reinterpret_cast<uint4*>(hi + r * g.ld_out + c) = *reinterpret_cast<uint4*>(h);
+    *reinterpret_cast<uint4*>(lo + r * g.ld_out + c) = *reinterpret_cast<uint4*>(l);
+  }
 }
 
 // out[c] = sum_i part[i, c] in a fixed order: 32 part-lanes x 32 columns per block, then an ordered shared-memory reduction
 __global__ void __launch_bounds__(1024) colsum_finish2_kernel(const float* __restrict__ part, float* __restrict__ out, int nparts, int cols) {
+  pdl_prologue();
   __shared__ float red[32][33];
   const int cx = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -468,6 +494,7 @@ __global__ void __launch_bounds__(1024) colsum_finish2_kernel(const float* __res
 // transposed split through a 32x32 smem tile: out[c, r]
 __global__ void split_bf16_t_kernel(const float* __restrict__ X, int rows, int cols, int64_t ld_in, __nv_bfloat16* __restrict__ hi,
                                     __nv_bfloat16* __restrict__ lo, int64_t ld_out) {
+  pdl_prologue();
   __shared__ float t[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -548,18 +575,39 @@ int lk_split_bf16(const float* X, int64_t rows, int64_t cols, int64_t ld_in, voi
                "lk_split_bf16: workspace too small for the fused column sums");
     const int nparts = (int)((rows + SPLIT_ROWS - 1) / SPLIT_ROWS);
     dim3 grid((unsigned)((ld_out + 255) / 256), (unsigned)nparts);
-    split_bf16_kernel<<<grid, 256, 0, st>>>(X, rows, (int)cols, ld_in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_out,
+    LK_LAUNCH((split_bf16_kernel), grid, 256, 0, st, X, rows, (int)cols, ld_in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_out,
                                             colsum ? (float*)workspace : nullptr);
     if (colsum) {
-      colsum_finish_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>((const float*)workspace, colsum, nparts, (int)cols);
+      LK_LAUNCH((colsum_finish2_kernel), (unsigned)((cols + 31) / 32), 1024, 0, st, (const float*)workspace, colsum, nparts, (int)cols);
       return check_launch("split_bf16", 2);
     }
   } else {
     LK_REQUIRE(ld_out >= rows && !colsum, LK_ERR_SHAPE, "lk_split_bf16: transposed pitch too small / no fused sums when transposing");
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((ld_out + 31) / 32));
-    split_bf16_t_kernel<<<grid, dim3(32, 8), 0, st>>>(X, (int)rows, (int)cols, ld_in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_out);
+    LK_LAUNCH((split_bf16_t_kernel), grid, dim3(32, 8), 0, st, X, (int)rows, (int)cols, ld_in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_out);
   }
   return check_launch("split_bf16");
+}
+
+int lk_split_bf16_multi(const lk_split_seg* segs, int n_segs, cudaStream_t st) {
+  LK_REQUIRE(n_segs >= 0 && n_segs <= LK_SPLIT_MAX_SEGS, LK_ERR_ARG, "lk_split_bf16_multi: %d segments (max %d)", n_segs, LK_SPLIT_MAX_SEGS);
+  if (n_segs == 0) return LK_OK;
+  SplitSegs ss = {};
+  int64_t most = 0;
+  for (int i = 0; i < n_segs; i++) {
+    const lk_split_seg& g = segs[i];
+    LK_REQUIRE(g.ld_out % 8 == 0 && g.ld_out >= g.cols && g.ld_in % 4 == 0 && g.rows >= 0, LK_ERR_SHAPE,
+               "lk_split_bf16_multi: segment %d has bad pitches (cols=%ld ld_in=%ld ld_out=%ld)", i, (long)g.cols, (long)g.ld_in, (long)g.ld_out);
+    LK_REQUIRE(((uintptr_t)g.X | (uintptr_t)g.hi | (uintptr_t)g.lo) % 16 == 0, LK_ERR_ARG, "lk_split_bf16_multi: segment %d is not 16-byte aligned", i);
+    ss.seg[i] = g;
+    const int64_t t = g.rows * (g.ld_out >> 3);
+    if (t > most) most = t;
+  }
+  if (most == 0) return LK_OK;
+  int64_t bx = (most + 255) / 256;
+  if (bx > 2 * kNumSMs) bx = 2 * kNumSMs;
+  LK_LAUNCH((split_bf16_multi_kernel), dim3((unsigned)bx, (unsigned)n_segs), 256, 0, st, ss);
+  return check_launch("split_bf16_multi");
 }
 
 size_t lk_tc_gemm_workspace_bytes(int64_t GM, int64_t GN, int64_t GK) {
@@ -633,14 +681,14 @@ int lk_tc_gemm_ex(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, con
   }
   int total = p.m_tiles * p.n_tiles * p.splits;
   int grid = total < kNumSMs ? total : kNumSMs;
-  if (a_mn) tc_gemm_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
-  else if (b_mn) tc_gemm_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
-  else tc_gemm_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, p);
+  if (a_mn) LK_LAUNCH((tc_gemm_kernel<true, true>), grid, NUM_THREADS, SMEM_BYTES, st, mAh, mAl, mBh, mBl, p);
+  else if (b_mn) LK_LAUNCH((tc_gemm_kernel<false, true>), grid, NUM_THREADS, SMEM_BYTES, st, mAh, mAl, mBh, mBl, p);
+  else LK_LAUNCH((tc_gemm_kernel<false, false>), grid, NUM_THREADS, SMEM_BYTES, st, mAh, mAl, mBh, mBl, p);
   rc = check_launch("tc_gemm");
   if (rc) return rc;
   if (p.splits > 1) return lk_splitk_reduce(p.partial, C, GM, GN, ldc, p.splits, ep->accumulate, st);
   if (ep->colsum) {
-    colsum_finish2_kernel<<<(unsigned)((GN + 31) / 32), 1024, 0, st>>>(p.colsum_part, ep->colsum, p.m_tiles * 4, (int)GN);
+    LK_LAUNCH((colsum_finish2_kernel), (unsigned)((GN + 31) / 32), 1024, 0, st, p.colsum_part, ep->colsum, p.m_tiles * 4, (int)GN);
     return check_launch("tc_gemm_colsum");
   }
   return LK_OK;

@@ -53,6 +53,7 @@ static size_t metric_carve(MetricWs& w, void* base, int64_t R) {
 }
 
 __global__ void metric_keys_kernel(const int64_t* __restrict__ groups, long long* __restrict__ keys, int* __restrict__ vals, int64_t R) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R) return;
   keys[i] = (long long)groups[i];   // cub's radix sort orders signed keys correctly (ascending, like pandas groupby)
@@ -61,6 +62,7 @@ __global__ void metric_keys_kernel(const int64_t* __restrict__ groups, long long
 
 __global__ void metric_gather_kernel(const int* __restrict__ svals, const float* __restrict__ scores, const int64_t* __restrict__ labels,
                                      float* __restrict__ s, float* __restrict__ y, int64_t R) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R) return;
   const int r = svals[i];
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(256) group_metrics_kernel(const float* __restr
                                                             const int* __restrict__ run_off, const int* __restrict__ run_len,
                                                             const int* __restrict__ num_runs, const double* __restrict__ dcs,
                                                             int n_disc, KList ks, float* __restrict__ per_group, int64_t cap) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (g >= *num_runs) return;
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(256) group_metrics_kernel(const float* __restr
 // out[m] = mean over groups of per_group[m][:] (fp64 accumulation in a fixed order); out[nm] = number of groups
 __global__ void __launch_bounds__(256) metric_mean_kernel(const float* __restrict__ per_group, const int* __restrict__ num_runs,
                                                           int64_t cap, int nm, double* __restrict__ out) {
+  pdl_prologue();
   __shared__ double sh[256];
   const int m = blockIdx.x;
   const int G = *num_runs;
@@ -195,16 +199,16 @@ int lk_group_metrics(const float* scores, const int64_t* labels, const int64_t* 
   kl.nk = nk;
   for (int i = 0; i < MAX_K; i++) kl.k[i] = i < nk ? ks[i] : 0;
   const unsigned nb = (unsigned)((R + 255) / 256);
-  metric_keys_kernel<<<nb, 256, 0, st>>>(groups, w.keys, w.vals, R);
+  LK_LAUNCH((metric_keys_kernel), nb, 256, 0, st, groups, w.keys, w.vals, R);
   size_t cb = w.cub_bytes;
   cub::DeviceRadixSort::SortPairs(w.cub, cb, w.keys, w.skeys, w.vals, w.svals, (int)R, 0, 64, st);   // LSD radix sort: stable
-  metric_gather_kernel<<<nb, 256, 0, st>>>(w.svals, scores, labels, w.s, w.y, R);
+  LK_LAUNCH((metric_gather_kernel), nb, 256, 0, st, w.svals, scores, labels, w.s, w.y, R);
   cb = w.cub_bytes;
   cub::DeviceRunLengthEncode::Encode(w.cub, cb, w.skeys, w.run_key, w.run_len, w.num_runs, (int)R, st);
   cb = w.cub_bytes;
   cub::DeviceScan::ExclusiveSum(w.cub, cb, w.run_len, w.run_off, (int)R, st);
-  group_metrics_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>(w.s, w.y, w.run_off, w.run_len, w.num_runs, disc_prefix, (int)n_disc, kl, pg, R);
-  metric_mean_kernel<<<2 + nk, 256, 0, st>>>(pg, w.num_runs, R, 2 + nk, out);
+  LK_LAUNCH((group_metrics_kernel), (unsigned)((R + 7) / 8), 256, 0, st, w.s, w.y, w.run_off, w.run_len, w.num_runs, disc_prefix, (int)n_disc, kl, pg, R);
+  LK_LAUNCH((metric_mean_kernel), 2 + nk, 256, 0, st, pg, w.num_runs, R, 2 + nk, out);
   return check_launch("group_metrics", 5);
 }
 

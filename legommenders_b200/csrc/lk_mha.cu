@@ -183,6 +183,7 @@ __device__ __forceinline__ uint32_t quad_bits(bool mine) {
 // ------------------------------------------------------------------------------------------------ forward
 template <int DH, int R>
 __global__ void __maxnreg__(DH <= 32 ? 96 : 168) mha_fwd_seq_kernel(MhaParams p) {   // 4 CTAs of 160 threads per SM at head dim 32
+  pdl_prologue();
   constexpr int W = DH / R;
   extern __shared__ __align__(16) float smem[];
   const int64_t n = blockIdx.x;
@@ -269,6 +270,7 @@ __global__ void __maxnreg__(DH <= 32 ? 96 : 168) mha_fwd_seq_kernel(MhaParams p)
 // whose L x L matrices do not fit shared memory).
 template <int DH, int R, bool SP>
 __global__ void __maxnreg__(DH <= 32 ? (SP ? 168 : 200) : 255) mha_bwd_seq_kernel(MhaParams p) {
+  pdl_prologue();
   constexpr int W = DH / R;
   extern __shared__ __align__(16) float smem[];
   const int64_t n = blockIdx.x;
@@ -515,7 +517,7 @@ static int launch_fwd(MhaParams p, int64_t N, cudaStream_t st) {
     attr = true;
   }
   dim3 grid((unsigned)N, (unsigned)(p.H / p.HG));
-  mha_fwd_seq_kernel<DH, R><<<grid, pick_threads(p.seq.S, p.HG, R), smem, st>>>(p);
+  LK_LAUNCH((mha_fwd_seq_kernel<DH, R>), grid, pick_threads(p.seq.S, p.HG, R), smem, st, p);
   return check_launch("mha_fwd");
 }
 template <int DH, int R, bool SP>
@@ -527,7 +529,7 @@ static int launch_bwd_sp(const MhaParams& p, int64_t N, size_t smem, cudaStream_
     attr = true;
   }
   dim3 grid((unsigned)N, (unsigned)(p.H / p.HG));
-  mha_bwd_seq_kernel<DH, R, SP><<<grid, pick_threads(p.seq.S, p.HG, R), smem, st>>>(p);
+  LK_LAUNCH((mha_bwd_seq_kernel<DH, R, SP>), grid, pick_threads(p.seq.S, p.HG, R), smem, st, p);
   return check_launch("mha_bwd");
 }
 template <int DH, int R>

@@ -107,12 +107,20 @@ struct EncSaved {
   uint64_t seed;
 };
 
-static EncPlanes weight_planes(Ctx& c, const EncWeights& w, int64_t D, int64_t A) {
+// operand planes of a weight matrix: the conversion is queued and all weights of the step are converted by ONE launch
+struct SplitQueue { lk_split_seg seg[LK_SPLIT_MAX_SEGS]; int n = 0; };
+static PlaneBuf queue_split(Ctx& c, SplitQueue& q, const float* W, int64_t rows, int64_t cols) {
+  PlaneBuf p = alloc_planes(c, rows, cols);
+  if (q.n < LK_SPLIT_MAX_SEGS) q.seg[q.n++] = lk_split_seg{W, p.hi, p.lo, rows, cols, cols, p.ld};
+  else c.rc = c.rc ? c.rc : LK_ERR_ARG;
+  return p;
+}
+static EncPlanes weight_planes(Ctx& c, SplitQueue& q, const EncWeights& w, int64_t D, int64_t A) {
   EncPlanes p;
-  p.in_w = split(c, w.in_w, 3 * D, D);
-  p.out_w = split(c, w.out_w, D, D);
-  p.lin_w = split(c, w.lin_w, D, D);
-  p.w1 = split(c, w.w1, A, D);
+  p.in_w = queue_split(c, q, w.in_w, 3 * D, D);
+  p.out_w = queue_split(c, q, w.out_w, D, D);
+  p.lin_w = queue_split(c, q, w.lin_w, D, D);
+  p.w1 = queue_split(c, q, w.w1, A, D);
   return p;
 }
 
@@ -221,9 +229,11 @@ static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const 
   const uint64_t s_embed = seed * 4 + 0, s_item = seed * 4 + 1, s_user = seed * 4 + 2;
 
   // ---- weights -> split-bf16 planes (parameters change every step) ------------------------------------------------
-  EncPlanes pi = weight_planes(c, wi, D, A);
-  EncPlanes pu = weight_planes(c, wu, D, A);
-  PlaneBuf pg = split(c, P(0), D, E);
+  SplitQueue wq;
+  EncPlanes pi = weight_planes(c, wq, wi, D, A);
+  EncPlanes pu = weight_planes(c, wq, wu, D, A);
+  PlaneBuf pg = queue_split(c, wq, P(0), D, E);
+  STEP(lk_split_bf16_multi(wq.seg, wq.n, st));
 
   // ---- embedding stage (concat_inputer.py:92-114 + embedding_hub.py:95-96) -------------------------------------------
   // x[t] = valid(title)·dropout(W·glove[title] + b) + category[cat] + special[sp]  — one contraction whose epilogue applies the row

@@ -21,6 +21,7 @@ __device__ __forceinline__ float warp_dot(const float* __restrict__ a, const flo
 __global__ void __launch_bounds__(SW * 32) dot_ce_fwd_kernel(const float* __restrict__ U, const float* __restrict__ V,
                                                              float* __restrict__ scores, float* __restrict__ probs,
                                                              float* __restrict__ rowloss, int64_t B, int C, int D) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * SW + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(SW * 32) dot_ce_fwd_kernel(const float* __rest
 __global__ void __launch_bounds__(SW * 32) dot_bce_fwd_kernel(const float* __restrict__ U, const float* __restrict__ V,
                                                               const float* __restrict__ y, float* __restrict__ scores,
                                                               float* __restrict__ rowloss, int64_t B, int D) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * SW + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -58,6 +60,7 @@ __global__ void __launch_bounds__(SW * 32) dot_bce_fwd_kernel(const float* __res
 
 // deterministic mean of a vector by one CTA
 __global__ void mean_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+  pdl_prologue();
   __shared__ float sh[256];
   float s = 0.f;
   for (int64_t i = threadIdx.x; i < n; i += 256) s += x[i];
@@ -75,6 +78,7 @@ __global__ void __launch_bounds__(SW * 32) dot_ce_bwd_kernel(const float* __rest
                                                              const float* __restrict__ probs, const float* __restrict__ dloss,
                                                              float* __restrict__ dU, float* __restrict__ dV, int64_t B, int C,
                                                              int D) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * SW + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -96,6 +100,7 @@ __global__ void __launch_bounds__(SW * 32) dot_ce_bwd_kernel(const float* __rest
 __global__ void __launch_bounds__(SW * 32) dot_bwd_kernel(const float* __restrict__ U, const float* __restrict__ V,
                                                           const float* __restrict__ dS, float* __restrict__ dU,
                                                           float* __restrict__ dV, int64_t B, int C, int D) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * SW + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -114,6 +119,7 @@ __global__ void __launch_bounds__(SW * 32) dot_bwd_kernel(const float* __restric
 
 __global__ void bce_dscore_kernel(const float* __restrict__ z, const float* __restrict__ y, const float* __restrict__ dloss,
                                   float* __restrict__ dz, int64_t B) {
+  pdl_prologue();
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float sig = 1.f / (1.f + expf(-z[b]));
@@ -124,6 +130,7 @@ __global__ void bce_dscore_kernel(const float* __restrict__ z, const float* __re
 __global__ void __launch_bounds__(SW * 32) cached_scores_kernel(const float* __restrict__ U, const float* __restrict__ I,
                                                                 const int64_t* __restrict__ uid, const int64_t* __restrict__ iid,
                                                                 float* __restrict__ out, int64_t R, int D) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * SW + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * SW;
@@ -151,6 +158,7 @@ __global__ void __launch_bounds__(SW * 32) cached_scores_kernel(const float* __r
 // out[r,:] = table[ids[r],:]  (cache indexing model/legommender.py:153-157; ids are always valid)
 __global__ void __launch_bounds__(SW * 32) index_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids,
                                                              float* __restrict__ out, int64_t R, int D) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * SW + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * SW;
@@ -161,12 +169,14 @@ __global__ void __launch_bounds__(SW * 32) index_rows_kernel(const float* __rest
 }
 
 __global__ void fill_kernel(float* __restrict__ p, float v, int64_t n) {
+  pdl_prologue();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             int64_t n, float lr_over_bc1, float b1, float b2, float eps, float inv_sqrt_bc2, float grad_scale) {
+  pdl_prologue();
   int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   if (i + 3 < n) {
@@ -205,7 +215,7 @@ extern "C" {
 int lk_dot_scores(const float* U, const float* V, float* scores, int64_t B, int64_t C, int64_t D, cudaStream_t st) {
   LK_REQUIRE(D % 4 == 0, LK_ERR_SHAPE, "lk_dot_scores: D=%ld must be a multiple of 4", (long)D);
   if (B == 0) return LK_OK;
-  dot_ce_fwd_kernel<<<(unsigned)((B + SW - 1) / SW), SW * 32, 0, st>>>(U, V, scores, nullptr, nullptr, B, (int)C, (int)D);
+  LK_LAUNCH((dot_ce_fwd_kernel), (unsigned)((B + SW - 1) / SW), SW * 32, 0, st, U, V, scores, nullptr, nullptr, B, (int)C, (int)D);
   return check_launch("dot_scores");
 }
 
@@ -213,8 +223,8 @@ int lk_dot_ce_fwd(const float* U, const float* V, float* scores, float* probs, f
                   int64_t D, cudaStream_t st) {
   LK_REQUIRE(D % 4 == 0, LK_ERR_SHAPE, "lk_dot_ce_fwd: D=%ld must be a multiple of 4", (long)D);
   LK_REQUIRE(B > 0 && C > 0, LK_ERR_SHAPE, "lk_dot_ce_fwd: empty batch");
-  dot_ce_fwd_kernel<<<(unsigned)((B + SW - 1) / SW), SW * 32, 0, st>>>(U, V, scores, probs, rowloss, B, (int)C, (int)D);
-  mean_kernel<<<1, 256, 0, st>>>(rowloss, loss, B);
+  LK_LAUNCH((dot_ce_fwd_kernel), (unsigned)((B + SW - 1) / SW), SW * 32, 0, st, U, V, scores, probs, rowloss, B, (int)C, (int)D);
+  LK_LAUNCH((mean_kernel), 1, 256, 0, st, rowloss, loss, B);
   return check_launch("dot_ce_fwd", 2);
 }
 
@@ -222,7 +232,7 @@ int lk_dot_ce_bwd(const float* U, const float* V, const float* probs, const floa
                   int64_t C, int64_t D, cudaStream_t st) {
   LK_REQUIRE(D % 4 == 0, LK_ERR_SHAPE, "lk_dot_ce_bwd: D=%ld must be a multiple of 4", (long)D);
   if (B == 0) return LK_OK;
-  dot_ce_bwd_kernel<<<(unsigned)((B + SW - 1) / SW), SW * 32, 0, st>>>(U, V, probs, dloss, dU, dV, B, (int)C, (int)D);
+  LK_LAUNCH((dot_ce_bwd_kernel), (unsigned)((B + SW - 1) / SW), SW * 32, 0, st, U, V, probs, dloss, dU, dV, B, (int)C, (int)D);
   return check_launch("dot_ce_bwd");
 }
 
@@ -230,7 +240,7 @@ int lk_dot_bwd(const float* U, const float* V, const float* dS, float* dU, float
                cudaStream_t st) {
   LK_REQUIRE(D % 4 == 0, LK_ERR_SHAPE, "lk_dot_bwd: D=%ld must be a multiple of 4", (long)D);
   if (B == 0) return LK_OK;
-  dot_bwd_kernel<<<(unsigned)((B + SW - 1) / SW), SW * 32, 0, st>>>(U, V, dS, dU, dV, B, (int)C, (int)D);
+  LK_LAUNCH((dot_bwd_kernel), (unsigned)((B + SW - 1) / SW), SW * 32, 0, st, U, V, dS, dU, dV, B, (int)C, (int)D);
   return check_launch("dot_bwd");
 }
 
@@ -238,8 +248,8 @@ int lk_dot_bce_fwd(const float* U, const float* V, const float* y, float* scores
                    cudaStream_t st) {
   LK_REQUIRE(D % 4 == 0, LK_ERR_SHAPE, "lk_dot_bce_fwd: D=%ld must be a multiple of 4", (long)D);
   LK_REQUIRE(B > 0, LK_ERR_SHAPE, "lk_dot_bce_fwd: empty batch");
-  dot_bce_fwd_kernel<<<(unsigned)((B + SW - 1) / SW), SW * 32, 0, st>>>(U, V, y, scores, rowloss, B, (int)D);
-  mean_kernel<<<1, 256, 0, st>>>(rowloss, loss, B);
+  LK_LAUNCH((dot_bce_fwd_kernel), (unsigned)((B + SW - 1) / SW), SW * 32, 0, st, U, V, y, scores, rowloss, B, (int)D);
+  LK_LAUNCH((mean_kernel), 1, 256, 0, st, rowloss, loss, B);
   return check_launch("dot_bce_fwd", 2);
 }
 
@@ -247,8 +257,8 @@ int lk_dot_bce_bwd(const float* U, const float* V, const float* y, const float* 
                    float* dV, int64_t B, int64_t D, cudaStream_t st) {
   LK_REQUIRE(D % 4 == 0, LK_ERR_SHAPE, "lk_dot_bce_bwd: D=%ld must be a multiple of 4", (long)D);
   if (B == 0) return LK_OK;
-  bce_dscore_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(scores, y, dloss, dz, B);
-  dot_bwd_kernel<<<(unsigned)((B + SW - 1) / SW), SW * 32, 0, st>>>(U, V, dz, dU, dV, B, 1, (int)D);
+  LK_LAUNCH((bce_dscore_kernel), (unsigned)((B + 255) / 256), 256, 0, st, scores, y, dloss, dz, B);
+  LK_LAUNCH((dot_bwd_kernel), (unsigned)((B + SW - 1) / SW), SW * 32, 0, st, U, V, dz, dU, dV, B, 1, (int)D);
   return check_launch("dot_bce_bwd", 2);
 }
 
@@ -258,7 +268,7 @@ int lk_cached_scores(const float* U, const float* I, const int64_t* uid, const i
   if (R == 0) return LK_OK;
   int64_t blocks = (R + 2 * SW - 1) / (2 * SW);
   if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
-  cached_scores_kernel<<<(unsigned)blocks, SW * 32, 0, st>>>(U, I, uid, iid, out, R, (int)D);
+  LK_LAUNCH((cached_scores_kernel), (unsigned)blocks, SW * 32, 0, st, U, I, uid, iid, out, R, (int)D);
   return check_launch("cached_scores");
 }
 
@@ -267,13 +277,13 @@ int lk_index_rows(const float* table, const int64_t* ids, float* out, int64_t R,
   if (R == 0) return LK_OK;
   int64_t blocks = (R + SW - 1) / SW;
   if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
-  index_rows_kernel<<<(unsigned)blocks, SW * 32, 0, st>>>(table, ids, out, R, (int)D);
+  LK_LAUNCH((index_rows_kernel), (unsigned)blocks, SW * 32, 0, st, table, ids, out, R, (int)D);
   return check_launch("index_rows");
 }
 
 int lk_fill_f32(float* p, float value, int64_t n, cudaStream_t st) {
   if (n == 0) return LK_OK;
-  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, value, n);
+  LK_LAUNCH((fill_kernel), (unsigned)((n + 255) / 256), 256, 0, st, p, value, n);
   return check_launch("fill");
 }
 
@@ -283,7 +293,7 @@ int lk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
   if (n == 0) return LK_OK;
   double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   int64_t n4 = (n + 3) / 4;
-  adam_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(p, g, m, v, n, (float)(lr / bc1), beta1, beta2, eps,
+  LK_LAUNCH((adam_kernel), (unsigned)((n4 + 255) / 256), 256, 0, st, p, g, m, v, n, (float)(lr / bc1), beta1, beta2, eps,
                                                           (float)(1.0 / sqrt(bc2)), grad_scale);
   return check_launch("adam_step");
 }

@@ -68,6 +68,26 @@ def split_planes(x2: torch.Tensor, transpose: bool = False, colsum: bool = False
     return (planes, cs) if colsum else planes
 
 
+class SplitSeg(ctypes.Structure):
+    """struct lk_split_seg (include/legommenders_b200.h)"""
+    _fields_ = [('X', ctypes.c_void_p), ('hi', ctypes.c_void_p), ('lo', ctypes.c_void_p), ('rows', ctypes.c_int64),
+                ('cols', ctypes.c_int64), ('ld_in', ctypes.c_int64), ('ld_out', ctypes.c_int64)]
+
+
+def split_planes_multi(mats):
+    """Planes of several fp32 matrices (e.g. all weights of a step) in ONE launch (lk_split_bf16_multi)."""
+    segs = (SplitSeg * len(mats))()
+    planes = []
+    for sg, x in zip(segs, mats):
+        rows, cols = x.shape
+        ld = (cols + 7) // 8 * 8
+        buf = torch.empty((2, rows, ld), dtype=torch.bfloat16, device=x.device)
+        planes.append(Planes(buf[0], buf[1], rows, cols, ld))
+        sg.X, sg.hi, sg.lo, sg.rows, sg.cols, sg.ld_in, sg.ld_out = ptr(x), ptr(buf[0]), ptr(buf[1]), rows, cols, x.stride(0), ld
+    call('lk_split_bf16_multi', ctypes.addressof(segs), len(mats))
+    return planes
+
+
 _wplanes = {}
 
 

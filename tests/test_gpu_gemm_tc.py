@@ -37,6 +37,19 @@ def test_split_planes(ops, rows, cols):
     assert (cs.double().cpu() - x.double().sum(0)).abs().max().item() <= 1e-5 * max(1.0, x.abs().sum(0).max().item())
 
 
+def test_split_planes_multi_matches_single(ops):
+    """All weight matrices of a step in one launch: bit-identical to the per-matrix split, pad columns zero."""
+    g = torch.Generator().manual_seed(11)
+    shapes = [(768, 256), (256, 256), (256, 300), (1, 4), (5, 12), (256, 256), (300, 64)]
+    mats = [(torch.randn(r, c, generator=g) * 2).cuda() for r, c in shapes]
+    multi = ops.split_planes_multi(mats)
+    for x, p in zip(mats, multi):
+        q = ops.split_planes(x)
+        assert p.ld == q.ld and torch.equal(p.hi, q.hi) and torch.equal(p.lo, q.lo)
+    with pytest.raises(RuntimeError):
+        ops.split_planes_multi([mats[0]] * 17)
+
+
 @pytest.mark.parametrize('M,N,K', [(128, 128, 64), (128, 128, 256), (300, 256, 256), (1000, 768, 256), (257, 64, 300),
                                    (4000, 256, 300), (513, 32, 64), (20000, 256, 256), (256, 256, 4096), (40000, 768, 256), (40000, 256, 300), (38000, 128, 64)])
 def test_tc_gemm_k_major(ops, M, N, K):
