@@ -53,6 +53,7 @@ struct MhaParams {
   float* colsum_part;               // bwd: optional [N, 3D] per-sequence column sums of dqkv
   SeqView seq;
   int D, H, HG;                     // HG heads per CTA
+  int ov_items;                     // work items beyond one CTA-full (their results are parked, see unpark)
   float scale, drop_p;
   uint32_t drop_thr;                // keep iff (hash >> 8) >= drop_thr, drop_thr = p * 2^24
   unsigned long long seed;
@@ -180,6 +181,30 @@ __device__ __forceinline__ uint32_t quad_bits(bool mine) {
   return (b >> ((threadIdx.x & 31) & ~(R - 1))) & ((1u << R) - 1u);
 }
 
+// Result tiles alias operand tiles that are dead by the time the results exist (one __syncthreads in between), which is what lets a
+// third backward / fifth forward CTA fit an SM.  A sequence needing more work items than the CTA has threads is processed in
+// rounds, LAST round first: the later rounds park their results in a small overflow area (slot = item - blockDim), only round 0 —
+// whose results are still in registers when every thread has finished reading the operands — writes the aliased tile directly.
+template <int R, int W>
+__device__ __forceinline__ void park_or_store(float* tile, float* ov, bool first_round, int slot, int i, int TP, int col, int r,
+                                              const float (&v)[W], float scale, bool row_ok) {
+  if (first_round) { if (row_ok) sts_slice<W>(tile + i * TP + col, v, scale); }
+  else sts_slice<W>(ov + (slot * R + r) * W, v, scale);
+}
+// overflow area -> tile (call between two __syncthreads)
+template <int DH, int R>
+__device__ __forceinline__ void unpark(float* tile, const float* ov, int items, int G, int L, int TP) {
+  constexpr int W = DH / R, W4 = W / 4;
+  const int n_ov = items - (int)blockDim.x;
+  for (int idx = threadIdx.x; idx < n_ov * R * W4; idx += blockDim.x) {
+    const int slot = idx / (R * W4), rem = idx - slot * (R * W4), r = rem / W4, w4 = rem - r * W4;
+    const Item it = item_of<R>((int)blockDim.x + slot, G, items);
+    const int i = it.g * R + r;
+    if (i < L)
+      *reinterpret_cast<float4*>(tile + i * TP + it.hl * DH + it.ds * W + w4 * 4) = *reinterpret_cast<const float4*>(ov + (slot * R + r) * W + w4 * 4);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 template <int DH, int R>
 __global__ void __maxnreg__(DH <= 32 ? 96 : 168) mha_fwd_seq_kernel(MhaParams p) {   // 4 CTAs of 160 threads per SM at head dim 32
@@ -192,10 +217,11 @@ __global__ void __maxnreg__(DH <= 32 ? 96 : 168) mha_fwd_seq_kernel(MhaParams p)
   if (L == 0) return;
   const int D = p.D, H = p.H, S = p.seq.S, HG = p.HG, TW = HG * DH, TP = TW + 4;
   const int h0 = blockIdx.y * HG, c0 = h0 * DH;          // first head / first column of this CTA
-  float* Ks = smem;                        // [S][TP]
+  float* Ks = smem;                        // [S][TP]; becomes the result tile once every thread is done with the keys
   float* Vs = Ks + (size_t)S * TP;
-  float* Os = Vs + (size_t)S * TP;         // result tile
-  float* valid = Os + (size_t)S * TP;      // [S]
+  float* Os = Ks;
+  float* valid = Vs + (size_t)S * TP;      // [S]
+  float* Ov = valid + ((S + 3) & ~3);      // results of the rounds after the first: [items - blockDim][R][W]
 
   const float* base = p.qkv + row0 * 3 * (int64_t)D;
   stage_tile(Ks, base + D + c0, 3 * D, L, TW);
@@ -207,56 +233,67 @@ __global__ void __maxnreg__(DH <= 32 ? 96 : 168) mha_fwd_seq_kernel(MhaParams p)
 
   const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
   const int G = (L + R - 1) / R, items = HG * G * R;
-  for (int w0 = 0; w0 < items; w0 += blockDim.x) {
+  const int rounds = (items + (int)blockDim.x - 1) / (int)blockDim.x;
+  for (int rd = rounds - 1; rd >= 0; rd--) {
+    const int w0 = rd * (int)blockDim.x;
+    const bool warp_on = w0 + (int)(threadIdx.x & ~31u) < items;     // warp-uniform: idle warps skip the key loop altogether
     const Item it = item_of<R>(w0 + threadIdx.x, G, items);
     const int h = h0 + it.hl, col = it.hl * DH + it.ds * W;
-    float q[R][W], acc[R][W], m[R], l[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      const int i = min(it.g * R + r, L - 1);
-      ldg_slice<W>(q[r], base + (int64_t)i * 3 * D + c0 + col, p.scale * kLog2e);
-      m[r] = -INFINITY; l[r] = 0.f;
-#pragma unroll
-      for (int w = 0; w < W; w++) acc[r][w] = 0.f;
-    }
-    const int my_i = min(it.g * R + it.ds, L - 1);
-    const uint32_t hb = attn_hash_base(p.seed, (uint64_t)(row0 + my_i) * H + h);
-    for (int j = 0; j < L; j++) {
-      if (valid[j] == 0.f) continue;                      // CTA-uniform
-      float kv[W], s[R];
-      lds_slice<W>(kv, Ks + j * TP + col);
-#pragma unroll
-      for (int r = 0; r < R; r++) s[r] = quad_sum<R>(dot_slice<W>(q[r], kv));
-      uint32_t bits = (1u << R) - 1u;
-      if (p.drop_p > 0.f) bits = quad_bits<R>(attn_keep(hb, j, p.drop_thr));
-      lds_slice<W>(kv, Vs + j * TP + col);
+    float acc[R][W], m[R], l[R];
+    if (warp_on) {
+      float q[R][W];
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        if (s[r] > m[r]) {                                // rescale the running sums (rare after the first keys)
-          const float c = ex2(m[r] - s[r]);               // 2^-inf = 0 on the first valid key
-          l[r] *= c;
+        const int i = min(it.g * R + r, L - 1);
+        ldg_slice<W>(q[r], base + (int64_t)i * 3 * D + c0 + col, p.scale * kLog2e);
+        m[r] = -INFINITY; l[r] = 0.f;
 #pragma unroll
-          for (int w = 0; w < W; w++) acc[r][w] *= c;
-          m[r] = s[r];
+        for (int w = 0; w < W; w++) acc[r][w] = 0.f;
+      }
+      const int my_i = min(it.g * R + it.ds, L - 1);
+      const uint32_t hb = attn_hash_base(p.seed, (uint64_t)(row0 + my_i) * H + h);
+      for (int j = 0; j < L; j++) {
+        if (valid[j] == 0.f) continue;                      // CTA-uniform
+        float kv[W], sc[R];
+        lds_slice<W>(kv, Ks + j * TP + col);
+#pragma unroll
+        for (int r = 0; r < R; r++) sc[r] = quad_sum<R>(dot_slice<W>(q[r], kv));
+        uint32_t bits = (1u << R) - 1u;
+        if (p.drop_p > 0.f) bits = quad_bits<R>(attn_keep(hb, j, p.drop_thr));
+        lds_slice<W>(kv, Vs + j * TP + col);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          if (sc[r] > m[r]) {                               // rescale the running sums (rare after the first keys)
+            const float c = ex2(m[r] - sc[r]);              // 2^-inf = 0 on the first valid key
+            l[r] *= c;
+#pragma unroll
+            for (int w = 0; w < W; w++) acc[r][w] *= c;
+            m[r] = sc[r];
+          }
+          float pr = ex2(sc[r] - m[r]);
+          l[r] += pr;
+          pr = ((bits >> r) & 1u) ? pr * inv_keep : 0.f;
+#pragma unroll
+          for (int w = 0; w < W; w++) acc[r][w] = fmaf(pr, kv[w], acc[r][w]);
         }
-        float pr = ex2(s[r] - m[r]);
-        l[r] += pr;
-        pr = ((bits >> r) & 1u) ? pr * inv_keep : 0.f;
-#pragma unroll
-        for (int w = 0; w < W; w++) acc[r][w] = fmaf(pr, kv[w], acc[r][w]);
       }
     }
+    if (rd == 0) __syncthreads();                           // nobody reads the key tile any more: it takes the results
     // all keys masked: l = 0 -> 0 * inf = NaN, as torch's softmax over an all -inf row
+    if (warp_on && it.active) {
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-      const int i = it.g * R + r;
-      if (it.active && i < L) {
-        sts_slice<W>(Os + i * TP + col, acc[r], 1.f / l[r]);
-        if (r == it.ds) p.lse[(row0 + i) * H + h] = (m[r] + log2f(l[r])) * kLn2;
+      for (int r = 0; r < R; r++) {
+        const int i = it.g * R + r;
+        park_or_store<R, W>(Os, Ov, rd == 0, w0 + (int)threadIdx.x - (int)blockDim.x, i, TP, col, r, acc[r], 1.f / l[r], i < L);
+        if (i < L && r == it.ds) p.lse[(row0 + i) * H + h] = (m[r] + log2f(l[r])) * kLn2;
       }
     }
   }
   __syncthreads();
+  if (rounds > 1) {
+    unpark<DH, R>(Os, Ov, items, G, L, TP);
+    __syncthreads();
+  }
   const int64_t off = row0 * (int64_t)D + c0;
   flush_tile(Os, L, TW, p.ctx ? p.ctx + off : nullptr, p.ctx_hi ? p.ctx_hi + off : nullptr, p.ctx_lo ? p.ctx_lo + off : nullptr, D, nullptr);
 }
@@ -279,17 +316,18 @@ __global__ void __maxnreg__(DH <= 32 ? (SP ? 168 : 200) : 255) mha_bwd_seq_kerne
   if (L == 0) return;
   const int D = p.D, H = p.H, S = p.seq.S, HG = p.HG, TW = HG * DH, TP = TW + 4;
   const int h0 = blockIdx.y * HG, c0 = h0 * DH;
-  float* T0 = smem;                        // A: K     B: Q
-  float* T1 = T0 + (size_t)S * TP;         // A: V     B: dO
-  float* U0 = T1 + (size_t)S * TP;         // A: dQ out   B: dK out
-  float* U1 = U0 + (size_t)S * TP;         //             B: dV out
-  float* lse_s = U1 + (size_t)S * TP;      // [HG][S]  log2-domain log-sum-exp
+  float* T0 = smem;                        // A: K              B: Q, then the dK results
+  float* T1 = T0 + (size_t)S * TP;         // A: V, then dQ     B: dO, then the dV results
+  float* lse_s = T1 + (size_t)S * TP;      // [HG][S]  log2-domain log-sum-exp
   float* Di_s = lse_s + (size_t)HG * S;    // [HG][S]
   uint32_t* hb_s = reinterpret_cast<uint32_t*>(Di_s + (size_t)HG * S);   // [HG][S] dropout hash of (row, head)
   float* valid = reinterpret_cast<float*>(hb_s + (size_t)HG * S);        // [S]
   const int LP = (S + 1) & ~1;                                           // even row pitch: phase B reads key pairs as float2
   float* Pd_s = valid + ((S + 3) & ~3);                                  // SP: [HG][S][LP]  p * keep
   float* dS_s = Pd_s + (SP ? (size_t)HG * S * LP : 0);                   // SP: [HG][S][LP]  dS * scale
+  float* Ov0 = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(dS_s + (SP ? (size_t)HG * S * LP : 0)) + 15) & ~(uintptr_t)15);
+                                                                         // results of the rounds after the first (see unpark)
+  float* Ov1 = Ov0 + (size_t)p.ov_items * R * W;
 
   const float* base = p.qkv + row0 * 3 * (int64_t)D;
   const float* gbase = p.dctx + row0 * (int64_t)D;
@@ -308,182 +346,197 @@ __global__ void __maxnreg__(DH <= 32 ? (SP ? 168 : 200) : 255) mha_bwd_seq_kerne
 
   const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
   const int G = (L + R - 1) / R, items = HG * G * R;
+  const int rounds = (items + (int)blockDim.x - 1) / (int)blockDim.x;
   float* dbase = p.dqkv ? p.dqkv + row0 * 3 * (int64_t)D + c0 : nullptr;
   __nv_bfloat16* hbase = p.dq_hi ? p.dq_hi + row0 * 3 * (int64_t)D + c0 : nullptr;
   __nv_bfloat16* lbase = p.dq_lo ? p.dq_lo + row0 * 3 * (int64_t)D + c0 : nullptr;
   float* csum = p.colsum_part ? p.colsum_part + n * 3 * (int64_t)D + c0 : nullptr;
 
   // ---- phase A ---------------------------------------------------------------------------------------------------
-  for (int w0 = 0; w0 < items; w0 += blockDim.x) {
+  for (int rd = rounds - 1; rd >= 0; rd--) {
+    const int w0 = rd * (int)blockDim.x;
+    const bool warp_on = w0 + (int)(threadIdx.x & ~31u) < items;     // warp-uniform: idle warps skip the key loop
     const Item it = item_of<R>(w0 + threadIdx.x, G, items);
     const int col = it.hl * DH + it.ds * W;
-    float q[R][W], g[R][W], dq[R][W], Di[R], lse2[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      const int i = min(it.g * R + r, L - 1);
-      float o[W];
-      ldg_slice<W>(q[r], base + (int64_t)i * 3 * D + c0 + col, p.scale * kLog2e);
-      ldg_slice<W>(g[r], gbase + (int64_t)i * D + c0 + col, 1.f);
-      ldg_slice<W>(o, obase + (int64_t)i * D + c0 + col, 1.f);
-      Di[r] = quad_sum<R>(dot_slice<W>(g[r], o));
-      lse2[r] = lse_s[it.hl * S + i];
-#pragma unroll
-      for (int w = 0; w < W; w++) dq[r][w] = 0.f;
-    }
-#pragma unroll
-    for (int r = 0; r < R; r++) {                       // lane ds publishes row ds (static register indexing)
-      const int i = it.g * R + r;
-      if (r == it.ds && it.active && i < L) Di_s[it.hl * S + i] = Di[r];
-    }
-    const uint32_t hb = hb_s[it.hl * S + min(it.g * R + it.ds, L - 1)];
-    for (int j = 0; j < L; j++) {
-      if (valid[j] == 0.f) continue;
-      float kv[W], vv[W], ps[R], pd[R];
-      lds_slice<W>(kv, T0 + j * TP + col);
-      lds_slice<W>(vv, T1 + j * TP + col);
+    float dq[R][W];
+    if (warp_on) {
+      float q[R][W], g[R][W], Di[R], lse2[R];
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        ps[r] = quad_sum<R>(dot_slice<W>(q[r], kv));
-        pd[r] = quad_sum<R>(dot_slice<W>(g[r], vv));
+        const int i = min(it.g * R + r, L - 1);
+        float o[W];
+        ldg_slice<W>(q[r], base + (int64_t)i * 3 * D + c0 + col, p.scale * kLog2e);
+        ldg_slice<W>(g[r], gbase + (int64_t)i * D + c0 + col, 1.f);
+        ldg_slice<W>(o, obase + (int64_t)i * D + c0 + col, 1.f);
+        Di[r] = quad_sum<R>(dot_slice<W>(g[r], o));
+        lse2[r] = lse_s[it.hl * S + i];
+#pragma unroll
+        for (int w = 0; w < W; w++) dq[r][w] = 0.f;
       }
-      uint32_t bits = (1u << R) - 1u;
-      if (p.drop_p > 0.f) bits = quad_bits<R>(attn_keep(hb, j, p.drop_thr));
 #pragma unroll
-      for (int r = 0; r < R; r++) {
-        const float pr = ex2(ps[r] - lse2[r]);
-        const bool kept = (bits >> r) & 1u;
-        const float dP = kept ? pd[r] * inv_keep : 0.f;
-        const float dS = pr * (dP - Di[r]);
+      for (int r = 0; r < R; r++) {                       // lane ds publishes row ds (static register indexing)
+        const int i = it.g * R + r;
+        if (r == it.ds && it.active && i < L) Di_s[it.hl * S + i] = Di[r];
+      }
+      const uint32_t hb = hb_s[it.hl * S + min(it.g * R + it.ds, L - 1)];
+      for (int j = 0; j < L; j++) {
+        if (valid[j] == 0.f) continue;
+        float kv[W], vv[W], ps[R], pd[R];
+        lds_slice<W>(kv, T0 + j * TP + col);
+        lds_slice<W>(vv, T1 + j * TP + col);
 #pragma unroll
-        for (int w = 0; w < W; w++) dq[r][w] = fmaf(dS, kv[w], dq[r][w]);
-        if (SP && r == it.ds && it.active) {              // lane ds publishes row ds of the quad
-          const int i = min(it.g * R + r, L - 1);
-          Pd_s[(it.hl * S + i) * LP + j] = kept ? pr * inv_keep : 0.f;
-          dS_s[(it.hl * S + i) * LP + j] = dS * p.scale;
+        for (int r = 0; r < R; r++) {
+          ps[r] = quad_sum<R>(dot_slice<W>(q[r], kv));
+          pd[r] = quad_sum<R>(dot_slice<W>(g[r], vv));
+        }
+        uint32_t bits = (1u << R) - 1u;
+        if (p.drop_p > 0.f) bits = quad_bits<R>(attn_keep(hb, j, p.drop_thr));
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const float pr = ex2(ps[r] - lse2[r]);
+          const bool kept = (bits >> r) & 1u;
+          const float dP = kept ? pd[r] * inv_keep : 0.f;
+          const float dS = pr * (dP - Di[r]);
+#pragma unroll
+          for (int w = 0; w < W; w++) dq[r][w] = fmaf(dS, kv[w], dq[r][w]);
+          if (SP && r == it.ds && it.active) {              // lane ds publishes row ds of the quad
+            const int i = min(it.g * R + r, L - 1);
+            Pd_s[(it.hl * S + i) * LP + j] = kept ? pr * inv_keep : 0.f;
+            dS_s[(it.hl * S + i) * LP + j] = dS * p.scale;
+          }
         }
       }
     }
+    if (rd == 0) __syncthreads();                           // K and V are dead: the V tile takes dQ
+    if (warp_on && it.active) {
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-      const int i = it.g * R + r;
-      if (it.active && i < L) sts_slice<W>(U0 + i * TP + col, dq[r], p.scale);
+      for (int r = 0; r < R; r++) {
+        const int i = it.g * R + r;
+        park_or_store<R, W>(T1, Ov0, rd == 0, w0 + (int)threadIdx.x - (int)blockDim.x, i, TP, col, r, dq[r], p.scale, i < L);
+      }
     }
   }
   __syncthreads();
-  flush_tile(U0, L, TW, dbase, hbase, lbase, 3 * D, csum);
-  // ---- phase B: re-stage Q and dO over K and V ---------------------------------------------------------------------
-  stage_tile(T0, base + c0, 3 * D, L, TW);
+  stage_tile(T0, base + c0, 3 * D, L, TW);                  // phase B's Q tile streams in while dQ is flushed
+  if (rounds > 1) {
+    unpark<DH, R>(T1, Ov0, items, G, L, TP);
+    __syncthreads();
+  }
+  flush_tile(T1, L, TW, dbase, hbase, lbase, 3 * D, csum);
+  __syncthreads();
+  // ---- phase B: Q and dO tiles over K and V --------------------------------------------------------------------------
   stage_tile(T1, gbase + c0, D, L, TW);
   cp_async_wait_all();
   __syncthreads();
-  if (SP) {
-    // phase A skipped masked keys: their columns of Pd / dS were never written, and rows of a quad beyond L were clamped
-    for (int w0 = 0; w0 < items; w0 += blockDim.x) {
-      const Item it = item_of<R>(w0 + threadIdx.x, G, items);
-      const int col = it.hl * DH + it.ds * W;
-      float dk[R][W], dv[R][W];
-      bool kok[R];
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        const int j = it.g * R + r;
-        kok[r] = j < L && valid[min(j, L - 1)] != 0.f;
-#pragma unroll
-        for (int w = 0; w < W; w++) { dk[r][w] = 0.f; dv[r][w] = 0.f; }
-      }
-      const float* pd_h = Pd_s + (it.hl * S * LP + it.g * R);
-      const float* ds_h = dS_s + (it.hl * S * LP + it.g * R);
-      const float* qp = T0 + col;
-      const float* gp = T1 + col;
-#pragma unroll 2
-      for (int i = 0; i < L; i++, pd_h += LP, ds_h += LP, qp += TP, gp += TP) {
-        float qv[W], gv[W], pk[R], dsv[R];
-        lds_slice<W>(qv, qp);
-        lds_slice<W>(gv, gp);
-        if (R == 2) {
-          const float2 a = *reinterpret_cast<const float2*>(pd_h), b = *reinterpret_cast<const float2*>(ds_h);
-          pk[0] = a.x; pk[R - 1] = a.y; dsv[0] = b.x; dsv[R - 1] = b.y;
-        } else {
-#pragma unroll
-          for (int r = 0; r < R; r++) { pk[r] = pd_h[r]; dsv[r] = ds_h[r]; }
-        }
+  for (int rd = rounds - 1; rd >= 0; rd--) {
+    const int w0 = rd * (int)blockDim.x;
+    const bool warp_on = w0 + (int)(threadIdx.x & ~31u) < items;
+    const Item it = item_of<R>(w0 + threadIdx.x, G, items);
+    const int col = it.hl * DH + it.ds * W;
+    float dk[R][W], dv[R][W];
+    float dk_scale = 1.f;
+    if (warp_on) {
+      if (SP) {
+        // phase A skipped masked keys: their columns of Pd / dS were never written, and rows of a quad beyond L were clamped
+        bool kok[R];
 #pragma unroll
         for (int r = 0; r < R; r++) {
-          const float a = kok[r] ? pk[r] : 0.f, b = kok[r] ? dsv[r] : 0.f;
+          const int j = it.g * R + r;
+          kok[r] = j < L && valid[min(j, L - 1)] != 0.f;
 #pragma unroll
-          for (int w = 0; w < W; w++) {
-            dv[r][w] = fmaf(a, gv[w], dv[r][w]);
-            dk[r][w] = fmaf(b, qv[w], dk[r][w]);
+          for (int w = 0; w < W; w++) { dk[r][w] = 0.f; dv[r][w] = 0.f; }
+        }
+        const float* pd_h = Pd_s + (it.hl * S * LP + it.g * R);
+        const float* ds_h = dS_s + (it.hl * S * LP + it.g * R);
+        const float* qp = T0 + col;
+        const float* gp = T1 + col;
+#pragma unroll 2
+        for (int i = 0; i < L; i++, pd_h += LP, ds_h += LP, qp += TP, gp += TP) {
+          float qv[W], gv[W], pk[R], dsv[R];
+          lds_slice<W>(qv, qp);
+          lds_slice<W>(gv, gp);
+          if (R == 2) {
+            const float2 a = *reinterpret_cast<const float2*>(pd_h), b = *reinterpret_cast<const float2*>(ds_h);
+            pk[0] = a.x; pk[R - 1] = a.y; dsv[0] = b.x; dsv[R - 1] = b.y;
+          } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) { pk[r] = pd_h[r]; dsv[r] = ds_h[r]; }
+          }
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            const float a = kok[r] ? pk[r] : 0.f, b = kok[r] ? dsv[r] : 0.f;
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+              dv[r][w] = fmaf(a, gv[w], dv[r][w]);
+              dk[r][w] = fmaf(b, qv[w], dk[r][w]);
+            }
           }
         }
-      }
+        // dS_s already carries the scale
+      } else {
+        float k[R][W], v[R][W];
+        uint32_t kvalid = 0;
 #pragma unroll
-      for (int r = 0; r < R; r++) {
-        const int j = it.g * R + r;
-        if (it.active && j < L) {
-          sts_slice<W>(U0 + j * TP + col, dk[r], 1.f);      // dS_s already carries the scale
-          sts_slice<W>(U1 + j * TP + col, dv[r], 1.f);
+        for (int r = 0; r < R; r++) {
+          const int j = it.g * R + r, jc = min(j, L - 1);
+          ldg_slice<W>(k[r], base + (int64_t)jc * 3 * D + D + c0 + col, p.scale * kLog2e);
+          ldg_slice<W>(v[r], base + (int64_t)jc * 3 * D + 2 * D + c0 + col, 1.f);
+          if (j < L && valid[jc] != 0.f) kvalid |= 1u << r;
+#pragma unroll
+          for (int w = 0; w < W; w++) { dk[r][w] = 0.f; dv[r][w] = 0.f; }
         }
+        const int my_j = it.g * R + it.ds;
+        const float* lse_h = lse_s + it.hl * S;
+        const float* Di_h = Di_s + it.hl * S;
+        const uint32_t* hb_h = hb_s + it.hl * S;
+        for (int i = 0; i < L; i++) {
+          float qv[W], gv[W], ps[R], pd[R];
+          lds_slice<W>(qv, T0 + i * TP + col);
+          lds_slice<W>(gv, T1 + i * TP + col);
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            ps[r] = quad_sum<R>(dot_slice<W>(k[r], qv));
+            pd[r] = quad_sum<R>(dot_slice<W>(v[r], gv));
+          }
+          uint32_t bits = (1u << R) - 1u;
+          if (p.drop_p > 0.f) bits = quad_bits<R>(attn_keep(hb_h[i], my_j, p.drop_thr));
+          bits &= kvalid;
+          const float lse_i = lse_h[i], Di = Di_h[i];
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            const float pr = ((kvalid >> r) & 1u) ? ex2(ps[r] - lse_i) : 0.f;
+            const bool kept = (bits >> r) & 1u;
+            const float pk = kept ? pr * inv_keep : 0.f;               // p * keep
+            const float dS = pr * ((kept ? pd[r] * inv_keep : 0.f) - Di);
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+              dv[r][w] = fmaf(pk, gv[w], dv[r][w]);
+              dk[r][w] = fmaf(dS, qv[w], dk[r][w]);
+            }
+          }
+        }
+        dk_scale = p.scale;   // scale*log2e sits on k here, so dk accumulated raw q: dK = scale * sum dS q
       }
     }
-  } else {
-    for (int w0 = 0; w0 < items; w0 += blockDim.x) {
-      const Item it = item_of<R>(w0 + threadIdx.x, G, items);
-      const int col = it.hl * DH + it.ds * W;
-      float k[R][W], v[R][W], dk[R][W], dv[R][W];
-      uint32_t kvalid = 0;
-  #pragma unroll
-      for (int r = 0; r < R; r++) {
-        const int j = it.g * R + r, jc = min(j, L - 1);
-        ldg_slice<W>(k[r], base + (int64_t)jc * 3 * D + D + c0 + col, p.scale * kLog2e);
-        ldg_slice<W>(v[r], base + (int64_t)jc * 3 * D + 2 * D + c0 + col, 1.f);
-        if (j < L && valid[jc] != 0.f) kvalid |= 1u << r;
-  #pragma unroll
-        for (int w = 0; w < W; w++) { dk[r][w] = 0.f; dv[r][w] = 0.f; }
-      }
-      const int my_j = it.g * R + it.ds;
-      const float* lse_h = lse_s + it.hl * S;
-      const float* Di_h = Di_s + it.hl * S;
-      const uint32_t* hb_h = hb_s + it.hl * S;
-      for (int i = 0; i < L; i++) {
-        float qv[W], gv[W], ps[R], pd[R];
-        lds_slice<W>(qv, T0 + i * TP + col);
-        lds_slice<W>(gv, T1 + i * TP + col);
-  #pragma unroll
-        for (int r = 0; r < R; r++) {
-          ps[r] = quad_sum<R>(dot_slice<W>(k[r], qv));
-          pd[r] = quad_sum<R>(dot_slice<W>(v[r], gv));
-        }
-        uint32_t bits = (1u << R) - 1u;
-        if (p.drop_p > 0.f) bits = quad_bits<R>(attn_keep(hb_h[i], my_j, p.drop_thr));
-        bits &= kvalid;
-        const float lse_i = lse_h[i], Di = Di_h[i];
-  #pragma unroll
-        for (int r = 0; r < R; r++) {
-          const float pr = ((kvalid >> r) & 1u) ? ex2(ps[r] - lse_i) : 0.f;
-          const bool kept = (bits >> r) & 1u;
-          const float pk = kept ? pr * inv_keep : 0.f;               // p * keep
-          const float dS = pr * ((kept ? pd[r] * inv_keep : 0.f) - Di);
-  #pragma unroll
-          for (int w = 0; w < W; w++) {
-            dv[r][w] = fmaf(pk, gv[w], dv[r][w]);
-            dk[r][w] = fmaf(dS, qv[w], dk[r][w]);
-          }
-        }
-      }
-      // dK carries q's prescale (scale*log2e is on k here, so dk accumulated raw q): dK = scale * Σ dS q
-  #pragma unroll
+    if (rd == 0) __syncthreads();                           // Q and dO are dead: their tiles take dK and dV
+    if (warp_on && it.active) {
+#pragma unroll
       for (int r = 0; r < R; r++) {
         const int j = it.g * R + r;
-        if (it.active && j < L) {
-          sts_slice<W>(U0 + j * TP + col, dk[r], p.scale);
-          sts_slice<W>(U1 + j * TP + col, dv[r], 1.f);
-        }
+        const int slot = w0 + (int)threadIdx.x - (int)blockDim.x;
+        park_or_store<R, W>(T0, Ov0, rd == 0, slot, j, TP, col, r, dk[r], dk_scale, j < L);
+        park_or_store<R, W>(T1, Ov1, rd == 0, slot, j, TP, col, r, dv[r], 1.f, j < L);
       }
     }
   }
   __syncthreads();
-  flush_tile(U0, L, TW, dbase ? dbase + D : nullptr, hbase ? hbase + D : nullptr, lbase ? lbase + D : nullptr, 3 * D, csum ? csum + D : nullptr);
-  flush_tile(U1, L, TW, dbase ? dbase + 2 * D : nullptr, hbase ? hbase + 2 * D : nullptr, lbase ? lbase + 2 * D : nullptr, 3 * D,
+  if (rounds > 1) {
+    unpark<DH, R>(T0, Ov0, items, G, L, TP);
+    unpark<DH, R>(T1, Ov1, items, G, L, TP);
+    __syncthreads();
+  }
+  flush_tile(T0, L, TW, dbase ? dbase + D : nullptr, hbase ? hbase + D : nullptr, lbase ? lbase + D : nullptr, 3 * D, csum ? csum + D : nullptr);
+  flush_tile(T1, L, TW, dbase ? dbase + 2 * D : nullptr, hbase ? hbase + 2 * D : nullptr, lbase ? lbase + 2 * D : nullptr, 3 * D,
              csum ? csum + 2 * D : nullptr);
 }
 
@@ -504,11 +557,17 @@ static int pick_threads(int64_t S, int hg, int R) {
   return (int)(t < 64 ? 64 : (t > MHA_THREADS ? MHA_THREADS : t));
 }
 
+static int overflow_items(int64_t S, int hg, int R, int threads) {
+  const int64_t items = (int64_t)hg * ((S + R - 1) / R) * R;
+  return items > threads ? (int)(items - threads) : 0;
+}
+
 template <int DH, int R>
 static int launch_fwd(MhaParams p, int64_t N, cudaStream_t st) {
   p.HG = pick_hg(p.H, DH);
-  const int TP = p.HG * DH + 4;
-  size_t smem = ((size_t)3 * p.seq.S * TP + p.seq.S) * sizeof(float);
+  const int TP = p.HG * DH + 4, S = p.seq.S, threads = pick_threads(S, p.HG, R);
+  p.ov_items = overflow_items(S, p.HG, R, threads);
+  size_t smem = ((size_t)2 * S * TP + ((S + 3) & ~3) + (size_t)p.ov_items * DH) * sizeof(float);
   LK_REQUIRE(smem <= 227 * 1024, LK_ERR_SHAPE, "lk_mha_fwd: tiles (%zu B) do not fit shared memory", smem);
   static bool attr = false;
   if (!attr) {
@@ -517,11 +576,11 @@ static int launch_fwd(MhaParams p, int64_t N, cudaStream_t st) {
     attr = true;
   }
   dim3 grid((unsigned)N, (unsigned)(p.H / p.HG));
-  LK_LAUNCH((mha_fwd_seq_kernel<DH, R>), grid, pick_threads(p.seq.S, p.HG, R), smem, st, p);
+  LK_LAUNCH((mha_fwd_seq_kernel<DH, R>), grid, threads, smem, st, p);
   return check_launch("mha_fwd");
 }
 template <int DH, int R, bool SP>
-static int launch_bwd_sp(const MhaParams& p, int64_t N, size_t smem, cudaStream_t st) {
+static int launch_bwd_sp(const MhaParams& p, int64_t N, size_t smem, int threads, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(mha_bwd_seq_kernel<DH, R, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -529,18 +588,19 @@ static int launch_bwd_sp(const MhaParams& p, int64_t N, size_t smem, cudaStream_
     attr = true;
   }
   dim3 grid((unsigned)N, (unsigned)(p.H / p.HG));
-  LK_LAUNCH((mha_bwd_seq_kernel<DH, R, SP>), grid, pick_threads(p.seq.S, p.HG, R), smem, st, p);
+  LK_LAUNCH((mha_bwd_seq_kernel<DH, R, SP>), grid, threads, smem, st, p);
   return check_launch("mha_bwd");
 }
 template <int DH, int R>
 static int launch_bwd(MhaParams p, int64_t N, cudaStream_t st) {
   p.HG = pick_hg(p.H, DH);
-  const int TP = p.HG * DH + 4, S = p.seq.S, LP = (S + 1) & ~1;
-  const size_t base = ((size_t)4 * S * TP + 3 * (size_t)p.HG * S + ((S + 3) & ~3)) * sizeof(float);
+  const int TP = p.HG * DH + 4, S = p.seq.S, LP = (S + 1) & ~1, threads = pick_threads(S, p.HG, R);
+  p.ov_items = overflow_items(S, p.HG, R, threads);
+  const size_t base = ((size_t)2 * S * TP + 3 * (size_t)p.HG * S + ((S + 3) & ~3) + 2 * (size_t)p.ov_items * DH + 4) * sizeof(float);
   const size_t with_p = base + (size_t)2 * p.HG * S * LP * sizeof(float);
-  if (with_p <= 227 * 1024) return launch_bwd_sp<DH, R, true>(p, N, with_p, st);
+  if (with_p <= 227 * 1024) return launch_bwd_sp<DH, R, true>(p, N, with_p, threads, st);
   LK_REQUIRE(base <= 227 * 1024, LK_ERR_SHAPE, "lk_mha_bwd: tiles (%zu B) do not fit shared memory", base);
-  return launch_bwd_sp<DH, R, false>(p, N, base, st);
+  return launch_bwd_sp<DH, R, false>(p, N, base, threads, st);
 }
 
 static void set_dropout(MhaParams& p, float drop_p, uint64_t seed) {
