@@ -173,6 +173,8 @@ def main():
     # ---------------- B200 arm ---------------------------------------------------------------------------------------
     import torch.distributed as dist
     if world_size > 1:
+        # the contract is ONE line on stdout: NCCL's own banner ("NCCL version ...", printed at VERSION/INFO level) must not join it
+        os.environ['NCCL_DEBUG'] = os.environ.get('LK_NCCL_DEBUG', 'WARN')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     import __graft_entry__ as ge
     if rank == 0:
@@ -277,20 +279,19 @@ def main():
     e2e_value = world_size * args.batch * args.steps / (ms_e2e / 1000.0)
 
     # per-entry-point device time over two extra steps (CUDA events around every C-ABI call on the launching stream)
+    # (every rank runs the two steps — they contain the gradient all-reduce — but only rank 0 times them)
     roof, shares = None, None
+    prof = None
     if rank == 0:
         if native is not None:
             _lib.native_profile_begin()
-            for i in range(2):
-                step(devb[i % POOL])
-            torch.cuda.synchronize()
-            shares, gemm = _lib.native_profile_end()
         else:
             prof = _lib.profile_begin()
-            for i in range(2):
-                step(devb[i % POOL])
-            torch.cuda.synchronize()
-            shares, gemm = _lib.profile_end(prof)
+    for i in range(2):
+        step(devb[i % POOL])
+    torch.cuda.synchronize()
+    if rank == 0:
+        shares, gemm = _lib.native_profile_end() if native is not None else _lib.profile_end(prof)
         pk = peaks()
         if gemm['ms'] > 0:
             ach = gemm['flops'] / (gemm['ms'] / 1e3) / 1e12
