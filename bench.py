@@ -55,6 +55,14 @@ def peaks():
     return dict(hbm=6650.0, tensor=1400.0, which='fallback')
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r1_traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))[kernel]['dram_bytes_per_launch']
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
@@ -161,6 +169,7 @@ def main():
         batches = host_batches_cpu(world, args.batch, 4)
         bsz = args.batch
         r = cpu_reference(world, batches, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+        base_cfg = dict(base_cfg, driver='reference CPU path restated on torch CPU (oracle/lego_oracle.py), all host threads', parallelism='cpu')
         line = dict(metric='NRMS train impressions/s', value=r['value'], unit='impressions/s', n_gpus=args.gpus, steps=args.steps,
                     warmup=args.warmup, ms_per_step=1000 * r['seconds'] / r['steps'], higher_is_better=True, scaling='weak',
                     vs_baseline=None, dtype='f32', data='synthetic', impl='reference', config=base_cfg,
@@ -298,7 +307,9 @@ def main():
             tc = gemm['name'] == 'lk_tc_gemm'
             roof = dict(bound='tensor', kernel='tc_gemm_kernel (tcgen05.mma, split-bf16 x3, fp32 TMEM accumulate)' if tc
                         else 'gemm_simt_kernel (fp32 FFMA)', achieved=ach, peak=pk['tensor'],
-                        unit='TFLOP/s', frac=ach / pk['tensor'], traffic=None, peak_source=pk['which'],
+                        unit='TFLOP/s', frac=ach / pk['tensor'], traffic=measured_traffic('tc_gemm_kernel') if tc else None,
+                        traffic_note='dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the tc_gemm launches of one step (profiles/r1_traffic.json, ncu --set full)',
+                        pipe_tflops=3 * ach if tc else ach, pipe_frac=(3 * ach if tc else ach) / pk['tensor'], peak_source=pk['which'],
                         share_of_step=gemm['ms'] / max(sum(shares.values()), 1e-9), launches=gemm['calls'],
                         per_shape=gemm.get('per_shape'),
                         note='achieved = algorithmic flops (2*M*N*K per call, counted once) / CUDA-event time of the calls in a live step'
@@ -316,6 +327,10 @@ def main():
                 e2e_wire_format=e2e_wire,
                 gpu_launches=launches, roofline=roof, kernel_ms_share=shares)
 
+    if world_size > 1 and not args.small and not args.no_extra:
+        multi = sharded_lookup_line(dev, rank, world_size, args.batch)       # collective: every rank takes part
+        if rank == 0:
+            line['extra'] = dict(sharded_word_table=multi)
     if rank == 0 and world_size == 1 and not args.small and not args.no_extra:
         line['extra'] = hbm_bound_lines(dev, world, peaks()['hbm'], model=model, resampler=resampler, tensor_peak=peaks()['tensor'])
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
@@ -328,6 +343,41 @@ def main():
     if world_size > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def sharded_lookup_line(dev, rank, world_size, batch):
+    """Config 4 (BASELINE.json): a 4M x 300 fp32 word table row-sharded over the ranks (id % N), one NRMS batch worth of Zipf token
+    ids per rank and step (history 100): dedup -> all-to-all ids -> lk_index_rows on the owner -> all-to-all rows.  Device-timed,
+    max over ranks; no parameter of the timed region is cached between steps."""
+    import torch.distributed as dist
+    from legommenders_b200 import sharding
+    from legommenders_b200.synth import zipf_probs
+    V, E, H, C, L = 4_000_000, 300, 100, 5, 20
+    local = torch.empty(((V - rank + world_size - 1) // world_size, E), dtype=torch.float32, device=dev).normal_(0, 0.4)
+    st = sharding.ShardedTable(local, V)
+    probs = torch.from_numpy(zipf_probs(V)).to(dev, dtype=torch.float32)
+    g = torch.Generator(device=dev).manual_seed(31 + rank)
+    n_tok = batch * (C + H) * L
+    pool = [torch.multinomial(probs, n_tok, replacement=True, generator=g) for _ in range(4)]
+    uniq = sum(int(torch.unique(p).numel()) for p in pool) / len(pool)
+    for i in range(3):
+        st.lookup_unique(pool[i % 4])
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    K = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        rows, inv = st.lookup_unique(pool[i % 4])
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / K], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    remote = uniq * (world_size - 1) / world_size
+    return dict(table_rows=V, embed_dim=E, rows_per_rank=int(local.shape[0]), tokens_per_rank_per_step=n_tok, unique_rows_per_rank=uniq,
+                ms_per_lookup=ms, tokens_per_s=world_size * n_tok / ms * 1e3, unique_rows_per_s=world_size * uniq / ms * 1e3,
+                nvlink_GBps_per_rank=remote * E * 4 / ms / 1e6,
+                note='includes the host round trip for the all-to-all split sizes; rows cross NVLink once per distinct token')
 
 
 def hbm_bound_lines(dev, world, hbm_peak, model=None, resampler=None, tensor_peak=1400.0):

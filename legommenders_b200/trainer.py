@@ -65,7 +65,10 @@ class NativeNRMSStep:
            'multi_head_attention.out_proj.bias', 'linear.weight', 'linear.bias', 'additive_attention.encoder.0.weight',
            'additive_attention.encoder.0.bias', 'additive_attention.encoder.2.weight']
 
-    def __init__(self, model, opt: FlatAdam):
+    def __init__(self, model, opt: FlatAdam, sharded_table=None):
+        """sharded_table: a sharding.ShardedTable holding the frozen title-word table row-sharded over the ranks (config 4).
+        Every step then exchanges the batch's DISTINCT token ids (all-to-all), receives their rows (all-to-all) and gathers
+        from that compact per-step table; the replicated table of the model is not touched."""
         import numpy as np
         from . import _lib
         from .embedding_hub import Table, Transformation
@@ -88,6 +91,9 @@ class NativeNRMSStep:
             raise ValueError('NativeNRMSStep expects the pretrained title table to be frozen')
         self.model, self.opt = model, opt
         self.glove = ttab.embedding.weight
+        self.sharded_table = sharded_table
+        if sharded_table is not None and sharded_table.local.shape[1] != self.glove.shape[1]:
+            raise ValueError('sharded table width differs from the title embedding width')
         mha = model.item_op.multi_head_attention
         self.D, self.heads = mha.embed_dim, mha.num_heads
         self.A = model.item_op.additive_attention.hidden_size
@@ -156,8 +162,14 @@ class NativeNRMSStep:
         self.calls += 1
         seed = (torch.initial_seed() * 1000003 + self.calls) & ((1 << 60) - 1)
         de, da = (self.drop_embed, self.drop_attn) if training else (0.0, 0.0)
-        call('lk_nrms_fwd_bwd', ptr(pk.ids[self.title_col]), ptr(pk.ids[self.cat_col]), ptr(pk.ids[self.special_col]), ptr(pk.cu),
-             pk.n, pk.rows, pk.max_len, ptr(cu_u), B, C, max_u, ptr(self.glove), ptr(self.opt.flat), ptr(self.opt.grad),
+        title_ids, table = pk.ids[self.title_col], self.glove
+        if self.sharded_table is not None:
+            # config 4: rows of this step's distinct tokens arrive over NVLink; `inverse` (-1 where the position is unset) indexes them
+            table, title_ids = self.sharded_table.lookup_unique(title_ids)
+            if table.shape[0] == 0:
+                table = table.new_zeros((1, table.shape[1]))
+        call('lk_nrms_fwd_bwd', ptr(title_ids), ptr(pk.ids[self.cat_col]), ptr(pk.ids[self.special_col]), ptr(pk.cu),
+             pk.n, pk.rows, pk.max_len, ptr(cu_u), B, C, max_u, ptr(table), ptr(self.opt.flat), ptr(self.opt.grad),
              self.offsets.ctypes.data, self.D, self.heads, self.A, self.E, self.n_cats, self.n_special, float(de), float(da), int(seed),
              ptr(self.loss), None, ptr(self.arena), self.arena.numel())
         return self.loss

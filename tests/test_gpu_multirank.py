@@ -139,6 +139,31 @@ def test_data_parallel_step_nccl():
     spawn(_dp_step)
 
 
+def _sharded_table_step(rank):
+    """Config 4: the native step fed from the row-sharded word table gives the loss and gradients of the replicated table."""
+    from legommenders_b200 import Env, sharding
+    from legommenders_b200.batching import BatchBuilder, tree_to_device
+    from legommenders_b200.trainer import FlatAdam, NativeNRMSStep
+    c, world, model, resampler = _build(rank)
+    Env.train()
+    rows = (np.arange(16) + 16 * rank) % world.n_train            # different impressions per rank
+    batch = tree_to_device(BatchBuilder(resampler, world, neg_count=4, seed=3 + rank, pin=False).train_batch(rows), Env.device)
+    opt = FlatAdam(model, lr=1e-3)
+    nat = NativeNRMSStep(model, opt)
+    l0 = nat.fwd_bwd(batch, training=False).item()
+    g0 = opt.grad.clone()
+    st = sharding.ShardedTable(sharding.shard_rows(nat.glove.detach(), rank, WORLD), nat.glove.shape[0])
+    nat2 = NativeNRMSStep(model, opt, sharded_table=st)
+    opt.grad.zero_()
+    l1 = nat2.fwd_bwd(batch, training=False).item()
+    assert l1 == l0                                               # the same rows reach the same kernels: bit-identical
+    assert torch.equal(opt.grad, g0)
+
+
+def test_sharded_table_native_step_nccl():
+    spawn(_sharded_table_step)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def _sharded_eval(rank):
     import cases
