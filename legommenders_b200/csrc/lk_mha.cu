@@ -25,6 +25,7 @@
 // packed rows with cumulative offsets `cu` (padding-free execution: pad tokens and pad history slots, which the
 // reference computes and then masks away, are never touched).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "lk_common.cuh"
 #include "../../include/legommenders_b200.h"
@@ -540,6 +541,416 @@ __global__ void __maxnreg__(DH <= 32 ? (SP ? 168 : 200) : 255) mha_bwd_seq_kerne
              csum ? csum + 2 * D : nullptr);
 }
 
+// ================================================================================================ tensor-core path (head dim 32)
+// Sequences of at most 64 tokens (every item, every 50-click history) run on mma.sync.m16n8k16 bf16 tiles, one WARP per
+// (sequence, head) and no shared operand staging at all: fragments are read straight from the fp32 rows (8-byte loads, L1/L2
+// resident), split into (hi, lo) bf16 in registers, and every product issues three MMAs (lo·hi, hi·lo, hi·hi) into fp32
+// accumulators — the same error-compensated scheme as the tcgen05 GEMM, so fp32 parity holds.  Transposed operands
+// (V for P·V, K for dS·K, Q / dO for the key-side gradients, dS^T / P^T) are produced from the row-major fragments with
+// movmatrix (8x8 b16 transpose across lanes).  Softmax, masking and dropout act on accumulator fragments: every (query, key)
+// pair is owned by exactly one lane, so nothing is computed twice.  Dropout bits are the same function of (row, head, key) as
+// in the SIMT kernels, which remain the path for longer sequences and other head dims.
+namespace tcm {
+
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& h, uint32_t& l) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+  const float r0 = x0 - __uint_as_float(h << 16), r1 = x1 - __uint_as_float(h & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(r1), "f"(r0));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += (ah + al) · (bh + bl) without the lo·lo term; small terms first
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1,
+                                     uint32_t bl0, uint32_t bl1) {
+  mma16816(c, al, bh0, bh1);
+  mma16816(c, ah, bl0, bl1);
+  mma16816(c, ah, bh0, bh1);
+}
+__device__ __forceinline__ uint32_t movm(uint32_t x) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(x));
+  return d;
+}
+__device__ __forceinline__ float2 ld2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_add(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+// A fragments (16 rows x 32 columns, two k-steps) of rows r0 / r1 of a row-major fp32 matrix, scaled
+__device__ __forceinline__ void load_a(const float* __restrict__ row0p, const float* __restrict__ row1p, int t, float s, uint32_t (&h)[2][4],
+                                       uint32_t (&l)[2][4]) {
+#pragma unroll
+  for (int kk = 0; kk < 2; kk++) {
+    const float2 a = ld2(row0p + kk * 16 + 2 * t), b = ld2(row1p + kk * 16 + 2 * t);
+    const float2 c = ld2(row0p + kk * 16 + 8 + 2 * t), d = ld2(row1p + kk * 16 + 8 + 2 * t);
+    split2(a.x * s, a.y * s, h[kk][0], l[kk][0]);
+    split2(b.x * s, b.y * s, h[kk][1], l[kk][1]);
+    split2(c.x * s, c.y * s, h[kk][2], l[kk][2]);
+    split2(d.x * s, d.y * s, h[kk][3], l[kk][3]);
+  }
+}
+// validity bits of up to 64 keys of this sequence (dense layout: the key mask; packed: every key below L)
+__device__ __forceinline__ unsigned long long key_bits(const MhaParams& p, int64_t n, int L, int lane) {
+  const bool dense = !p.seq.cu && p.seq.mask;
+  const int S = p.seq.S;
+  const bool a = lane < L && (!dense || p.seq.mask[n * S + lane] > 0);
+  const bool b = lane + 32 < L && (!dense || p.seq.mask[n * S + lane + 32] > 0);
+  const uint32_t lo = __ballot_sync(0xffffffffu, a), hi = __ballot_sync(0xffffffffu, b);
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+constexpr int TC_MAX_L = 64;
+constexpr int TCP = 136;   // fp32 pitch of a 128-column (4 heads x 32) tile: 8-byte fragment loads of 8 rows x 4 lanes hit 32 distinct banks
+
+// [L][128] columns of a row-major fp32 matrix -> shared tile with pitch TCP, 16 bytes per cp.async
+__device__ __forceinline__ void stage128(float* T, const float* __restrict__ src, int64_t ld, int L) {
+  for (int idx = threadIdx.x; idx < L * 32; idx += blockDim.x) {
+    const int r = idx >> 5, c = (idx & 31) * 4;
+    cp_async16(T + r * TCP + c, src + (int64_t)r * ld + c);
+  }
+}
+
+__global__ void __launch_bounds__(128, 4) mha_fwd_tc_kernel(MhaParams p) {
+  pdl_prologue();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int64_t n = blockIdx.x;
+  int64_t row0; int L;
+  seq_range(p.seq, n, row0, L);
+  if (L == 0) return;
+  extern __shared__ __align__(16) float smem[];
+  const int D = p.D, H = p.H, h = blockIdx.y * 4 + warp, c0 = h * 32, cw = warp * 32;
+  const float* base = p.qkv + row0 * 3 * (int64_t)D;
+  float* Ks = smem;                               // [L][TCP]: the four heads of this CTA
+  float* Vs = Ks + (size_t)p.seq.S * TCP;
+  stage128(Ks, base + D + blockIdx.y * 128, 3 * D, L);
+  stage128(Vs, base + 2 * D + blockIdx.y * 128, 3 * D, L);
+  const unsigned long long kv = key_bits(p, n, L, lane);
+  const float qs = p.scale * kLog2e;
+  const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+  const int nt = (L + 7) >> 3, mt = (L + 15) >> 4;
+  cp_async_wait_all();
+  __syncthreads();
+  for (int m = 0; m < mt; m++) {
+    const int i0 = m * 16 + g, i1 = i0 + 8, i0c = min(i0, L - 1), i1c = min(i1, L - 1);
+    uint32_t qh[2][4], ql[2][4];
+    load_a(base + (int64_t)i0c * 3 * D + c0, base + (int64_t)i1c * 3 * D + c0, t, qs, qh, ql);
+    float c[8][4];
+#pragma unroll
+    for (int nn = 0; nn < 8; nn++) {
+      c[nn][0] = c[nn][1] = c[nn][2] = c[nn][3] = 0.f;
+      if (nn < nt) {                                               // warp-uniform
+        const float* kp = Ks + min(nn * 8 + g, L - 1) * TCP + cw + 2 * t;
+#pragma unroll
+        for (int kk = 0; kk < 2; kk++) {
+          const float2 k0 = *reinterpret_cast<const float2*>(kp + kk * 16), k1 = *reinterpret_cast<const float2*>(kp + kk * 16 + 8);
+          uint32_t bh0, bl0, bh1, bl1;
+          split2(k0.x, k0.y, bh0, bl0);
+          split2(k1.x, k1.y, bh1, bl1);
+          mma3(c[nn], qh[kk], ql[kk], bh0, bh1, bl0, bl1);
+        }
+      }
+    }
+    // ---- softmax over the keys of rows i0 (c[.][0..1]) and i1 (c[.][2..3]); scores are in the log2 domain
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nn = 0; nn < 8; nn++) {
+      if (nn < nt) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int j = nn * 8 + 2 * t + e;
+          if (!((kv >> j) & 1ull)) { c[nn][e] = -INFINITY; c[nn][2 + e] = -INFINITY; }
+          mx0 = fmaxf(mx0, c[nn][e]);
+          mx1 = fmaxf(mx1, c[nn][2 + e]);
+        }
+      }
+    }
+    mx0 = quad_max(mx0); mx1 = quad_max(mx1);
+    const uint32_t hb0 = attn_hash_base(p.seed, (uint64_t)(row0 + i0c) * H + h), hb1 = attn_hash_base(p.seed, (uint64_t)(row0 + i1c) * H + h);
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nn = 0; nn < 8; nn++) {
+      if (nn < nt) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int j = nn * 8 + 2 * t + e;
+          const float p0 = ex2(c[nn][e] - mx0), p1 = ex2(c[nn][2 + e] - mx1);   // masked keys: 2^-inf = 0; all masked: NaN as torch
+          l0 += p0; l1 += p1;
+          bool k0 = true, k1 = true;
+          if (p.drop_p > 0.f) { k0 = attn_keep(hb0, j, p.drop_thr); k1 = attn_keep(hb1, j, p.drop_thr); }
+          c[nn][e] = k0 ? p0 * inv_keep : 0.f;
+          c[nn][2 + e] = k1 ? p1 * inv_keep : 0.f;
+        }
+      }
+    }
+    l0 = quad_add(l0); l1 = quad_add(l1);
+    if (t == 0) {
+      if (i0 < L) p.lse[(row0 + i0) * H + h] = (mx0 + log2f(l0)) * kLn2;
+      if (i1 < L) p.lse[(row0 + i1) * H + h] = (mx1 + log2f(l1)) * kLn2;
+    }
+    // ---- O = P·V: the probability fragments of two key tiles are the A operand of one 16-key step
+    float o[4][4];
+#pragma unroll
+    for (int dn = 0; dn < 4; dn++) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      if (kk * 16 < L) {
+        uint32_t ph[4], pl[4];
+        split2(c[2 * kk][0], c[2 * kk][1], ph[0], pl[0]);
+        split2(c[2 * kk][2], c[2 * kk][3], ph[1], pl[1]);
+        split2(c[2 * kk + 1][0], c[2 * kk + 1][1], ph[2], pl[2]);
+        split2(c[2 * kk + 1][2], c[2 * kk + 1][3], ph[3], pl[3]);
+        const float* va = Vs + min(kk * 16 + g, L - 1) * TCP + cw + 2 * t;
+        const float* vb = Vs + min(kk * 16 + 8 + g, L - 1) * TCP + cw + 2 * t;
+#pragma unroll
+        for (int dn = 0; dn < 4; dn++) {
+          const float2 xa = *reinterpret_cast<const float2*>(va + dn * 8), xb = *reinterpret_cast<const float2*>(vb + dn * 8);
+          uint32_t ah, al, bh, bl;
+          split2(xa.x, xa.y, ah, al);
+          split2(xb.x, xb.y, bh, bl);
+          mma3(o[dn], ph, pl, movm(ah), movm(bh), movm(al), movm(bl));
+        }
+      }
+    }
+    const float r0 = 1.f / l0, r1 = 1.f / l1;
+#pragma unroll
+    for (int dn = 0; dn < 4; dn++) {
+      const int col = c0 + dn * 8 + 2 * t;
+#pragma unroll
+      for (int rr = 0; rr < 2; rr++) {
+        const int i = rr ? i1 : i0;
+        if (i < L) {
+          const float x0 = o[dn][2 * rr] * (rr ? r1 : r0), x1 = o[dn][2 * rr + 1] * (rr ? r1 : r0);
+          const int64_t off = (row0 + i) * (int64_t)D + col;
+          if (p.ctx) *reinterpret_cast<float2*>(p.ctx + off) = make_float2(x0, x1);
+          if (p.ctx_hi) {
+            uint32_t hh, ll;
+            split2(x0, x1, hh, ll);
+            *reinterpret_cast<uint32_t*>(p.ctx_hi + off) = hh;
+            *reinterpret_cast<uint32_t*>(p.ctx_lo + off) = ll;
+          }
+        }
+      }
+    }
+  }
+}
+
+// A fragments from a shared tile (plain loads: the tile pointer is a shared-memory address)
+__device__ __forceinline__ void load_a_s(const float* row0p, const float* row1p, int t, float s, uint32_t (&h)[2][4], uint32_t (&l)[2][4]) {
+#pragma unroll
+  for (int kk = 0; kk < 2; kk++) {
+    const float2 a = *reinterpret_cast<const float2*>(row0p + kk * 16 + 2 * t), b = *reinterpret_cast<const float2*>(row1p + kk * 16 + 2 * t);
+    const float2 c = *reinterpret_cast<const float2*>(row0p + kk * 16 + 8 + 2 * t), d = *reinterpret_cast<const float2*>(row1p + kk * 16 + 8 + 2 * t);
+    split2(a.x * s, a.y * s, h[kk][0], l[kk][0]);
+    split2(b.x * s, b.y * s, h[kk][1], l[kk][1]);
+    split2(c.x * s, c.y * s, h[kk][2], l[kk][2]);
+    split2(d.x * s, d.y * s, h[kk][3], l[kk][3]);
+  }
+}
+__device__ __forceinline__ float col_add(float v) {     // sum over the 8 row groups of a fragment column (lanes with equal t)
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  return v + __shfl_xor_sync(0xffffffffu, v, 16);
+}
+
+// Backward, one warp per (sequence, head).  Outer loop over 16-key tiles j (their K / V fragments and the dK / dV accumulators stay
+// in registers), inner loop over 16-query tiles i: S and dP blocks are recomputed once per (i, j) pair, turned into dS and P∘keep
+// in place, and feed three more contractions: dQ(i) += dS·K(j) (accumulated in a shared tile whose columns this warp owns),
+// dK(j) += dS^T·Q(i), dV(j) += (P∘keep)^T·dO(i).  Q and dO of the CTA's four heads are staged once in shared memory.
+__global__ void __launch_bounds__(128, 3) mha_bwd_tc_kernel(MhaParams p) {
+  pdl_prologue();
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int64_t n = blockIdx.x;
+  int64_t row0; int L;
+  seq_range(p.seq, n, row0, L);
+  if (L == 0) return;
+  const int D = p.D, H = p.H, S = p.seq.S, h = blockIdx.y * 4 + warp, c0 = h * 32, cw = warp * 32;
+  const float* base = p.qkv + row0 * 3 * (int64_t)D;
+  const float* gbase = p.dctx + row0 * (int64_t)D;
+  const float* obase = p.ctx + row0 * (int64_t)D;
+  float* Qs = smem;                                // [S][TCP] q (unscaled)
+  float* Gs = Qs + (size_t)S * TCP;                // dO
+  float* dQs = Gs + (size_t)S * TCP;               // dQ accumulators
+  float* Ds = dQs + (size_t)S * TCP;               // [4][TC_MAX_L]  D_i = dO_i · O_i
+  stage128(Qs, base + blockIdx.y * 128, 3 * D, L);
+  stage128(Gs, gbase + blockIdx.y * 128, D, L);
+  for (int idx = threadIdx.x; idx < L * 32; idx += blockDim.x)
+    *reinterpret_cast<float4*>(dQs + (idx >> 5) * TCP + (idx & 31) * 4) = f4_zero();
+  const unsigned long long kv = key_bits(p, n, L, lane);
+  const float qs = p.scale * kLog2e;
+  const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+  const int mt = (L + 15) >> 4;
+  cp_async_wait_all();
+  __syncthreads();
+  for (int m = 0; m < mt; m++) {
+    const int i0 = m * 16 + g, i1 = i0 + 8, i0c = min(i0, L - 1), i1c = min(i1, L - 1);
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int dn = 0; dn < 4; dn++) {
+      const float2 a = *reinterpret_cast<const float2*>(Gs + i0c * TCP + cw + dn * 8 + 2 * t), oa = ld2(obase + (int64_t)i0c * D + c0 + dn * 8 + 2 * t);
+      const float2 b = *reinterpret_cast<const float2*>(Gs + i1c * TCP + cw + dn * 8 + 2 * t), ob = ld2(obase + (int64_t)i1c * D + c0 + dn * 8 + 2 * t);
+      d0 = fmaf(a.x, oa.x, fmaf(a.y, oa.y, d0));
+      d1 = fmaf(b.x, ob.x, fmaf(b.y, ob.y, d1));
+    }
+    d0 = quad_add(d0); d1 = quad_add(d1);
+    if (t == 0) {
+      if (i0 < L) Ds[warp * TC_MAX_L + i0] = d0;
+      if (i1 < L) Ds[warp * TC_MAX_L + i1] = d1;
+    }
+  }
+  __syncwarp();
+
+  float ksum[4][2], vsum[4][2];
+#pragma unroll
+  for (int dn = 0; dn < 4; dn++) ksum[dn][0] = ksum[dn][1] = vsum[dn][0] = vsum[dn][1] = 0.f;
+  float* dbase = p.dqkv ? p.dqkv + row0 * 3 * (int64_t)D + c0 : nullptr;
+  __nv_bfloat16* hbase = p.dq_hi ? p.dq_hi + row0 * 3 * (int64_t)D + c0 : nullptr;
+  __nv_bfloat16* lbase = p.dq_lo ? p.dq_lo + row0 * 3 * (int64_t)D + c0 : nullptr;
+  auto emit = [&](int64_t off, float x0, float x1) {       // two adjacent result columns: fp32 and / or planes
+    if (dbase) *reinterpret_cast<float2*>(dbase + off) = make_float2(x0, x1);
+    if (hbase) {
+      uint32_t hh, ll;
+      split2(x0, x1, hh, ll);
+      *reinterpret_cast<uint32_t*>(hbase + off) = hh;
+      *reinterpret_cast<uint32_t*>(lbase + off) = ll;
+    }
+  };
+
+  for (int jt = 0; jt < mt; jt++) {
+    uint32_t kh[2][2][2], kl[2][2][2], vh[2][2][2], vl[2][2][2];
+#pragma unroll
+    for (int nn = 0; nn < 2; nn++) {
+      const int64_t jr = min(jt * 16 + nn * 8 + g, L - 1);
+      const float* kp = base + jr * 3 * D + D + c0 + 2 * t;
+      const float* vp = kp + D;
+#pragma unroll
+      for (int kk = 0; kk < 2; kk++) {
+        const float2 k0 = ld2(kp + kk * 16), k1 = ld2(kp + kk * 16 + 8), v0 = ld2(vp + kk * 16), v1 = ld2(vp + kk * 16 + 8);
+        split2(k0.x, k0.y, kh[nn][kk][0], kl[nn][kk][0]);
+        split2(k1.x, k1.y, kh[nn][kk][1], kl[nn][kk][1]);
+        split2(v0.x, v0.y, vh[nn][kk][0], vl[nn][kk][0]);
+        split2(v1.x, v1.y, vh[nn][kk][1], vl[nn][kk][1]);
+      }
+    }
+    float dk[4][4], dv[4][4];
+#pragma unroll
+    for (int dn = 0; dn < 4; dn++) dk[dn][0] = dk[dn][1] = dk[dn][2] = dk[dn][3] = dv[dn][0] = dv[dn][1] = dv[dn][2] = dv[dn][3] = 0.f;
+    for (int m = 0; m < mt; m++) {
+      const int i0 = m * 16 + g, i1 = i0 + 8, i0c = min(i0, L - 1), i1c = min(i1, L - 1);
+      const bool r0ok = i0 < L, r1ok = i1 < L;
+      uint32_t qh[2][4], ql[2][4], gh[2][4], gl[2][4];
+      load_a_s(Qs + i0c * TCP + cw, Qs + i1c * TCP + cw, t, qs, qh, ql);
+      load_a_s(Gs + i0c * TCP + cw, Gs + i1c * TCP + cw, t, 1.f, gh, gl);
+      float cs[2][4], cp[2][4];
+#pragma unroll
+      for (int nn = 0; nn < 2; nn++) {
+        cs[nn][0] = cs[nn][1] = cs[nn][2] = cs[nn][3] = 0.f;
+        cp[nn][0] = cp[nn][1] = cp[nn][2] = cp[nn][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 2; kk++) {
+          mma3(cs[nn], qh[kk], ql[kk], kh[nn][kk][0], kh[nn][kk][1], kl[nn][kk][0], kl[nn][kk][1]);
+          mma3(cp[nn], gh[kk], gl[kk], vh[nn][kk][0], vh[nn][kk][1], vl[nn][kk][0], vl[nn][kk][1]);
+        }
+      }
+      const float l20 = p.lse[(row0 + i0c) * H + h] * kLog2e, l21 = p.lse[(row0 + i1c) * H + h] * kLog2e;
+      const float D0 = Ds[warp * TC_MAX_L + i0c], D1 = Ds[warp * TC_MAX_L + i1c];
+      const uint32_t hb0 = attn_hash_base(p.seed, (uint64_t)(row0 + i0c) * H + h), hb1 = attn_hash_base(p.seed, (uint64_t)(row0 + i1c) * H + h);
+#pragma unroll
+      for (int nn = 0; nn < 2; nn++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int j = jt * 16 + nn * 8 + 2 * t + e;
+          const bool ok = (kv >> j) & 1ull;
+          const float p0 = (ok && r0ok) ? ex2(cs[nn][e] - l20) : 0.f, p1 = (ok && r1ok) ? ex2(cs[nn][2 + e] - l21) : 0.f;
+          bool k0 = true, k1 = true;
+          if (p.drop_p > 0.f) { k0 = attn_keep(hb0, j, p.drop_thr); k1 = attn_keep(hb1, j, p.drop_thr); }
+          const float dP0 = k0 ? cp[nn][e] * inv_keep : 0.f, dP1 = k1 ? cp[nn][2 + e] * inv_keep : 0.f;
+          cs[nn][e] = p0 * (dP0 - D0);                         // dS (the softmax scale is applied on the way out)
+          cs[nn][2 + e] = p1 * (dP1 - D1);
+          cp[nn][e] = k0 ? p0 * inv_keep : 0.f;                // P ∘ keep
+          cp[nn][2 + e] = k1 ? p1 * inv_keep : 0.f;
+        }
+      }
+      uint32_t sh[4], sl[4], ph[4], pl[4];
+      split2(cs[0][0], cs[0][1], sh[0], sl[0]); split2(cs[0][2], cs[0][3], sh[1], sl[1]);
+      split2(cs[1][0], cs[1][1], sh[2], sl[2]); split2(cs[1][2], cs[1][3], sh[3], sl[3]);
+      split2(cp[0][0], cp[0][1], ph[0], pl[0]); split2(cp[0][2], cp[0][3], ph[1], pl[1]);
+      split2(cp[1][0], cp[1][1], ph[2], pl[2]); split2(cp[1][2], cp[1][3], ph[3], pl[3]);
+      // dQ(i) += scale * dS · K(j)
+#pragma unroll
+      for (int dn = 0; dn < 4; dn++) {
+        const int kk = dn >> 1, r = dn & 1;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        mma3(acc, sh, sl, movm(kh[0][kk][r]), movm(kh[1][kk][r]), movm(kl[0][kk][r]), movm(kl[1][kk][r]));
+        if (r0ok) {
+          float2* q = reinterpret_cast<float2*>(dQs + i0 * TCP + cw + dn * 8 + 2 * t);
+          float2 v = *q; v.x = fmaf(acc[0], p.scale, v.x); v.y = fmaf(acc[1], p.scale, v.y); *q = v;
+        }
+        if (r1ok) {
+          float2* q = reinterpret_cast<float2*>(dQs + i1 * TCP + cw + dn * 8 + 2 * t);
+          float2 v = *q; v.x = fmaf(acc[2], p.scale, v.x); v.y = fmaf(acc[3], p.scale, v.y); *q = v;
+        }
+      }
+      // key side: dK(j) += dS^T · Q(i),  dV(j) += (P∘keep)^T · dO(i)
+      uint32_t th[4] = {movm(sh[0]), movm(sh[2]), movm(sh[1]), movm(sh[3])}, tl[4] = {movm(sl[0]), movm(sl[2]), movm(sl[1]), movm(sl[3])};
+      uint32_t uh[4] = {movm(ph[0]), movm(ph[2]), movm(ph[1]), movm(ph[3])}, ul[4] = {movm(pl[0]), movm(pl[2]), movm(pl[1]), movm(pl[3])};
+#pragma unroll
+      for (int dn = 0; dn < 4; dn++) {
+        const int kk = dn >> 1, r = dn & 1;
+        mma3(dk[dn], th, tl, movm(qh[kk][2 * r]), movm(qh[kk][2 * r + 1]), movm(ql[kk][2 * r]), movm(ql[kk][2 * r + 1]));
+        mma3(dv[dn], uh, ul, movm(gh[kk][2 * r]), movm(gh[kk][2 * r + 1]), movm(gl[kk][2 * r]), movm(gl[kk][2 * r + 1]));
+      }
+    }
+    // rows j of dK (q carried scale*log2e: undo the log2e) and dV
+    const int j0 = jt * 16 + g, j1 = j0 + 8;
+#pragma unroll
+    for (int dn = 0; dn < 4; dn++) {
+#pragma unroll
+      for (int rr = 0; rr < 2; rr++) {
+        const int j = rr ? j1 : j0;
+        if (j < L) {
+          const float x0 = dk[dn][2 * rr] * kLn2, x1 = dk[dn][2 * rr + 1] * kLn2, y0 = dv[dn][2 * rr], y1 = dv[dn][2 * rr + 1];
+          const int64_t off = (int64_t)j * 3 * D + dn * 8 + 2 * t;
+          emit(off + D, x0, x1);
+          emit(off + 2 * D, y0, y1);
+          ksum[dn][0] += x0; ksum[dn][1] += x1; vsum[dn][0] += y0; vsum[dn][1] += y1;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // dQ rows out of this warp's columns of the shared tile, and the per-sequence column sums (in_proj bias gradient)
+  float* csum = p.colsum_part ? p.colsum_part + n * 3 * (int64_t)D + c0 : nullptr;
+#pragma unroll
+  for (int dn = 0; dn < 4; dn++) {
+    float q0 = 0.f, q1 = 0.f;
+    for (int i = g; i < L; i += 8) {
+      const float2 v = *reinterpret_cast<const float2*>(dQs + i * TCP + cw + dn * 8 + 2 * t);
+      emit((int64_t)i * 3 * D + dn * 8 + 2 * t, v.x, v.y);
+      q0 += v.x; q1 += v.y;
+    }
+    if (csum) {
+      q0 = col_add(q0); q1 = col_add(q1);
+      const float k0 = col_add(ksum[dn][0]), k1 = col_add(ksum[dn][1]), v0 = col_add(vsum[dn][0]), v1 = col_add(vsum[dn][1]);
+      if (g == 0) {
+        const int col = dn * 8 + 2 * t;
+        csum[col] = q0; csum[col + 1] = q1;
+        csum[D + col] = k0; csum[D + col + 1] = k1;
+        csum[2 * D + col] = v0; csum[2 * D + col + 1] = v1;
+      }
+    }
+  }
+}
+
+}  // namespace tcm
+
 // heads per CTA: the largest divisor of H with HG*DH <= 128 columns
 static int pick_hg(int H, int dh) {
   int hg = 128 / dh;
@@ -603,6 +1014,12 @@ static int launch_bwd(MhaParams p, int64_t N, cudaStream_t st) {
   return launch_bwd_sp<DH, R, false>(p, N, base, threads, st);
 }
 
+// tensor-core kernels: head dim 32, heads in groups of four, at most 64 tokens per sequence (LK_MHA_TC=0 forces the SIMT kernels)
+static bool tc_path_ok(const MhaParams& p, int64_t S) {
+  static const bool on = [] { const char* e = getenv("LK_MHA_TC"); return !(e && e[0] == '0'); }();
+  return on && p.D / p.H == 32 && p.H % 4 == 0 && S <= tcm::TC_MAX_L;
+}
+
 static void set_dropout(MhaParams& p, float drop_p, uint64_t seed) {
   p.drop_p = drop_p;
   p.seed = (unsigned long long)seed;
@@ -631,7 +1048,19 @@ int lk_mha_fwd(const float* qkv, const int64_t* mask, const int32_t* cu, float* 
   switch (dh) {
     case 8: return launch_fwd<8, 2>(p, N, st);
     case 16: return launch_fwd<16, 2>(p, N, st);
-    case 32: return launch_fwd<32, 2>(p, N, st);
+    case 32:
+      if (tc_path_ok(p, S)) {
+        const size_t smem = (size_t)2 * S * tcm::TCP * sizeof(float);
+        static bool attr = false;
+        if (!attr) {
+          cudaFuncSetAttribute(tcm::mha_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * tcm::TC_MAX_L * tcm::TCP * (int)sizeof(float));
+          cudaFuncSetAttribute(tcm::mha_fwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          attr = true;
+        }
+        LK_LAUNCH((tcm::mha_fwd_tc_kernel), dim3((unsigned)N, (unsigned)(H / 4)), 128, smem, st, p);
+        return check_launch("mha_fwd_tc");
+      }
+      return launch_fwd<32, 2>(p, N, st);
     case 64: return launch_fwd<64, 4>(p, N, st);
   }
   LK_REQUIRE(false, LK_ERR_SHAPE, "lk_mha_fwd: head dim %d not in {8,16,32,64}", dh);
@@ -655,7 +1084,20 @@ int lk_mha_bwd(const float* qkv, const int64_t* mask, const int32_t* cu, const f
   switch (dh) {
     case 8: return launch_bwd<8, 2>(p, N, st);
     case 16: return launch_bwd<16, 2>(p, N, st);
-    case 32: return launch_bwd<32, 2>(p, N, st);
+    case 32:
+      if (tc_path_ok(p, S)) {
+        const size_t smem = ((size_t)3 * S * tcm::TCP + 4 * tcm::TC_MAX_L) * sizeof(float);
+        static bool attr = false;
+        if (!attr) {
+          cudaFuncSetAttribute(tcm::mha_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (3 * tcm::TC_MAX_L * tcm::TCP + 4 * tcm::TC_MAX_L) * (int)sizeof(float));
+          cudaFuncSetAttribute(tcm::mha_bwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          attr = true;
+        }
+        LK_LAUNCH((tcm::mha_bwd_tc_kernel), dim3((unsigned)N, (unsigned)(H / 4)), 128, smem, st, p);
+        return check_launch("mha_bwd_tc");
+      }
+      return launch_bwd<32, 2>(p, N, st);
     case 64: return launch_bwd<64, 4>(p, N, st);
   }
   LK_REQUIRE(false, LK_ERR_SHAPE, "lk_mha_bwd: head dim %d not in {8,16,32,64}", dh);

@@ -183,7 +183,7 @@ def test_conv1d_relu_mask(ops, N_, S, Cin, Cout):
 
 
 # ------------------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize('N_,S,D,H', [(11, 33, 256, 8), (4, 50, 256, 8), (7, 12, 64, 8), (3, 70, 64, 2), (2, 1, 32, 4), (3, 100, 256, 8),
+@pytest.mark.parametrize('N_,S,D,H', [(11, 33, 256, 8), (4, 50, 256, 8), (5, 64, 128, 4), (6, 17, 256, 8), (3, 16, 128, 4), (7, 12, 64, 8), (3, 70, 64, 2), (2, 1, 32, 4), (3, 100, 256, 8),
                                        (5, 9, 128, 2), (4, 31, 64, 4)])
 def test_mha_core(ops, N_, S, D, H):
     g = torch.Generator().manual_seed(S + D)
@@ -214,8 +214,10 @@ def test_mha_core(ops, N_, S, D, H):
     qkv_g = dev(qkv_c.detach().float()).requires_grad_(True)
     c = ops.mha_core(qkv_g, dev(mask), H)
     c.backward(dev(dctx))
-    assert rel(c, cr) <= 3e-6
-    assert rel(qkv_g.grad, qkv_c.grad) <= 5e-6
+    # head dim 32 with <= 64 tokens runs on bf16x3 tensor-core tiles (products exact to ~2^-17), the rest on fp32 FMAs
+    tc = D // H == 32 and H % 4 == 0 and S <= 64
+    assert rel(c, cr) <= (2e-5 if tc else 3e-6)
+    assert rel(qkv_g.grad, qkv_c.grad) <= (3e-5 if tc else 5e-6)
 
 
 @pytest.mark.parametrize('N_,S,D,A', [(13, 33, 256, 256), (5, 50, 256, 256), (9, 11, 64, 32), (3, 1, 64, 32)])
