@@ -24,17 +24,26 @@
 namespace lk {
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3, UMMA_K = 16, ACC_STAGES = 2;
-constexpr int TILE_BYTES = BM * BK * 2;        // one plane of one operand: 16 KiB
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi, A_lo, B_hi, B_lo
-constexpr int TMEM_COLS = ACC_STAGES * BN;     // 256 fp32 columns
-constexpr int EPI_WARPS = 16;              // warp (q, cg): TMEM lanes 32q..32q+31, columns 32cg..32cg+31 of the tile
-constexpr int EPI_CHUNKS = BN / (EPI_WARPS / 4) / 16;   // 16-column chunks per warp
+// Two tile shapes.  128x128 (3 stages of 64 KB) is the general one.  128x256 (2 stages of 96 KB, the whole TMEM as the
+// double-buffered accumulator) reads every A tile once instead of twice; see pick_bn for where it pays.
+constexpr int BM = 128, BK = 64, UMMA_K = 16, ACC_STAGES = 2;
+constexpr int TILE_BYTES = BM * BK * 2;        // one plane of a 128-row operand tile: 16 KiB
+template <int BN> struct Cfg {
+  static constexpr int STAGES = BN == 256 ? 2 : 3;
+  static constexpr int TILE_B = BN * BK * 2;                    // one plane of the B tile
+  static constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * TILE_B;   // A_hi, A_lo, B_hi, B_lo
+  static constexpr int TMEM_COLS = ACC_STAGES * BN;             // fp32 accumulator columns (256 or 512)
+  static constexpr int EPI_CHUNKS = BN / 4 / 16;                // 16-column chunks per epilogue warp
+};
+constexpr int EPI_WARPS = 16;              // warp (q, cg): TMEM lanes 32q..32q+31, column group cg (a quarter of the tile's columns)
 constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;   // TMA warp, MMA warp, epilogue warps
 constexpr int EPI_LD = 16;                 // staged epilogue rows are unpadded; an XOR swizzle of the 16-byte column keeps both
                                            // the row-per-lane writes and the 4-lanes-per-row reads free of bank conflicts
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 32 * EPI_LD * 4 /*epilogue staging*/;
+constexpr int SMEM_BYTES = 3 * 4 * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 32 * EPI_LD * 4 /*epilogue staging*/;
+static_assert(Cfg<128>::STAGES * Cfg<128>::STAGE_BYTES == 3 * 4 * TILE_BYTES && Cfg<256>::STAGES * Cfg<256>::STAGE_BYTES == 3 * 4 * TILE_BYTES,
+              "both tile shapes use the same 192 KiB operand ring");
 static_assert(SMEM_BYTES <= 227 * 1024, "tc_gemm shared memory budget");
+constexpr int MAX_STAGES = 3;
 
 struct Params {
   float* C;                 // [GM, ldc] (or split partials [splits, GM, GN] when partial != null)
@@ -110,9 +119,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
   return d;
 }
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp: InstrDescriptor): fp32 accumulate, bf16 A/B
-__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn) {
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int bn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+         ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 // (hi, lo) bf16 planes of four floats: two packed cvt.rn.bf16x2 per plane; hi's fp32 image is its bits shifted up
@@ -132,8 +141,10 @@ __device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
 // 32*cg..32*cg+31.  Per 16-column chunk: tcgen05.ld (row = lane) -> bias / activation / dropout / row mask in registers
 // -> transpose through a warp-private shared tile -> 64-byte-contiguous row segments to global (a warp store covers 8 rows).
 
+template <int BN>
 __device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, int acc, int q, int cg, int lane, int m0, int n0,
                                            int split, bool has_k, float inv_keep, float* stage) {
+  constexpr int EPI_CHUNKS = Cfg<BN>::EPI_CHUNKS;
   const int row = m0 + q * 32 + lane;
   const bool row_ok = row < p.GM;
   float* out;
@@ -244,17 +255,19 @@ __device__ __forceinline__ void store_tile(const Params& p, uint32_t tmem_base, 
   }
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const Params p) {
   pdl_trigger();   // the wait comes after the CTA set-up below (barriers, TMEM allocation, descriptor prefetch touch no global data)
   extern __shared__ uint8_t smem_raw[];
+  constexpr int STAGES = Cfg<BN>::STAGES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES, TILE_B = Cfg<BN>::TILE_B, TMEM_COLS = Cfg<BN>::TMEM_COLS;
+  constexpr int OFF_BH = 2 * TILE_BYTES, OFF_BL = 2 * TILE_BYTES + TILE_B;      // A_hi at 0, A_lo at TILE_BYTES
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024-byte alignment
   uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
   uint64_t* full_bar = bars;                     // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;           // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;       // [ACC_STAGES]
+  uint64_t* empty_bar = bars + MAX_STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * MAX_STAGES;   // [ACC_STAGES]
   uint64_t* tempty_bar = tfull_bar + ACC_STAGES; // [ACC_STAGES]
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + ACC_STAGES);
 
@@ -314,13 +327,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             tma_load_2d(sa + TILE_BYTES, &mapAl, fb, k0, m0);
           }
           if (B_MN) {
-            tma_load_2d(sa + 2 * TILE_BYTES, &mapBh, fb, n0, k0);
-            tma_load_2d(sa + 2 * TILE_BYTES + TILE_BYTES / 2, &mapBh, fb, n0 + 64, k0);
-            tma_load_2d(sa + 3 * TILE_BYTES, &mapBl, fb, n0, k0);
-            tma_load_2d(sa + 3 * TILE_BYTES + TILE_BYTES / 2, &mapBl, fb, n0 + 64, k0);
+#pragma unroll
+            for (int c = 0; c < BN / 64; c++) {            // 64 MN-elements x 64 k per box
+              tma_load_2d(sa + OFF_BH + c * (TILE_BYTES / 2), &mapBh, fb, n0 + 64 * c, k0);
+              tma_load_2d(sa + OFF_BL + c * (TILE_BYTES / 2), &mapBl, fb, n0 + 64 * c, k0);
+            }
           } else {
-            tma_load_2d(sa + 2 * TILE_BYTES, &mapBh, fb, k0, n0);
-            tma_load_2d(sa + 3 * TILE_BYTES, &mapBl, fb, k0, n0);
+            tma_load_2d(sa + OFF_BH, &mapBh, fb, k0, n0);
+            tma_load_2d(sa + OFF_BL, &mapBl, fb, k0, n0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -329,7 +343,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer ---------------------------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(A_MN, B_MN);
+      constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BN);
       constexpr uint32_t a_kstep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2);   // bytes per UMMA_K step inside a tile
       constexpr uint32_t b_kstep = B_MN ? (UMMA_K * 128) : (UMMA_K * 2);
       int stage = 0, acc = 0;
@@ -348,8 +362,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
           for (int k = 0; k < BK / UMMA_K; k++) {
             const uint64_t ah = make_desc(sa + k * a_kstep, A_MN);
             const uint64_t al = make_desc(sa + TILE_BYTES + k * a_kstep, A_MN);
-            const uint64_t bh = make_desc(sa + 2 * TILE_BYTES + k * b_kstep, B_MN);
-            const uint64_t bl = make_desc(sa + 3 * TILE_BYTES + k * b_kstep, B_MN);
+            const uint64_t bh = make_desc(sa + OFF_BH + k * b_kstep, B_MN);
+            const uint64_t bl = make_desc(sa + OFF_BL + k * b_kstep, B_MN);
             umma_bf16(d_tmem, al, bh, idesc, (kb > kb0 || k > 0) ? 1u : 0u);   // small terms first
             umma_bf16(d_tmem, ah, bl, idesc, 1u);
             umma_bf16(d_tmem, ah, bh, idesc, 1u);
@@ -377,7 +391,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       const bool has_k = kb1 > kb0;
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
-      store_tile(p, tmem_base, acc, q, cg, lane, m0, n0, split, has_k, inv_keep, stage);
+      store_tile<BN>(p, tmem_base, acc, q, cg, lane, m0, n0, split, has_k, inv_keep, stage);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
@@ -544,7 +558,18 @@ static int make_map(CUtensorMap* m, const void* base, int64_t inner, int64_t out
   return LK_OK;
 }
 
+// Tile width.  Measured on the NRMS step (profiles/r1_04): the wide tile wins a few percent at N = 768 (QKV, its weight gradient)
+// and loses 10-15 % at N = 256, where 333 wide tiles quantise badly over 148 SMs and the two-stage ring covers less latency —
+// so it is used for 512 <= N <= 4096 only.  LK_TC_BN=128 / 256 forces a shape (256 still needs N % 256 == 0).
+static int pick_bn(int64_t GN) {
+  static const int forced = [] { const char* e = getenv("LK_TC_BN"); return e ? atoi(e) : 0; }();
+  if (forced == 128 || GN % 256 != 0) return 128;
+  if (forced == 256) return 256;
+  return (GN >= 512 && GN <= 4096) ? 256 : 128;
+}
+
 static int pick_splits(int64_t GM, int64_t GN, int64_t GK) {
+  const int BN = pick_bn(GN);
   int64_t tiles = ((GM + BM - 1) / BM) * ((GN + BN - 1) / BN);
   int64_t kb = (GK + BK - 1) / BK;
   if (tiles >= kNumSMs || kb < 8) return 1;
@@ -631,6 +656,7 @@ int lk_tc_gemm_ex(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, con
   if (GM == 0 || GN == 0) return LK_OK;
   CUtensorMap mAh, mAl, mBh, mBl;
   int rc;
+  const int BN = pick_bn(GN);
   if (a_mn) {   // A stored [GK, GM] (GM contiguous)
     if ((rc = make_map(&mAh, A_hi, GM, GK, lda, 64))) return rc;
     if ((rc = make_map(&mAl, A_lo, GM, GK, lda, 64))) return rc;
@@ -674,16 +700,25 @@ int lk_tc_gemm_ex(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, con
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(tc_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_kernel<false, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_kernel<false, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_kernel<true, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_kernel<false, false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_kernel<false, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(tc_gemm_kernel<true, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     attr_set = true;
   }
   int total = p.m_tiles * p.n_tiles * p.splits;
   int grid = total < kNumSMs ? total : kNumSMs;
-  if (a_mn) LK_LAUNCH((tc_gemm_kernel<true, true>), grid, NUM_THREADS, SMEM_BYTES, st, mAh, mAl, mBh, mBl, p);
-  else if (b_mn) LK_LAUNCH((tc_gemm_kernel<false, true>), grid, NUM_THREADS, SMEM_BYTES, st, mAh, mAl, mBh, mBl, p);
-  else LK_LAUNCH((tc_gemm_kernel<false, false>), grid, NUM_THREADS, SMEM_BYTES, st, mAh, mAl, mBh, mBl, p);
+  if (BN == 256) {
+    if (a_mn) LK_LAUNCH((tc_gemm_kernel<true, true, 256>), grid, NUM_THREADS, SMEM_BYTES, st, mAh, mAl, mBh, mBl, p);
+    else if (b_mn) LK_LAUNCH((tc_gemm_kernel<false, true, 256>), grid, NUM_THREADS, SMEM_BYTES, st, mAh, mAl, mBh, mBl, p);
+    else LK_LAUNCH((tc_gemm_kernel<false, false, 256>), grid, NUM_THREADS, SMEM_BYTES, st, mAh, mAl, mBh, mBl, p);
+  } else {
+    if (a_mn) LK_LAUNCH((tc_gemm_kernel<true, true, 128>), grid, NUM_THREADS, SMEM_BYTES, st, mAh, mAl, mBh, mBl, p);
+    else if (b_mn) LK_LAUNCH((tc_gemm_kernel<false, true, 128>), grid, NUM_THREADS, SMEM_BYTES, st, mAh, mAl, mBh, mBl, p);
+    else LK_LAUNCH((tc_gemm_kernel<false, false, 128>), grid, NUM_THREADS, SMEM_BYTES, st, mAh, mAl, mBh, mBl, p);
+  }
   rc = check_launch("tc_gemm");
   if (rc) return rc;
   if (p.splits > 1) return lk_splitk_reduce(p.partial, C, GM, GN, ldc, p.splits, ep->accumulate, st);

@@ -596,6 +596,18 @@ __device__ __forceinline__ void load_a(const float* __restrict__ row0p, const fl
     split2(d.x * s, d.y * s, h[kk][3], l[kk][3]);
   }
 }
+// A fragments from a shared tile (plain loads: the tile pointer is a shared-memory address)
+__device__ __forceinline__ void load_a_s(const float* row0p, const float* row1p, int t, float s, uint32_t (&h)[2][4], uint32_t (&l)[2][4]) {
+#pragma unroll
+  for (int kk = 0; kk < 2; kk++) {
+    const float2 a = *reinterpret_cast<const float2*>(row0p + kk * 16 + 2 * t), b = *reinterpret_cast<const float2*>(row1p + kk * 16 + 2 * t);
+    const float2 c = *reinterpret_cast<const float2*>(row0p + kk * 16 + 8 + 2 * t), d = *reinterpret_cast<const float2*>(row1p + kk * 16 + 8 + 2 * t);
+    split2(a.x * s, a.y * s, h[kk][0], l[kk][0]);
+    split2(b.x * s, b.y * s, h[kk][1], l[kk][1]);
+    split2(c.x * s, c.y * s, h[kk][2], l[kk][2]);
+    split2(d.x * s, d.y * s, h[kk][3], l[kk][3]);
+  }
+}
 // validity bits of up to 64 keys of this sequence (dense layout: the key mask; packed: every key below L)
 __device__ __forceinline__ unsigned long long key_bits(const MhaParams& p, int64_t n, int L, int lane) {
   const bool dense = !p.seq.cu && p.seq.mask;
@@ -617,18 +629,24 @@ __device__ __forceinline__ void stage128(float* T, const float* __restrict__ src
   }
 }
 
-__global__ void __launch_bounds__(128, 4) mha_fwd_tc_kernel(MhaParams p) {
+// MW warps share a head: warp (head, mw) takes the 16-query tiles mw, mw + MW, ...  MW = 1 when there are thousands of sequences
+// (items); MW = 4 when a launch has few (the 64 click histories of a batch), so that a 50-token history is four warps deep, not one.
+template <int MW>
+__global__ void __launch_bounds__(128 * MW, MW == 1 ? 4 : 1) mha_fwd_tc_kernel(MhaParams p) {
   pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int hw = warp & 3, mw = warp >> 2;
   const int64_t n = blockIdx.x;
   int64_t row0; int L;
   seq_range(p.seq, n, row0, L);
   if (L == 0) return;
   extern __shared__ __align__(16) float smem[];
-  const int D = p.D, H = p.H, h = blockIdx.y * 4 + warp, c0 = h * 32, cw = warp * 32;
+  const int D = p.D, H = p.H, S = p.seq.S, h = blockIdx.y * 4 + hw, c0 = h * 32, cw = hw * 32;
   const float* base = p.qkv + row0 * 3 * (int64_t)D;
   float* Ks = smem;                               // [L][TCP]: the four heads of this CTA
-  float* Vs = Ks + (size_t)p.seq.S * TCP;
+  float* Vs = Ks + (size_t)S * TCP;
+  float* Qs = Vs + (size_t)S * TCP;
+  stage128(Qs, base + blockIdx.y * 128, 3 * D, L);
   stage128(Ks, base + D + blockIdx.y * 128, 3 * D, L);
   stage128(Vs, base + 2 * D + blockIdx.y * 128, 3 * D, L);
   const unsigned long long kv = key_bits(p, n, L, lane);
@@ -637,10 +655,10 @@ __global__ void __launch_bounds__(128, 4) mha_fwd_tc_kernel(MhaParams p) {
   const int nt = (L + 7) >> 3, mt = (L + 15) >> 4;
   cp_async_wait_all();
   __syncthreads();
-  for (int m = 0; m < mt; m++) {
+  for (int m = mw; m < mt; m += MW) {
     const int i0 = m * 16 + g, i1 = i0 + 8, i0c = min(i0, L - 1), i1c = min(i1, L - 1);
     uint32_t qh[2][4], ql[2][4];
-    load_a(base + (int64_t)i0c * 3 * D + c0, base + (int64_t)i1c * 3 * D + c0, t, qs, qh, ql);
+    load_a_s(Qs + i0c * TCP + cw, Qs + i1c * TCP + cw, t, qs, qh, ql);
     float c[8][4];
 #pragma unroll
     for (int nn = 0; nn < 8; nn++) {
@@ -741,18 +759,6 @@ __global__ void __launch_bounds__(128, 4) mha_fwd_tc_kernel(MhaParams p) {
   }
 }
 
-// A fragments from a shared tile (plain loads: the tile pointer is a shared-memory address)
-__device__ __forceinline__ void load_a_s(const float* row0p, const float* row1p, int t, float s, uint32_t (&h)[2][4], uint32_t (&l)[2][4]) {
-#pragma unroll
-  for (int kk = 0; kk < 2; kk++) {
-    const float2 a = *reinterpret_cast<const float2*>(row0p + kk * 16 + 2 * t), b = *reinterpret_cast<const float2*>(row1p + kk * 16 + 2 * t);
-    const float2 c = *reinterpret_cast<const float2*>(row0p + kk * 16 + 8 + 2 * t), d = *reinterpret_cast<const float2*>(row1p + kk * 16 + 8 + 2 * t);
-    split2(a.x * s, a.y * s, h[kk][0], l[kk][0]);
-    split2(b.x * s, b.y * s, h[kk][1], l[kk][1]);
-    split2(c.x * s, c.y * s, h[kk][2], l[kk][2]);
-    split2(d.x * s, d.y * s, h[kk][3], l[kk][3]);
-  }
-}
 __device__ __forceinline__ float col_add(float v) {     // sum over the 8 row groups of a fragment column (lanes with equal t)
   v += __shfl_xor_sync(0xffffffffu, v, 4);
   v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -763,33 +769,41 @@ __device__ __forceinline__ float col_add(float v) {     // sum over the 8 row gr
 // in registers), inner loop over 16-query tiles i: S and dP blocks are recomputed once per (i, j) pair, turned into dS and P∘keep
 // in place, and feed three more contractions: dQ(i) += dS·K(j) (accumulated in a shared tile whose columns this warp owns),
 // dK(j) += dS^T·Q(i), dV(j) += (P∘keep)^T·dO(i).  Q and dO of the CTA's four heads are staged once in shared memory.
-__global__ void __launch_bounds__(128, 3) mha_bwd_tc_kernel(MhaParams p) {
+// JW warps share a head: warp (head, jw) takes the key tiles jw, jw + JW, ... and accumulates its dQ contribution in its OWN shared
+// tile; the JW tiles are added in a fixed order at the end (deterministic, no atomics).  JW = 1 for the items, 2 for small launches.
+template <int JW>
+__global__ void __launch_bounds__(128 * JW, JW == 1 ? 3 : 1) mha_bwd_tc_kernel(MhaParams p) {
   pdl_prologue();
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int hw = warp & 3, jw = warp >> 2;
   const int64_t n = blockIdx.x;
   int64_t row0; int L;
   seq_range(p.seq, n, row0, L);
   if (L == 0) return;
-  const int D = p.D, H = p.H, S = p.seq.S, h = blockIdx.y * 4 + warp, c0 = h * 32, cw = warp * 32;
+  const int D = p.D, H = p.H, S = p.seq.S, h = blockIdx.y * 4 + hw, c0 = h * 32, cw = hw * 32;
   const float* base = p.qkv + row0 * 3 * (int64_t)D;
   const float* gbase = p.dctx + row0 * (int64_t)D;
   const float* obase = p.ctx + row0 * (int64_t)D;
   float* Qs = smem;                                // [S][TCP] q (unscaled)
   float* Gs = Qs + (size_t)S * TCP;                // dO
-  float* dQs = Gs + (size_t)S * TCP;               // dQ accumulators
-  float* Ds = dQs + (size_t)S * TCP;               // [4][TC_MAX_L]  D_i = dO_i · O_i
+  float* dQall = Gs + (size_t)S * TCP;             // [JW][S][TCP] dQ accumulators, one tile per key-tile warp
+  float* Ds = dQall + (size_t)JW * S * TCP;        // [4][TC_MAX_L]  D_i = dO_i · O_i
+  float* Cs = Ds + 4 * TC_MAX_L;                   // [JW][4][64] column sums of the dK / dV rows of each warp (JW > 1)
+  float* dQs = dQall + (size_t)jw * S * TCP;
   stage128(Qs, base + blockIdx.y * 128, 3 * D, L);
   stage128(Gs, gbase + blockIdx.y * 128, D, L);
-  for (int idx = threadIdx.x; idx < L * 32; idx += blockDim.x)
-    *reinterpret_cast<float4*>(dQs + (idx >> 5) * TCP + (idx & 31) * 4) = f4_zero();
+  for (int idx = threadIdx.x; idx < JW * L * 32; idx += blockDim.x) {
+    const int w = idx / (L * 32), r = idx - w * (L * 32);
+    *reinterpret_cast<float4*>(dQall + ((size_t)w * S + (r >> 5)) * TCP + (r & 31) * 4) = f4_zero();
+  }
   const unsigned long long kv = key_bits(p, n, L, lane);
   const float qs = p.scale * kLog2e;
   const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
   const int mt = (L + 15) >> 4;
   cp_async_wait_all();
   __syncthreads();
-  for (int m = 0; m < mt; m++) {
+  for (int m = jw; m < mt; m += JW) {
     const int i0 = m * 16 + g, i1 = i0 + 8, i0c = min(i0, L - 1), i1c = min(i1, L - 1);
     float d0 = 0.f, d1 = 0.f;
 #pragma unroll
@@ -801,11 +815,11 @@ __global__ void __launch_bounds__(128, 3) mha_bwd_tc_kernel(MhaParams p) {
     }
     d0 = quad_add(d0); d1 = quad_add(d1);
     if (t == 0) {
-      if (i0 < L) Ds[warp * TC_MAX_L + i0] = d0;
-      if (i1 < L) Ds[warp * TC_MAX_L + i1] = d1;
+      if (i0 < L) Ds[hw * TC_MAX_L + i0] = d0;
+      if (i1 < L) Ds[hw * TC_MAX_L + i1] = d1;
     }
   }
-  __syncwarp();
+  if (JW == 1) __syncwarp(); else __syncthreads();
 
   float ksum[4][2], vsum[4][2];
 #pragma unroll
@@ -823,7 +837,7 @@ __global__ void __launch_bounds__(128, 3) mha_bwd_tc_kernel(MhaParams p) {
     }
   };
 
-  for (int jt = 0; jt < mt; jt++) {
+  for (int jt = jw; jt < mt; jt += JW) {
     uint32_t kh[2][2][2], kl[2][2][2], vh[2][2][2], vl[2][2][2];
 #pragma unroll
     for (int nn = 0; nn < 2; nn++) {
@@ -860,7 +874,7 @@ __global__ void __launch_bounds__(128, 3) mha_bwd_tc_kernel(MhaParams p) {
         }
       }
       const float l20 = p.lse[(row0 + i0c) * H + h] * kLog2e, l21 = p.lse[(row0 + i1c) * H + h] * kLog2e;
-      const float D0 = Ds[warp * TC_MAX_L + i0c], D1 = Ds[warp * TC_MAX_L + i1c];
+      const float D0 = Ds[hw * TC_MAX_L + i0c], D1 = Ds[hw * TC_MAX_L + i1c];
       const uint32_t hb0 = attn_hash_base(p.seed, (uint64_t)(row0 + i0c) * H + h), hb1 = attn_hash_base(p.seed, (uint64_t)(row0 + i1c) * H + h);
 #pragma unroll
       for (int nn = 0; nn < 2; nn++) {
@@ -925,20 +939,51 @@ __global__ void __launch_bounds__(128, 3) mha_bwd_tc_kernel(MhaParams p) {
       }
     }
   }
-  __syncwarp();
-  // dQ rows out of this warp's columns of the shared tile, and the per-sequence column sums (in_proj bias gradient)
   float* csum = p.colsum_part ? p.colsum_part + n * 3 * (int64_t)D + c0 : nullptr;
+  if (JW > 1) {
+    // the key-tile warps of a head hand their dK / dV column sums to warp (head, 0), which also adds up the JW dQ tiles
+    if (csum) {
+#pragma unroll
+      for (int dn = 0; dn < 4; dn++) {
+        const float k0 = col_add(ksum[dn][0]), k1 = col_add(ksum[dn][1]), v0 = col_add(vsum[dn][0]), v1 = col_add(vsum[dn][1]);
+        if (g == 0) {
+          float* c = Cs + ((size_t)jw * 4 + hw) * 64 + dn * 8 + 2 * t;
+          c[0] = k0; c[1] = k1; c[32] = v0; c[33] = v1;
+        }
+      }
+    }
+    __syncthreads();
+    if (jw != 0) return;
+  } else {
+    __syncwarp();
+  }
+  // dQ rows out of this head's columns of the shared tile(s), and the per-sequence column sums (in_proj bias gradient)
 #pragma unroll
   for (int dn = 0; dn < 4; dn++) {
     float q0 = 0.f, q1 = 0.f;
     for (int i = g; i < L; i += 8) {
-      const float2 v = *reinterpret_cast<const float2*>(dQs + i * TCP + cw + dn * 8 + 2 * t);
+      float2 v = *reinterpret_cast<const float2*>(dQall + i * TCP + cw + dn * 8 + 2 * t);
+#pragma unroll
+      for (int w = 1; w < JW; w++) {
+        const float2 u = *reinterpret_cast<const float2*>(dQall + ((size_t)w * S + i) * TCP + cw + dn * 8 + 2 * t);
+        v.x += u.x; v.y += u.y;
+      }
       emit((int64_t)i * 3 * D + dn * 8 + 2 * t, v.x, v.y);
       q0 += v.x; q1 += v.y;
     }
     if (csum) {
       q0 = col_add(q0); q1 = col_add(q1);
-      const float k0 = col_add(ksum[dn][0]), k1 = col_add(ksum[dn][1]), v0 = col_add(vsum[dn][0]), v1 = col_add(vsum[dn][1]);
+      float k0, k1, v0, v1;
+      if (JW == 1) {
+        k0 = col_add(ksum[dn][0]); k1 = col_add(ksum[dn][1]); v0 = col_add(vsum[dn][0]); v1 = col_add(vsum[dn][1]);
+      } else {
+        k0 = k1 = v0 = v1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < JW; w++) {
+          const float* c = Cs + ((size_t)w * 4 + hw) * 64 + dn * 8 + 2 * t;
+          k0 += c[0]; k1 += c[1]; v0 += c[32]; v1 += c[33];
+        }
+      }
       if (g == 0) {
         const int col = dn * 8 + 2 * t;
         csum[col] = q0; csum[col + 1] = q1;
@@ -1020,6 +1065,9 @@ static bool tc_path_ok(const MhaParams& p, int64_t S) {
   return on && p.D / p.H == 32 && p.H % 4 == 0 && S <= tcm::TC_MAX_L;
 }
 
+// few sequences with more than one 16-token tile: spread each head over four warps
+static bool tc_small_launch(int64_t N, int64_t H, int64_t S) { return S > 16 && N * (H / 4) <= 2 * kNumSMs; }
+
 static void set_dropout(MhaParams& p, float drop_p, uint64_t seed) {
   p.drop_p = drop_p;
   p.seed = (unsigned long long)seed;
@@ -1050,14 +1098,18 @@ int lk_mha_fwd(const float* qkv, const int64_t* mask, const int32_t* cu, float* 
     case 16: return launch_fwd<16, 2>(p, N, st);
     case 32:
       if (tc_path_ok(p, S)) {
-        const size_t smem = (size_t)2 * S * tcm::TCP * sizeof(float);
+        const size_t smem = (size_t)3 * S * tcm::TCP * sizeof(float);
         static bool attr = false;
         if (!attr) {
-          cudaFuncSetAttribute(tcm::mha_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * tcm::TC_MAX_L * tcm::TCP * (int)sizeof(float));
-          cudaFuncSetAttribute(tcm::mha_fwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          const int mx = 3 * tcm::TC_MAX_L * tcm::TCP * (int)sizeof(float);
+          cudaFuncSetAttribute(tcm::mha_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+          cudaFuncSetAttribute(tcm::mha_fwd_tc_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          cudaFuncSetAttribute(tcm::mha_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
           attr = true;
         }
-        LK_LAUNCH((tcm::mha_fwd_tc_kernel), dim3((unsigned)N, (unsigned)(H / 4)), 128, smem, st, p);
+        const dim3 grid((unsigned)N, (unsigned)(H / 4));
+        if (tc_small_launch(N, H, S)) LK_LAUNCH((tcm::mha_fwd_tc_kernel<4>), grid, 512, smem, st, p);
+        else LK_LAUNCH((tcm::mha_fwd_tc_kernel<1>), grid, 128, smem, st, p);
         return check_launch("mha_fwd_tc");
       }
       return launch_fwd<32, 2>(p, N, st);
@@ -1086,15 +1138,21 @@ int lk_mha_bwd(const float* qkv, const int64_t* mask, const int32_t* cu, const f
     case 16: return launch_bwd<16, 2>(p, N, st);
     case 32:
       if (tc_path_ok(p, S)) {
-        const size_t smem = ((size_t)3 * S * tcm::TCP + 4 * tcm::TC_MAX_L) * sizeof(float);
+        const bool small = tc_small_launch(N, H, S);
+        const int JW = small ? 2 : 1;   // 2 x 128 threads keep the 168 registers the kernel needs (4 would cap it at 128 and spill)
+        const size_t smem = ((size_t)(2 + JW) * S * tcm::TCP + 4 * tcm::TC_MAX_L + (size_t)JW * 4 * 64) * sizeof(float);
+        LK_REQUIRE(smem <= 227 * 1024, LK_ERR_SHAPE, "lk_mha_bwd: tiles (%zu B) do not fit shared memory", smem);
         static bool attr = false;
         if (!attr) {
-          cudaFuncSetAttribute(tcm::mha_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (3 * tcm::TC_MAX_L * tcm::TCP + 4 * tcm::TC_MAX_L) * (int)sizeof(float));
-          cudaFuncSetAttribute(tcm::mha_bwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          cudaFuncSetAttribute(tcm::mha_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (3 * tcm::TC_MAX_L * tcm::TCP + 4 * tcm::TC_MAX_L + 4 * 64) * (int)sizeof(float));
+          cudaFuncSetAttribute(tcm::mha_bwd_tc_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          cudaFuncSetAttribute(tcm::mha_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
           attr = true;
         }
-        LK_LAUNCH((tcm::mha_bwd_tc_kernel), dim3((unsigned)N, (unsigned)(H / 4)), 128, smem, st, p);
+        const dim3 grid((unsigned)N, (unsigned)(H / 4));
+        if (small) LK_LAUNCH((tcm::mha_bwd_tc_kernel<2>), grid, 256, smem, st, p);
+        else LK_LAUNCH((tcm::mha_bwd_tc_kernel<1>), grid, 128, smem, st, p);
         return check_launch("mha_bwd_tc");
       }
       return launch_bwd<32, 2>(p, N, st);

@@ -137,3 +137,19 @@ def test_tc_gemm_input_gradient_with_untransposed_weight(ops, M, N, K):
     w = torch.randn(K, N, generator=g) / K ** 0.5
     y, _, _ = ops.tc_gemm_ex(ops.split_planes(dy.cuda()), ops.split_planes(w.cuda()), M, N, K, b_mn=True)
     assert rel(y, dy.double() @ w.double()) <= 3e-5
+
+
+@pytest.mark.parametrize('M,N,K', [(1000, 768, 256), (300, 512, 320), (4000, 1024, 64)])
+def test_tc_gemm_wide_tile(ops, M, N, K):
+    """512 <= N <= 4096 with N % 256 == 0 runs on 128x256 tiles (two 96 KB stages, the whole TMEM): same answer as fp64."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    y = ops.tc_gemm(ops.split_planes(a.cuda()), ops.split_planes(b.cuda()), False, M, N, K, bias=bias.cuda())
+    assert rel(y, a.double() @ b.double().t() + bias.double()) <= 3e-5
+    # weight-gradient layout (both operands MN-major, reduction over rows) at a wide N
+    dy = torch.randn(K * 8, 256, generator=g)
+    x = torch.randn(K * 8, N, generator=g)
+    dw = ops.tc_gemm(ops.split_planes(dy.cuda()), ops.split_planes(x.cuda()), True, 256, N, K * 8)
+    assert rel(dw, dy.double().t() @ x.double()) <= 3e-5
