@@ -183,7 +183,10 @@ def main():
     import torch.distributed as dist
     if world_size > 1:
         # the contract is ONE line on stdout: NCCL's own banner ("NCCL version ...", printed at VERSION/INFO level) must not join it
-        os.environ['NCCL_DEBUG'] = os.environ.get('LK_NCCL_DEBUG', 'WARN')
+        if 'LK_NCCL_DEBUG' in os.environ:
+            os.environ['NCCL_DEBUG'] = os.environ['LK_NCCL_DEBUG']
+        else:
+            os.environ.pop('NCCL_DEBUG', None)       # default level: silent
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     import __graft_entry__ as ge
     if rank == 0:
