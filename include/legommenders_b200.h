@@ -63,7 +63,9 @@ int lk_pack_item_tokens(const int64_t* const* tables, int64_t* const* outs, int 
 
 /* backward of the whole ConcatInputer embedding stage (concat_inputer.py:105-113 + embedding_hub.py:95-96) in one pass over
  * dx [T,D]:  dP = dx·dropout(seed)·(title id > -1) as split-bf16 planes [T, ld] (operand of the projection weight gradient),
- * g_bias [D] = column sums of dP, g_cat [n_cats, D] / g_special [n_special, D] = per-id sums of dx.  Deterministic. */
+ * g_bias [D] = column sums of dP, g_cat [n_cats, D] / g_special [n_special, D] = per-id sums of dx.  Deterministic.
+ * With all three gradient pointers null the per-block partials [ceil(T/128), (1+n_cats+n_special)*D] stay in `workspace`
+ * (row layout: bias | categories | special tokens) for a later lk_colsum_finish_multi. */
 size_t lk_concat_embed_bwd_workspace_bytes(int64_t T, int64_t D, int64_t n_cats, int64_t n_special);
 int lk_concat_embed_bwd(const float* dx, const int64_t* title_ids, const int64_t* cat_ids, const int64_t* special_ids, int64_t T,
                         int64_t D, int64_t n_cats, int64_t n_special, float drop_p, uint64_t seed, void* dp_hi, void* dp_lo, int64_t ld,
@@ -87,6 +89,20 @@ int lk_linear_bwd_weight(const float* dY, const float* X, float* dW, float* db, 
 /* C[m,n] (+)= sum_z partial[z,m,n] in fixed z order (deterministic split reduction) */
 int lk_splitk_reduce(const float* partial, float* C, int64_t M, int64_t N, int64_t ldc, int splits, int accumulate,
                      cudaStream_t stream);
+/* Several column reductions in ONE launch: out[c] (+)= sum_i part[i*stride + c], i < nparts, fixed summation order (deterministic).
+ * A training step leaves a dozen bias / small-table gradient partials behind (GEMM epilogues, the plane split, per-sequence sums of
+ * the attention and pooling kernels); finishing them one launch each costs more than the work.  At most LK_COLSUM_MAX_JOBS jobs. */
+#define LK_COLSUM_MAX_JOBS 16
+typedef struct lk_colsum_job {
+  const float* part;
+  float* out;
+  int64_t nparts, cols, stride;
+  int accumulate;
+} lk_colsum_job;
+int lk_colsum_finish_multi(const lk_colsum_job* jobs, int n_jobs, cudaStream_t stream);
+/* lk_split_bf16 with the column sums left as partials: part [ceil(rows/64), cols] (see lk_colsum_finish_multi) */
+int lk_split_bf16_partial(const float* X, int64_t rows, int64_t cols, int64_t ld_in, void* hi, void* lo, int64_t ld_out, float* part,
+                          cudaStream_t stream);
 size_t lk_colsum_workspace_bytes(int64_t M, int64_t N);
 int lk_colsum(const float* X, float* out, int64_t M, int64_t N, int accumulate, void* workspace, size_t workspace_bytes,
               cudaStream_t stream);
@@ -132,6 +148,8 @@ typedef struct lk_gemm_epilogue {
   void* out_lo;
   int64_t ld_planes;
   float* colsum;              /* [GN] */
+  float* colsum_part;         /* deferred column sums: [ceil(GM/128)*4, GN] partial sums are left here (no finishing launch);
+                                 finish them later with lk_colsum_finish_multi.  Mutually exclusive with colsum. */
 } lk_gemm_epilogue;
 /* a_mn/b_mn: operand stored [rows, k] (0, K-major) or [k, rows] (1, MN-major); (1,0) is not instantiated */
 int lk_tc_gemm_ex(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const void* B_hi, const void* B_lo, int64_t ldb, int b_mn,

@@ -44,6 +44,8 @@ SIGNATURES = {
     'lk_split_bf16_workspace_bytes': ('qq', 'z'),
     'lk_split_bf16': ('pqqqppqippzs', 'i'),
     'lk_split_bf16_multi': ('pis', 'i'),
+    'lk_split_bf16_partial': ('pqqqppqps', 'i'),
+    'lk_colsum_finish_multi': ('pis', 'i'),
     'lk_tc_gemm_workspace_bytes': ('qqq', 'z'),
     'lk_tc_gemm_ex': ('ppqippqipqqqqppzs', 'i'),
     'lk_tc_gemm': ('ppqippqipqqqqppifuipzs', 'i'),

@@ -476,6 +476,7 @@ int lk_concat_embed_bwd(const float* dx, const int64_t* title_ids, const int64_t
                                                      (unsigned long long)seed, (__nv_bfloat16*)dp_hi, (__nv_bfloat16*)dp_lo, (int)ld,
                                                      (float*)workspace);
   }
+  if (!g_bias && !g_cat && !g_special) return check_launch("concat_embed_bwd");   // deferred: the caller reduces workspace[nblk, NT*D] itself
   const float* part = (const float*)workspace;
   const int64_t stride = (int64_t)NT * D;
   LK_LAUNCH((partial_finish_kernel), (unsigned)((D + 31) / 32), 1024, 0, st, part, nblk, stride, (int)D, g_bias);

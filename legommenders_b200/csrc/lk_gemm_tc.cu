@@ -505,6 +505,33 @@ __global__ void __launch_bounds__(1024) colsum_finish2_kernel(const float* __res
   }
 }
 
+// several column reductions in one launch (blockIdx.y = job): 32 part-lanes x 32 columns per block, ordered shared-memory combine
+struct ColsumJobs { lk_colsum_job job[LK_COLSUM_MAX_JOBS]; };
+__global__ void __launch_bounds__(1024) colsum_finish_multi_kernel(const ColsumJobs jobs) {
+  pdl_prologue();
+  __shared__ float red[32][33];
+  const lk_colsum_job& j = jobs.job[blockIdx.y];
+  const int cx = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  for (int64_t cb = blockIdx.x; cb * 32 < j.cols; cb += gridDim.x) {
+    const int64_t c = cb * 32 + cx;
+    float s0 = 0.f, s1 = 0.f;
+    if (c < j.cols) {
+      int64_t i = pl;
+      for (; i + 32 < j.nparts; i += 64) { s0 += j.part[i * j.stride + c]; s1 += j.part[(i + 32) * j.stride + c]; }
+      if (i < j.nparts) s0 += j.part[i * j.stride + c];
+    }
+    red[pl][cx] = s0 + s1;
+    __syncthreads();
+    if (pl == 0 && c < j.cols) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; i++) t += red[i][cx];
+      j.out[c] = j.accumulate ? j.out[c] + t : t;
+    }
+    __syncthreads();
+  }
+}
+
 // transposed split through a 32x32 smem tile: out[c, r]
 __global__ void split_bf16_t_kernel(const float* __restrict__ X, int rows, int cols, int64_t ld_in, __nv_bfloat16* __restrict__ hi,
                                     __nv_bfloat16* __restrict__ lo, int64_t ld_out) {
@@ -573,7 +600,7 @@ static int pick_splits(int64_t GM, int64_t GN, int64_t GK) {
   int64_t tiles = ((GM + BM - 1) / BM) * ((GN + BN - 1) / BN);
   int64_t kb = (GK + BK - 1) / BK;
   if (tiles >= kNumSMs || kb < 8) return 1;
-  int64_t s = (2 * kNumSMs + tiles - 1) / tiles;
+  int64_t s = kNumSMs / tiles;       // one wave of (tile, split) work items: twice as many only doubles the partials to write and re-read
   if (s > kb / 4) s = kb / 4;
   return (int)(s < 1 ? 1 : s);
 }
@@ -614,6 +641,36 @@ int lk_split_bf16(const float* X, int64_t rows, int64_t cols, int64_t ld_in, voi
   return check_launch("split_bf16");
 }
 
+int lk_colsum_finish_multi(const lk_colsum_job* jobs, int n_jobs, cudaStream_t st) {
+  LK_REQUIRE(n_jobs >= 0 && n_jobs <= LK_COLSUM_MAX_JOBS, LK_ERR_ARG, "lk_colsum_finish_multi: %d jobs (max %d)", n_jobs, LK_COLSUM_MAX_JOBS);
+  ColsumJobs cj = {};
+  int n = 0;
+  int64_t most = 0;
+  for (int i = 0; i < n_jobs; i++) {
+    const lk_colsum_job& j = jobs[i];
+    LK_REQUIRE(j.cols >= 0 && j.nparts >= 0 && j.stride >= j.cols, LK_ERR_SHAPE, "lk_colsum_finish_multi: job %d has a bad shape", i);
+    LK_REQUIRE(j.cols == 0 || (j.out && (j.part || j.nparts == 0)), LK_ERR_ARG, "lk_colsum_finish_multi: job %d has null pointers", i);
+    if (j.cols == 0) continue;
+    cj.job[n++] = j;
+    if ((j.cols + 31) / 32 > most) most = (j.cols + 31) / 32;
+  }
+  if (n == 0) return LK_OK;
+  if (most > 64) most = 64;       // wider jobs loop over their column blocks
+  LK_LAUNCH((colsum_finish_multi_kernel), dim3((unsigned)most, (unsigned)n), 1024, 0, st, cj);
+  return check_launch("colsum_finish_multi");
+}
+
+int lk_split_bf16_partial(const float* X, int64_t rows, int64_t cols, int64_t ld_in, void* hi, void* lo, int64_t ld_out, float* part,
+                          cudaStream_t st) {
+  LK_REQUIRE(ld_out % 8 == 0 && ld_out >= cols && ld_in % 4 == 0, LK_ERR_SHAPE, "lk_split_bf16_partial: bad pitches");
+  LK_REQUIRE(part != nullptr, LK_ERR_ARG, "lk_split_bf16_partial: no buffer for the partial column sums");
+  if (rows == 0 || cols == 0) return LK_OK;
+  const int nparts = (int)((rows + SPLIT_ROWS - 1) / SPLIT_ROWS);
+  dim3 grid((unsigned)((ld_out + 255) / 256), (unsigned)nparts);
+  LK_LAUNCH((split_bf16_kernel), grid, 256, 0, st, X, rows, (int)cols, ld_in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_out, part);
+  return check_launch("split_bf16_partial");
+}
+
 int lk_split_bf16_multi(const lk_split_seg* segs, int n_segs, cudaStream_t st) {
   LK_REQUIRE(n_segs >= 0 && n_segs <= LK_SPLIT_MAX_SEGS, LK_ERR_ARG, "lk_split_bf16_multi: %d segments (max %d)", n_segs, LK_SPLIT_MAX_SEGS);
   if (n_segs == 0) return LK_OK;
@@ -650,7 +707,7 @@ int lk_tc_gemm_ex(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, con
   LK_REQUIRE(!(a_mn && !b_mn), LK_ERR_ARG, "lk_tc_gemm: MN-major A with K-major B is not instantiated");
   LK_REQUIRE(((uintptr_t)A_hi | (uintptr_t)A_lo | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C | (uintptr_t)ep->out_hi |
               (uintptr_t)ep->out_lo) % 16 == 0, LK_ERR_ARG, "lk_tc_gemm: operands must be 16-byte aligned");
-  LK_REQUIRE(C || ep->out_hi || ep->colsum, LK_ERR_ARG, "lk_tc_gemm: no output requested");
+  LK_REQUIRE(C || ep->out_hi || ep->colsum || ep->colsum_part, LK_ERR_ARG, "lk_tc_gemm: no output requested");
   LK_REQUIRE(!ep->out_hi || (ep->out_lo && ep->ld_planes % 8 == 0 && ep->ld_planes >= GN), LK_ERR_ARG, "lk_tc_gemm: bad output planes");
   LK_REQUIRE(!ep->accumulate || C, LK_ERR_ARG, "lk_tc_gemm: accumulate needs C");
   if (GM == 0 || GN == 0) return LK_OK;
@@ -681,7 +738,7 @@ int lk_tc_gemm_ex(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, con
   p.splits = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
   p.partial = nullptr;
   const bool plain = !ep->bias && !ep->rowmask && ep->act == 0 && ep->drop_p == 0.f && !ep->add_ids0 && !ep->add_ids1 && !ep->out_hi &&
-                     !ep->colsum;
+                     !ep->colsum && !ep->colsum_part;
   if (p.splits > 1) {
     LK_REQUIRE(workspace && workspace_bytes >= (size_t)p.splits * GM * GN * sizeof(float), LK_ERR_ARG, "lk_tc_gemm: workspace too small");
     LK_REQUIRE(plain && C, LK_ERR_ARG, "lk_tc_gemm: split reduction has no fused epilogue");
@@ -693,6 +750,8 @@ int lk_tc_gemm_ex(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, con
   p.add_ids[0] = ep->add_ids0; p.add_tab[0] = ep->add_tab0; p.add_ids[1] = ep->add_ids1; p.add_tab[1] = ep->add_tab1;
   p.out_hi = (__nv_bfloat16*)ep->out_hi; p.out_lo = (__nv_bfloat16*)ep->out_lo; p.ld_planes = (int)ep->ld_planes;
   p.colsum_part = nullptr;
+  LK_REQUIRE(!(ep->colsum && ep->colsum_part), LK_ERR_ARG, "lk_tc_gemm: colsum and colsum_part are mutually exclusive");
+  if (ep->colsum_part) p.colsum_part = ep->colsum_part;      // deferred: the caller finishes the partials
   if (ep->colsum) {
     LK_REQUIRE(workspace && workspace_bytes >= (size_t)p.m_tiles * 4 * GN * sizeof(float), LK_ERR_ARG, "lk_tc_gemm: workspace too small for column sums");
     p.colsum_part = (float*)workspace;

@@ -47,7 +47,15 @@ struct Ctx {
   size_t ws_bytes;
   int rc;
   bool dry;          // sizing pass: walk the allocations, launch nothing
+  lk_colsum_job jobs[LK_COLSUM_MAX_JOBS];   // bias / small-table gradient reductions, all finished by ONE launch at the end of the step
+  int n_jobs;
 };
+
+// out[c] = sum_i part[i*stride + c]: queued; the partial buffer must stay untouched until the end of the step
+static void defer_colsum(Ctx& c, const float* part, float* out, int64_t nparts, int64_t cols, int64_t stride) {
+  if (c.n_jobs < LK_COLSUM_MAX_JOBS) c.jobs[c.n_jobs++] = lk_colsum_job{part, out, nparts, cols, stride, 0};
+  else c.rc = c.rc ? c.rc : LK_ERR_ARG;
+}
 
 #define STEP_L(label, expr, flops)                              \
   do {                                                          \
@@ -88,11 +96,13 @@ static void gemm_wgrad(Ctx& c, const PlaneBuf& dY, const PlaneBuf& X, float* dW,
   STEP_L(label, lk_tc_gemm(dY.hi, dY.lo, dY.ld, 1, X.hi, X.lo, X.ld, 1, dW, K, N, K, T, nullptr, nullptr, 0, 0.f, 0, 0, c.ws, c.ws_bytes,
                            c.st), 2.0 * T * N * K);
 }
-static lk_gemm_epilogue ep_planes(const PlaneBuf& out, const float* bias = nullptr, float* colsum = nullptr) {
+static lk_gemm_epilogue ep_planes(const PlaneBuf& out, const float* bias = nullptr, float* colsum_part = nullptr) {
   lk_gemm_epilogue ep = {};
-  ep.bias = bias; ep.out_hi = out.hi; ep.out_lo = out.lo; ep.ld_planes = out.ld; ep.colsum = colsum;
+  ep.bias = bias; ep.out_hi = out.hi; ep.out_lo = out.lo; ep.ld_planes = out.ld; ep.colsum_part = colsum_part;
   return ep;
 }
+static int64_t gemm_colsum_parts(int64_t M) { return (M + 127) / 128 * 4; }   // per-(128-row tile, lane quarter) partials of lk_tc_gemm
+static int64_t split_colsum_parts(int64_t M) { return (M + 63) / 64; }        // per-64-row-block partials of lk_split_bf16_partial
 
 struct EncWeights {   // one AttentionOperator
   const float *in_w, *in_b, *out_w, *out_b, *lin_w, *lin_b, *w1, *b1, *w2;
@@ -151,33 +161,47 @@ static void enc_fwd(Ctx& c, EncSaved& s, const EncWeights& w, const EncPlanes& w
 }
 
 // backward of enc_fwd: drep [N,D] -> dX [T,D] (or nothing when dX == null); parameter gradients into w.g_*
-static void enc_bwd(Ctx& c, const EncSaved& s, const EncWeights& w, const EncPlanes& wp, int64_t D, int64_t H, int64_t A, float drop_attn,
-                    const float* drep, float* dX) {
+// the five bias-type gradients of an encoder are left as partial sums in buffers that live until the end of the step
+struct EncPartials { float *dw2p, *b1p, *linbp, *outbp, *binp; };
+static EncPartials alloc_partials(Ctx& c, int64_t T, int64_t N, int64_t D, int64_t A) {
+  EncPartials q;
+  q.dw2p = c.a.f32(N * A);                          // per-sequence partials of dw2
+  q.b1p = c.a.f32(split_colsum_parts(T) * A);
+  q.linbp = c.a.f32(gemm_colsum_parts(T) * D);
+  q.outbp = c.a.f32(gemm_colsum_parts(T) * D);
+  q.binp = c.a.f32(N * 3 * D);                      // per-sequence column sums of dqkv
+  return q;
+}
+
+static void enc_bwd(Ctx& c, const EncSaved& s, const EncWeights& w, const EncPlanes& wp, const EncPartials& q, int64_t D, int64_t H, int64_t A,
+                    float drop_attn, const float* drep, float* dX) {
   const int64_t T = s.T, N = s.N;
   const size_t mark = c.a.off;
   float* dlin = c.a.f32(T * D);
   float* dpre = c.a.f32(T * A);
-  float* dw2p = c.a.f32(N * A);
-  STEP(lk_additive_pool_bwd(s.lin, s.hid, w.w2, s.alpha, s.cu, drep, dlin, dpre, dw2p, N, s.S, D, A, 0, c.st));
-  STEP(lk_colsum(dw2p, w.g_w2, N, A, 0, c.ws, c.ws_bytes, c.st));
-  PlaneBuf dprep = split(c, dpre, T, A, w.g_b1);
+  STEP(lk_additive_pool_bwd(s.lin, s.hid, w.w2, s.alpha, s.cu, drep, dlin, dpre, q.dw2p, N, s.S, D, A, 0, c.st));
+  defer_colsum(c, q.dw2p, w.g_w2, N, A, A);
+  PlaneBuf dprep = alloc_planes(c, T, A);
+  STEP(lk_split_bf16_partial(dpre, T, A, A, dprep.hi, dprep.lo, dprep.ld, q.b1p, c.st));
+  defer_colsum(c, q.b1p, w.g_b1, split_colsum_parts(T), A, A);
   gemm_wgrad(c, dprep, s.linp, w.g_w1, T, A, D);
   // dlin = alpha*drep (already in dlin) + dpre·W1 -> only its planes and column sums are needed downstream
   PlaneBuf dlinp = alloc_planes(c, T, D);
-  lk_gemm_epilogue ep = ep_planes(dlinp, nullptr, w.g_lin_b);
+  lk_gemm_epilogue ep = ep_planes(dlinp, nullptr, q.linbp);
   ep.accumulate = 1; ep.store_c_off = 1;
   gemm(c, "dlin", dprep, wp.w1, 1, dlin, T, D, A, ep);
+  defer_colsum(c, q.linbp, w.g_lin_b, gemm_colsum_parts(T), D, D);
   gemm_wgrad(c, dlinp, s.outp, w.g_lin_w, T, D, D);
   PlaneBuf doutp = alloc_planes(c, T, D);
-  gemm(c, "dout", dlinp, wp.lin_w, 1, nullptr, T, D, D, ep_planes(doutp, nullptr, w.g_out_b));
+  gemm(c, "dout", dlinp, wp.lin_w, 1, nullptr, T, D, D, ep_planes(doutp, nullptr, q.outbp));
+  defer_colsum(c, q.outbp, w.g_out_b, gemm_colsum_parts(T), D, D);
   gemm_wgrad(c, doutp, s.ctxp, w.g_out_w, T, D, D);
   float* dctx = dlin;   // dlin is dead once its planes exist
   ep = {};
   gemm(c, "dctx", doutp, wp.out_w, 1, dctx, T, D, D, ep);
   PlaneBuf dqkvp = alloc_planes(c, T, 3 * D);
-  float* binp = c.a.f32(N * 3 * D);            // per-sequence column sums of dqkv
-  STEP(lk_mha_bwd(s.qkv, nullptr, s.cu, s.ctx, s.lse, dctx, nullptr, dqkvp.hi, dqkvp.lo, binp, N, s.S, D, H, drop_attn, s.seed, c.st));
-  STEP(lk_colsum(binp, w.g_in_b, N, 3 * D, 0, c.ws, c.ws_bytes, c.st));
+  STEP(lk_mha_bwd(s.qkv, nullptr, s.cu, s.ctx, s.lse, dctx, nullptr, dqkvp.hi, dqkvp.lo, q.binp, N, s.S, D, H, drop_attn, s.seed, c.st));
+  defer_colsum(c, q.binp, w.g_in_b, N, 3 * D, 3 * D);
   gemm_wgrad(c, dqkvp, s.xp, w.g_in_w, T, 3 * D, D);
   if (dX) gemm(c, "dx", dqkvp, wp.in_w, 1, dX, T, D, 3 * D, ep);
   c.a.off = mark;   // all temporaries of this backward are dead (stream order keeps reuse safe)
@@ -218,6 +242,7 @@ static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const 
   c.st = st;
   c.rc = 0;
   c.dry = dry;
+  c.n_jobs = 0;
   c.ws_bytes = scratch_bytes(T > 0 ? T : 1, n_items, D, A, E, n_cats, n_special);
   c.ws = c.a.take(c.ws_bytes);
 
@@ -271,15 +296,25 @@ static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const 
   float* drep = c.a.f32(n_items * D);
   float* duser = c.a.f32(B * D);
   STEP(lk_dot_ce_bwd(su.rep, si.rep, probs, one, duser, drep, B, C, D, st));          // dV -> drep[0 : B*C]
-  enc_bwd(c, su, wu, pu, D, heads, A, drop_attn, duser, drep + B * C * D);             // dX_u -> drep[B*C :]
+  const EncPartials qu = alloc_partials(c, Tu, B, D, A), qi = alloc_partials(c, T, n_items, D, A);
+  const size_t eb_bytes = lk_concat_embed_bwd_workspace_bytes(T, D, n_cats, n_special);
+  float* ebp = (float*)c.a.take(eb_bytes);                                               // per-block partials of the embedding-stage gradients
+  enc_bwd(c, su, wu, pu, qu, D, heads, A, drop_attn, duser, drep + B * C * D);         // dX_u -> drep[B*C :]
   float* dx = c.a.f32(T * D);
-  enc_bwd(c, si, wi, pi, D, heads, A, drop_attn, drep, dx);
+  enc_bwd(c, si, wi, pi, qi, D, heads, A, drop_attn, drep, dx);
 
-  // embedding stage backward in one pass over dx: small-table gradients, dP planes, bias gradient
+  // embedding stage backward in one pass over dx: small-table gradients, dP planes, bias gradient (partials, finished below)
   PlaneBuf dpp = alloc_planes(c, T, D);
-  STEP(lk_concat_embed_bwd(dx, title_ids, cat_ids, special_ids, T, D, n_cats, n_special, drop_embed, s_embed, dpp.hi, dpp.lo, dpp.ld, G(1),
-                           G(2), G(3), c.ws, c.ws_bytes, st));
+  STEP(lk_concat_embed_bwd(dx, title_ids, cat_ids, special_ids, T, D, n_cats, n_special, drop_embed, s_embed, dpp.hi, dpp.lo, dpp.ld, nullptr,
+                           nullptr, nullptr, ebp, eb_bytes, st));
+  {
+    const int64_t nblk = (T + 127) / 128, stride = (1 + n_cats + n_special) * D;
+    defer_colsum(c, ebp, G(1), nblk, D, stride);
+    defer_colsum(c, ebp + D, G(2), nblk, n_cats * D, stride);
+    defer_colsum(c, ebp + (1 + n_cats) * D, G(3), nblk, n_special * D, stride);
+  }
   gemm_wgrad(c, dpp, gp, G(0), T, D, E);
+  STEP(lk_colsum_finish_multi(c.jobs, c.n_jobs, st));       // every bias / small-table gradient of the step in one launch
 
   if (high_out) *high_out = c.a.high;
   LK_REQUIRE(c.a.ok, LK_ERR_ARG, "lk_nrms_fwd_bwd: arena too small (%zu bytes given, %zu needed)", arena_bytes, c.a.high);

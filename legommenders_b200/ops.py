@@ -88,6 +88,20 @@ def split_planes_multi(mats):
     return planes
 
 
+class ColsumJob(ctypes.Structure):
+    """struct lk_colsum_job (include/legommenders_b200.h)"""
+    _fields_ = [('part', ctypes.c_void_p), ('out', ctypes.c_void_p), ('nparts', ctypes.c_int64), ('cols', ctypes.c_int64),
+                ('stride', ctypes.c_int64), ('accumulate', ctypes.c_int)]
+
+
+def colsum_finish_multi(jobs):
+    """jobs: list of (part [nparts, stride>=cols] fp32, out [cols] fp32, accumulate) -> every out[c] (+)= sum_i part[i, c], ONE launch."""
+    arr = (ColsumJob * len(jobs))()
+    for a, (part, out, acc) in zip(arr, jobs):
+        a.part, a.out, a.nparts, a.cols, a.stride, a.accumulate = ptr(part), ptr(out), part.shape[0], out.numel(), part.stride(0), int(acc)
+    call('lk_colsum_finish_multi', ctypes.addressof(arr), len(jobs))
+
+
 _wplanes = {}
 
 
@@ -131,7 +145,8 @@ class GemmEpilogue(ctypes.Structure):
     _fields_ = [('bias', ctypes.c_void_p), ('rowmask', ctypes.c_void_p), ('rowmask_is_ids', ctypes.c_int), ('act', ctypes.c_int),
                 ('drop_p', ctypes.c_float), ('seed', ctypes.c_uint64), ('accumulate', ctypes.c_int), ('store_c_off', ctypes.c_int),
                 ('add_ids0', ctypes.c_void_p), ('add_tab0', ctypes.c_void_p), ('add_ids1', ctypes.c_void_p), ('add_tab1', ctypes.c_void_p),
-                ('out_hi', ctypes.c_void_p), ('out_lo', ctypes.c_void_p), ('ld_planes', ctypes.c_int64), ('colsum', ctypes.c_void_p)]
+                ('out_hi', ctypes.c_void_p), ('out_lo', ctypes.c_void_p), ('ld_planes', ctypes.c_int64), ('colsum', ctypes.c_void_p),
+                ('colsum_part', ctypes.c_void_p)]
 
 
 def tc_gemm_ex(A: Planes, B: Planes, GM, GN, GK, b_mn=False, a_mn=False, out=None, store_c=True, bias=None, rowmask=None,

@@ -153,3 +153,43 @@ def test_tc_gemm_wide_tile(ops, M, N, K):
     x = torch.randn(K * 8, N, generator=g)
     dw = ops.tc_gemm(ops.split_planes(dy.cuda()), ops.split_planes(x.cuda()), True, 256, N, K * 8)
     assert rel(dw, dy.double().t() @ x.double()) <= 3e-5
+
+
+def test_deferred_column_sums(ops):
+    """Bias-type gradients left as partial sums by their producers (GEMM epilogue, plane split, per-sequence sums) and finished by
+    ONE lk_colsum_finish_multi launch: equal to the direct reductions, deterministic, strided jobs and wide jobs included."""
+    import ctypes
+    from legommenders_b200._lib import call, ptr
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 1000, 256, 256
+    a, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / 16
+    ap, bp = ops.split_planes(a.cuda()), ops.split_planes(b.cuda())
+    nparts = (M + 127) // 128 * 4
+    part = torch.full((nparts, N), float('nan'), device='cuda')
+    ep = ops.GemmEpilogue()
+    ep.colsum_part = ptr(part)
+    y = torch.empty(M, N, device='cuda')
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device='cuda')
+    call('lk_tc_gemm_ex', ptr(ap.hi), ptr(ap.lo), ap.ld, 0, ptr(bp.hi), ptr(bp.lo), bp.ld, 0, ptr(y), N, M, N, K, ctypes.addressof(ep), ptr(ws),
+         ws.numel())
+    # plane split with partial column sums
+    x = torch.randn(777, 256, generator=g).cuda()
+    hi = torch.empty(2, 777, 256, dtype=torch.bfloat16, device='cuda')
+    sp = torch.full(((777 + 63) // 64, 256), float('nan'), device='cuda')
+    call('lk_split_bf16_partial', ptr(x), 777, 256, 256, ptr(hi[0]), ptr(hi[1]), 256, ptr(sp))
+    ref_planes = ops.split_planes(x)
+    assert torch.equal(hi[0], ref_planes.hi) and torch.equal(hi[1], ref_planes.lo)
+    # a strided job (columns 256.. of a wider partial array) and a wide one (4608 columns, several column blocks per CTA)
+    wide = torch.randn(333, 5632, generator=g).cuda()
+    outs = [torch.empty(N, device='cuda'), torch.empty(256, device='cuda'), torch.empty(4608, device='cuda'), torch.empty(256, device='cuda')]
+    jobs = [(part, outs[0], False), (sp, outs[1], False), (wide[:, 256:4864], outs[2], False), (wide[:, :256], outs[3], False)]
+    ops.colsum_finish_multi(jobs)
+    again = [torch.empty_like(o) for o in outs]
+    ops.colsum_finish_multi([(j[0], o, False) for j, o in zip(jobs, again)])
+    refs = [y.double().sum(0), x.double().sum(0), wide[:, 256:4864].double().sum(0), wide[:, :256].double().sum(0)]
+    for o, o2, r in zip(outs, again, refs):
+        assert torch.equal(o, o2)
+        assert (o.double() - r).abs().max().item() <= 2e-5 * max(1.0, r.abs().max().item())
+    acc = outs[3].clone()
+    ops.colsum_finish_multi([(wide[:, :256], acc, True)])
+    assert torch.allclose(acc, 2 * outs[3], rtol=1e-6)
