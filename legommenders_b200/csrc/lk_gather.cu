@@ -291,12 +291,18 @@ __global__ void __launch_bounds__(256) concat_embed_bwd_kernel(const float* __re
   for (int i = ct; i < NT * D4; i += cols) reinterpret_cast<float4*>(mine)[i] = f4_zero();
   __syncthreads();
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  // one column quad per thread (D <= 4 * cols): the next row's dx is requested before this row is processed, so the walk over the
+  // rows is not a chain of exposed global-load latencies
+  float4 nxt = f4_zero();
+  if (rl < nrows && ct < D4) nxt = ldg4_stream(dx + (r0 + rl) * D + ct * 4);
   for (int i = rl; i < nrows; i += EB_LANES) {
     const int64_t row = r0 + i;
     const bool tv = s_title[i] != 0;
     const int ci = s_cat[i], si = s_sp[i];
+    const float4 cur = nxt;
+    if (i + EB_LANES < nrows && ct < D4) nxt = ldg4_stream(dx + (row + EB_LANES) * D + ct * 4);
     for (int c = ct; c < D4; c += cols) {
-      const float4 g = ldg4_stream(dx + row * D + c * 4);
+      const float4 g = cur;
       float4 m = f4_zero();
       if (tv) {
         m = g;

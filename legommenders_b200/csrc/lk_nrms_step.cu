@@ -11,6 +11,7 @@
 // the candidates, the rest are the valid history items user by user, so their encodings are directly the user encoder's
 // packed token rows with offsets cu_users[B+1].
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "lk_common.cuh"
 #include "../../include/legommenders_b200.h"
@@ -49,7 +50,30 @@ struct Ctx {
   bool dry;          // sizing pass: walk the allocations, launch nothing
   lk_colsum_job jobs[LK_COLSUM_MAX_JOBS];   // bias / small-table gradient reductions, all finished by ONE launch at the end of the step
   int n_jobs;
+  // side stream: weight gradients are leaves of the backward graph (only the optimiser reads them).  Those of the user encoder
+  // (1.7 k rows: 28-CTA contractions that are pure latency on the main stream) are issued here and joined once, at the end of the step.
+  cudaStream_t side;
+  cudaEvent_t fork_ev[8], join_ev;
+  int n_fork;
+  void* ws_side;
+  size_t ws_side_bytes;
+  bool side_used;
 };
+
+struct SideState { cudaStream_t st = nullptr; cudaEvent_t fork_ev[8]; cudaEvent_t join_ev; bool ok = false; };
+static SideState& side_state() {
+  static SideState s;
+  if (!s.ok && !s.st) {
+    const char* e = getenv("LK_SIDE_STREAM");
+    if (!(e && e[0] == '0') && cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) == cudaSuccess) {
+      s.ok = true;
+      for (auto& ev : s.fork_ev) s.ok = s.ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+      s.ok = s.ok && cudaEventCreateWithFlags(&s.join_ev, cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!s.st) s.st = (cudaStream_t)-1;     // tried once
+  }
+  return s;
+}
 
 // out[c] = sum_i part[i*stride + c]: queued; the partial buffer must stay untouched until the end of the step
 static void defer_colsum(Ctx& c, const float* part, float* out, int64_t nparts, int64_t cols, int64_t stride) {
@@ -90,9 +114,19 @@ static void gemm(Ctx& c, const char* what, const PlaneBuf& A, const PlaneBuf& B,
   STEP_L(label, lk_tc_gemm_ex(A.hi, A.lo, A.ld, 0, B.hi, B.lo, B.ld, b_mn, Y, N, M, N, K, &ep, c.ws, c.ws_bytes, c.st), 2.0 * M * N * K);
 }
 // dW[N,K] = dY[T,N]^T · X[T,K]
-static void gemm_wgrad(Ctx& c, const PlaneBuf& dY, const PlaneBuf& X, float* dW, int64_t T, int64_t N, int64_t K) {
+static void gemm_wgrad(Ctx& c, const PlaneBuf& dY, const PlaneBuf& X, float* dW, int64_t T, int64_t N, int64_t K, bool on_side = false) {
   char label[40];
   snprintf(label, sizeof(label), "gemm_wgrad %ldx%ldx%ld", (long)N, (long)K, (long)T);
+  if (on_side && c.side && !c.dry && c.rc == 0 && !prof_enabled() && c.n_fork < 8) {
+    // operands are complete at this point of the main stream: fork, contract on the side stream with its own scratch
+    cudaEventRecord(c.fork_ev[c.n_fork], c.st);
+    cudaStreamWaitEvent(c.side, c.fork_ev[c.n_fork], 0);
+    c.n_fork++;
+    c.side_used = true;
+    c.rc = lk_tc_gemm(dY.hi, dY.lo, dY.ld, 1, X.hi, X.lo, X.ld, 1, dW, K, N, K, T, nullptr, nullptr, 0, 0.f, 0, 0, c.ws_side, c.ws_side_bytes,
+                      c.side);
+    return;
+  }
   STEP_L(label, lk_tc_gemm(dY.hi, dY.lo, dY.ld, 1, X.hi, X.lo, X.ld, 1, dW, K, N, K, T, nullptr, nullptr, 0, 0.f, 0, 0, c.ws, c.ws_bytes,
                            c.st), 2.0 * T * N * K);
 }
@@ -174,7 +208,7 @@ static EncPartials alloc_partials(Ctx& c, int64_t T, int64_t N, int64_t D, int64
 }
 
 static void enc_bwd(Ctx& c, const EncSaved& s, const EncWeights& w, const EncPlanes& wp, const EncPartials& q, int64_t D, int64_t H, int64_t A,
-                    float drop_attn, const float* drep, float* dX) {
+                    float drop_attn, const float* drep, float* dX, bool side = false) {
   const int64_t T = s.T, N = s.N;
   const size_t mark = c.a.off;
   float* dlin = c.a.f32(T * D);
@@ -184,27 +218,29 @@ static void enc_bwd(Ctx& c, const EncSaved& s, const EncWeights& w, const EncPla
   PlaneBuf dprep = alloc_planes(c, T, A);
   STEP(lk_split_bf16_partial(dpre, T, A, A, dprep.hi, dprep.lo, dprep.ld, q.b1p, c.st));
   defer_colsum(c, q.b1p, w.g_b1, split_colsum_parts(T), A, A);
-  gemm_wgrad(c, dprep, s.linp, w.g_w1, T, A, D);
+  gemm_wgrad(c, dprep, s.linp, w.g_w1, T, A, D, side);
   // dlin = alpha*drep (already in dlin) + dpre·W1 -> only its planes and column sums are needed downstream
   PlaneBuf dlinp = alloc_planes(c, T, D);
   lk_gemm_epilogue ep = ep_planes(dlinp, nullptr, q.linbp);
   ep.accumulate = 1; ep.store_c_off = 1;
   gemm(c, "dlin", dprep, wp.w1, 1, dlin, T, D, A, ep);
   defer_colsum(c, q.linbp, w.g_lin_b, gemm_colsum_parts(T), D, D);
-  gemm_wgrad(c, dlinp, s.outp, w.g_lin_w, T, D, D);
+  gemm_wgrad(c, dlinp, s.outp, w.g_lin_w, T, D, D, side);
   PlaneBuf doutp = alloc_planes(c, T, D);
   gemm(c, "dout", dlinp, wp.lin_w, 1, nullptr, T, D, D, ep_planes(doutp, nullptr, q.outbp));
   defer_colsum(c, q.outbp, w.g_out_b, gemm_colsum_parts(T), D, D);
-  gemm_wgrad(c, doutp, s.ctxp, w.g_out_w, T, D, D);
+  gemm_wgrad(c, doutp, s.ctxp, w.g_out_w, T, D, D, side);
   float* dctx = dlin;   // dlin is dead once its planes exist
   ep = {};
   gemm(c, "dctx", doutp, wp.out_w, 1, dctx, T, D, D, ep);
   PlaneBuf dqkvp = alloc_planes(c, T, 3 * D);
   STEP(lk_mha_bwd(s.qkv, nullptr, s.cu, s.ctx, s.lse, dctx, nullptr, dqkvp.hi, dqkvp.lo, q.binp, N, s.S, D, H, drop_attn, s.seed, c.st));
   defer_colsum(c, q.binp, w.g_in_b, N, 3 * D, 3 * D);
-  gemm_wgrad(c, dqkvp, s.xp, w.g_in_w, T, 3 * D, D);
+  gemm_wgrad(c, dqkvp, s.xp, w.g_in_w, T, 3 * D, D, side);
   if (dX) gemm(c, "dx", dqkvp, wp.in_w, 1, dX, T, D, 3 * D, ep);
-  c.a.off = mark;   // all temporaries of this backward are dead (stream order keeps reuse safe)
+  // all temporaries of this backward are dead (stream order keeps reuse safe) — unless side-stream contractions still read them:
+  // then they stay allocated until the join at the end of the step (the sizing pass takes the same branch)
+  if (!side) c.a.off = mark;
 }
 
 }  // namespace nrms
@@ -245,6 +281,23 @@ static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const 
   c.n_jobs = 0;
   c.ws_bytes = scratch_bytes(T > 0 ? T : 1, n_items, D, A, E, n_cats, n_special);
   c.ws = c.a.take(c.ws_bytes);
+  const int64_t Tu_ = n_items - B * C > 0 ? n_items - B * C : 1;
+  c.ws_side_bytes = lk_tc_gemm_workspace_bytes(3 * D, D, Tu_) + (1 << 16);      // the largest user-encoder weight gradient (in_proj)
+  {
+    size_t o = lk_tc_gemm_workspace_bytes(D, D, Tu_), a1 = lk_tc_gemm_workspace_bytes(A, D, Tu_);
+    if (o + (1 << 16) > c.ws_side_bytes) c.ws_side_bytes = o + (1 << 16);
+    if (a1 + (1 << 16) > c.ws_side_bytes) c.ws_side_bytes = a1 + (1 << 16);
+  }
+  c.ws_side = c.a.take(c.ws_side_bytes);
+  c.side = nullptr; c.n_fork = 0; c.side_used = false;
+  if (!dry) {
+    SideState& ss = side_state();
+    if (ss.ok) {
+      c.side = ss.st;
+      for (int i = 0; i < 8; i++) c.fork_ev[i] = ss.fork_ev[i];
+      c.join_ev = ss.join_ev;
+    }
+  }
 
   auto P = [&](int i) { return params + offsets[i]; };
   auto G = [&](int i) { return grads + offsets[i]; };
@@ -299,7 +352,7 @@ static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const 
   const EncPartials qu = alloc_partials(c, Tu, B, D, A), qi = alloc_partials(c, T, n_items, D, A);
   const size_t eb_bytes = lk_concat_embed_bwd_workspace_bytes(T, D, n_cats, n_special);
   float* ebp = (float*)c.a.take(eb_bytes);                                               // per-block partials of the embedding-stage gradients
-  enc_bwd(c, su, wu, pu, qu, D, heads, A, drop_attn, duser, drep + B * C * D);         // dX_u -> drep[B*C :]
+  enc_bwd(c, su, wu, pu, qu, D, heads, A, drop_attn, duser, drep + B * C * D, true);   // dX_u -> drep[B*C :]; weight gradients on the side stream
   float* dx = c.a.f32(T * D);
   enc_bwd(c, si, wi, pi, qi, D, heads, A, drop_attn, drep, dx);
 
@@ -315,6 +368,10 @@ static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const 
   }
   gemm_wgrad(c, dpp, gp, G(0), T, D, E);
   STEP(lk_colsum_finish_multi(c.jobs, c.n_jobs, st));       // every bias / small-table gradient of the step in one launch
+  if (c.side_used) {                                        // join: everything after this call on `st` sees the side stream's gradients
+    cudaEventRecord(c.join_ev, c.side);
+    cudaStreamWaitEvent(st, c.join_ev, 0);
+  }
 
   if (high_out) *high_out = c.a.high;
   LK_REQUIRE(c.a.ok, LK_ERR_ARG, "lk_nrms_fwd_bwd: arena too small (%zu bytes given, %zu needed)", arena_bytes, c.a.high);
