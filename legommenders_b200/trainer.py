@@ -55,6 +55,105 @@ class FlatAdam:
                       beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, grad_scale=1.0 / self.world)
         ops.invalidate_weight_planes()   # the kernel updated the parameters behind torch's version counters
 
+    # ---- checkpoint compatibility with the reference's torch.optim.Adam (base_lego.py:198-204, 228-267) ----------------
+    def _slices(self):
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            yield p, off, n
+            off += (n + 3) // 4 * 4
+
+    def state_dict(self) -> dict:
+        """The state dict `torch.optim.Adam(filter(requires_grad, model.parameters()))` would hold after the same steps: per-parameter
+        `step` / `exp_avg` / `exp_avg_sq` keyed by the parameter's position, one param group."""
+        state = {}
+        if self.step_count > 0:
+            for i, (p, off, n) in enumerate(self._slices()):
+                state[i] = dict(step=torch.tensor(float(self.step_count)), exp_avg=self.m[off:off + n].view_as(p).clone(),
+                                exp_avg_sq=self.v[off:off + n].view_as(p).clone())
+        group = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
+                     capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False, params=list(range(len(self.params))))
+        return dict(state=state, param_groups=[group])
+
+    def load_state_dict(self, sd: dict):
+        """Accepts a `torch.optim.Adam` state dict of the same parameter list (a reference checkpoint's `optimizer` entry)."""
+        groups = sd['param_groups']
+        if len(groups) != 1:
+            raise ValueError('FlatAdam holds one parameter group (the reference\'s two-group item_lr set-up is not on this path)')
+        g = groups[0]
+        if len(g['params']) != len(self.params):
+            raise ValueError(f'optimizer state has {len(g["params"])} parameters, the model has {len(self.params)} trainable ones')
+        self.lr, self.betas, self.eps = float(g['lr']), tuple(g['betas']), float(g['eps'])
+        if g.get('weight_decay', 0) or g.get('amsgrad', False) or g.get('maximize', False):
+            raise ValueError('weight_decay / amsgrad / maximize are not used by the reference and not supported')
+        self.m.zero_(); self.v.zero_()
+        steps = set()
+        for pos, (p, off, n) in zip(g['params'], self._slices()):
+            st = sd['state'].get(pos)
+            if st is None:
+                continue
+            if tuple(st['exp_avg'].shape) != tuple(p.shape):
+                raise ValueError(f'optimizer state {pos} has shape {tuple(st["exp_avg"].shape)}, parameter has {tuple(p.shape)}')
+            self.m[off:off + n].copy_(st['exp_avg'].reshape(-1))
+            self.v[off:off + n].copy_(st['exp_avg_sq'].reshape(-1))
+            steps.add(int(float(st['step'])))
+        if len(steps) > 1:
+            raise ValueError(f'parameters were stepped a different number of times: {sorted(steps)}')
+        self.step_count = steps.pop() if steps else 0
+
+
+class LinearWarmupSchedule:
+    """`transformers.get_linear_schedule_with_warmup` (base_lego.py:211-223): lr = base * step / n_warmup while warming up, then a linear
+    decay to 0 at `n_training`.  `step()` after every optimiser step; state dict interchangeable with the reference's LambdaLR."""
+
+    def __init__(self, opt: FlatAdam, n_warmup: int, n_training: int):
+        self.opt, self.n_warmup, self.n_training = opt, int(n_warmup), int(n_training)
+        self.base_lr = opt.lr
+        self.last_epoch = 0
+        opt.lr = self.base_lr * self.factor(0)
+
+    def factor(self, step: int) -> float:
+        if step < self.n_warmup:
+            return float(step) / float(max(1, self.n_warmup))
+        return max(0.0, float(self.n_training - step) / float(max(1, self.n_training - self.n_warmup)))
+
+    def step(self):
+        self.last_epoch += 1
+        self.opt.lr = self.base_lr * self.factor(self.last_epoch)
+
+    def get_last_lr(self):
+        return [self.opt.lr]
+
+    def state_dict(self) -> dict:
+        return dict(base_lrs=[self.base_lr], last_epoch=self.last_epoch, verbose=False, _step_count=self.last_epoch + 1,
+                    _get_lr_called_within_step=False, _last_lr=[self.opt.lr], lr_lambdas=[None])
+
+    def load_state_dict(self, sd: dict):
+        self.base_lr = float(sd['base_lrs'][0])
+        self.last_epoch = int(sd['last_epoch'])
+        self.opt.lr = self.base_lr * self.factor(self.last_epoch)
+
+
+def save_checkpoint(path: str, model: torch.nn.Module, opt: FlatAdam, scheduler: LinearWarmupSchedule = None):
+    """base_lego.py:255-265 — `{model, optimizer, scheduler}` with the reference's key names, loadable by the reference."""
+    sd = dict(model={k: v.detach().clone() for k, v in model.state_dict().items()}, optimizer=opt.state_dict(),
+              scheduler=scheduler.state_dict() if scheduler is not None else {})
+    torch.save(sd, path)
+
+
+def load_checkpoint(path: str, model: torch.nn.Module, opt: FlatAdam = None, scheduler: LinearWarmupSchedule = None, strict: bool = True,
+                    model_only: bool = False):
+    """base_lego.py:228-253.  Parameters live in FlatAdam's flat buffer: values are copied INTO the existing storage (views stay valid)."""
+    sd = torch.load(path, map_location=next(model.parameters()).device, weights_only=False)
+    missing = model.load_state_dict(sd['model'], strict=strict)
+    ops.invalidate_weight_planes()
+    if not model_only:
+        if opt is not None:
+            opt.load_state_dict(sd['optimizer'])
+        if scheduler is not None and sd.get('scheduler'):
+            scheduler.load_state_dict(sd['scheduler'])
+    return missing
+
 
 class NativeNRMSStep:
     """Training step of the NRMS configuration through the native driver `lk_nrms_fwd_bwd` (csrc/lk_nrms_step.cu):

@@ -178,3 +178,54 @@ def test_embedding_hub_errors_and_names():
         eh3.load_pretrained_embedding(np.zeros((10, 48), np.float32), vocab_name='glove')
         eh3.register_vocab(Vocab('glove', 11))
     Env.device = None
+
+
+def test_checkpoint_interchange_with_torch_adam(tmp_path):
+    """ FlatAdam / LinearWarmupSchedule state dicts are the reference's torch.optim.Adam / LambdaLR ones: a reference
+    checkpoint loads into the flat buffers, and a checkpoint written here loads into torch.optim.Adam (base_lego.py:228-265)."""
+    from transformers import get_linear_schedule_with_warmup
+    from legommenders_b200.trainer import FlatAdam, LinearWarmupSchedule, load_checkpoint, save_checkpoint
+    torch.manual_seed(0)
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+    ref[0].bias.requires_grad_(False)                                # a frozen parameter is skipped by both optimisers
+    ropt = torch.optim.Adam(filter(lambda p: p.requires_grad, ref.parameters()), lr=1e-3)
+    rsch = get_linear_schedule_with_warmup(ropt, num_warmup_steps=3, num_training_steps=10)
+    lrs = []
+    for i in range(4):
+        ropt.zero_grad()
+        ref(torch.full((2, 6), float(i + 1))).sum().backward()
+        ropt.step(); rsch.step()
+        lrs.append(rsch.get_last_lr()[0])
+    path = str(tmp_path / 'ref.pt')
+    torch.save(dict(model=ref.state_dict(), optimizer=ropt.state_dict(), scheduler=rsch.state_dict()), path)
+
+    mine = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+    mine[0].bias.requires_grad_(False)
+    opt = FlatAdam(mine, lr=1e-3)
+    sch = LinearWarmupSchedule(opt, 3, 10)
+    assert [round(sch.base_lr * sch.factor(k), 12) for k in range(1, 5)] == [round(x, 12) for x in lrs]
+    load_checkpoint(path, mine, opt, sch)
+    for a, b in zip(mine.parameters(), ref.parameters()):
+        assert torch.equal(a, b)
+        assert a.data_ptr() >= opt.flat.data_ptr() or not a.requires_grad       # still views of the flat buffer
+    assert opt.step_count == 4 and abs(opt.lr - lrs[-1]) < 1e-15
+    rstate = ropt.state_dict()['state']
+    for i, (p, off, n) in enumerate(opt._slices()):
+        assert torch.equal(opt.m[off:off + n].view_as(p), rstate[i]['exp_avg'])
+        assert torch.equal(opt.v[off:off + n].view_as(p), rstate[i]['exp_avg_sq'])
+    # and back: our checkpoint loads into the reference's optimiser / scheduler objects
+    out = str(tmp_path / 'mine.pt')
+    save_checkpoint(out, mine, opt, sch)
+    sd = torch.load(out, weights_only=False)
+    fresh = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+    fresh[0].bias.requires_grad_(False)
+    fresh.load_state_dict(sd['model'], strict=True)
+    fopt = torch.optim.Adam(filter(lambda p: p.requires_grad, fresh.parameters()), lr=1.0)
+    fopt.load_state_dict(sd['optimizer'])
+    fsch = get_linear_schedule_with_warmup(fopt, num_warmup_steps=3, num_training_steps=10)
+    fsch.load_state_dict(sd['scheduler'])
+    assert fsch.last_epoch == 4 and abs(fsch.get_last_lr()[0] - lrs[-1]) < 1e-15
+    fs = fopt.state_dict()['state']
+    assert all(torch.equal(fs[i]['exp_avg'], rstate[i]['exp_avg']) and float(fs[i]['step']) == 4.0 for i in rstate)
+    with pytest.raises(ValueError):
+        opt.load_state_dict(dict(state={}, param_groups=[dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, params=[0])]))
