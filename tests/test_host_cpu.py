@@ -36,6 +36,27 @@ def test_library_exports_every_declared_symbol():
     assert b'sm_100a' in lib.lk_version()
 
 
+def test_ctypes_signatures_match_the_header_arity_and_structs():
+    """The binding is hand-written: every entry point's argument COUNT must equal the header's, and the two structs that cross the
+    boundary by pointer must have the layout the C compiler gives them (sizes checked against the documented field lists)."""
+    import ctypes
+    from legommenders_b200 import _lib, ops
+    text = open(os.path.join(ROOT, 'include', 'legommenders_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    decls = re.findall(r'\b(?:int|size_t|const char\*|void|unsigned long long)\s+(lk_\w+)\s*\(([^;{]*?)\)\s*;', text, flags=re.S)
+    assert len(decls) == len(_lib.SIGNATURES)
+    for name, args in decls:
+        a = args.strip()
+        n = 0 if a in ('', 'void') else len(a.split(','))
+        assert len(_lib.SIGNATURES[name][0]) == n, f'{name}: header has {n} arguments, the binding {len(_lib.SIGNATURES[name][0])}'
+    # struct lk_gemm_epilogue: 17 fields; lk_split_seg: 7 x 8 bytes; lk_colsum_job: 5 x 8 + int (padded to 48)
+    assert ctypes.sizeof(ops.SplitSeg) == 56 and ctypes.sizeof(ops.ColsumJob) == 48
+    fields = [f[0] for f in ops.GemmEpilogue._fields_]
+    body = re.search(r'typedef struct lk_gemm_epilogue \{(.*?)\} lk_gemm_epilogue;', text, flags=re.S).group(1)
+    declared = re.findall(r'(\w+);', body)
+    assert fields == declared, (fields, declared)
+
+
 def test_workspace_queries_do_not_need_a_gpu():
     from legommenders_b200 import _lib
     assert _lib.query('lk_linear_bwd_weight_workspace_bytes', 116160, 256, 256) > 256 * 256 * 4
