@@ -41,6 +41,58 @@ def build_caches(model, item_contents, user_contents, group=None):
         cacher.user.rows = None
 
 
+def build_caches_device(model, batcher, item_page: int = 8192, user_page: int = 4096):
+    """Both representation caches from id lists only (the fast pagers of the reference, loader/pager/fast_{item,user}_pager.py, taken
+    to the device): the per-item token layouts already live on the device in `batcher` (batching.DeviceBatcher), so a page of items is
+    one `lk_pack_item_tokens` launch + the packed item encoder, and a page of users is an `lk_index_rows` gather of its history items'
+    rows from the fresh item cache (the reference's own short-circuit, legommender.py:153-157) + the packed user encoder.  No per-item or
+    per-user Python, nothing but id lists and offsets crosses PCIe.  Leaves the cachers exactly as `ReprCacher.cache` does.
+    Needs the packed item / user operators (NRMS / Ada configurations) and users with at least one click (config/data/mind.yaml:15-17)."""
+    import ctypes
+    from collections import OrderedDict
+    import numpy as np
+    from ._lib import call
+    from .packing import Packed
+    cacher, dev = model.cacher, Env.device
+    if not (model._packed_items() and getattr(model.user_op, 'supports_packed', False) and cacher.use_item_content):
+        raise ValueError('build_caches_device needs packed item and user operators over item content')
+    cacher.clean()
+    n_items, n_users = len(batcher.item_len), len(batcher.hist)
+    item_repr = model.item_op.get_full_placeholder(n_items).to(dev)
+    tp = (ctypes.c_void_p * len(batcher.cols))(*[t.data_ptr() for t in batcher.tables])
+    with torch.no_grad():
+        for s in range(0, n_items, item_page):
+            e = min(s + item_page, n_items)
+            lens = batcher.item_len[s:e]
+            cu = np.zeros(e - s + 1, dtype=np.int32)
+            np.cumsum(lens, out=cu[1:])
+            items = torch.arange(s, e, dtype=torch.int64, device=dev)
+            cu_d = torch.from_numpy(cu).to(dev)
+            outs = [torch.empty(int(cu[-1]), dtype=torch.int64, device=dev) for _ in batcher.cols]
+            op = (ctypes.c_void_p * len(batcher.cols))(*[t.data_ptr() for t in outs])
+            call('lk_pack_item_tokens', ctypes.addressof(tp), ctypes.addressof(op), len(batcher.cols), items.data_ptr(), cu_d.data_ptr(),
+                 e - s, batcher.S)
+            pk = Packed(OrderedDict(zip(batcher.cols, outs)), cu_d, e - s, int(cu[-1]), int(lens.max()))
+            emb = model.item_op.inputer.get_embeddings({'input_ids': pk.ids})
+            item_repr[s:e] = model.item_op(emb, cu=pk.cu, max_len=pk.max_len)
+        cacher.item.repr = item_repr
+        cacher.item._set_cached(True)
+        user_repr = cacher.user.placeholder.to(dev)
+        for s in range(0, n_users, user_page):
+            e = min(s + user_page, n_users)
+            hists = batcher.hist[s:e]
+            hl = np.fromiter((len(h) for h in hists), dtype=np.int64, count=e - s)
+            if hl.min() < 1:
+                raise ValueError('build_caches_device: a user without clicks (the reference filters those out)')
+            cu = np.zeros(e - s + 1, dtype=np.int32)
+            np.cumsum(hl, out=cu[1:])
+            ids = torch.from_numpy(np.concatenate(hists)).to(dev)
+            rows = ops.index_rows(item_repr, ids)
+            user_repr[s:e] = model.user_op(rows, cu=torch.from_numpy(cu).to(dev), max_len=int(hl.max()))
+        cacher.user.repr = user_repr
+        cacher.user._set_cached(True)
+
+
 def cached_scores(model, user_ids: torch.Tensor, item_ids: torch.Tensor, chunk_rows: int = 1 << 24) -> torch.Tensor:
     """score[r] = <user.repr[user_ids[r]], item.repr[item_ids[r]]> for every row (device tensor, fp32)."""
     cacher = model.cacher

@@ -295,3 +295,32 @@ def test_device_batcher_packs_bit_exact():
     l2 = native.fwd_bwd(idb, training=False).item()
     assert l1 == l2
     assert DeviceBatcher.h2d_bytes(hb) < 0.05 * sum(v.numel() * 8 for v in wire['history']['input_ids'].values())
+
+
+def test_device_cache_build_matches_cacher():
+    """evaluate.build_caches_device (id lists only, packed encoders, users from item-cache rows) leaves the same two caches as the
+    cacher contract (ReprCacher.cache over the Resampler's per-item / per-user contents), and the same metrics."""
+    from legommenders_b200 import DataSet, Env, evaluate
+    from legommenders_b200.batching import DeviceBatcher
+    c = cases.CASES['nrms_small']
+    g = cases.load('nrms_small')
+    world, llm = cases.make_world(c)
+    model, resampler, cfg = build(c, world, llm)
+    Env.test()
+    model.eval()
+    model.cacher.cache(item_contents=resampler.item_cache, user_contents=DataSet(world.fast_table(), resampler))
+    ref_i, ref_u = model.cacher.item.repr.clone(), model.cacher.user.repr.clone()
+    model.cacher.clean()
+    assert not Env.item_cache and not Env.user_cache
+    dbat = DeviceBatcher(resampler, world, Env.device)
+    evaluate.build_caches_device(model, dbat, item_page=300, user_page=70)          # several ragged pages
+    assert Env.item_cache and Env.user_cache and model.cacher.item.cached and model.cacher.user.cached
+    assert helpers.normwise(model.cacher.item.repr.cpu().numpy(), ref_i.cpu().numpy()) <= 1e-5
+    assert helpers.normwise(model.cacher.user.repr.cpu().numpy(), ref_u.cpu().numpy()) <= 1e-5
+    assert helpers.normwise(model.cacher.user.repr.cpu().numpy(), g['user_repr']) <= TOL
+    vals, scores, _ = evaluate.evaluate(model, torch.from_numpy(world.eval_users), torch.from_numpy(world.eval_items),
+                                        torch.from_numpy(g['eval_labels']))
+    for (k, v), ref in zip(vals.items(), g['metrics']):
+        assert round(v, 4) == round(float(ref), 4), k
+    model.cacher.clean()
+    Env.train()
