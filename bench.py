@@ -413,7 +413,10 @@ def hbm_bound_lines(dev, world, hbm_peak, model=None, resampler=None, tensor_pea
                 fn()
             except Exception as e:   # noqa: BLE001
                 out[name] = dict(error=f'{type(e).__name__}: {e}'[:300])
-            torch.cuda.synchronize()
+            try:
+                torch.cuda.synchronize()
+            except Exception as e:   # noqa: BLE001 — the bench line must still be printed
+                out.setdefault(name, {})['sync_error'] = f'{type(e).__name__}: {e}'[:200]
             return fn
         return deco
 
@@ -489,6 +492,25 @@ def hbm_bound_lines(dev, world, hbm_peak, model=None, resampler=None, tensor_pea
         Env.train(); model.train()
         out['item_cache_build'] = dict(items=len(contents), seconds=dt, items_per_s=len(contents) / dt,
                                        note='ItemCacher.cache(resampler.item_cache): host stacking of per-item id rows (Python) + packed NRMS item encoder per page, wall clock')
+
+    # (a15, device side) both caches from id lists only: evaluate.build_caches_device
+    @guarded('cache_build_device')
+    def _():
+        from legommenders_b200 import Env, evaluate as ev
+        from legommenders_b200.batching import DeviceBatcher
+        Env.test(); model.eval()
+        dbat = DeviceBatcher(resampler, world, dev)
+        ev.build_caches_device(model, dbat)                  # warm-up (allocator, kernel attributes)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        ev.build_caches_device(model, dbat)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        n_i, n_u = int(model.cacher.item.repr.shape[0]), len(dbat.hist)
+        model.cacher.clean()
+        Env.train(); model.train()
+        out['cache_build_device'] = dict(items=n_i, users=n_u, seconds=dt, items_and_users_per_s=(n_i + n_u) / dt,
+                                         note='item pages: lk_pack_item_tokens + packed NRMS item encoder; user pages: lk_index_rows over the item cache + packed NRMS user encoder; wall clock incl. host offset arithmetic')
 
     # (2) LLM-embedding item path (config 5): frozen [1M, 4096] item table -> tensor-core projection to 256-d, then the catalog
     # scoring sweep of 4096 users against the 1M projected items.  The frozen table is held as split-bf16 planes (same bytes as fp32).
