@@ -25,6 +25,10 @@ typedef struct CUstream_st* cudaStream_t;
 #endif
 
 const char* lk_version(void);
+/* Id bounds: every gather / index / scoring kernel treats an id outside [0, table_rows) as an invalid position (zero row, zero score;
+ * never dereferenced) and adds 1 per offending id to this DEVICE counter (null = do not count).  The reference raises IndexError
+ * (aten::embedding / tensor indexing, model/legommender.py:153-157); the host mirror raises it when it next reads the counter. */
+void lk_set_id_violation_counter(int32_t* device_counter);
 const char* lk_last_error(void);
 /* 1 when the library was compiled for sm_100a and the current device is compute capability 10.x */
 int lk_device_ok(void);
@@ -40,13 +44,13 @@ int lk_profile_collect(char* names, int name_stride, float* ms, double* flops, i
 /* ---- (1) EmbeddingHub token gather — model/inputer/concat_inputer.py:105-113, simple_inputer.py:51-64,
  *      loader/embedding_hub.py:378-385 (aten::embedding + mask multiply + add) ------------------------- */
 /* out[m,:] (+)= valid(m) ? table[ids[m],:] : 0, valid = mask ? mask[m]>0 : ids[m]>-1 */
-int lk_gather_rows(const int64_t* ids, const int64_t* mask, const float* table, float* out, int64_t M, int64_t E,
+int lk_gather_rows(const int64_t* ids, const int64_t* mask, const float* table, int64_t table_rows, float* out, int64_t M, int64_t E,
                    int accumulate, cudaStream_t stream);
 /* gather straight into split-bf16 planes (A operand of the projection GEMM): hi/lo [M, ld], rows with ids<0 are zero */
-int lk_gather_split_bf16(const int64_t* ids, const float* table, void* hi, void* lo, int64_t M, int64_t E, int64_t ld,
+int lk_gather_split_bf16(const int64_t* ids, const float* table, int64_t table_rows, void* hi, void* lo, int64_t M, int64_t E, int64_t ld,
                          cudaStream_t stream);
 /* gather + masked pooling over S tokens (model/operators/pooling_operator.py:46-56): mode 0 mean, 1 max, 2 sum */
-int lk_gather_pool(const int64_t* ids, const int64_t* mask, const float* table, float* out, int64_t N, int64_t S, int64_t E,
+int lk_gather_pool(const int64_t* ids, const int64_t* mask, const float* table, int64_t table_rows, float* out, int64_t N, int64_t S, int64_t E,
                    int mode, cudaStream_t stream);
 /* backward of the gather for trainable tables (autograd of aten::embedding): sorted-index segmented
  * scatter-add, deterministic.  dtable[ids[p],:] (+)= scale[p] * src[p / row_div,:] for valid p */
@@ -214,9 +218,9 @@ int lk_dot_bce_bwd(const float* U, const float* V, const float* y, const float* 
                    float* dU, float* dV, int64_t B, int64_t D, cudaStream_t stream);
 
 /* ---- (5) cached evaluation — model/legommender.py:153-157, 202-203; base_lego.py:373-394 -------------- */
-int lk_cached_scores(const float* U, const float* I, const int64_t* uid, const int64_t* iid, float* out, int64_t R, int64_t D,
-                     cudaStream_t stream);
-int lk_index_rows(const float* table, const int64_t* ids, float* out, int64_t R, int64_t D, cudaStream_t stream);
+int lk_cached_scores(const float* U, int64_t n_users, const float* I, int64_t n_items, const int64_t* uid, const int64_t* iid, float* out,
+                     int64_t R, int64_t D, cudaStream_t stream);
+int lk_index_rows(const float* table, int64_t table_rows, const int64_t* ids, float* out, int64_t R, int64_t D, cudaStream_t stream);
 
 /* ---- group metrics of the evaluation phase — utils/metrics.py:88-160, 223-235, 313-369 (MetricPool.calculate with GAUC, MRR,
  *      NDCG@k).  groups: any int64 key (user id); rows of a group need not be contiguous.  ks: HOST array of nk <= 8 nDCG
@@ -231,11 +235,11 @@ int lk_group_metrics(const float* scores, const int64_t* labels, const int64_t* 
 /* ---- native training-step driver: the whole Legommender.forward + backward of the NRMS configuration
  *      (model/legommender.py:219-263 with config/model/nrms.yaml) over packed rows in ONE call; see csrc/lk_nrms_step.cu.
  *      offsets[22]: element offsets into params/grads (order documented at the definition). */
-size_t lk_nrms_arena_bytes(int64_t T_max, int64_t N_max, int64_t B, int64_t D, int64_t A, int64_t E, int64_t H, int64_t n_cats,
+size_t lk_nrms_arena_bytes(int64_t T_max, int64_t N_max, int64_t B, int64_t C, int64_t D, int64_t A, int64_t E, int64_t H, int64_t n_cats,
                            int64_t n_special);
 int lk_nrms_fwd_bwd(const int64_t* title_ids, const int64_t* cat_ids, const int64_t* special_ids, const int32_t* cu_items,
                     int64_t n_items, int64_t T, int64_t S_max, const int32_t* cu_users, int64_t B, int64_t C, int64_t H_max,
-                    const float* glove_table, const float* params, float* grads, const int64_t* offsets, int64_t D, int64_t heads,
+                    const float* glove_table, int64_t glove_rows, const float* params, float* grads, const int64_t* offsets, int64_t D, int64_t heads,
                     int64_t A, int64_t E, int64_t n_cats, int64_t n_special, float drop_embed, float drop_attn, uint64_t seed,
                     float* loss_out, float* scores_out, void* arena, size_t arena_bytes, cudaStream_t stream);
 int lk_fill_f32(float* p, float value, int64_t n, cudaStream_t stream);

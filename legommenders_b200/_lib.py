@@ -26,9 +26,10 @@ SIGNATURES = {
     'lk_launch_count': ('', 'u'),
     'lk_profile_enable': ('i', 'v'),
     'lk_profile_collect': ('pipppi', 'i'),
-    'lk_gather_rows': ('ppppqqis', 'i'),
-    'lk_gather_pool': ('ppppqqqis', 'i'),
-    'lk_gather_split_bf16': ('ppppqqqs', 'i'),
+    'lk_set_id_violation_counter': ('p', 'v'),
+    'lk_gather_rows': ('pppqpqqis', 'i'),
+    'lk_gather_pool': ('pppqpqqqis', 'i'),
+    'lk_gather_split_bf16': ('ppqppqqqs', 'i'),
     'lk_scatter_add_workspace_bytes': ('qqq', 'z'),
     'lk_scatter_add_sorted': ('ppppqpqqqipzs', 'i'),
     'lk_pack_item_tokens': ('ppippqqs', 'i'),
@@ -67,14 +68,14 @@ SIGNATURES = {
     'lk_dot_bwd': ('pppppqqqs', 'i'),
     'lk_dot_bce_fwd': ('ppppppqqs', 'i'),
     'lk_dot_bce_bwd': ('ppppppppqqs', 'i'),
-    'lk_cached_scores': ('pppppqqs', 'i'),
-    'lk_index_rows': ('pppqqs', 'i'),
+    'lk_cached_scores': ('pqpqpppqqs', 'i'),
+    'lk_index_rows': ('pqppqqs', 'i'),
     'lk_group_metrics_workspace_bytes': ('qi', 'z'),
     'lk_group_metrics': ('pppqpipqpppzs', 'i'),
     'lk_adam_step': ('ppppqffffqfs', 'i'),
     'lk_fill_f32': ('pfqs', 'i'),
-    'lk_nrms_arena_bytes': ('qqqqqqqqq', 'z'),
-    'lk_nrms_fwd_bwd': ('ppppqqqpqqqpppp' + 'qqqqqq' + 'ffu' + 'pppzs', 'i'),
+    'lk_nrms_arena_bytes': ('qqqqqqqqqq', 'z'),
+    'lk_nrms_fwd_bwd': ('ppppqqqpqqqpqppp' + 'qqqqqq' + 'ffu' + 'pppzs', 'i'),
 }
 
 _lib = None
@@ -140,6 +141,8 @@ def call(name: str, *args):
         rc = getattr(lib, name)(*args, stream())
     if rc != 0:
         raise RuntimeError(f'{name} failed ({rc}): {lib.lk_last_error().decode()}')
+    if _CHECK_NOW and _viol:
+        raise_on_bad_ids(name)
 
 
 def profile_begin():
@@ -195,6 +198,36 @@ def native_profile_end():
                 name='lk_tc_gemm' if gemms else None, per_shape={g['name']: dict(ms=round(g['ms'], 4), calls=g['calls'],
                 tflops=round(g['flops'] / max(g['ms'], 1e-9) / 1e9, 1)) for g in gemms})
     return dict(sorted(shares.items(), key=lambda kv: -kv[1])), gemm
+
+
+_viol = {}
+
+
+def id_violation_counter(device=None) -> torch.Tensor:
+    """The device int32 counter the kernels add out-of-range ids to (one per device, registered with the library on first use)."""
+    device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    c = _viol.get(key)
+    if c is None:
+        c = torch.zeros(1, dtype=torch.int32, device=torch.device('cuda', key))
+        _viol[key] = c
+    load().lk_set_id_violation_counter(c.data_ptr())
+    return c
+
+
+def raise_on_bad_ids(where: str = ''):
+    """Read the counter (a device->host sync: call it where the host synchronises anyway) and raise the reference's IndexError."""
+    bad = 0
+    for c in _viol.values():
+        n = int(c.item())
+        if n:
+            c.zero_()
+            bad += n
+    if bad:
+        raise IndexError(f'{bad} id(s) out of range in a gather / index / scoring kernel{" (" + where + ")" if where else ""}')
+
+
+_CHECK_NOW = os.environ.get('LK_CHECK_IDS', '0') == '1'      # debug: synchronise and check after every id-consuming call
 
 
 def query(name: str, *args) -> int:

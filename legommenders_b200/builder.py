@@ -25,6 +25,7 @@ MODEL_META = {
     'nrms': dict(item='Attention', user='Attention', predictor='Dot'),
     'naml': dict(item='CNN', user='Ada', predictor='Dot'),
     'llmid': dict(item=None, user='Ada', predictor='Dot'),          # id-based path with per-item LLM embeddings
+    'pool': dict(item='Pooling', user='Ada', predictor='Dot'),      # masked-mean item encoder (pooling_operator.py) + Ada users
 }
 
 
@@ -41,6 +42,11 @@ def model_config(kind: str, hidden: int, heads: int = 8, additive: int = 256, dr
         return dict(use_item_content=True, hidden_size=hidden, item_hidden_size=hidden, neg_count=neg_count,
                     use_neg_sampling=use_neg_sampling,
                     item_config=dict(dropout=dropout, kernel_size=3, additive_hidden_size=additive),
+                    user_config=dict(additive_hidden_size=additive,
+                                     inputer_config=dict(use_cls_token=False, use_sep_token=False)))
+    if kind == 'pool':
+        return dict(use_item_content=True, hidden_size=hidden, item_hidden_size=hidden, neg_count=neg_count,
+                    use_neg_sampling=use_neg_sampling, item_config=dict(flatten=False, max_pooling=False),
                     user_config=dict(additive_hidden_size=additive,
                                      inputer_config=dict(use_cls_token=False, use_sep_token=False)))
     if kind == 'llmid':
@@ -73,7 +79,7 @@ def build_model(world, kind: str = 'nrms', hidden: int = 256, heads: int = 8, ad
     cfg.set_column_map(cm)
 
     eh = EmbeddingHub(embedding_dim=cfg.item_hidden_size, transformation='auto', transformation_dropout=dropout)
-    if kind in ('nrms', 'naml'):
+    if kind != 'llmid':
         eh.load_pretrained_embedding(world.word_table, vocab_name=world.word_vocab, frozen=True)
         eh.register_ut(item_ut, item_inputs)
     else:

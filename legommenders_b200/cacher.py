@@ -50,6 +50,8 @@ class BaseCacher:
         if not self._activate:
             return
         self.repr = self._cache(contents)
+        from ._lib import raise_on_bad_ids
+        raise_on_bad_ids(type(self).__name__)      # building a cache is a synchronisation point: out-of-range ids -> IndexError
         self._set_cached(True)
 
     def clean(self):
@@ -70,7 +72,7 @@ class ItemCacher(BaseCacher):
                 page = stack_trees(contents[s:s + self.page_size])
                 n = len(contents[s:s + self.page_size])
                 if self.encode_packed is not None:
-                    out[s:s + n] = self.encode_packed(page['input_ids'], op.inputer.get_mask(page))[0]
+                    out[s:s + n] = self.encode_packed(page['input_ids'], op.inputer.get_mask(page), training=False)[0]
                 else:
                     emb = op.inputer.get_embeddings(page, training=False)
                     out[s:s + n] = op(emb, mask=op.inputer.get_mask(page))
@@ -86,7 +88,7 @@ class UserCacher(BaseCacher):
         self.rows = None    # user-sharded evaluation (sharding.py): only these positions of `contents` are encoded
 
     def _cache(self, contents):
-        out = self.placeholder.to(Env.device)
+        out = torch.zeros_like(self.placeholder, device=Env.device)   # a fresh buffer every time: un-encoded rows are zeros, never stale
         todo = list(range(len(contents))) if self.rows is None else [int(i) for i in self.rows]
         with torch.no_grad():
             for s in range(0, len(todo), self.page_size):

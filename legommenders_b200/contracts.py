@@ -13,6 +13,14 @@ import torch
 from torch import nn
 
 
+_index = [0]
+
+
+def _next_index() -> int:
+    _index[0] += 1
+    return _index[0]
+
+
 # ---------------------------------------------------------------------------------------------------------------- inputer
 class BaseInputer:
     """Turns one item sample (dict column -> token ids) into the integer layout an operator consumes, and a collated batch of
@@ -63,12 +71,13 @@ class BaseOperator(nn.Module):
     flatten_mode = False
 
     def __init__(self, config: BaseOperatorConfig, lego_config, target_user=False):
-        super().__init__()
+        nn.Module.__init__(self)   # not super(): integration.dual() puts the reference's base behind this class in the MRO
         self.config, self.lego_config, self.target_user = config, lego_config, target_user
         side = 'user' if target_user else 'item'
         self.inputer = self.inputer_class(ut=getattr(lego_config, f'{side}_ut'), inputs=getattr(lego_config, f'{side}_inputs'),
                                           eh=lego_config.eh, **config.inputer_config)
         self._calls = 0
+        self._index = _next_index()
 
     def forward(self, embeddings, mask=None, **kwargs):
         raise NotImplementedError(f'{self.classname} has no forward')
@@ -101,7 +110,7 @@ class BaseOperator(nn.Module):
     def _next_seed(self) -> int:
         """A fresh counter-based dropout stream per (module, call); forward and backward of a call share it."""
         self._calls += 1
-        return (torch.initial_seed() * 1000003 + id(self) % 65521 * 8191 + self._calls) & ((1 << 62) - 1)
+        return (torch.initial_seed() * 1000003 + self._index * 8191 + self._calls) & ((1 << 62) - 1)
 
 
 # -------------------------------------------------------------------------------------------------------------- predictor
@@ -119,7 +128,7 @@ class BasePredictor(nn.Module):
     keep_input_dim = False
 
     def __init__(self, config: BasePredictorConfig, lego_config):
-        super().__init__()
+        nn.Module.__init__(self)
         self.config, self.lego_config = config, lego_config
 
     def predict(self, user_embeddings, item_embeddings):

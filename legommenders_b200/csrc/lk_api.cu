@@ -20,6 +20,8 @@ bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("LK_PDL"); return !(e && e[0] == '0'); }();
   return on;
 }
+static int32_t* g_id_viol = nullptr;
+int32_t* id_violations() { return g_id_viol; }
 static unsigned long long g_launches = 0;
 void count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 
@@ -45,6 +47,8 @@ void prof_end(cudaStream_t st) { cudaEventRecord(g_recs.back().e1, st); }
 extern "C" {
 
 unsigned long long lk_launch_count(void) { return __atomic_load_n(&lk::g_launches, __ATOMIC_RELAXED); }
+
+void lk_set_id_violation_counter(int32_t* device_counter) { lk::g_id_viol = device_counter; }
 
 const char* lk_version(void) { return "legommenders_b200 0.1 (sm_100a)"; }
 

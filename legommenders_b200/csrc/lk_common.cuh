@@ -52,6 +52,16 @@ __device__ __forceinline__ void pdl_prologue() {
 }
 bool pdl_enabled();
 
+// Id bounds (the reference raises IndexError on an out-of-range id; here the kernels never dereference one): an id outside
+// [0, rows) reads as an INVALID position (zero row / zero score) and is counted in the device counter registered with
+// lk_set_id_violation_counter (null: not counted).  Host code reads the counter at its next natural synchronisation point.
+int32_t* id_violations();
+__device__ __forceinline__ bool id_in_range(int64_t id, int64_t rows, int32_t* viol) {
+  if ((uint64_t)id < (uint64_t)rows) return true;
+  if (viol) atomicAdd(viol, 1);
+  return false;
+}
+
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

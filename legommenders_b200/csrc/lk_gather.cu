@@ -21,8 +21,8 @@ constexpr int GW = 8;  // warps per block in the gather kernels
 // plain gather: one warp per row, 16-byte vector loads, fused validity mask
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GW * 32) gather_rows_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
-                                                              const float* __restrict__ table, float* __restrict__ out,
-                                                              int64_t M, int E, int accumulate) {
+                                                              const float* __restrict__ table, int64_t V, int32_t* viol,
+                                                              float* __restrict__ out, int64_t M, int E, int accumulate) {
   pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * GW + (threadIdx.x >> 5);
@@ -31,6 +31,8 @@ __global__ void __launch_bounds__(GW * 32) gather_rows_kernel(const int64_t* __r
   for (int64_t m = warp; m < M; m += nwarps) {
     int64_t id = ids[m];
     bool valid = mask ? (mask[m] > 0) : (id > -1);
+    if (valid && lane == 0) valid = id_in_range(id, V, viol);
+    valid = __shfl_sync(0xffffffffu, valid, 0);
     float* o = out + m * E;
     if (valid) {
       const float* src = table + id * (int64_t)E;
@@ -47,6 +49,7 @@ __global__ void __launch_bounds__(GW * 32) gather_rows_kernel(const int64_t* __r
 
 // gather straight into split-bf16 planes (the A operand of the projection GEMM): row m of hi/lo = split(table[ids[m]]) or 0
 __global__ void __launch_bounds__(GW * 32) gather_split_kernel(const int64_t* __restrict__ ids, const float* __restrict__ table,
+                                                               int64_t V, int32_t* viol,
                                                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                                                int64_t M, int E, int ld) {
   pdl_prologue();
@@ -55,7 +58,11 @@ __global__ void __launch_bounds__(GW * 32) gather_split_kernel(const int64_t* __
   const int64_t nwarps = (int64_t)gridDim.x * GW;
   const int L4 = ld >> 2;
   for (int64_t m = warp; m < M; m += nwarps) {
-    const int64_t id = ids[m];
+    int64_t id = ids[m];
+    if (id > -1) {
+      bool ok = lane == 0 ? id_in_range(id, V, viol) : true;
+      if (!__shfl_sync(0xffffffffu, ok, 0)) id = -1;
+    }
     const float* src = table + id * (int64_t)E;
     for (int c = lane; c < L4; c += 32) {
       float4 v = f4_zero();
@@ -78,8 +85,8 @@ __global__ void __launch_bounds__(GW * 32) gather_split_kernel(const int64_t* __
 // ------------------------------------------------------------------------------------------------
 template <int MODE>  // 0 mean, 1 max, 2 sum
 __global__ void __launch_bounds__(GW * 32) gather_pool_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
-                                                              const float* __restrict__ table, float* __restrict__ out,
-                                                              int64_t N, int S, int E) {
+                                                              const float* __restrict__ table, int64_t V, int32_t* viol,
+                                                              float* __restrict__ out, int64_t N, int S, int E) {
   pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t n = (int64_t)blockIdx.x * GW + (threadIdx.x >> 5);
@@ -101,6 +108,10 @@ __global__ void __launch_bounds__(GW * 32) gather_pool_kernel(const int64_t* __r
       if (t < S) {
         int64_t id = idr[t];
         ok[u] = mr ? (mr[t] > 0) : (id > -1);
+        if (ok[u] && (uint64_t)id >= (uint64_t)V) {       // every lane sees the same id: lane 0 of column block 0 counts it
+          if (lane == 0 && blockIdx.y == 0 && viol) atomicAdd(viol, 1);
+          ok[u] = false;
+        }
         if (ok[u] && col_ok) v[u] = ldg4(table + id * (int64_t)E + c);
       }
     }
@@ -419,34 +430,36 @@ using namespace lk;
 
 extern "C" {
 
-int lk_gather_rows(const int64_t* ids, const int64_t* mask, const float* table, float* out, int64_t M, int64_t E,
+int lk_gather_rows(const int64_t* ids, const int64_t* mask, const float* table, int64_t V, float* out, int64_t M, int64_t E,
                    int accumulate, cudaStream_t st) {
   LK_REQUIRE(E % 4 == 0, LK_ERR_SHAPE, "lk_gather_rows: row width %ld must be a multiple of 4 floats (16-byte loads)", (long)E);
   if (M == 0) return LK_OK;
   int64_t blocks = (M + GW - 1) / GW;
   if (blocks > (int64_t)kNumSMs * 64) blocks = (int64_t)kNumSMs * 64;
-  LK_LAUNCH((gather_rows_kernel), (unsigned)blocks, GW * 32, 0, st, ids, mask, table, out, M, (int)E, accumulate);
+  LK_LAUNCH((gather_rows_kernel), (unsigned)blocks, GW * 32, 0, st, ids, mask, table, V, id_violations(), out, M, (int)E, accumulate);
   return check_launch("gather_rows");
 }
 
-int lk_gather_split_bf16(const int64_t* ids, const float* table, void* hi, void* lo, int64_t M, int64_t E, int64_t ld, cudaStream_t st) {
+int lk_gather_split_bf16(const int64_t* ids, const float* table, int64_t V, void* hi, void* lo, int64_t M, int64_t E, int64_t ld,
+                         cudaStream_t st) {
   LK_REQUIRE(E % 4 == 0 && ld % 8 == 0 && ld >= E, LK_ERR_SHAPE, "lk_gather_split_bf16: E=%ld must be a multiple of 4, ld=%ld of 8", (long)E, (long)ld);
   if (M == 0) return LK_OK;
   int64_t blocks = (M + GW - 1) / GW;
   if (blocks > (int64_t)kNumSMs * 64) blocks = (int64_t)kNumSMs * 64;
-  LK_LAUNCH((gather_split_kernel), (unsigned)blocks, GW * 32, 0, st, ids, table, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, M, (int)E, (int)ld);
+  LK_LAUNCH((gather_split_kernel), (unsigned)blocks, GW * 32, 0, st, ids, table, V, id_violations(), (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, M, (int)E,
+            (int)ld);
   return check_launch("gather_split");
 }
 
-int lk_gather_pool(const int64_t* ids, const int64_t* mask, const float* table, float* out, int64_t N, int64_t S, int64_t E,
+int lk_gather_pool(const int64_t* ids, const int64_t* mask, const float* table, int64_t V, float* out, int64_t N, int64_t S, int64_t E,
                    int mode, cudaStream_t st) {
   LK_REQUIRE(E % 4 == 0, LK_ERR_SHAPE, "lk_gather_pool: row width %ld must be a multiple of 4 floats", (long)E);
   LK_REQUIRE(mode >= 0 && mode <= 2, LK_ERR_ARG, "lk_gather_pool: mode must be 0 (mean), 1 (max) or 2 (sum)");
   if (N == 0) return LK_OK;
   dim3 grid((unsigned)((N + GW - 1) / GW), (unsigned)((E + 127) / 128));
-  if (mode == 0) LK_LAUNCH((gather_pool_kernel<0>), grid, GW * 32, 0, st, ids, mask, table, out, N, (int)S, (int)E);
-  else if (mode == 1) LK_LAUNCH((gather_pool_kernel<1>), grid, GW * 32, 0, st, ids, mask, table, out, N, (int)S, (int)E);
-  else LK_LAUNCH((gather_pool_kernel<2>), grid, GW * 32, 0, st, ids, mask, table, out, N, (int)S, (int)E);
+  if (mode == 0) LK_LAUNCH((gather_pool_kernel<0>), grid, GW * 32, 0, st, ids, mask, table, V, id_violations(), out, N, (int)S, (int)E);
+  else if (mode == 1) LK_LAUNCH((gather_pool_kernel<1>), grid, GW * 32, 0, st, ids, mask, table, V, id_violations(), out, N, (int)S, (int)E);
+  else LK_LAUNCH((gather_pool_kernel<2>), grid, GW * 32, 0, st, ids, mask, table, V, id_violations(), out, N, (int)S, (int)E);
   return check_launch("gather_pool");
 }
 

@@ -278,7 +278,7 @@ static size_t scratch_bytes(int64_t T, int64_t N, int64_t D, int64_t A, int64_t 
 
 static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const int64_t* cat_ids, const int64_t* special_ids,
                     const int32_t* cu_items, int64_t n_items, int64_t T, int64_t S_max, const int32_t* cu_users, int64_t B, int64_t C,
-                    int64_t H_max, const float* glove_table, const float* params, float* grads, const int64_t* offsets, int64_t D,
+                    int64_t H_max, const float* glove_table, int64_t glove_rows, const float* params, float* grads, const int64_t* offsets, int64_t D,
                     int64_t heads, int64_t A, int64_t E, int64_t n_cats, int64_t n_special, float drop_embed, float drop_attn,
                     uint64_t seed, float* loss_out, float* scores_out, void* arena, size_t arena_bytes, cudaStream_t st) {
   Ctx c;
@@ -332,7 +332,7 @@ static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const 
   // x[t] = valid(title)·dropout(W·glove[title] + b) + category[cat] + special[sp]  — one contraction whose epilogue applies the row
   // mask (title id > -1), adds the two small-table rows and writes x directly as the item encoder's operand planes
   PlaneBuf gp = alloc_planes(c, T, E);
-  STEP(lk_gather_split_bf16(title_ids, glove_table, gp.hi, gp.lo, T, E, gp.ld, st));
+  STEP(lk_gather_split_bf16(title_ids, glove_table, glove_rows, gp.hi, gp.lo, T, E, gp.ld, st));
 
   // ---- item encoder over all packed items, user encoder over the packed history encodings ---------------------------------
   EncSaved si;
@@ -396,11 +396,11 @@ static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const 
 extern "C" {
 
 // exact: the sizing pass walks the same allocation sequence as a real step (no launches, no memory behind the arena)
-size_t lk_nrms_arena_bytes(int64_t T_max, int64_t N_max, int64_t B, int64_t D, int64_t A, int64_t E, int64_t H, int64_t n_cats,
+size_t lk_nrms_arena_bytes(int64_t T_max, int64_t N_max, int64_t B, int64_t C, int64_t D, int64_t A, int64_t E, int64_t H, int64_t n_cats,
                            int64_t n_special) {
   static const int64_t zeros[22] = {0};
   size_t high = 0;
-  nrms_run(true, &high, nullptr, nullptr, nullptr, nullptr, N_max + B, T_max, 1, nullptr, B, 1, 1, nullptr, nullptr, nullptr, zeros, D, H, A,
+  nrms_run(true, &high, nullptr, nullptr, nullptr, nullptr, N_max, T_max, 1, nullptr, B, C, 1, nullptr, 0, nullptr, nullptr, zeros, D, H, A,
            E, n_cats, n_special, 0.f, 0.f, 0, nullptr, nullptr, nullptr, ~(size_t)0 >> 1, nullptr);
   return high + 4096;
 }
@@ -412,12 +412,18 @@ size_t lk_nrms_arena_bytes(int64_t T_max, int64_t N_max, int64_t B, int64_t D, i
 //   13..21 user_op: same nine
 int lk_nrms_fwd_bwd(const int64_t* title_ids, const int64_t* cat_ids, const int64_t* special_ids, const int32_t* cu_items,
                     int64_t n_items, int64_t T, int64_t S_max, const int32_t* cu_users, int64_t B, int64_t C, int64_t H_max,
-                    const float* glove_table, const float* params, float* grads, const int64_t* offsets, int64_t D, int64_t heads,
+                    const float* glove_table, int64_t glove_rows, const float* params, float* grads, const int64_t* offsets, int64_t D, int64_t heads,
                     int64_t A, int64_t E, int64_t n_cats, int64_t n_special, float drop_embed, float drop_attn, uint64_t seed,
                     float* loss_out, float* scores_out, void* arena, size_t arena_bytes, cudaStream_t st) {
   LK_REQUIRE(n_items >= B * C && B > 0 && C > 0, LK_ERR_ARG, "lk_nrms_fwd_bwd: the first B*C items must be the candidates");
   LK_REQUIRE(D % 8 == 0 && A % 8 == 0 && E % 4 == 0 && D % heads == 0, LK_ERR_SHAPE, "lk_nrms_fwd_bwd: unsupported dims");
-  return nrms_run(false, nullptr, title_ids, cat_ids, special_ids, cu_items, n_items, T, S_max, cu_users, B, C, H_max, glove_table, params,
+  {   // walk the allocation sequence with the real shapes BEFORE anything is launched: an arena that is too small must never be used
+    size_t need = 0;
+    nrms_run(true, &need, nullptr, nullptr, nullptr, nullptr, n_items, T, S_max, nullptr, B, C, H_max, nullptr, 0, params, grads, offsets, D, heads,
+             A, E, n_cats, n_special, drop_embed, drop_attn, seed, nullptr, scores_out, nullptr, ~(size_t)0 >> 1, nullptr);
+    LK_REQUIRE(need <= arena_bytes, LK_ERR_ARG, "lk_nrms_fwd_bwd: arena too small (%zu bytes given, %zu needed)", arena_bytes, need);
+  }
+  return nrms_run(false, nullptr, title_ids, cat_ids, special_ids, cu_items, n_items, T, S_max, cu_users, B, C, H_max, glove_table, glove_rows, params,
                   grads, offsets, D, heads, A, E, n_cats, n_special, drop_embed, drop_attn, seed, loss_out, scores_out, arena,
                   arena_bytes, st);
 }

@@ -129,17 +129,29 @@ __global__ void bce_dscore_kernel(const float* __restrict__ z, const float* __re
 // cached evaluation: out[r] = <U[uid[r]], I[iid[r]]>; one warp per row, two rows in flight per warp
 __global__ void __launch_bounds__(SW * 32) cached_scores_kernel(const float* __restrict__ U, const float* __restrict__ I,
                                                                 const int64_t* __restrict__ uid, const int64_t* __restrict__ iid,
-                                                                float* __restrict__ out, int64_t R, int D) {
+                                                                float* __restrict__ out, int64_t R, int D, int64_t n_users,
+                                                                int64_t n_items, int32_t* viol) {
   pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * SW + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * SW;
   for (int64_t r = warp * 2; r < R; r += nwarps * 2) {
     const bool two = r + 1 < R;
-    const float* u0 = U + uid[r] * (int64_t)D;
-    const float* v0 = I + iid[r] * (int64_t)D;
-    const float* u1 = two ? U + uid[r + 1] * (int64_t)D : u0;
-    const float* v1 = two ? I + iid[r + 1] * (int64_t)D : v0;
+    int64_t ua = uid[r], ia = iid[r], ub = two ? uid[r + 1] : ua, ib = two ? iid[r + 1] : ia;
+    // out-of-range ids (the reference raises IndexError): counted, scored as 0, never dereferenced
+    bool ok0 = true, ok1 = true;
+    if (lane == 0) {
+      ok0 = id_in_range(ua, n_users, viol) & id_in_range(ia, n_items, viol);
+      ok1 = !two || (id_in_range(ub, n_users, viol) & id_in_range(ib, n_items, viol));
+    }
+    ok0 = __shfl_sync(0xffffffffu, ok0, 0);
+    ok1 = __shfl_sync(0xffffffffu, ok1, 0);
+    if (!ok0) ua = ia = 0;
+    if (!ok1) ub = ib = 0;
+    const float* u0 = U + ua * (int64_t)D;
+    const float* v0 = I + ia * (int64_t)D;
+    const float* u1 = U + ub * (int64_t)D;
+    const float* v1 = I + ib * (int64_t)D;
     float s0 = 0.f, s1 = 0.f;
     for (int c = lane * 4; c < D; c += 128) {
       float4 a0 = ldg4(u0 + c), b0 = ldg4(v0 + c), a1 = ldg4(u1 + c), b1 = ldg4(v1 + c);
@@ -149,22 +161,25 @@ __global__ void __launch_bounds__(SW * 32) cached_scores_kernel(const float* __r
     s0 = warp_sum(s0);
     s1 = warp_sum(s1);
     if (lane == 0) {
-      out[r] = s0;
-      if (two) out[r + 1] = s1;
+      out[r] = ok0 ? s0 : 0.f;
+      if (two) out[r + 1] = ok1 ? s1 : 0.f;
     }
   }
 }
 
 // out[r,:] = table[ids[r],:]  (cache indexing model/legommender.py:153-157; ids are always valid)
 __global__ void __launch_bounds__(SW * 32) index_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids,
-                                                             float* __restrict__ out, int64_t R, int D) {
+                                                             float* __restrict__ out, int64_t R, int D, int64_t V, int32_t* viol) {
   pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * SW + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * SW;
   for (int64_t r = warp; r < R; r += nwarps) {
-    const float* src = table + ids[r] * (int64_t)D;
-    for (int c = lane * 4; c < D; c += 128) st4(out + r * (int64_t)D + c, ldg4(src + c));
+    const int64_t id = ids[r];
+    bool ok = lane == 0 ? id_in_range(id, V, viol) : true;
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    const float* src = table + (ok ? id : 0) * (int64_t)D;
+    for (int c = lane * 4; c < D; c += 128) st4(out + r * (int64_t)D + c, ok ? ldg4(src + c) : f4_zero());
   }
 }
 
@@ -262,22 +277,22 @@ int lk_dot_bce_bwd(const float* U, const float* V, const float* y, const float* 
   return check_launch("dot_bce_bwd", 2);
 }
 
-int lk_cached_scores(const float* U, const float* I, const int64_t* uid, const int64_t* iid, float* out, int64_t R, int64_t D,
-                     cudaStream_t st) {
+int lk_cached_scores(const float* U, int64_t n_users, const float* I, int64_t n_items, const int64_t* uid, const int64_t* iid, float* out,
+                     int64_t R, int64_t D, cudaStream_t st) {
   LK_REQUIRE(D % 4 == 0, LK_ERR_SHAPE, "lk_cached_scores: D=%ld must be a multiple of 4", (long)D);
   if (R == 0) return LK_OK;
   int64_t blocks = (R + 2 * SW - 1) / (2 * SW);
   if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
-  LK_LAUNCH((cached_scores_kernel), (unsigned)blocks, SW * 32, 0, st, U, I, uid, iid, out, R, (int)D);
+  LK_LAUNCH((cached_scores_kernel), (unsigned)blocks, SW * 32, 0, st, U, I, uid, iid, out, R, (int)D, n_users, n_items, id_violations());
   return check_launch("cached_scores");
 }
 
-int lk_index_rows(const float* table, const int64_t* ids, float* out, int64_t R, int64_t D, cudaStream_t st) {
+int lk_index_rows(const float* table, int64_t V, const int64_t* ids, float* out, int64_t R, int64_t D, cudaStream_t st) {
   LK_REQUIRE(D % 4 == 0, LK_ERR_SHAPE, "lk_index_rows: D=%ld must be a multiple of 4", (long)D);
   if (R == 0) return LK_OK;
   int64_t blocks = (R + SW - 1) / SW;
   if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
-  LK_LAUNCH((index_rows_kernel), (unsigned)blocks, SW * 32, 0, st, table, ids, out, R, (int)D);
+  LK_LAUNCH((index_rows_kernel), (unsigned)blocks, SW * 32, 0, st, table, ids, out, R, (int)D, V, id_violations());
   return check_launch("index_rows");
 }
 

@@ -22,6 +22,15 @@ from . import ops
 from .env import Env
 
 
+_module_index = [0]
+
+
+def next_module_index() -> int:
+    """Stable per-module index for the counter-based dropout streams: construction order, not id() (reproducible across runs)."""
+    _module_index[0] += 1
+    return _module_index[0]
+
+
 class _Weight(nn.Module):
     def __init__(self, weight: torch.Tensor, requires_grad=True):
         super().__init__()
@@ -51,7 +60,7 @@ class Table(nn.Module):
             weight = torch.empty(num_embeddings, embedding_dim).normal_()
         self.weight = nn.Parameter(weight, requires_grad=requires_grad)
 
-    def lookup_add(self, base, ids, mask=None, training=False):
+    def lookup_add(self, base, ids, mask=None, training=None):
         return ops.gather_add(base, ids, mask, self.weight)
 
     def forward(self, indexes):
@@ -67,12 +76,15 @@ class Transformation(nn.Module):
         self.linear = _Affine(self.embedding.weight.shape[1], to_dimension)
         self.p = float(transformation_dropout)
         self._calls = 0
+        self._index = next_module_index()
 
     def _seed(self):
         self._calls += 1
-        return (torch.initial_seed() * 1000003 + id(self) % 65521 * 8191 + self._calls) & ((1 << 62) - 1)
+        return (torch.initial_seed() * 1000003 + self._index * 8191 + self._calls) & ((1 << 62) - 1)
 
-    def lookup_add(self, base, ids, mask=None, training=False):
+    def lookup_add(self, base, ids, mask=None, training=None):
+        """`training=None` follows this module's own flag (model.eval() switches every dropout off, base_lego.py:417)."""
+        training = self.training if training is None else training
         valid = mask if mask is not None else ops.valid_mask(ids)
         rows = ops.gather_add(None, ids, valid, self.embedding.weight)
         p = self.p if (training and self.p > 0) else 0.0

@@ -5,8 +5,29 @@ phase flags to pick loss vs scores (model/legommender.py:260-263), and every mod
 """
 import torch
 
+_BRIDGED = ('device', 'simple_dev', 'is_training', 'is_evaluating', 'is_testing', 'item_cache', 'user_cache', 'lm_cache')
 
-class Env:
+
+class _EnvMeta(type):
+    """When bound to the reference's `loader.env.Env` (integration.bind_reference_env) the phase flags, the device and the cache flags
+    read and write THROUGH to it, so a run driven by the reference's trainer and this package's kernels share one global state."""
+    _target = None
+
+    def __getattribute__(cls, name):
+        if name in _BRIDGED:
+            target = type.__getattribute__(cls, '_target')
+            if target is not None:
+                return getattr(target, name)
+        return type.__getattribute__(cls, name)
+
+    def __setattr__(cls, name, value):
+        if name in _BRIDGED and type.__getattribute__(cls, '_target') is not None:
+            setattr(type.__getattribute__(cls, '_target'), name, value)
+            return
+        type.__setattr__(cls, name, value)
+
+
+class Env(metaclass=_EnvMeta):
     device = None          # assigned directly, as base_lego.py:120 does
     simple_dev = False
     UNSET = -1
@@ -50,6 +71,11 @@ class Env:
     @classmethod
     def set_lm_cache(cls, flag):
         cls.lm_cache = flag
+
+    @classmethod
+    def bind(cls, target=None):
+        """Delegate the shared flags to another Env class (the reference's); bind(None) restores the local state."""
+        type.__setattr__(cls, '_target', target)
 
     @classmethod
     def use_cuda(cls, index: int = 0):

@@ -57,6 +57,8 @@ def build_caches_device(model, batcher, item_page: int = 8192, user_page: int = 
     if not (model._packed_items() and getattr(model.user_op, 'supports_packed', False) and cacher.use_item_content):
         raise ValueError('build_caches_device needs packed item and user operators over item content')
     cacher.clean()
+    was_training = model.training
+    model.eval()                      # caches never carry dropout noise, whatever phase the caller is in (base_lego.py:417)
     n_items, n_users = len(batcher.item_len), len(batcher.hist)
     item_repr = model.item_op.get_full_placeholder(n_items).to(dev)
     tp = (ctypes.c_void_p * len(batcher.cols))(*[t.data_ptr() for t in batcher.tables])
@@ -73,11 +75,11 @@ def build_caches_device(model, batcher, item_page: int = 8192, user_page: int = 
             call('lk_pack_item_tokens', ctypes.addressof(tp), ctypes.addressof(op), len(batcher.cols), items.data_ptr(), cu_d.data_ptr(),
                  e - s, batcher.S)
             pk = Packed(OrderedDict(zip(batcher.cols, outs)), cu_d, e - s, int(cu[-1]), int(lens.max()))
-            emb = model.item_op.inputer.get_embeddings({'input_ids': pk.ids})
+            emb = model.item_op.inputer.get_embeddings({'input_ids': pk.ids}, training=False)
             item_repr[s:e] = model.item_op(emb, cu=pk.cu, max_len=pk.max_len)
         cacher.item.repr = item_repr
         cacher.item._set_cached(True)
-        user_repr = cacher.user.placeholder.to(dev)
+        user_repr = torch.zeros_like(cacher.user.placeholder, device=dev)
         for s in range(0, n_users, user_page):
             e = min(s + user_page, n_users)
             hists = batcher.hist[s:e]
@@ -91,6 +93,7 @@ def build_caches_device(model, batcher, item_page: int = 8192, user_page: int = 
             user_repr[s:e] = model.user_op(rows, cu=torch.from_numpy(cu).to(dev), max_len=int(hl.max()))
         cacher.user.repr = user_repr
         cacher.user._set_cached(True)
+    model.train(was_training)
 
 
 def cached_scores(model, user_ids: torch.Tensor, item_ids: torch.Tensor, chunk_rows: int = 1 << 24) -> torch.Tensor:
@@ -117,11 +120,21 @@ def evaluate(model, user_ids, item_ids, labels, groups=None, metrics: Sequence[s
     user_ids, item_ids, labels, groups = (torch.as_tensor(t).reshape(-1) for t in (user_ids, item_ids, labels, groups))
     rows: Optional[torch.Tensor] = None
     if world > 1:
-        rows = sharding.owned_rows(groups, rank, world)
+        # the user cache is partitioned by user id (build_caches: rank r holds the rows of users r, r+world, ...), so rows MUST be
+        # partitioned by user id as well; a group key other than the user id could straddle ranks or hit un-encoded cache rows
+        if groups is not user_ids and not torch.equal(groups, user_ids):
+            raise ValueError('sharded evaluation groups by user id (config/data/mind.yaml:24); pass groups=None or groups == user_ids')
+        rows = sharding.owned_rows(user_ids, rank, world)
         user_ids, item_ids, labels, groups = user_ids[rows], item_ids[rows], labels[rows], groups[rows]
-    scores = cached_scores(model, user_ids, item_ids)
     pool = MetricPool.parse(metrics)
-    vals = pool.calculate(scores, labels, groups)
+    if user_ids.numel() == 0:        # a rank that owns no rows still takes part in the all-reduce below (0 sums, 0 groups)
+        if world == 1:
+            raise ValueError('no rows to evaluate')
+        scores = torch.empty(0, dtype=torch.float32, device=Env.device)
+        vals, pool.n_groups = OrderedDict((k, 0.0) for k in metrics), 0
+    else:
+        scores = cached_scores(model, user_ids, item_ids)
+        vals = pool.calculate(scores, labels, groups)
     if world > 1:
         local = torch.tensor(list(vals.values()), dtype=torch.float64, device=Env.device)
         means, _ = sharding.reduce_group_means(local, pool.n_groups, group)

@@ -77,8 +77,8 @@ class ConcatInputer(BaseInputer):
 
     def get_embeddings(self, batched_samples, training=None):
         """Σ_cols [ids>-1]·table_c[ids] (concat_inputer.py:92-114).  The caller's ids are NOT mutated
-        (the reference's in-place `seq *= mask` is an artefact)."""
-        training = Env.is_training if training is None else training
+        (the reference's in-place `seq *= mask` is an artefact).
+        `training=None`: dropout follows each table module's own `.training` flag, as nn.Dropout does in the reference."""
         out = None
         for col, ids in batched_samples['input_ids'].items():
             ids = ids.to(Env.device, non_blocking=True)

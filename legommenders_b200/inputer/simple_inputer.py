@@ -36,7 +36,6 @@ class SimpleInputer(BaseInputer):
 
     def get_embeddings(self, batched_samples, training=None):
         """Per column mask·table[ids] with the stored attention mask, no sum (simple_inputer.py:43-66)."""
-        training = Env.is_training if training is None else training
         out = OrderedDict()
         for col, ids in batched_samples['input_ids'].items():
             vocab = self.ut.meta.features[col].tokenizer.vocab.name

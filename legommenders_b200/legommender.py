@@ -69,10 +69,10 @@ class Legommender(nn.Module):
         return (self.packed and self.item_op is not None and getattr(self.item_op, 'supports_packed', False)
                 and getattr(self.item_op.inputer, 'output_single_sequence', False))
 
-    def encode_items_packed(self, input_ids: dict, mask: torch.Tensor, item_valid=None, keep_empty=True):
+    def encode_items_packed(self, input_ids: dict, mask: torch.Tensor, item_valid=None, keep_empty=True, training=None):
         """Encode items given per-column ids [N,S] + mask [N,S] without touching pad tokens -> ([n,D], Packed)."""
         pk = pack_tokens(input_ids, mask, item_valid, keep_empty=keep_empty)
-        emb = self.item_op.inputer.get_embeddings({'input_ids': pk.ids})
+        emb = self.item_op.inputer.get_embeddings({'input_ids': pk.ids}, training=training)
         return self.item_op(emb, cu=pk.cu, max_len=pk.max_len), pk
 
     def _forward_packed(self, batch: dict):

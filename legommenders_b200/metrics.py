@@ -13,7 +13,7 @@ from typing import List, Sequence
 import numpy as np
 import torch
 
-from ._lib import call, ptr, query, workspace
+from ._lib import call, ptr, query, raise_on_bad_ids, workspace
 from .env import Env
 
 SUPPORTED = ('GAUC', 'MRR', 'NDCG')
@@ -63,6 +63,7 @@ class MetricPool:
         ws = workspace(nbytes, dev, 'metrics')
         call('lk_group_metrics', ptr(s), ptr(y), ptr(g), R, ks.ctypes.data, nk, ptr(disc_d), n_disc, ptr(out), ptr(pg), ptr(ws), ws.numel())
         host = out.cpu().numpy()          # the one device->host read of the evaluation
+        raise_on_bad_ids('evaluation')     # the stream is drained here anyway: surface out-of-range user / item ids as IndexError
         self.n_groups = int(host[2 + nk])
         self.values = OrderedDict()
         for n in self.names:

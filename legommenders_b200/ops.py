@@ -13,7 +13,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib
-from ._lib import call, ptr, query, workspace
+from ._lib import call, id_violation_counter, ptr, query, raise_on_bad_ids, workspace
 
 ACT_NONE, ACT_TANH, ACT_RELU = 0, 1, 2
 POOL_MEAN, POOL_MAX, POOL_SUM = 0, 1, 2
@@ -325,7 +325,8 @@ class _GatherAdd(Function):
         else:
             out = _f32(base).clone()
             acc = 1
-        call('lk_gather_rows', ptr(ids), ptr(mask), ptr(table), ptr(out), M, E, acc)
+        id_violation_counter(table.device)
+        call('lk_gather_rows', ptr(ids), ptr(mask), ptr(table), table.shape[0], ptr(out), M, E, acc)
         ctx.save_for_backward(ids, mask)
         ctx.tshape = tuple(table.shape)
         ctx.has_base = base is not None
@@ -355,7 +356,8 @@ class _GatherPool(Function):
         N, S = ids.shape
         E = table.shape[1]
         out = torch.empty((N, E), dtype=torch.float32, device=table.device)
-        call('lk_gather_pool', ptr(ids), ptr(mask), ptr(table), ptr(out), N, S, E, mode)
+        id_violation_counter(table.device)
+        call('lk_gather_pool', ptr(ids), ptr(mask), ptr(table), table.shape[0], ptr(out), N, S, E, mode)
         ctx.save_for_backward(ids, mask)
         ctx.tshape, ctx.mode = tuple(table.shape), mode
         return out
@@ -648,7 +650,8 @@ def cached_scores(user_repr, item_repr, user_ids, item_ids, out=None):
     R, D = user_ids.numel(), user_repr.shape[1]
     if out is None:
         out = torch.empty((R,), dtype=torch.float32, device=user_repr.device)
-    call('lk_cached_scores', ptr(user_repr), ptr(item_repr), ptr(user_ids), ptr(item_ids), ptr(out), R, D)
+    id_violation_counter(user_repr.device)
+    call('lk_cached_scores', ptr(user_repr), user_repr.shape[0], ptr(item_repr), item_repr.shape[0], ptr(user_ids), ptr(item_ids), ptr(out), R, D)
     return out
 
 
@@ -656,7 +659,8 @@ def index_rows(table, ids):
     """table[ids] for cache indexing — legommender.py:153-157."""
     table, flat = _f32(table), _i64(ids.reshape(-1))
     out = torch.empty((flat.numel(), table.shape[1]), dtype=torch.float32, device=table.device)
-    call('lk_index_rows', ptr(table), ptr(flat), ptr(out), flat.numel(), table.shape[1])
+    id_violation_counter(table.device)
+    call('lk_index_rows', ptr(table), table.shape[0], ptr(flat), ptr(out), flat.numel(), table.shape[1])
     return out.view(*ids.shape, table.shape[1])
 
 

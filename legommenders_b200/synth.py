@@ -83,7 +83,7 @@ class MindWorld:
     def __init__(self, n_items=2000, n_words=5000, n_users=500, n_cats=18, title_len=30, hist_len=50,
                  n_train=4096, n_eval_groups=200, eval_group_mean=36, min_title=5, max_neg=100,
                  embed_dim=300, seed=DEFAULT_SEED, title_col='title@glove', word_vocab='glove',
-                 glove_std=0.4, make_table=True):
+                 glove_std=0.4, make_table=True, min_hist=1):
         rng = np.random.default_rng(seed)
         self.seed = seed
         self.n_items, self.n_words, self.n_users, self.n_cats = n_items, n_words, n_users, n_cats
@@ -104,7 +104,7 @@ class MindWorld:
         # ---- users ------------------------------------------------------------------
         ip = zipf_probs(n_items)
         iperm = rng.permutation(n_items)
-        hl = rng.integers(1, hist_len + 1, size=n_users)
+        hl = rng.integers(min(min_hist, hist_len), hist_len + 1, size=n_users)
         hflat = iperm[rng.choice(n_items, size=int(hl.sum()), p=ip)]
         hoffs = np.concatenate([[0], np.cumsum(hl)])
         self.hist_lens = hl.astype(np.int64)

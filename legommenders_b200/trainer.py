@@ -223,12 +223,12 @@ class NativeNRMSStep:
         self.loss = torch.zeros((), dtype=torch.float32, device=opt.flat.device)
         self.calls = 0
 
-    def _ensure_arena(self, T, N, B):
+    def _ensure_arena(self, T, N, B, C):
         """Grow-only arena sized by the driver's own sizing pass, with 20% head-room so that it is queried rarely."""
         cap = getattr(self, '_cap', None)
-        if self.arena is None or T > cap[0] or N > cap[1] or B > cap[2]:
-            cap = (int(T * 1.2) + 64, int(N * 1.2) + 8, B)
-            need = self._lib.query('lk_nrms_arena_bytes', cap[0], cap[1], B, self.D, self.A, self.E, self.heads, self.n_cats, self.n_special)
+        if self.arena is None or T > cap[0] or N > cap[1] or B > cap[2] or C > cap[3]:
+            cap = (int(T * 1.2) + 64, int(N * 1.2) + 8, B, C)
+            need = self._lib.query('lk_nrms_arena_bytes', cap[0], cap[1], B, C, self.D, self.A, self.E, self.heads, self.n_cats, self.n_special)
             self.arena = torch.empty(int(need), dtype=torch.uint8, device=self.opt.flat.device)
             self._cap = cap
 
@@ -257,7 +257,7 @@ class NativeNRMSStep:
         """Enqueue forward + backward; gradients land in opt.grad, the loss (device scalar) is returned."""
         from ._lib import call, ptr
         pk, cu_u, max_u, B, C = self.pack(batch)
-        self._ensure_arena(pk.rows, pk.n, B)
+        self._ensure_arena(pk.rows, pk.n, B, C)
         self.calls += 1
         seed = (torch.initial_seed() * 1000003 + self.calls) & ((1 << 60) - 1)
         de, da = (self.drop_embed, self.drop_attn) if training else (0.0, 0.0)
@@ -268,7 +268,7 @@ class NativeNRMSStep:
             if table.shape[0] == 0:
                 table = table.new_zeros((1, table.shape[1]))
         call('lk_nrms_fwd_bwd', ptr(title_ids), ptr(pk.ids[self.cat_col]), ptr(pk.ids[self.special_col]), ptr(pk.cu),
-             pk.n, pk.rows, pk.max_len, ptr(cu_u), B, C, max_u, ptr(table), ptr(self.opt.flat), ptr(self.opt.grad),
+             pk.n, pk.rows, pk.max_len, ptr(cu_u), B, C, max_u, ptr(table), table.shape[0], ptr(self.opt.flat), ptr(self.opt.grad),
              self.offsets.ctypes.data, self.D, self.heads, self.A, self.E, self.n_cats, self.n_special, float(de), float(da), int(seed),
              ptr(self.loss), None, ptr(self.arena), self.arena.numel())
         return self.loss

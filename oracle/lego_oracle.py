@@ -266,7 +266,7 @@ class ModelSpec:
 
     def __init__(self, kind: str, heads: int = 8, col_vocab: Optional[Dict[str, str]] = None,
                  use_neg_sampling: bool = True, item_vocab: str = 'item_id'):
-        assert kind in ('nrms', 'naml', 'llmid')
+        assert kind in ('nrms', 'naml', 'llmid', 'pool')
         self.kind, self.heads = kind, heads
         self.col_vocab = col_vocab or {}
         self.use_neg_sampling = use_neg_sampling
@@ -292,6 +292,11 @@ def item_content(state: dict, spec: ModelSpec, tree: dict) -> torch.Tensor:
         am = OrderedDict((c, _flat(v)) for c, v in tree['attention_mask'].items())
         x = simple_embeddings(state, ids, am, spec.col_vocab)
         r = cnn_operator(state, 'item_op.', x, am)
+    elif spec.kind == 'pool':
+        ids = OrderedDict((c, _flat(v)) for c, v in tree['input_ids'].items())
+        B = next(iter(tree['input_ids'].values())).shape[0]
+        am = OrderedDict((c, _flat(v)) for c, v in tree['attention_mask'].items())
+        r = pooling_operator(simple_embeddings(state, ids, am, spec.col_vocab), am)
     else:
         raise ValueError(spec.kind)
     return r.view(B, -1, r.shape[-1])
@@ -500,7 +505,7 @@ def state_shapes(kind: str, D: int, A: int, E: int, n_words: int, n_cats: int, n
         s[prefix + 'linear.bias'] = (D,)
         additive(prefix)
 
-    if kind in ('nrms', 'naml'):
+    if kind in ('nrms', 'naml', 'pool'):
         s['embedding_vocab_table.glove.embedding.weight'] = (n_words, E)
         s['embedding_vocab_table.glove.linear.weight'] = (D, E)
         s['embedding_vocab_table.glove.linear.bias'] = (D,)
@@ -515,6 +520,8 @@ def state_shapes(kind: str, D: int, A: int, E: int, n_words: int, n_cats: int, n
         s['item_op.linear.weight'] = (D, D)
         s['item_op.linear.bias'] = (D,)
         additive('item_op.')
+        additive('user_op.')
+    elif kind == 'pool':
         additive('user_op.')
     else:
         s['embedding_vocab_table.item_id.embedding.weight'] = (n_items, E)

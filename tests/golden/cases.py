@@ -19,6 +19,16 @@ _small_world = dict(n_items=150, n_words=400, n_users=48, n_train=64, n_eval_gro
 _full_world = dict(n_items=400, n_words=1500, n_users=64, n_train=64, n_eval_groups=16, eval_group_mean=10,
                    title_len=30, hist_len=50, embed_dim=300)
 
+_h100_world = dict(n_items=300, n_words=1200, n_users=48, n_train=48, n_eval_groups=8, eval_group_mean=8,
+                   title_len=30, hist_len=100, embed_dim=300, min_hist=60)
+_hot_small = {'glove.linear.weight': 2, 'item_op.multi_head_attention.in_proj_weight': 3, 'item_op.linear.weight': 2,
+              'item_op.additive_attention.encoder.0.weight': 16, 'item_op.additive_attention.encoder.2.weight': 24,
+              'user_op.multi_head_attention.in_proj_weight': 3, 'user_op.linear.weight': 3,
+              'user_op.additive_attention.encoder.0.weight': 4, 'user_op.additive_attention.encoder.2.weight': 16}
+_hot_full = {'item_op.additive_attention.encoder.0.weight': 2, 'item_op.additive_attention.encoder.2.weight': 24,
+             'user_op.multi_head_attention.in_proj_weight': 1.5, 'user_op.linear.weight': 1.5,
+             'user_op.additive_attention.encoder.0.weight': 4, 'user_op.additive_attention.encoder.2.weight': 12}
+
 CASES = OrderedDict(
     nrms_small=dict(kind='nrms', hidden=64, heads=8, additive=32, batch=6, seed=11, world=_small_world, cached_eval=True),
     naml_small=dict(kind='naml', hidden=64, heads=8, additive=32, batch=6, seed=12, world=_small_world, cached_eval=True),
@@ -28,6 +38,19 @@ CASES = OrderedDict(
                         use_neg_sampling=False),
     nrms_full=dict(kind='nrms', hidden=256, heads=8, additive=256, batch=4, seed=21, world=_full_world, full_grads=False),
     naml_full=dict(kind='naml', hidden=256, heads=8, additive=256, batch=4, seed=22, world=_full_world, full_grads=False),
+    # "hot" states: selected weights scaled up so that EVERY parameter gradient (the additive-attention ones included, which are
+    # ~1e-7 of the largest gradient at the plain init scale) is a few percent of the largest or more -> per-tensor 1e-4 bars, no floor
+    nrms_small_hot=dict(kind='nrms', hidden=64, heads=8, additive=32, batch=6, seed=11, world=_small_world, strict_grads=True,
+                        boost=_hot_small),
+    nrms_full_hot=dict(kind='nrms', hidden=256, heads=8, additive=256, batch=4, seed=21, world=_full_world, full_grads=False,
+                       strict_grads=True, boost=_hot_full),
+    # history 100 (BASELINE config 4): user sequences beyond the 64-token tensor-core attention kernels
+    nrms_h100=dict(kind='nrms', hidden=256, heads=8, additive=256, batch=3, seed=23, world=_h100_world, full_grads=False),
+    # 4096-d LLM item embeddings (BASELINE config 5) at model level
+    llmid_4096=dict(kind='llmid', hidden=64, heads=8, additive=32, batch=6, seed=24, world=_small_world, llm_dim=4096,
+                    llm_scale=0.05, cached_eval=True, full_grads=False),
+    # masked-mean PoolingOperator item encoder (a10) + Ada users
+    pool_small=dict(kind='pool', hidden=64, heads=8, additive=32, batch=6, seed=25, world=_small_world, cached_eval=True),
 )
 
 
@@ -36,7 +59,7 @@ def make_world(c: dict):
     llm = None
     if c['kind'] == 'llmid':
         rng = np.random.default_rng(c['seed'] + 1000)
-        llm = rng.standard_normal((world.n_items, c['llm_dim'])).astype(np.float32)
+        llm = (rng.standard_normal((world.n_items, c['llm_dim'])) * c.get('llm_scale', 1.0)).astype(np.float32)
     return world, llm
 
 
@@ -46,6 +69,11 @@ def make_state(c: dict, world, shapes: dict, llm=None) -> dict:
     for k in shapes:
         if k.endswith('.embedding.weight'):
             state[k] = llm if c['kind'] == 'llmid' else world.word_table
+    for pattern, factor in c.get('boost', {}).items():
+        hit = [k for k in state if pattern in k]
+        assert hit, pattern
+        for k in hit:
+            state[k] = (state[k] * np.float32(factor)).astype(np.float32)
     return state
 
 

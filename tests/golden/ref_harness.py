@@ -76,6 +76,13 @@ def build_reference(world, model='nrms', hidden=256, neg_count=4, dropout=0.0, h
         user_cfg = dict(additive_hidden_size=additive,
                         inputer_config=dict(use_cls_token=False, use_sep_token=False))
         use_item_content = True
+    elif model == 'pool':
+        from model.operators.pooling_operator import PoolingOperator
+        item_cls, user_cls = PoolingOperator, AdaOperator
+        item_cfg = dict(flatten=False, max_pooling=False)
+        user_cfg = dict(additive_hidden_size=additive,
+                        inputer_config=dict(use_cls_token=False, use_sep_token=False))
+        use_item_content = True
     elif model == 'llmid':
         item_cls, user_cls = None, AdaOperator
         item_cfg = None
@@ -95,7 +102,7 @@ def build_reference(world, model='nrms', hidden=256, neg_count=4, dropout=0.0, h
 
     eh = EmbeddingHub(embedding_dim=cfg.item_hidden_size, transformation='auto', transformation_dropout=dropout)
     tmp = None
-    if model in ('nrms', 'naml'):
+    if model != 'llmid':
         if glove_npy is None:
             tmp = tempfile.NamedTemporaryFile(suffix='.npy', delete=False)
             np.save(tmp.name, world.word_table)

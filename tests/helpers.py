@@ -20,6 +20,32 @@ def normwise(a, b) -> float:
     return float(num / den) if den > 0 else float(num)
 
 
+def grad_bound(c, ref_max: float, scale: float, tol: float) -> float:
+    """Allowed max-abs error of one parameter gradient.  Cases flagged `strict_grads` ("hot" states, every gradient a few percent of the
+    largest or more) are held PER TENSOR to tol x that tensor's own max, no floor.  The plain-init cases keep a floor of 5 % of the largest
+    gradient: their additive-attention gradients are ~1e-7 of it, below fp32 resolution of the sums they come from."""
+    if c.get('strict_grads'):
+        return tol * ref_max
+    return tol * max(ref_max, 5e-2 * scale)
+
+
+def check_grads(c, grads: dict, ref_grads: dict, tol: float, golden=None):
+    """grads vs the oracle's full gradients and, when given, the golden file's (full tensors or strided samples)."""
+    scale = max(np.abs(v).max() for v in ref_grads.values())
+    assert set(grads) == set(ref_grads)
+    for k, ref in ref_grads.items():
+        err = np.abs(grads[k] - ref).max()
+        assert err <= grad_bound(c, np.abs(ref).max(), scale, tol), (k, err, np.abs(ref).max(), scale)
+        if golden is None:
+            continue
+        if 'grad/' + k in golden.files:
+            gref = golden['grad/' + k]
+            assert np.abs(grads[k] - gref).max() <= grad_bound(c, np.abs(gref).max(), scale, tol), k
+        else:
+            gmax = float(golden['gradmax/' + k])
+            assert np.abs(cases.sample_strided(grads[k]) - golden['gradsample/' + k]).max() <= grad_bound(c, gmax, scale, tol), k
+
+
 def case_spec(c, world):
     return O.ModelSpec(c['kind'], c['heads'], {world.title_col: world.word_vocab, 'category': 'category'},
                        use_neg_sampling=c.get('use_neg_sampling', True))

@@ -366,6 +366,37 @@ def test_cached_scores(ops, R):
         assert torch.equal(ops.index_rows(dev(I), dev(iid.view(-1, 1))).cpu(), I[iid].view(R, 1, D))   # cache indexing: bit-exact
 
 
+def test_out_of_range_ids_raise_index_error(ops):
+    """The reference raises IndexError on an out-of-range id (aten::embedding / tensor indexing).  Here the kernels never dereference
+    one: the position reads as a zero row / zero score, is counted on the device, and the host raises at its next sync point."""
+    from legommenders_b200 import _lib
+    g = torch.Generator().manual_seed(9)
+    NU, NI, D = 40, 50, 64
+    U, I = torch.randn(NU, D, generator=g), torch.randn(NI, D, generator=g)
+    uid = torch.tensor([0, 39, 40, 3, -1, 7])              # 40 and -1 are outside [0, NU)
+    iid = torch.tensor([1, 49, 2, 50, 4, 123456789012])    # 50 and 123456789012 are outside [0, NI)
+    out = ops.cached_scores(dev(U), dev(I), dev(uid), dev(iid)).cpu()
+    ok = torch.tensor([True, True, False, False, False, False])
+    assert torch.equal(out[~ok], torch.zeros(4))
+    assert rel(out[ok], (U[uid[ok]] * I[iid[ok]]).sum(-1)) <= 2e-6
+    with pytest.raises(IndexError, match='5 id'):
+        _lib.raise_on_bad_ids()
+    _lib.raise_on_bad_ids()                                 # the counter is reset by the raise
+    rows = ops.index_rows(dev(I), dev(torch.tensor([3, 50, 49]))).cpu()
+    assert torch.equal(rows[0], I[3]) and torch.equal(rows[2], I[49]) and torch.equal(rows[1], torch.zeros(D))
+    with pytest.raises(IndexError):
+        _lib.raise_on_bad_ids()
+    table = dev(torch.randn(30, 16, generator=g))
+    ids = dev(torch.tensor([[0, 29, 30, -1], [5, 31, -1, -1]]))
+    pooled = ops.gather_pool(ids, None, table, ops.POOL_SUM).cpu()
+    t = table.cpu()
+    assert torch.allclose(pooled[0], t[0] + t[29]) and torch.allclose(pooled[1], t[5])     # 30 / 31 dropped, -1 is the usual padding
+    emb = ops.gather_add(None, ids, None, table).cpu()
+    assert torch.equal(emb[0, 2], torch.zeros(16)) and torch.equal(emb[0, 1], t[29])
+    with pytest.raises(IndexError, match='4 id'):
+        _lib.raise_on_bad_ids()
+
+
 def test_adam_matches_torch(ops):
     g = torch.Generator().manual_seed(4)
     n = 10007

@@ -27,11 +27,11 @@ def test_forward_backward_matches_reference(name):
     for k, v in r['grads'].items():
         if 'grad/' + k in g.files:
             ref = g['grad/' + k]
-            assert np.abs(v - ref).max() <= TOL * max(np.abs(ref).max(), 5e-2 * scale), k
+            assert np.abs(v - ref).max() <= helpers.grad_bound(c, np.abs(ref).max(), scale, TOL), k
         else:
             assert abs(np.linalg.norm(v.astype(np.float64)) - float(g['gradnorm/' + k])) <= 1e-4 * max(float(g['gradnorm/' + k]), 5e-2 * scale), k
             ref = g['gradsample/' + k]
-            assert np.abs(cases.sample_strided(v) - ref).max() <= TOL * max(float(g['gradmax/' + k]), 5e-2 * scale), k
+            assert np.abs(cases.sample_strided(v) - ref).max() <= helpers.grad_bound(c, float(g['gradmax/' + k]), scale, TOL), k
 
 
 @pytest.mark.parametrize('name', [n for n, c in cases.CASES.items() if c.get('cached_eval')])
