@@ -163,6 +163,33 @@ int lk_tc_gemm(const void* A_hi, const void* A_lo, int64_t lda, int a_mn, const 
                float* C, int64_t ldc, int64_t GM, int64_t GN, int64_t GK, const float* bias, const int64_t* rowmask, int act,
                float drop_p, uint64_t seed, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+/* ---- fused chain of up to three [M,256] x [256,256] contractions (csrc/lk_chain.cu): result g is the A operand of contraction g+1 and
+ *      never leaves the SM (TMEM -> registers -> split-bf16 shared-memory operand).  Replaces, per encoder pass, the three nn.Linear calls
+ *      out_proj -> linear -> additive W1 (model/operators/attention_operator.py:55-58, model/common/attention.py:31-33) and, backward, their
+ *      three input-gradient contractions.  b_mn = 0: weights stored [N, K] (forward, y = x·Wᵀ); b_mn = 1: stored [K, N] (dX = dY·W).
+ *      Per contraction: r = acc + bias + addsrc[m,:]; r = act(r); stored as fp32 / planes; column sums (bias gradients) left as
+ *      [ceil(M/128)*4, 256] partials; rowdot_part[m, 0..3] = four partial sums of r[m,:]·dotvec (additive-attention scores). */
+typedef struct lk_chain_stage {
+  const void* w_hi;           /* bf16 planes of the 256 x 256 weight, pitch ldw */
+  const void* w_lo;
+  int64_t ldw;
+  const float* bias;          /* [256] or null */
+  const float* addsrc;        /* fp32 [M, 256] or null */
+  int act;                    /* 0 none, 1 tanh */
+  float* out_f32;             /* [M, 256] or null */
+  void* out_hi;               /* bf16 [M, ld_planes] or null */
+  void* out_lo;
+  int64_t ld_planes;
+  float* colsum_part;         /* [ceil(M/128)*4, 256] or null */
+  const float* dotvec;        /* [256] or null */
+  float* rowdot_part;         /* [M, 4] */
+} lk_chain_stage;
+int lk_tc_chain(const void* A_hi, const void* A_lo, int64_t lda, int64_t M, const lk_chain_stage* stages, int n_stages, int b_mn,
+                cudaStream_t stream);
+/* debug: with LK_CHAIN_TRACE=1 in the environment CTA 0 of every lk_tc_chain launch stamps clock64 at its pipeline events; this copies the
+ * 4 x 256 stamps of the last launch to the host (synchronises) */
+int lk_tc_chain_trace(long long* host_out, int cap);
+
 /* ---- NAML Conv1d(k,'same') as implicit-im2col GEMM — model/operators/cnn_operator.py:33-38,54-58.
  *      Wr[o, j*Cin+i] = W[o,i,j];  Wd[i, j*Cout+o] = W[o,i,taps-1-j];  rows = N*S token rows */
 int lk_conv1d_fwd(const float* X, const float* Wr, const float* bias, const int64_t* rowmask, float* Y, int64_t rows,
@@ -197,6 +224,13 @@ int lk_additive_pool_fwd(const float* X, const float* Hd, const float* w2, const
 int lk_additive_pool_bwd(const float* X, const float* Hd, const float* w2, const float* alpha, const int32_t* cu, const float* dOut,
                          float* dX, float* dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A, int accumulate_dx,
                          cudaStream_t stream);
+/* the same two kernels over the outputs of lk_tc_chain: rows X as split-bf16 planes (hi + lo) instead of fp32, scores as the chain's four
+ * row-dot partials s_part [rows, 4] instead of Hd·w2 (packed rows only) */
+int lk_additive_pool_fwd_planes(const void* X_hi, const void* X_lo, int64_t ldx, const float* s_part, const int32_t* cu, float* out, float* alpha,
+                                int64_t N, int64_t S, int64_t D, cudaStream_t stream);
+int lk_additive_pool_bwd_planes(const void* X_hi, const void* X_lo, int64_t ldx, const float* Hd, const float* w2, const float* alpha, const int32_t* cu,
+                                const float* dOut, float* dX, float* dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A,
+                                cudaStream_t stream);
 /* PoolingOperator on gathered embeddings — model/operators/pooling_operator.py:46-56 (mode 0 mean, 1 max) */
 int lk_masked_pool(const float* X, const int64_t* mask, float* out, int64_t N, int64_t S, int64_t D, int mode,
                    cudaStream_t stream);

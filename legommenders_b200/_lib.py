@@ -59,6 +59,8 @@ SIGNATURES = {
     'lk_mha_fwd': ('pppppppqqqqfus', 'i'),
     'lk_mha_bwd': ('ppppppppppqqqqfus', 'i'),
     'lk_additive_pool_fwd': ('pppppppqqqqs', 'i'),
+    'lk_additive_pool_fwd_planes': ('ppqpppp' + 'qqqs', 'i'),
+    'lk_additive_pool_bwd_planes': ('ppqpppppppp' + 'qqqqs', 'i'),
     'lk_additive_pool_bwd': ('pppppppppqqqqis', 'i'),
     'lk_masked_pool': ('pppqqqis', 'i'),
     'lk_masked_mean_pool_bwd': ('pppqqqs', 'i'),
@@ -74,6 +76,8 @@ SIGNATURES = {
     'lk_group_metrics': ('pppqpipqpppzs', 'i'),
     'lk_adam_step': ('ppppqffffqfs', 'i'),
     'lk_fill_f32': ('pfqs', 'i'),
+    'lk_tc_chain': ('ppqqpiis', 'i'),
+    'lk_tc_chain_trace': ('pi', 'i'),
     'lk_nrms_arena_bytes': ('qqqqqqqqqq', 'z'),
     'lk_nrms_fwd_bwd': ('ppppqqqpqqqpqppp' + 'qqqqqq' + 'ffu' + 'pppzs', 'i'),
 }

@@ -4,6 +4,8 @@
 //   s[t] = w2 · tanh(W1 x[t] + b1);  a[t] = exp(s[t]) * mask[t];  alpha = a / (sum_t a + eps32);  out = sum_t alpha[t] x[t]
 // The W1 GEMM (+bias+tanh) is done by the linear kernels; this file fuses everything after it.
 // One CTA owns one sequence; masked positions are never loaded.
+#include <cuda_bf16.h>
+
 #include "lk_common.cuh"
 #include "../../include/legommenders_b200.h"
 
@@ -37,7 +39,22 @@ __device__ __forceinline__ float4 group_sum(float4 v, const ColSplit& c, float4*
   return v;
 }
 
-__global__ void __launch_bounds__(AT) additive_pool_fwd_kernel(const float* __restrict__ X, const float* __restrict__ Hd,
+// Rows of X either as fp32 or as the split-bf16 image (hi + lo, 16 mantissa bits) the fused GEMM chain leaves behind (lk_tc_chain):
+// same bytes per element, and the fp32 copy of `lin` then never has to be written at all.
+struct RowSrc {
+  const float* f32;
+  const __nv_bfloat16 *hi, *lo;
+  int64_t ld;                    // pitch of the planes
+};
+__device__ __forceinline__ float4 load4(const RowSrc& X, int64_t row, int D, int c) {
+  if (X.f32) return ldg4(X.f32 + row * D + c);
+  const uint2 h = __ldg(reinterpret_cast<const uint2*>(X.hi + row * X.ld + c));
+  const uint2 l = __ldg(reinterpret_cast<const uint2*>(X.lo + row * X.ld + c));
+  return make_float4(__uint_as_float(h.x << 16) + __uint_as_float(l.x << 16), __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u),
+                     __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16), __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u));
+}
+
+__global__ void __launch_bounds__(AT) additive_pool_fwd_kernel(const RowSrc X, const float* __restrict__ Hd, const float* __restrict__ s_part,
                                                                const float* __restrict__ w2, const int64_t* __restrict__ mask,
                                                                const int* __restrict__ cu, float* __restrict__ out,
                                                                float* __restrict__ alpha, int Smax, int D, int A) {
@@ -49,17 +66,26 @@ __global__ void __launch_bounds__(AT) additive_pool_fwd_kernel(const float* __re
   const int S = cu ? cu[n + 1] - cu[n] : Smax;
   if (cu) mask = nullptr;                               // packed rows are all valid
   const int64_t mrow = n * Smax;
-  X += r0 * D; Hd += r0 * A; alpha += r0;
+  alpha += r0;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int t = w; t < S; t += AT / 32) {
-    bool valid = mask ? mask[mrow + t] > 0 : true;
-    float s = 0.f;
-    if (valid) {
-      const float* h = Hd + t * (int64_t)A;
-      for (int c = lane * 4; c < A; c += 128) s += f4_dot(ldg4(h + c), ldg4(w2 + c));
-      s = warp_sum(s);
+  if (s_part) {      // scores already reduced by the producer of Hd (four partial sums per row, fixed order)
+    for (int t = threadIdx.x; t < S; t += AT) {
+      const bool valid = mask ? mask[mrow + t] > 0 : true;
+      const float4 sp = ldg4(s_part + (r0 + t) * 4);
+      a_s[t] = valid ? expf((sp.x + sp.y) + (sp.z + sp.w)) : 0.f;
     }
-    if (lane == 0) a_s[t] = valid ? expf(s) : 0.f;
+  } else {
+    const float* Hr = Hd + r0 * A;
+    for (int t = w; t < S; t += AT / 32) {
+      bool valid = mask ? mask[mrow + t] > 0 : true;
+      float s = 0.f;
+      if (valid) {
+        const float* h = Hr + t * (int64_t)A;
+        for (int c = lane * 4; c < A; c += 128) s += f4_dot(ldg4(h + c), ldg4(w2 + c));
+        s = warp_sum(s);
+      }
+      if (lane == 0) a_s[t] = valid ? expf(s) : 0.f;
+    }
   }
   __syncthreads();
   float Z = 0.f;
@@ -74,7 +100,7 @@ __global__ void __launch_bounds__(AT) additive_pool_fwd_kernel(const float* __re
 #pragma unroll 4
       for (int t = cs.rg; t < S; t += cs.groups) {
         const float al = a_s[t] * inv;
-        if (al != 0.f) f4_fma(acc, al, ldg4(X + t * (int64_t)D + q * 4));
+        if (al != 0.f) f4_fma(acc, al, load4(X, r0 + t, D, q * 4));
       }
     }
     acc = group_sum(acc, cs, red);
@@ -83,7 +109,7 @@ __global__ void __launch_bounds__(AT) additive_pool_fwd_kernel(const float* __re
 }
 
 // dX[t,:] (+)= alpha[t] * dOut ;  dpre[t,:] = ds[t] * w2 * (1 - h^2) ;  dw2_part[n,:] = sum_t ds[t] * h[t,:]
-__global__ void __launch_bounds__(AT) additive_pool_bwd_kernel(const float* __restrict__ X, const float* __restrict__ Hd,
+__global__ void __launch_bounds__(AT) additive_pool_bwd_kernel(const RowSrc X, const float* __restrict__ Hd,
                                                                const float* __restrict__ w2, const float* __restrict__ alpha,
                                                                const int* __restrict__ cu, const float* __restrict__ dOut,
                                                                float* __restrict__ dX, float* __restrict__ dpre,
@@ -95,7 +121,7 @@ __global__ void __launch_bounds__(AT) additive_pool_bwd_kernel(const float* __re
   const int64_t n = blockIdx.x;
   const int64_t r0 = cu ? cu[n] : n * Smax;
   const int S = cu ? cu[n + 1] - cu[n] : Smax;
-  X += r0 * D; Hd += r0 * A; alpha += r0; dX += r0 * D; dpre += r0 * A;
+  Hd += r0 * A; alpha += r0; dX += r0 * D; dpre += r0 * A;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int t = threadIdx.x; t < S; t += AT) al_s[t] = alpha[t];
   __syncthreads();
@@ -103,8 +129,7 @@ __global__ void __launch_bounds__(AT) additive_pool_bwd_kernel(const float* __re
   for (int t = w; t < S; t += AT / 32) {
     float s = 0.f;
     if (al_s[t] != 0.f) {
-      const float* x = X + t * (int64_t)D;
-      for (int c = lane * 4; c < D; c += 128) s += f4_dot(ldg4(x + c), ldg4(g + c));
+      for (int c = lane * 4; c < D; c += 128) s += f4_dot(load4(X, r0 + t, D, c), ldg4(g + c));
       s = warp_sum(s);
     }
     if (lane == 0) da_s[t] = s;
@@ -202,24 +227,49 @@ using namespace lk;
 
 extern "C" {
 
-int lk_additive_pool_fwd(const float* X, const float* Hd, const float* w2, const int64_t* mask, const int32_t* cu, float* out,
-                         float* alpha, int64_t N, int64_t S, int64_t D, int64_t A, cudaStream_t st) {
+static int pool_fwd(const RowSrc& X, const float* Hd, const float* s_part, const float* w2, const int64_t* mask, const int32_t* cu, float* out,
+                    float* alpha, int64_t N, int64_t S, int64_t D, int64_t A, cudaStream_t st) {
   LK_REQUIRE(D % 4 == 0 && A % 4 == 0, LK_ERR_SHAPE, "lk_additive_pool_fwd: D=%ld, A=%ld must be multiples of 4", (long)D, (long)A);
   LK_REQUIRE(S <= MAXS, LK_ERR_SHAPE, "lk_additive_pool_fwd: S=%ld exceeds %d", (long)S, MAXS);
+  LK_REQUIRE(Hd || s_part, LK_ERR_ARG, "lk_additive_pool_fwd: needs the hidden rows or their w2 row dots");
   if (N == 0) return LK_OK;
-  LK_LAUNCH((additive_pool_fwd_kernel), (unsigned)N, AT, 0, st, X, Hd, w2, mask, cu, out, alpha, (int)S, (int)D, (int)A);
+  LK_LAUNCH((additive_pool_fwd_kernel), (unsigned)N, AT, 0, st, X, Hd, s_part, w2, mask, cu, out, alpha, (int)S, (int)D, (int)A);
   return check_launch("additive_pool_fwd");
 }
-
-int lk_additive_pool_bwd(const float* X, const float* Hd, const float* w2, const float* alpha, const int32_t* cu, const float* dOut,
-                         float* dX, float* dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A, int accumulate_dx,
-                         cudaStream_t st) {
+static int pool_bwd(const RowSrc& X, const float* Hd, const float* w2, const float* alpha, const int32_t* cu, const float* dOut, float* dX,
+                    float* dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A, int accumulate_dx, cudaStream_t st) {
   LK_REQUIRE(D % 4 == 0 && A % 4 == 0, LK_ERR_SHAPE, "lk_additive_pool_bwd: D=%ld, A=%ld must be multiples of 4", (long)D, (long)A);
   LK_REQUIRE(S <= MAXS, LK_ERR_SHAPE, "lk_additive_pool_bwd: S=%ld exceeds %d", (long)S, MAXS);
   if (N == 0) return LK_OK;
   LK_LAUNCH((additive_pool_bwd_kernel), (unsigned)N, AT, 0, st, X, Hd, w2, alpha, cu, dOut, dX, dpre, dw2_part, (int)S, (int)D, (int)A,
                                                       accumulate_dx);
   return check_launch("additive_pool_bwd");
+}
+
+int lk_additive_pool_fwd(const float* X, const float* Hd, const float* w2, const int64_t* mask, const int32_t* cu, float* out,
+                         float* alpha, int64_t N, int64_t S, int64_t D, int64_t A, cudaStream_t st) {
+  return pool_fwd(RowSrc{X, nullptr, nullptr, 0}, Hd, nullptr, w2, mask, cu, out, alpha, N, S, D, A, st);
+}
+
+int lk_additive_pool_bwd(const float* X, const float* Hd, const float* w2, const float* alpha, const int32_t* cu, const float* dOut,
+                         float* dX, float* dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A, int accumulate_dx,
+                         cudaStream_t st) {
+  return pool_bwd(RowSrc{X, nullptr, nullptr, 0}, Hd, w2, alpha, cu, dOut, dX, dpre, dw2_part, N, S, D, A, accumulate_dx, st);
+}
+
+int lk_additive_pool_fwd_planes(const void* X_hi, const void* X_lo, int64_t ldx, const float* s_part, const int32_t* cu, float* out, float* alpha,
+                                int64_t N, int64_t S, int64_t D, cudaStream_t st) {
+  LK_REQUIRE(X_hi && X_lo && ldx % 4 == 0 && ldx >= D && s_part && cu, LK_ERR_ARG, "lk_additive_pool_fwd_planes: packed rows as planes + row-dot partials");
+  return pool_fwd(RowSrc{nullptr, (const __nv_bfloat16*)X_hi, (const __nv_bfloat16*)X_lo, ldx}, nullptr, s_part, nullptr, nullptr, cu, out, alpha, N, S, D, 4,
+                  st);
+}
+
+int lk_additive_pool_bwd_planes(const void* X_hi, const void* X_lo, int64_t ldx, const float* Hd, const float* w2, const float* alpha, const int32_t* cu,
+                                const float* dOut, float* dX, float* dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A,
+                                cudaStream_t st) {
+  LK_REQUIRE(X_hi && X_lo && ldx % 4 == 0 && ldx >= D && cu, LK_ERR_ARG, "lk_additive_pool_bwd_planes: packed rows as planes");
+  return pool_bwd(RowSrc{nullptr, (const __nv_bfloat16*)X_hi, (const __nv_bfloat16*)X_lo, ldx}, Hd, w2, alpha, cu, dOut, dX, dpre, dw2_part, N, S, D, A, 0,
+                  st);
 }
 
 int lk_masked_pool(const float* X, const int64_t* mask, float* out, int64_t N, int64_t S, int64_t D, int mode, cudaStream_t st) {

@@ -153,7 +153,8 @@ struct EncWeights {   // one AttentionOperator
 struct EncPlanes { PlaneBuf in_w, out_w, lin_w, w1; };
 struct EncSaved {
   PlaneBuf xp, ctxp, outp, linp;
-  float *qkv, *ctx, *lse, *lin, *hid, *alpha, *rep;
+  float *qkv, *ctx, *lse, *lin, *hid, *alpha, *rep, *spart;
+  bool chained;        // out -> linear -> W1 ran as ONE fused kernel (lk_tc_chain): no fp32 `lin`, scores as row-dot partials
   const int32_t* cu;
   int64_t T, N, S;
   uint64_t seed;
@@ -178,8 +179,21 @@ static EncPlanes weight_planes(Ctx& c, SplitQueue& q, const EncWeights& w, int64
 
 // attention_operator.py:46-59 over packed rows: s.xp = planes of the input rows [T,D].  Tensors that only feed the next
 // contraction (ctx, out) leave their producer as split-bf16 planes; fp32 copies exist only where a SIMT kernel reads them.
+// The fused chain kernel is specialised to 256-wide contractions (hidden_size = additive_hidden_size = 256, the shipped nrms.yaml);
+// other widths, and LK_CHAIN=0, take the GEMM-by-GEMM path.
+static bool use_chain(int64_t D, int64_t A) {
+  static const bool on = [] { const char* e = getenv("LK_CHAIN"); return !(e && e[0] == '0'); }();
+  return on && D == 256 && A == 256;
+}
+static lk_chain_stage chain_stage(const PlaneBuf& W) {
+  lk_chain_stage st = {};
+  st.w_hi = W.hi; st.w_lo = W.lo; st.ldw = W.ld;
+  return st;
+}
+
 static void enc_fwd(Ctx& c, EncSaved& s, const EncWeights& w, const EncPlanes& wp, int64_t D, int64_t H, int64_t A, float drop_attn) {
   const int64_t T = s.T, N = s.N;
+  s.chained = use_chain(D, A);
   s.qkv = c.a.f32(T * 3 * D);
   lk_gemm_epilogue ep = {};
   ep.bias = w.in_b;
@@ -188,6 +202,24 @@ static void enc_fwd(Ctx& c, EncSaved& s, const EncWeights& w, const EncPlanes& w
   s.ctxp = alloc_planes(c, T, D);
   s.lse = c.a.f32(T * H);
   STEP(lk_mha_fwd(s.qkv, nullptr, s.cu, s.ctx, s.ctxp.hi, s.ctxp.lo, s.lse, N, s.S, D, H, drop_attn, s.seed, c.st));
+  if (s.chained) {
+    s.outp = alloc_planes(c, T, D);
+    s.linp = alloc_planes(c, T, D);
+    s.hid = c.a.f32(T * A);
+    s.spart = c.a.f32(T * 4);
+    s.alpha = c.a.f32(T);
+    s.rep = c.a.f32(N * D);
+    s.lin = nullptr;
+    lk_chain_stage st[3] = {chain_stage(wp.out_w), chain_stage(wp.lin_w), chain_stage(wp.w1)};
+    st[0].bias = w.out_b; st[0].out_hi = s.outp.hi; st[0].out_lo = s.outp.lo; st[0].ld_planes = s.outp.ld;
+    st[1].bias = w.lin_b; st[1].out_hi = s.linp.hi; st[1].out_lo = s.linp.lo; st[1].ld_planes = s.linp.ld;
+    st[2].bias = w.b1; st[2].act = 1; st[2].out_f32 = s.hid; st[2].dotvec = w.w2; st[2].rowdot_part = s.spart;
+    char label[40];
+    snprintf(label, sizeof(label), "chain_fwd %ldx256x256 x3", (long)T);
+    STEP_L(label, lk_tc_chain(s.ctxp.hi, s.ctxp.lo, s.ctxp.ld, T, st, 3, 0, c.st), 3 * 2.0 * T * D * D);
+    STEP(lk_additive_pool_fwd_planes(s.linp.hi, s.linp.lo, s.linp.ld, s.spart, s.cu, s.rep, s.alpha, N, s.S, D, c.st));
+    return;
+  }
   s.outp = alloc_planes(c, T, D);
   gemm(c, "out", s.ctxp, wp.out_w, 0, nullptr, T, D, D, ep_planes(s.outp, w.out_b));
   s.lin = c.a.f32(T * D);
@@ -221,12 +253,38 @@ static void enc_bwd(Ctx& c, const EncSaved& s, const EncWeights& w, const EncPla
   const size_t mark = c.a.off;
   float* dlin = c.a.f32(T * D);
   float* dpre = c.a.f32(T * A);
-  STEP(lk_additive_pool_bwd(s.lin, s.hid, w.w2, s.alpha, s.cu, drep, dlin, dpre, q.dw2p, N, s.S, D, A, 0, c.st));
+  if (s.chained) STEP(lk_additive_pool_bwd_planes(s.linp.hi, s.linp.lo, s.linp.ld, s.hid, w.w2, s.alpha, s.cu, drep, dlin, dpre, q.dw2p, N, s.S, D, A, c.st));
+  else STEP(lk_additive_pool_bwd(s.lin, s.hid, w.w2, s.alpha, s.cu, drep, dlin, dpre, q.dw2p, N, s.S, D, A, 0, c.st));
   defer_colsum(c, q.dw2p, w.g_w2, N, A, A);
   PlaneBuf dprep = alloc_planes(c, T, A);
   STEP(lk_split_bf16_partial(dpre, T, A, A, dprep.hi, dprep.lo, dprep.ld, q.b1p, c.st));
   defer_colsum(c, q.b1p, w.g_b1, split_colsum_parts(T), A, A);
   gemm_wgrad(c, dprep, s.linp, w.g_w1, T, A, D, side);
+  if (s.chained) {
+    // dpre -> dlin (= alpha*drep + dpre·W1) -> dout -> dctx in one kernel; the two intermediate tiles leave only as the planes the weight
+    // gradients contract and as column-sum partials (bias gradients)
+    PlaneBuf dlinp = alloc_planes(c, T, D), doutp = alloc_planes(c, T, D);
+    float* dctx = c.a.f32(T * D);
+    lk_chain_stage st[3] = {chain_stage(wp.w1), chain_stage(wp.lin_w), chain_stage(wp.out_w)};
+    st[0].addsrc = dlin; st[0].out_hi = dlinp.hi; st[0].out_lo = dlinp.lo; st[0].ld_planes = dlinp.ld; st[0].colsum_part = q.linbp;
+    st[1].out_hi = doutp.hi; st[1].out_lo = doutp.lo; st[1].ld_planes = doutp.ld; st[1].colsum_part = q.outbp;
+    st[2].out_f32 = dctx;
+    char label[40];
+    snprintf(label, sizeof(label), "chain_bwd %ldx256x256 x3", (long)T);
+    STEP_L(label, lk_tc_chain(dprep.hi, dprep.lo, dprep.ld, T, st, 3, 1, c.st), 3 * 2.0 * T * D * D);
+    defer_colsum(c, q.linbp, w.g_lin_b, gemm_colsum_parts(T), D, D);
+    defer_colsum(c, q.outbp, w.g_out_b, gemm_colsum_parts(T), D, D);
+    gemm_wgrad(c, dlinp, s.outp, w.g_lin_w, T, D, D, side);
+    gemm_wgrad(c, doutp, s.ctxp, w.g_out_w, T, D, D, side);
+    PlaneBuf dqkvp = alloc_planes(c, T, 3 * D);
+    STEP(lk_mha_bwd(s.qkv, nullptr, s.cu, s.ctx, s.lse, dctx, nullptr, dqkvp.hi, dqkvp.lo, q.binp, N, s.S, D, H, drop_attn, s.seed, c.st));
+    defer_colsum(c, q.binp, w.g_in_b, N, 3 * D, 3 * D);
+    gemm_wgrad(c, dqkvp, s.xp, w.g_in_w, T, 3 * D, D, side);
+    lk_gemm_epilogue ep0 = {};
+    if (dX) gemm(c, "dx", dqkvp, wp.in_w, 1, dX, T, D, 3 * D, ep0);
+    if (!side) c.a.off = mark;
+    return;
+  }
   // dlin = alpha*drep (already in dlin) + dpre·W1 -> only its planes and column sums are needed downstream
   PlaneBuf dlinp = alloc_planes(c, T, D);
   lk_gemm_epilogue ep = ep_planes(dlinp, nullptr, q.linbp);

@@ -149,6 +149,45 @@ class GemmEpilogue(ctypes.Structure):
                 ('colsum_part', ctypes.c_void_p)]
 
 
+class ChainStage(ctypes.Structure):
+    """struct lk_chain_stage (include/legommenders_b200.h)"""
+    _fields_ = [('w_hi', ctypes.c_void_p), ('w_lo', ctypes.c_void_p), ('ldw', ctypes.c_int64), ('bias', ctypes.c_void_p),
+                ('addsrc', ctypes.c_void_p), ('act', ctypes.c_int), ('out_f32', ctypes.c_void_p), ('out_hi', ctypes.c_void_p),
+                ('out_lo', ctypes.c_void_p), ('ld_planes', ctypes.c_int64), ('colsum_part', ctypes.c_void_p), ('dotvec', ctypes.c_void_p),
+                ('rowdot_part', ctypes.c_void_p)]
+
+
+def tc_chain(A: Planes, stages, b_mn=False):
+    """lk_tc_chain: up to three chained [M,256]x[256,256] contractions with the intermediates kept on chip.
+    stages: list of dicts(w=Planes, bias=, addsrc=, act=, want_f32=, want_planes=, want_colsum=, dotvec=).
+    Returns per stage a dict with the requested outputs (f32, planes, colsum_part [tiles*4,256], rowdot_part [M,4])."""
+    M = A.rows
+    dev = A.hi.device
+    arr = (ChainStage * len(stages))()
+    outs = []
+    for a, s in zip(arr, stages):
+        o = {}
+        w = s['w']
+        a.w_hi, a.w_lo, a.ldw = ptr(w.hi), ptr(w.lo), w.ld
+        a.bias, a.addsrc, a.act = ptr(s.get('bias')), ptr(s.get('addsrc')), int(s.get('act', 0))
+        if s.get('want_f32'):
+            o['f32'] = torch.empty((M, 256), dtype=torch.float32, device=dev)
+            a.out_f32 = ptr(o['f32'])
+        if s.get('want_planes'):
+            o['planes'] = Planes(torch.empty((M, 256), dtype=torch.bfloat16, device=dev), torch.empty((M, 256), dtype=torch.bfloat16, device=dev),
+                                 M, 256, 256)
+            a.out_hi, a.out_lo, a.ld_planes = ptr(o['planes'].hi), ptr(o['planes'].lo), 256
+        if s.get('want_colsum'):
+            o['colsum_part'] = torch.zeros(((M + 127) // 128 * 4, 256), dtype=torch.float32, device=dev)
+            a.colsum_part = ptr(o['colsum_part'])
+        if s.get('dotvec') is not None:
+            o['rowdot_part'] = torch.zeros((M, 4), dtype=torch.float32, device=dev)
+            a.dotvec, a.rowdot_part = ptr(s['dotvec']), ptr(o['rowdot_part'])
+        outs.append(o)
+    call('lk_tc_chain', ptr(A.hi), ptr(A.lo), A.ld, M, ctypes.addressof(arr), len(stages), int(b_mn))
+    return outs
+
+
 def tc_gemm_ex(A: Planes, B: Planes, GM, GN, GK, b_mn=False, a_mn=False, out=None, store_c=True, bias=None, rowmask=None,
                rowmask_is_ids=False, act=0, drop_p=0.0, seed=0, accumulate=False, add0=None, add1=None, want_planes=False,
                want_colsum=False):

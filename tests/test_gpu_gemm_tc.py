@@ -193,3 +193,51 @@ def test_deferred_column_sums(ops):
     acc = outs[3].clone()
     ops.colsum_finish_multi([(wide[:, :256], acc, True)])
     assert torch.allclose(acc, 2 * outs[3], rtol=1e-6)
+
+
+@pytest.mark.parametrize('M', [128, 100, 300, 1748, 20000, 42587])
+@pytest.mark.parametrize('b_mn', [False, True])
+def test_tc_chain(ops, M, b_mn):
+    """lk_tc_chain: three chained 256x256 contractions with on-chip intermediates, every fused output against fp64:
+    forward flavour (bias, bias, bias+tanh+row dot) with K-major weights; backward flavour (addend + column sums) with MN-major weights."""
+    g = torch.Generator().manual_seed(M + int(b_mn))
+    D = 256
+    a = torch.randn(M, D, generator=g)
+    ws = [torch.randn(D, D, generator=g) / D ** 0.5 for _ in range(3)]
+    bs = [torch.randn(D, generator=g) * 0.1 for _ in range(3)]
+    add = torch.randn(M, D, generator=g)
+    dot = torch.randn(D, generator=g)
+    ad, wd = a.double(), [w.double() for w in ws]
+    mm = (lambda x, w: x @ w) if b_mn else (lambda x, w: x @ w.t())
+    A = ops.split_planes(a.cuda())
+    W = [ops.split_planes(w.cuda()) for w in ws]
+    if not b_mn:
+        r0 = mm(ad, wd[0]) + bs[0].double()
+        r1 = mm(r0, wd[1]) + bs[1].double()
+        r2 = torch.tanh(mm(r1, wd[2]) + bs[2].double())
+        outs = ops.tc_chain(A, [dict(w=W[0], bias=bs[0].cuda(), want_planes=True),
+                                dict(w=W[1], bias=bs[1].cuda(), want_f32=True, want_planes=True),
+                                dict(w=W[2], bias=bs[2].cuda(), act=1, want_f32=True, dotvec=dot.cuda())], b_mn=False)
+        assert rel(outs[0]['planes'].hi.float() + outs[0]['planes'].lo.float(), r0) <= 2e-5
+        assert rel(outs[1]['f32'], r1) <= 2e-5
+        assert rel(outs[1]['planes'].hi.float() + outs[1]['planes'].lo.float(), r1) <= 2e-5
+        assert rel(outs[2]["f32"], r2) <= 6e-5
+        assert rel(outs[2]["rowdot_part"].double().sum(1), r2 @ dot.double()) <= 6e-5
+    else:
+        r0 = mm(ad, wd[0]) + add.double()
+        r1 = mm(r0, wd[1])
+        r2 = mm(r1, wd[2])
+        outs = ops.tc_chain(A, [dict(w=W[0], addsrc=add.cuda(), want_planes=True, want_colsum=True),
+                                dict(w=W[1], want_planes=True, want_colsum=True),
+                                dict(w=W[2], want_f32=True)], b_mn=True)
+        assert rel(outs[0]['planes'].hi.float() + outs[0]['planes'].lo.float(), r0) <= 2e-5
+        assert rel(outs[1]['planes'].hi.float() + outs[1]['planes'].lo.float(), r1) <= 2e-5
+        assert rel(outs[2]["f32"], r2) <= 6e-5
+        for o, r in ((outs[0], r0), (outs[1], r1)):
+            cs = o['colsum_part'].double().sum(0).cpu()
+            assert (cs - r.sum(0)).abs().max().item() <= 2e-5 * r.abs().sum(0).max().item()
+    # one- and two-contraction chains run through the same kernel
+    one = ops.tc_chain(A, [dict(w=W[0], want_f32=True) if b_mn else dict(w=W[0], bias=bs[0].cuda(), want_f32=True)], b_mn=b_mn)
+    assert rel(one[0]['f32'], mm(ad, wd[0]) + (0 if b_mn else bs[0].double())) <= 2e-5
+    two = ops.tc_chain(A, [dict(w=W[0]), dict(w=W[1], want_f32=True)], b_mn=b_mn)
+    assert rel(two[1]['f32'], mm(mm(ad, wd[0]), wd[1])) <= 2e-5

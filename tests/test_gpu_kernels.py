@@ -379,7 +379,7 @@ def test_out_of_range_ids_raise_index_error(ops):
     ok = torch.tensor([True, True, False, False, False, False])
     assert torch.equal(out[~ok], torch.zeros(4))
     assert rel(out[ok], (U[uid[ok]] * I[iid[ok]]).sum(-1)) <= 2e-6
-    with pytest.raises(IndexError, match='5 id'):
+    with pytest.raises(IndexError, match='4 id'):
         _lib.raise_on_bad_ids()
     _lib.raise_on_bad_ids()                                 # the counter is reset by the raise
     rows = ops.index_rows(dev(I), dev(torch.tensor([3, 50, 49]))).cpu()

@@ -200,6 +200,28 @@ def test_native_step_driver_parity(name):
     assert all(np.isfinite(losses)) and np.mean(losses[-5:]) < np.mean(losses[:5])
 
 
+def test_exact_fp32_mode_gradients(monkeypatch):
+    """With the tensor-core contractions switched off (ops.USE_TC = False: the exact-fp32 SIMT GEMMs) every gradient of the hot state agrees
+    with the fp64 oracle to 2e-5 of its own max — the split-bf16 planes, not the kernels' logic, set the 1e-4..3e-4 of the default mode."""
+    from legommenders_b200 import Env, ops
+    monkeypatch.setattr(ops, 'USE_TC', False)
+    c = cases.CASES['nrms_small_hot']
+    g = cases.load('nrms_small_hot')
+    world, llm = cases.make_world(c)
+    model, _, _ = build(c, world, llm)
+    batch = cases.unflatten_batch(g)
+    ref = helpers.oracle_run(c, world, llm, batch, dtype=torch.float64)
+    Env.train()
+    model.train()
+    loss = model(batch=copy.deepcopy(batch))
+    loss.backward()
+    assert abs(loss.item() - ref['loss']) <= 2e-6 * abs(ref['loss'])
+    for n, p in model.named_parameters():
+        if p.requires_grad:
+            r = ref['grads'][n]
+            assert np.abs(p.grad.cpu().numpy() - r).max() <= 2e-5 * np.abs(r).max(), n
+
+
 # ------------------------------------------------------------------------------------------------ evaluation on the device
 @pytest.mark.parametrize('R,G,ties', [(2000, 60, True), (5000, 400, False), (64, 1, True), (70000, 2500, True)])
 def test_group_metrics_kernel_matches_oracle(R, G, ties):
