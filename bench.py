@@ -252,19 +252,67 @@ def main():
             ms = t.item()
         return ms, w0, w1, dict(median=per[len(per) // 2], min=per[0], max=per[-1])
 
+    # The product's data path (batching.DeviceResampler): a step starts from B impression indices; negative sampling, history
+    # concatenation and offsets are ONE kernel over device-resident tables (lk_resample_batch, enqueued one step ahead on a side stream so
+    # that the four integers the host needs to size the step are back before it starts), token ids are expanded by lk_pack_item_tokens.
+    #   value : indices of all timed steps resident in HBM before the clock starts; nothing is memoised — sampling and packing run every step
+    #   e2e   : the same loop with the indices in pinned host memory (H2D of 8 B per impression inside the timed region, through the public
+    #           DeviceResampler.submit / take + NativeNRMSStep.step calls) and a device->host read of the loss every step
     sampler = ClockSampler(local_rank) if rank == 0 else None   # started before the warm-up: its start-up is not timed
     for i in range(max(args.warmup, 3, POOL)):
         step(devb[i % POOL])
-    l0 = _lib.load().lk_launch_count()
-    ms, w0, w1, per_step = timed(lambda i: step(devb[i % POOL]), args.steps)
-    launches = int(_lib.load().lk_launch_count() - l0)
+    n_loop = args.steps + 4
+    rows_host = rng.integers(0, world.n_train, size=(n_loop, args.batch))
+    if native is not None:
+        from legommenders_b200.batching import DeviceResampler
+        dres = DeviceResampler(resampler, world, dev, neg_count=NEG, seed=3000 + rank, max_batch=args.batch)
+        rows_dev = torch.from_numpy(rows_host).to(dev)
+
+        def resident_step(i):
+            dres.submit(rows_dev[i + 1])
+            return step(dres.take())
+
+        loss_pin = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_ev = [torch.cuda.Event() for _ in range(2)]
+        losses_read = []
+
+        def e2e_step(i):
+            # every step's loss crosses to the host inside the timed region; the host READS it one step later (pinned buffer + event), so
+            # that the read does not drain the device between steps — what a training loop that logs its loss does
+            dres.submit(rows_host[i + 1])
+            loss = step(dres.take())
+            loss_pin[i & 1].copy_(loss, non_blocking=True)
+            loss_ev[i & 1].record()
+            if i > 0:
+                loss_ev[(i - 1) & 1].synchronize()
+                losses_read.append(float(loss_pin[(i - 1) & 1]))
+            return loss
+
+        for fn, src in ((resident_step, rows_dev), (e2e_step, rows_host)):       # warm both variants (allocator, pinned buffers)
+            dres.submit(src[0])
+            for i in range(3):
+                fn(i)
+            dres.take()
+        dres.submit(rows_dev[0])
+        l0 = _lib.load().lk_launch_count()
+        ms, w0, w1, per_step = timed(resident_step, args.steps)
+        launches = int(_lib.load().lk_launch_count() - l0)
+        dres.take()
+        dres.submit(rows_host[0])
+        del losses_read[:]
+        ms_e2e, _, _, per_step_e2e = timed(e2e_step, args.steps)       # timed() synchronises at the end: the last loss has landed too
+        losses_read.append(float(loss_pin[(args.steps - 1) & 1]))
+        assert len(losses_read) == args.steps and all(np.isfinite(losses_read)), losses_read
+        dres.take()
+        h2d_ids, d2h_e2e = args.batch * 8, 4 + 16        # indices up; loss + the resampler's four step-size integers down
+    else:
+        l0 = _lib.load().lk_launch_count()
+        ms, w0, w1, per_step = timed(lambda i: step(devb[i % POOL]), args.steps)
+        launches = int(_lib.load().lk_launch_count() - l0)
     clocks = sampler.stop(w0, w1) if sampler else None
     value = world_size * args.batch * args.steps / (ms / 1000.0)
 
-    # e2e: host (pinned) batch -> H2D -> step -> D2H loss read, every step.
-    #   wire : the reference's collated batch (int64 [B,55,S] trees, 3.7 MB) copied up, packed on the device
-    #   ids  : the product's data path (batching.DeviceBatcher): item-id list + offsets copied up (~50 KB), token ids expanded on the
-    #          device from the resident per-item token tables; same packed rows, bit for bit
+    # the reference's wire format for comparison: the collated batch (int64 [B,55,S] trees, 3.7 MB) copied up and packed on the device
     def e2e_wire_step(i):
         b = tree_to_device(host[i % POOL], dev, non_blocking=True)
         return step(b).item()
@@ -274,20 +322,8 @@ def main():
     ms_wire, _, _, per_step_wire = timed(e2e_wire_step, args.steps)
     e2e_wire = dict(value=world_size * args.batch * args.steps / (ms_wire / 1000.0), unit='impressions/s', h2d_bytes_per_step=h2d,
                     d2h_bytes_per_step=4, ms_per_step=ms_wire / args.steps, ms_per_step_dist=per_step_wire)
-    if native is not None:
-        from legommenders_b200.batching import DeviceBatcher
-        dbat = DeviceBatcher(resampler, world, dev, neg_count=NEG, seed=2000 + rank)
-        hostb = [dbat.host_batch(rng.integers(0, world.n_train, size=args.batch)) for _ in range(POOL)]
-        h2d_ids = DeviceBatcher.h2d_bytes(hostb[0])
-
-        def e2e_step(i):
-            return step(dbat.to_device(hostb[i % POOL])).item()
-
-        for i in range(3):
-            e2e_step(i)
-        ms_e2e, _, _, per_step_e2e = timed(e2e_step, args.steps)
-    else:
-        ms_e2e, per_step_e2e, h2d_ids = ms_wire, per_step_wire, h2d
+    if native is None:
+        ms_e2e, per_step_e2e, h2d_ids, d2h_e2e = ms_wire, per_step_wire, h2d, 4
     e2e_value = world_size * args.batch * args.steps / (ms_e2e / 1000.0)
 
     # per-entry-point device time over two extra steps (CUDA events around every C-ABI call on the launching stream)
@@ -321,11 +357,12 @@ def main():
     line = dict(metric='NRMS train impressions/s', value=value, unit='impressions/s', n_gpus=world_size, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms / args.steps, ms_per_step_dist=per_step, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', impl='b200',
-                config=dict(base_cfg, l2='per-step working set (~1 GB of activations) exceeds the 126 MB L2; batches rotate through a pool of 8'),
+                config=dict(base_cfg, l2='per-step working set (~1 GB of activations) exceeds the 126 MB L2; every step samples a fresh batch (nothing memoised)',
+                            inputs='impression indices resident in HBM; negative sampling, history concat and token packing run inside every timed step'),
                 clocks=clocks,
-                e2e=dict(value=e2e_value, unit='impressions/s', h2d_bytes_per_step=h2d_ids, d2h_bytes_per_step=4,
+                e2e=dict(value=e2e_value, unit='impressions/s', h2d_bytes_per_step=h2d_ids, d2h_bytes_per_step=d2h_e2e,
                          ms_per_step=ms_e2e / args.steps, ms_per_step_dist=per_step_e2e,
-                         path='id-only host batch -> H2D -> lk_pack_item_tokens -> lk_nrms_fwd_bwd -> allreduce -> Adam -> D2H loss'
+                         path='impression indices (pinned host) -> H2D -> lk_resample_batch (side stream, one step ahead) -> lk_pack_item_tokens -> lk_nrms_fwd_bwd -> allreduce -> Adam -> D2H loss (async copy every step, read by the host one step later)'
                          if native is not None else 'wire-format batch'),
                 e2e_wire_format=e2e_wire,
                 gpu_launches=launches, roofline=roof, kernel_ms_share=shares)

@@ -65,6 +65,22 @@ int lk_scatter_add_sorted(const int64_t* ids, const int64_t* mask, const float* 
 int lk_pack_item_tokens(const int64_t* const* tables, int64_t* const* outs, int ncols, const int64_t* items, const int32_t* cu, int64_t n,
                         int64_t S, cudaStream_t stream);
 
+/* ---- device-side Resampler (csrc/lk_resample.cu) — loader/resampler.py:139-259 taken to the device: from B impression rows to the id lists
+ *      and offsets of a packed training batch in ONE launch.  Negatives = min(K, len) distinct positions of the user's negative list in random
+ *      order + uniform item ids (Philox4x32-10 keyed by (seed, impression row)); histories are the users' valid clicks (padding is never
+ *      materialised).  All tables are device arrays: imp_user / imp_pos [n_imps], CSR negatives (neg_off [n_users+1], neg_items), CSR histories
+ *      (hist_off, hist_items), item_len [n_items] = valid tokens per item.  Outputs: items [n] (B*(K+1) candidates, then history items user by
+ *      user), cu_items [n+1], cu_users [B+1], user_ids [B], meta[4] = {T token rows, n, longest item, longest history} (meta[0] = -1 and
+ *      meta[1] = n when items_cap is too small). */
+#define LK_MAX_NEG 16
+int lk_resample_batch(const int64_t* rows, int64_t B, int K, uint64_t seed, const int64_t* imp_user, const int64_t* imp_pos,
+                      const int64_t* neg_off, const int64_t* neg_items, const int64_t* hist_off, const int64_t* hist_items,
+                      const int32_t* item_len, int64_t n_items, int64_t n_imps, int64_t n_users, int64_t* items, int32_t* cu_items,
+                      int32_t* cu_users, int64_t* user_ids, int32_t* meta, int64_t items_cap, cudaStream_t stream);
+/* HOST restatement of one impression's candidate draw (the same inline function the kernel executes; no device needed): cand_out[K+1] */
+int lk_resample_reference(uint64_t seed, int64_t row, int64_t pos, const int64_t* negs, int64_t n_negs, int K, int64_t n_items,
+                          int64_t* cand_out);
+
 /* backward of the whole ConcatInputer embedding stage (concat_inputer.py:105-113 + embedding_hub.py:95-96) in one pass over
  * dx [T,D]:  dP = dx·dropout(seed)·(title id > -1) as split-bf16 planes [T, ld] (operand of the projection weight gradient),
  * g_bias [D] = column sums of dP, g_cat [n_cats, D] / g_special [n_special, D] = per-id sums of dx.  Deterministic.

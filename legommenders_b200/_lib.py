@@ -76,6 +76,8 @@ SIGNATURES = {
     'lk_group_metrics': ('pppqpipqpppzs', 'i'),
     'lk_adam_step': ('ppppqffffqfs', 'i'),
     'lk_fill_f32': ('pfqs', 'i'),
+    'lk_resample_batch': ('pqiuppppppp' + 'qqq' + 'ppppp' + 'qs', 'i'),
+    'lk_resample_reference': ('uqqpqiqp', 'i'),
     'lk_tc_chain': ('ppqqpiis', 'i'),
     'lk_tc_chain_trace': ('pi', 'i'),
     'lk_nrms_arena_bytes': ('qqqqqqqqqq', 'z'),

@@ -53,10 +53,10 @@ class BatchBuilder:
                 cand[b, 1 + k:] = self.rng.integers(0, self.world.n_items, size=K - k)
         return cand
 
-    def train_batch(self, rows: np.ndarray) -> dict:
-        """rows: indices into the world's training impressions."""
+    def train_batch(self, rows: np.ndarray, cand: np.ndarray = None) -> dict:
+        """rows: indices into the world's training impressions; cand [B, 1+K]: explicit candidate ids (default: sampled here)."""
         users, pos = self.world.train_users[rows], self.world.train_pos[rows]
-        cand = torch.from_numpy(self.sample_candidates(users, pos))
+        cand = torch.from_numpy(self.sample_candidates(users, pos) if cand is None else np.asarray(cand, dtype=np.int64))
         ut = torch.from_numpy(users)
         pin = (lambda t: t.pin_memory()) if self.pin else (lambda t: t)
         batch = OrderedDict()
@@ -142,3 +142,143 @@ class DeviceBatcher:
     @staticmethod
     def h2d_bytes(hb: dict) -> int:
         return sum(hb[k].numel() * hb[k].element_size() for k in ('items', 'cu', 'cu_users'))
+
+
+class DeviceResampler:
+    """The Resampler on the device, one step ahead (loader/resampler.py:139-259).
+
+    Everything the reference's per-sample Python does for a training batch — negative sampling from the user's true-negative list plus
+    uniform ids, candidate order [pos, negs...], the user's click history, offsets — is ONE kernel (`lk_resample_batch`) over device-resident
+    tables; the only per-step host->device traffic is the B impression indices (8 B each).  The step needs four integers on the host to size
+    its launches (token rows T, items n, longest item, longest history); they come back through pinned memory while the PREVIOUS step is still
+    running: `submit(rows)` enqueues on a side stream, `take()` returns the oldest submitted batch (carrying its packed rows, as
+    DeviceBatcher.to_device does).  Draws are Philox4x32-10 keyed by (seed, impression row): a batch is a pure function of (rows, seed).
+    """
+
+    def __init__(self, resampler, world, device, neg_count: int = 4, seed: int = 0, max_batch: int = 512, depth: int = 3):
+        import ctypes
+        from ._lib import load
+        self.world, self.device, self.K, self.seed = world, device, neg_count, int(seed)
+        trees = stack_trees(resampler.item_cache)
+        self.cols = list(trees['input_ids'].keys())
+        mask = trees['attention_mask']
+        if isinstance(mask, dict):
+            raise ValueError('DeviceResampler needs a single-sequence inputer (ConcatInputer)')
+        self.S = mask.shape[1]
+        dev = device
+        self.tables = [trees['input_ids'][c].to(dev).contiguous() for c in self.cols]
+        self.item_len = mask.sum(dim=1).to(torch.int32).to(dev)
+        self.n_items = int(self.item_len.numel())
+
+        def csr(lists):
+            off = np.zeros(len(lists) + 1, dtype=np.int64)
+            np.cumsum([len(x) for x in lists], out=off[1:])
+            flat = np.concatenate([np.asarray(x, dtype=np.int64) for x in lists]) if off[-1] else np.zeros(0, dtype=np.int64)
+            return torch.from_numpy(off).to(dev), torch.from_numpy(np.ascontiguousarray(flat)).to(dev)
+
+        self.neg_off, self.neg_items = csr(world.negs)
+        self.hist_off, self.hist_items = csr(world.histories)
+        self.imp_user = torch.from_numpy(world.train_users).to(dev)
+        self.imp_pos = torch.from_numpy(world.train_pos).to(dev)
+        self.n_users, self.n_imps = len(world.histories), len(world.train_users)
+        self.max_batch = max_batch
+        cap = max_batch * (neg_count + 1 + world.hist_len)
+        self.cap = cap
+        self.stream = torch.cuda.Stream(device=dev)
+        self.slots = []
+        for _ in range(depth):
+            self.slots.append(dict(rows_host=torch.empty(max_batch, dtype=torch.int64).pin_memory(),
+                                   rows=torch.empty(max_batch, dtype=torch.int64, device=dev),
+                                   items=torch.empty(cap, dtype=torch.int64, device=dev),
+                                   cu=torch.empty(cap + 1, dtype=torch.int32, device=dev),
+                                   cu_users=torch.empty(max_batch + 1, dtype=torch.int32, device=dev),
+                                   user_ids=torch.empty(max_batch, dtype=torch.int64, device=dev),
+                                   meta=torch.zeros(4, dtype=torch.int32, device=dev),
+                                   meta_host=torch.zeros(4, dtype=torch.int32).pin_memory(),
+                                   ready=torch.cuda.Event(), consumed=torch.cuda.Event(), B=0, busy=False))
+        self._head = self._tail = 0
+        self._last = None
+        self._lib = load()
+        self._tp = (ctypes.c_void_p * len(self.cols))(*[t.data_ptr() for t in self.tables])
+
+    def submit(self, rows):
+        """Enqueue the batch of impression `rows` on the side stream (returns immediately).  rows: numpy / host tensor (copied up through
+        pinned memory, 8 B per impression) or an int64 CUDA tensor already resident on the device."""
+        from ._lib import call, id_violation_counter
+        slot = self.slots[self._head % len(self.slots)]
+        if slot['busy']:
+            raise RuntimeError('DeviceResampler: more batches in flight than slots (take() the oldest first)')
+        B = len(rows)
+        if B > self.max_batch:
+            raise ValueError(f'batch of {B} impressions exceeds max_batch={self.max_batch}')
+        resident = isinstance(rows, torch.Tensor) and rows.is_cuda
+        if not resident:
+            slot['rows_host'][:B] = torch.as_tensor(np.asarray(rows), dtype=torch.int64)
+        id_violation_counter(self.device)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(slot['consumed'])            # the step that used this slot's buffers has been enqueued and will finish first
+            if resident:
+                src = rows                                       # must be complete already (the caller's responsibility, as for any input)
+            else:
+                slot['rows'][:B].copy_(slot['rows_host'][:B], non_blocking=True)
+                src = slot['rows']
+            slot['src'] = src                                    # keep a resident rows tensor alive until the kernel has run
+            call('lk_resample_batch', src.data_ptr(), B, self.K, self.seed, self.imp_user.data_ptr(), self.imp_pos.data_ptr(),
+                 self.neg_off.data_ptr(), self.neg_items.data_ptr(), self.hist_off.data_ptr(), self.hist_items.data_ptr(),
+                 self.item_len.data_ptr(), self.n_items, self.n_imps, self.n_users, slot['items'].data_ptr(), slot['cu'].data_ptr(),
+                 slot['cu_users'].data_ptr(), slot['user_ids'].data_ptr(), slot['meta'].data_ptr(), self.cap)
+            slot['meta_host'].copy_(slot['meta'], non_blocking=True)
+            slot['ready'].record(self.stream)
+        slot['B'], slot['busy'] = B, True
+        self._head += 1
+
+    def take(self) -> dict:
+        """The oldest submitted batch, expanded to packed token rows on the current stream -> a batch NativeNRMSStep accepts."""
+        import ctypes
+        from ._lib import call
+        from .packing import Packed
+        if self._tail == self._head:
+            raise RuntimeError('DeviceResampler.take() without a submitted batch')
+        main = torch.cuda.current_stream()
+        if self._last is not None:
+            self._last['consumed'].record(main)                 # everything that reads the previous slot's buffers is enqueued by now
+        slot = self.slots[self._tail % len(self.slots)]
+        self._tail += 1
+        slot['ready'].synchronize()                             # normally complete long ago: it was submitted a whole step earlier
+        T, n, max_len, max_hist = (int(v) for v in slot['meta_host'].tolist())
+        if T < 0:
+            raise RuntimeError(f'DeviceResampler: batch of {n} items exceeds the item buffer ({self.cap})')
+        main.wait_event(slot['ready'])
+        B, C = slot['B'], self.K + 1
+        outs = [torch.empty(T, dtype=torch.int64, device=self.device) for _ in self.cols]
+        op = (ctypes.c_void_p * len(self.cols))(*[t.data_ptr() for t in outs])
+        call('lk_pack_item_tokens', ctypes.addressof(self._tp), ctypes.addressof(op), len(self.cols), slot['items'].data_ptr(),
+             slot['cu'].data_ptr(), n, self.S)
+        pk = Packed(OrderedDict(zip(self.cols, outs)), slot['cu'][:n + 1], n, T, max_len)
+        slot['busy'] = False
+        self._last = slot
+        return {'__lk_packed__': (pk, slot['cu_users'][:B + 1], max_hist, B, C), '__keep__': (slot['items'],), 'user_id': slot['user_ids'][:B],
+                '__items__': slot['items'][:n]}
+
+    def replay_host(self, rows: np.ndarray):
+        """The same batch from the host restatement (`lk_resample_reference`): (items, cu_items, cu_users) as numpy arrays."""
+        import ctypes
+        C = self.K + 1
+        cand = np.zeros((len(rows), C), dtype=np.int64)
+        buf = (ctypes.c_int64 * C)()
+        for b, r in enumerate(rows):
+            u = int(self.world.train_users[r])
+            negs = np.ascontiguousarray(self.world.negs[u], dtype=np.int64)
+            rc = self._lib.lk_resample_reference(self.seed, int(r), int(self.world.train_pos[r]), negs.ctypes.data, len(negs), self.K,
+                                                 self.n_items, ctypes.cast(buf, ctypes.c_void_p))
+            if rc:
+                raise RuntimeError(self._lib.lk_last_error().decode())
+            cand[b] = list(buf)
+        hists = [np.asarray(self.world.histories[int(self.world.train_users[r])], dtype=np.int64) for r in rows]
+        items = np.concatenate([cand.reshape(-1)] + hists)
+        lens = self.item_len.cpu().numpy()[items]
+        cu = np.zeros(len(items) + 1, dtype=np.int32)
+        np.cumsum(lens, out=cu[1:])
+        cu_u = np.zeros(len(rows) + 1, dtype=np.int32)
+        np.cumsum([len(h) for h in hists], out=cu_u[1:])
+        return items, cu, cu_u
