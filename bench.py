@@ -44,6 +44,7 @@ def parse():
     ap.add_argument('--no-extra', action='store_true', help='skip the cached-eval / gather HBM lines')
     ap.add_argument('--autograd', action='store_true', help='drive the kernels through torch.autograd instead of the native step driver')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
+    ap.add_argument('--no-parity-check', action='store_true', help='N > 1: skip the multi-rank correctness checks that run before timing')
     return ap.parse_args()
 
 
@@ -182,11 +183,12 @@ def main():
     # ---------------- B200 arm ---------------------------------------------------------------------------------------
     import torch.distributed as dist
     if world_size > 1:
-        # the contract is ONE line on stdout: NCCL's own banner ("NCCL version ...", printed at VERSION/INFO level) must not join it
-        if 'LK_NCCL_DEBUG' in os.environ:
-            os.environ['NCCL_DEBUG'] = os.environ['LK_NCCL_DEBUG']
-        else:
-            os.environ.pop('NCCL_DEBUG', None)       # default level: silent
+        # the contract is ONE line on stdout, and NCCL_DEBUG output goes to stdout by default: send it to a per-process file instead and
+        # replay it on STDERR at the end (rank 0), so that whoever set NCCL_DEBUG (the driver's rank check) still sees the communicator lines
+        nccl_log = None
+        if os.environ.get('NCCL_DEBUG') and not os.environ.get('NCCL_DEBUG_FILE'):
+            nccl_log = f'/tmp/lk_nccl_{os.getpid()}.log'
+            os.environ['NCCL_DEBUG_FILE'] = nccl_log
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     import __graft_entry__ as ge
     if rank == 0:
@@ -214,6 +216,16 @@ def main():
     h2d = tree_bytes(host[0])
 
     native = None if args.autograd else NativeNRMSStep(model, opt)
+    parity = None
+    if world_size > 1 and native is not None and not args.no_parity_check:
+        try:
+            parity = parity_self_check(dev, rank, world_size, model, native, opt, resampler, world, args.batch)
+        except Exception as e:   # noqa: BLE001 — reported in the line, never hidden
+            parity = f'self-check raised {type(e).__name__}: {e}'[:300]
+        flag = torch.tensor([0 if parity == 'ok' else 1], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if flag.item() and parity == 'ok':
+            parity = 'another rank reported a mismatch'
 
     def step(batch):
         """One training step.  Default: the native driver (ONE C-ABI call enqueues forward+backward, then allreduce + Adam);
@@ -367,10 +379,18 @@ def main():
                 e2e_wire_format=e2e_wire,
                 gpu_launches=launches, roofline=roof, kernel_ms_share=shares)
 
+    if parity is not None:
+        line['parity_check'] = parity
     if world_size > 1 and not args.small and not args.no_extra:
-        multi = sharded_lookup_line(dev, rank, world_size, args.batch)       # collective: every rank takes part
+        extra = {}
+        for name, fn in (('sharded_word_table', lambda: sharded_lookup_line(dev, rank, world_size, args.batch)),
+                         ('cached_eval_sharded', lambda: sharded_eval_line(dev, rank, world_size, model, resampler, world))):
+            try:                                                             # collective: every rank takes part
+                extra[name] = fn()
+            except Exception as e:   # noqa: BLE001
+                extra[name] = dict(error=f'{type(e).__name__}: {e}'[:300])
         if rank == 0:
-            line['extra'] = dict(sharded_word_table=multi)
+            line['extra'] = extra
     if rank == 0 and world_size == 1 and not args.small and not args.no_extra:
         line['extra'] = hbm_bound_lines(dev, world, peaks()['hbm'], model=model, resampler=resampler, tensor_peak=peaks()['tensor'])
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
@@ -383,6 +403,112 @@ def main():
     if world_size > 1:
         dist.barrier()
         dist.destroy_process_group()
+        if rank == 0 and nccl_log and os.path.exists(nccl_log):
+            with open(nccl_log) as f:
+                sys.stderr.write(f.read())
+
+
+def parity_self_check(dev, rank, W, model, native, opt, resampler, world, batch):
+    """N > 1 only: the multi-rank correctness checks of tests/test_gpu_multirank.py, run on the box that is about to be timed (the driver's
+    GPU-test box has one GPU).  (1) data-parallel gradients (local batch, all-reduce mean) == gradients of the GLOBAL batch computed by one
+    rank; (2) row-sharded table lookup bit-identical to indexing the replicated table; (3) sharded cached evaluation (user caches and rows
+    partitioned by user id, item cache all-gathered) gives the metrics of the unsharded evaluation.  -> 'ok' or a description."""
+    import torch.distributed as dist
+    from legommenders_b200 import Env, evaluate as ev, sharding
+    from legommenders_b200.batching import DeviceBatcher, DeviceResampler
+    problems = []
+    # (1) ---------------------------------------------------------------------------------------------------------------
+    B = min(batch, 32)
+    dres = DeviceResampler(resampler, world, dev, neg_count=NEG, seed=9, max_batch=B * W)
+    all_rows = np.arange(B * W) % world.n_train
+    dres.submit(all_rows[rank * B:(rank + 1) * B])
+    native.fwd_bwd(dres.take(), training=False)
+    g_dp = opt.grad.clone()
+    dist.all_reduce(g_dp, op=dist.ReduceOp.SUM)
+    g_dp /= W
+    dres.submit(all_rows)
+    loss_g = native.fwd_bwd(dres.take(), training=False).item()
+    g_glob = opt.grad.clone()
+    err = float((g_dp - g_glob).abs().max() / g_glob.abs().max())
+    if not err <= 5e-5:
+        problems.append(f'dp gradients differ from the global-batch gradients: {err:.2e}')
+    # (2) ---------------------------------------------------------------------------------------------------------------
+    V, E = 200_000, 300
+    gen = torch.Generator(device=dev).manual_seed(123)           # same table on every rank
+    full = torch.empty((V, E), dtype=torch.float32, device=dev).normal_(0, 0.4, generator=gen)
+    st = sharding.ShardedTable(sharding.shard_rows(full, rank, W), V)
+    ids = torch.randint(-1, V, (50_000,), generator=torch.Generator(device=dev).manual_seed(1000 + rank), device=dev)
+    rows, inv = st.lookup_unique(ids)
+    got = rows[inv.clamp(min=0)] * (inv >= 0).unsqueeze(1)
+    want = full[ids.clamp(min=0)] * (ids >= 0).unsqueeze(1)
+    if not torch.equal(got, want):
+        problems.append('sharded lookup is not bit-identical to the replicated table')
+    del full, st
+    # (3) ---------------------------------------------------------------------------------------------------------------
+    Env.test(); model.eval()
+    dbat = DeviceBatcher(resampler, world, dev)
+    eu, ei, el = (torch.from_numpy(a) for a in (world.eval_users, world.eval_items, world.eval_click))
+    ev.build_caches_device(model, dbat)                           # sharded: item slices all-gathered, users by id % W
+    sharded, _, _ = ev.evaluate(model, eu, ei, el)
+    item_repr = model.cacher.item.repr
+    user_parts = model.cacher.user.repr.clone()
+    dist.all_reduce(user_parts, op=dist.ReduceOp.SUM)             # every user row was filled by exactly one rank (zeros elsewhere)
+    model.cacher.user.repr = user_parts
+    full_vals, _, _ = ev.evaluate(model, eu, ei, el, shard=False)
+    for k in sharded:
+        if abs(sharded[k] - full_vals[k]) > 2e-6:
+            problems.append(f'sharded evaluation {k}: {sharded[k]} vs {full_vals[k]}')
+    model.cacher.clean()
+    Env.train(); model.train()
+    return 'ok' if not problems else '; '.join(problems)
+
+
+def sharded_eval_line(dev, rank, W, model, resampler, world):
+    """Config 3 (BASELINE.json metric: cached-eval scores/s): representation caches built from id lists on the device (items sliced over
+    the ranks and all-gathered, users partitioned by user id), then every validation row scored by the rank that owns its user and the
+    five default metrics reduced with one all-reduce.  Device-timed, max over ranks; ids start in pinned host memory."""
+    import torch.distributed as dist
+    from legommenders_b200 import Env, evaluate as ev
+    from legommenders_b200.batching import DeviceBatcher
+    Env.test(); model.eval()
+    dbat = DeviceBatcher(resampler, world, dev)
+    ev.build_caches_device(model, dbat)                           # warm-up
+    torch.cuda.synchronize()
+    if W > 1:
+        dist.barrier()
+    t0 = time.time()
+    ev.build_caches_device(model, dbat)
+    torch.cuda.synchronize()
+    if W > 1:
+        dist.barrier()
+    build_s = time.time() - t0
+    from legommenders_b200 import sharding
+    R = int(len(world.eval_users))
+    own = sharding.owned_rows(torch.from_numpy(world.eval_users), rank, W)      # the evaluation set is partitioned by user id ONCE (layout, untimed)
+    hu, hi_, hl = (torch.from_numpy(a)[own].pin_memory() for a in (world.eval_users, world.eval_items, world.eval_click))
+    res = {}
+    for _ in range(2):
+        res['m'] = ev.evaluate(model, hu, hi_, hl, presharded=True)[0]
+    torch.cuda.synchronize()
+    if W > 1:
+        dist.barrier()
+    reps = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        res['m'] = ev.evaluate(model, hu, hi_, hl, presharded=True)[0]
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+    if W > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    model.cacher.clean()
+    Env.train(); model.train()
+    return dict(rows=R, rows_this_rank=int(hu.numel()), n_gpus=W, ms=ms, scores_per_s=R / ms * 1e3, cache_build_seconds=build_s,
+                items=int(world.n_items), users=int(world.n_users), metrics={k: round(float(v), 4) for k, v in res['m'].items()},
+                note='evaluate(presharded): pinned host ids of the rows whose user this rank owns -> H2D -> lk_cached_scores -> lk_group_metrics -> all-reduce of (sum, count); '
+                     'cache build = evaluate.build_caches_device (wall clock, incl. the item-cache all-gather)')
 
 
 def sharded_lookup_line(dev, rank, world_size, batch):

@@ -41,13 +41,15 @@ def build_caches(model, item_contents, user_contents, group=None):
         cacher.user.rows = None
 
 
-def build_caches_device(model, batcher, item_page: int = 8192, user_page: int = 4096):
+def build_caches_device(model, batcher, item_page: int = 8192, user_page: int = 4096, group=None):
     """Both representation caches from id lists only (the fast pagers of the reference, loader/pager/fast_{item,user}_pager.py, taken
     to the device): the per-item token layouts already live on the device in `batcher` (batching.DeviceBatcher), so a page of items is
     one `lk_pack_item_tokens` launch + the packed item encoder, and a page of users is an `lk_index_rows` gather of its history items'
     rows from the fresh item cache (the reference's own short-circuit, legommender.py:153-157) + the packed user encoder.  No per-item or
     per-user Python, nothing but id lists and offsets crosses PCIe.  Leaves the cachers exactly as `ReprCacher.cache` does.
-    Needs the packed item / user operators (NRMS / Ada configurations) and users with at least one click (config/data/mind.yaml:15-17)."""
+    Needs the packed item / user operators (NRMS / Ada configurations) and users with at least one click (config/data/mind.yaml:15-17).
+    With several ranks (SURVEY §8e, config 3): every rank encodes a contiguous slice of the items, one all-gather replicates the item cache;
+    users are partitioned by `user_id % world` — rank r fills only its rows of the user cache, the rows `evaluate()` makes it score."""
     import ctypes
     from collections import OrderedDict
     import numpy as np
@@ -56,6 +58,7 @@ def build_caches_device(model, batcher, item_page: int = 8192, user_page: int = 
     cacher, dev = model.cacher, Env.device
     if not (model._packed_items() and getattr(model.user_op, 'supports_packed', False) and cacher.use_item_content):
         raise ValueError('build_caches_device needs packed item and user operators over item content')
+    rank, world = sharding._world(group)
     cacher.clean()
     was_training = model.training
     model.eval()                      # caches never carry dropout noise, whatever phase the caller is in (base_lego.py:417)
@@ -63,8 +66,9 @@ def build_caches_device(model, batcher, item_page: int = 8192, user_page: int = 
     item_repr = model.item_op.get_full_placeholder(n_items).to(dev)
     tp = (ctypes.c_void_p * len(batcher.cols))(*[t.data_ptr() for t in batcher.tables])
     with torch.no_grad():
-        for s in range(0, n_items, item_page):
-            e = min(s + item_page, n_items)
+        i0, i1 = sharding.item_slice(n_items, rank, world)
+        for s in range(i0, i1, item_page):
+            e = min(s + item_page, i1)
             lens = batcher.item_len[s:e]
             cu = np.zeros(e - s + 1, dtype=np.int32)
             np.cumsum(lens, out=cu[1:])
@@ -77,20 +81,27 @@ def build_caches_device(model, batcher, item_page: int = 8192, user_page: int = 
             pk = Packed(OrderedDict(zip(batcher.cols, outs)), cu_d, e - s, int(cu[-1]), int(lens.max()))
             emb = model.item_op.inputer.get_embeddings({'input_ids': pk.ids}, training=False)
             item_repr[s:e] = model.item_op(emb, cu=pk.cu, max_len=pk.max_len)
+        if world > 1:
+            item_repr = sharding.gather_item_cache(item_repr[i0:i1].contiguous(), n_items, group)
         cacher.item.repr = item_repr
         cacher.item._set_cached(True)
         user_repr = torch.zeros_like(cacher.user.placeholder, device=dev)
-        for s in range(0, n_users, user_page):
-            e = min(s + user_page, n_users)
-            hists = batcher.hist[s:e]
-            hl = np.fromiter((len(h) for h in hists), dtype=np.int64, count=e - s)
+        mine = np.arange(rank, n_users, world)                    # the users this rank owns (all of them on one GPU)
+        for s in range(0, len(mine), user_page):
+            page = mine[s:s + user_page]
+            hists = [batcher.hist[int(u)] for u in page]
+            hl = np.fromiter((len(h) for h in hists), dtype=np.int64, count=len(page))
             if hl.min() < 1:
                 raise ValueError('build_caches_device: a user without clicks (the reference filters those out)')
-            cu = np.zeros(e - s + 1, dtype=np.int32)
+            cu = np.zeros(len(page) + 1, dtype=np.int32)
             np.cumsum(hl, out=cu[1:])
             ids = torch.from_numpy(np.concatenate(hists)).to(dev)
             rows = ops.index_rows(item_repr, ids)
-            user_repr[s:e] = model.user_op(rows, cu=torch.from_numpy(cu).to(dev), max_len=int(hl.max()))
+            rep = model.user_op(rows, cu=torch.from_numpy(cu).to(dev), max_len=int(hl.max()))
+            if world == 1:
+                user_repr[int(page[0]):int(page[0]) + len(page)] = rep
+            else:
+                user_repr[torch.from_numpy(page).to(dev)] = rep
         cacher.user.repr = user_repr
         cacher.user._set_cached(True)
     model.train(was_training)
@@ -111,15 +122,18 @@ def cached_scores(model, user_ids: torch.Tensor, item_ids: torch.Tensor, chunk_r
     return out
 
 
-def evaluate(model, user_ids, item_ids, labels, groups=None, metrics: Sequence[str] = DEFAULT_METRICS, group=None):
+def evaluate(model, user_ids, item_ids, labels, groups=None, metrics: Sequence[str] = DEFAULT_METRICS, group=None, shard: bool = True,
+             presharded: bool = False):
     """-> (OrderedDict metric -> float, scores of the rows this rank owns, row indices owned).
     `groups` defaults to `user_ids` (config/data/mind.yaml:24).  With several ranks each scores the rows whose group key it
-    owns; metric means are combined with one all-reduce, so every rank returns the global values."""
-    rank, world = sharding._world(group)
+    owns; metric means are combined with one all-reduce, so every rank returns the global values.
+    presharded=True: the rows passed in are already this rank's share (`sharding.owned_rows` applied once to the evaluation set, SURVEY §8e
+    "rows pre-partitioned by group"); only the metric reduction is collective then."""
+    rank, world = sharding._world(group) if shard else (0, 1)      # shard=False: this rank evaluates every row itself (needs full caches)
     groups = user_ids if groups is None else groups
     user_ids, item_ids, labels, groups = (torch.as_tensor(t).reshape(-1) for t in (user_ids, item_ids, labels, groups))
     rows: Optional[torch.Tensor] = None
-    if world > 1:
+    if world > 1 and not presharded:
         # the user cache is partitioned by user id (build_caches: rank r holds the rows of users r, r+world, ...), so rows MUST be
         # partitioned by user id as well; a group key other than the user id could straddle ranks or hit un-encoded cache rows
         if groups is not user_ids and not torch.equal(groups, user_ids):
