@@ -383,7 +383,7 @@ def main():
         line['parity_check'] = parity
     if world_size > 1 and not args.small and not args.no_extra:
         extra = {}
-        for name, fn in (('sharded_word_table', lambda: sharded_lookup_line(dev, rank, world_size, args.batch)),
+        for name, fn in (('config4_sharded_table_train', lambda: config4_line(dev, rank, world_size, args.batch)),
                          ('cached_eval_sharded', lambda: sharded_eval_line(dev, rank, world_size, model, resampler, world))):
             try:                                                             # collective: every rank takes part
                 extra[name] = fn()
@@ -511,39 +511,86 @@ def sharded_eval_line(dev, rank, W, model, resampler, world):
                      'cache build = evaluate.build_caches_device (wall clock, incl. the item-cache all-gather)')
 
 
-def sharded_lookup_line(dev, rank, world_size, batch):
-    """Config 4 (BASELINE.json): a 4M x 300 fp32 word table row-sharded over the ranks (id % N), one NRMS batch worth of Zipf token
-    ids per rank and step (history 100): dedup -> all-to-all ids -> lk_index_rows on the owner -> all-to-all rows.  Device-timed,
-    max over ranks; no parameter of the timed region is cached between steps."""
+def config4_line(dev, rank, W, batch, steps=20):
+    """Config 4 (BASELINE.json): NRMS training with a 4M x 300 fp32 word table ROW-SHARDED over the ranks (row i on rank i % W) and
+    history length 100.  Every step: lk_resample_batch -> lk_pack_item_tokens -> sharded lookup of the batch's distinct title tokens
+    (lk_shard_plan: dedup + owner bucketing on the device, fixed-capacity NCCL all-to-all of ids, lk_shard_gather on the owner, all-to-all
+    of rows) -> lk_nrms_fwd_bwd on the compact table -> gradient all-reduce -> Adam.  Device-timed, max over ranks; the lookup is also
+    timed alone on the same batches."""
     import torch.distributed as dist
-    from legommenders_b200 import sharding
-    from legommenders_b200.synth import zipf_probs
-    V, E, H, C, L = 4_000_000, 300, 100, 5, 20
-    local = torch.empty(((V - rank + world_size - 1) // world_size, E), dtype=torch.float32, device=dev).normal_(0, 0.4)
+    from legommenders_b200 import Env, builder, sharding
+    from legommenders_b200.batching import DeviceResampler
+    from legommenders_b200.synth import MindWorld
+    from legommenders_b200.trainer import FlatAdam, NativeNRMSStep
+    V, E, H = 4_000_000, 300, 100
+    w4 = MindWorld(seed=4242, make_table=False, **dict(WORKLOAD, n_words=V, hist_len=H, n_train=50_000, n_eval_groups=8, eval_group_mean=4))
+    # the model's own (replicated) table parameter is an UNINITIALISED device placeholder of the right shape: with a sharded table the step
+    # never reads it (trainer.NativeNRMSStep), it only satisfies the EmbeddingHub's vocabulary-size check
+    w4.word_table = torch.empty((V, E), dtype=torch.float32, device=dev)
+    torch.manual_seed(77)
+    model4, res4, _ = builder.build_model(w4, 'nrms', hidden=HIDDEN, heads=HEADS, additive=ADDITIVE, dropout=DROPOUT, neg_count=NEG,
+                                          device_index=dev.index)
+    local = torch.empty(((V - rank + W - 1) // W, E), dtype=torch.float32, device=dev).normal_(0, 0.4)
     st = sharding.ShardedTable(local, V)
-    probs = torch.from_numpy(zipf_probs(V)).to(dev, dtype=torch.float32)
-    g = torch.Generator(device=dev).manual_seed(31 + rank)
-    n_tok = batch * (C + H) * L
-    pool = [torch.multinomial(probs, n_tok, replacement=True, generator=g) for _ in range(4)]
-    uniq = sum(int(torch.unique(p).numel()) for p in pool) / len(pool)
-    for i in range(3):
-        st.lookup_unique(pool[i % 4])
-    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-    K = 20
+    opt4 = FlatAdam(model4, lr=1e-3)
+    nat4 = NativeNRMSStep(model4, opt4, sharded_table=st)
+    Env.train(); model4.train()
+    dres = DeviceResampler(res4, w4, dev, neg_count=NEG, seed=500 + rank, max_batch=batch)
+    rng = np.random.default_rng(900 + rank)
+    rows = torch.from_numpy(rng.integers(0, w4.n_train, size=(steps + 8, batch))).to(dev)
+
+    def one(i):
+        dres.submit(rows[i + 1])
+        return nat4.step(dres.take())
+
+    def sync():
+        torch.cuda.synchronize()
+        if W > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    dres.submit(rows[0])
+    for i in range(5):
+        one(i)
+    sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(K):
-        rows, inv = st.lookup_unique(pool[i % 4])
+    for i in range(5, 5 + steps):
+        loss = one(i)
     e1.record()
-    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / K], device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item()
-    remote = uniq * (world_size - 1) / world_size
-    return dict(table_rows=V, embed_dim=E, rows_per_rank=int(local.shape[0]), tokens_per_rank_per_step=n_tok, unique_rows_per_rank=uniq,
-                ms_per_lookup=ms, tokens_per_s=world_size * n_tok / ms * 1e3, unique_rows_per_s=world_size * uniq / ms * 1e3,
-                nvlink_GBps_per_rank=remote * E * 4 / ms / 1e6,
-                note='includes the host round trip for the all-to-all split sizes; rows cross NVLink once per distinct token')
+    sync()
+    st.check()
+    last = dres.take()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    # the lookup alone, on the last batch's title tokens
+    pk = last['__lk_packed__'][0]
+    title = pk.ids[nat4.title_col]
+    for _ in range(3):
+        st.lookup_unique(title)
+    sync()
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record()
+    for _ in range(steps):
+        tab, inv = st.lookup_unique(title)
+    l1.record()
+    sync()
+    t2 = torch.tensor([l0.elapsed_time(l1) / steps], device=dev)
+    uniq = torch.tensor([float(torch.unique(title[title >= 0]).numel())], device=dev)
+    if W > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        dist.all_reduce(uniq, op=dist.ReduceOp.SUM)
+    ms, ms_l, u = t.item(), t2.item(), uniq.item() / W
+    out = dict(workload='NRMS train, 4M x 300 word table row-sharded over the ranks, history 100, 1+4 candidates, hidden 256', n_gpus=W,
+               batch_per_gpu=batch, impressions_per_s=W * batch / ms * 1e3, ms_per_step=ms, loss=float(loss.item()),
+               token_rows_last_batch=int(pk.rows), items_last_batch=int(pk.n), ms_per_lookup=ms_l, unique_rows_per_rank=u, bucket_capacity=st._cap,
+               nvlink_GBps_per_rank=(W - 1) * st._cap * E * 4 / ms_l / 1e6 if W > 1 else 0.0,
+               useful_nvlink_GBps_per_rank=u * (W - 1) / W * E * 4 / ms_l / 1e6 if W > 1 else 0.0,
+               note='lookup = lk_shard_plan + lk_shard_inverse + all-to-all(ids, fixed capacity) + lk_shard_gather + all-to-all(rows): no sort, no split '
+                    'sizes, no host round trip; rows cross NVLink once per distinct token; user encoder histories up to 100 run the SIMT attention kernels')
+    del model4, opt4, nat4, st, local, w4.word_table
+    torch.cuda.empty_cache()
+    return out
 
 
 def hbm_bound_lines(dev, world, hbm_peak, model=None, resampler=None, tensor_peak=1400.0):
@@ -674,6 +721,11 @@ def hbm_bound_lines(dev, world, hbm_peak, model=None, resampler=None, tensor_pea
         Env.train(); model.train()
         out['cache_build_device'] = dict(items=n_i, users=n_u, seconds=dt, items_and_users_per_s=(n_i + n_u) / dt,
                                          note='item pages: lk_pack_item_tokens + packed NRMS item encoder; user pages: lk_index_rows over the item cache + packed NRMS user encoder; wall clock incl. host offset arithmetic')
+
+    # config 4 on one GPU (the row-sharded table with a single shard: same kernels, no NVLink traffic); the N > 1 lines are in SCALE
+    @guarded('config4_sharded_table_train')
+    def _():
+        out['config4_sharded_table_train'] = config4_line(dev, 0, 1, 64)
 
     # (2) LLM-embedding item path (config 5): frozen [1M, 4096] item table -> tensor-core projection to 256-d, then the catalog
     # scoring sweep of 4096 users against the 1M projected items.  The frozen table is held as split-bf16 planes (same bytes as fp32).

@@ -65,6 +65,17 @@ int lk_scatter_add_sorted(const int64_t* ids, const int64_t* mask, const float* 
 int lk_pack_item_tokens(const int64_t* const* tables, int64_t* const* outs, int ncols, const int64_t* items, const int32_t* cu, int64_t n,
                         int64_t S, cudaStream_t stream);
 
+/* ---- row-sharded word table (BASELINE config 4; csrc/lk_shard.cu): the integer side of the all-to-all lookup on the device — dedup +
+ *      owner bucketing into fixed-capacity send buckets (no split sizes to exchange, no host round trip), inverse index, owner-side gather.
+ *      Row i lives on rank i % W at local index i / W.  Before lk_shard_plan: keys[slots] = -1, counts[W] = 0, overflow[0] = 0,
+ *      send_ids[W*cap] = -1.  inverse[p] = row of the [W*cap, E] receive buffer holding position p's row (-1: unset position). */
+int64_t lk_shard_hash_slots(int64_t P);
+int lk_shard_plan(const int64_t* ids, int64_t P, int W, int64_t cap, int64_t* keys, int32_t* vals, int64_t slots, int32_t* counts,
+                  int64_t* send_ids, int32_t* overflow, cudaStream_t stream);
+int lk_shard_inverse(const int64_t* ids, int64_t P, const int64_t* keys, const int32_t* vals, int64_t slots, int64_t* inverse,
+                     cudaStream_t stream);
+int lk_shard_gather(const int64_t* ids, int64_t M, int W, const float* local, int64_t local_rows, int64_t E, float* out, cudaStream_t stream);
+
 /* ---- device-side Resampler (csrc/lk_resample.cu) — loader/resampler.py:139-259 taken to the device: from B impression rows to the id lists
  *      and offsets of a packed training batch in ONE launch.  Negatives = min(K, len) distinct positions of the user's negative list in random
  *      order + uniform item ids (Philox4x32-10 keyed by (seed, impression row)); histories are the users' valid clicks (padding is never

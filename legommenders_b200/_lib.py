@@ -76,6 +76,10 @@ SIGNATURES = {
     'lk_group_metrics': ('pppqpipqpppzs', 'i'),
     'lk_adam_step': ('ppppqffffqfs', 'i'),
     'lk_fill_f32': ('pfqs', 'i'),
+    'lk_shard_hash_slots': ('q', 'q'),
+    'lk_shard_plan': ('pqiqppqppps', 'i'),
+    'lk_shard_inverse': ('pqppqps', 'i'),
+    'lk_shard_gather': ('pqipqqps', 'i'),
     'lk_resample_batch': ('pqiuppppppp' + 'qqq' + 'ppppp' + 'qs', 'i'),
     'lk_resample_reference': ('uqqpqiqp', 'i'),
     'lk_tc_chain': ('ppqqpiis', 'i'),

@@ -66,7 +66,10 @@ class ShardedTable:
     """Frozen `[V, E]` fp32 table, row `i` stored on rank `i % world` at local index `i // world`."""
 
     def __init__(self, local_rows: torch.Tensor, num_rows: int, group=None,
-                 gather_fn: Optional[Callable[[torch.Tensor, torch.Tensor], torch.Tensor]] = None):
+                 gather_fn: Optional[Callable[[torch.Tensor, torch.Tensor], torch.Tensor]] = None, cap_factor: float = 1.5):
+        self._device_gather = gather_fn is None
+        self.cap_factor, self._cap, self._buf_key, self._buf = cap_factor, None, None, None
+        self._overflow = torch.zeros(1, dtype=torch.int32, device=local_rows.device) if local_rows.is_cuda else None
         self.local = local_rows
         self.num_rows = num_rows
         self.group = group
@@ -97,11 +100,84 @@ class ShardedTable:
         return out
 
     def lookup_unique(self, ids: torch.Tensor):
-        """-> (rows [U, E] of the unique valid ids, inverse [*ids.shape] with -1 at invalid positions).
+        """-> (rows [U, E] of the distinct valid ids, inverse [*ids.shape] with -1 at invalid positions).
         The NRMS step gathers straight from this compact table with `inverse` as the id tensor, so token rows cross
-        NVLink once per distinct token, not once per occurrence."""
+        NVLink once per distinct token, not once per occurrence.
+        CUDA ids take the device plan (`lookup_unique_device`: no sort, no split sizes, no host round trip); host ids (the gloo tests of the
+        integer bookkeeping) take the index-arithmetic plan above."""
+        if ids.is_cuda and self._device_gather:
+            return self.lookup_unique_device(ids)
         plan = plan_lookup(ids, self.world)
         return self.exchange(plan), plan.inverse.reshape(plan.shape)
+
+    # ---- device plan (csrc/lk_shard.cu) ------------------------------------------------------------------------------------------------
+    def _buffers(self, P: int, cap: int):
+        from ._lib import query
+        slots = query('lk_shard_hash_slots', P)
+        key = (slots, cap)
+        if self._buf_key != key:
+            dev, W, E = self.local.device, self.world, self.local.shape[1]
+            neg = torch.empty(slots + W * cap, dtype=torch.int64, device=dev)           # [hash keys | send buckets]: one fill(-1)
+            zero = torch.zeros(W + 1, dtype=torch.int32, device=dev)                    # [bucket counts | overflow]
+            self._buf = dict(slots=slots, neg=neg, keys=neg[:slots], send=neg[slots:], vals=torch.empty(slots, dtype=torch.int32, device=dev),
+                             zero=zero, recv=torch.empty(W * cap, dtype=torch.int64, device=dev),
+                             rows_out=torch.empty((W * cap, E), dtype=torch.float32, device=dev))
+            self._buf_key = key
+        return self._buf
+
+    def _plan(self, flat: torch.Tensor, cap: int):
+        from ._lib import call
+        W, P = self.world, flat.numel()
+        b = self._buffers(P, cap)
+        b['neg'].fill_(-1)
+        b['zero'].zero_()
+        call('lk_shard_plan', flat.data_ptr(), P, W, cap, b['keys'].data_ptr(), b['vals'].data_ptr(), b['slots'], b['zero'].data_ptr(),
+             b['send'].data_ptr(), b['zero'][W:].data_ptr())
+        return b
+
+    def lookup_unique_device(self, ids: torch.Tensor):
+        """Fixed-capacity all-to-all lookup: dedup + owner bucketing in one kernel (hash + atomics), equal-split NCCL all-to-all of the id
+        buckets, owner-side gather, equal-split all-to-all of the row buckets.  -> (rows [W*cap, E], inverse).  The bucket capacity (the same
+        on every rank) is measured once, on the first call: largest bucket over all ranks x `cap_factor`.  A later overflow is counted on
+        the device and raised by `check()`, which the caller runs wherever it synchronises anyway."""
+        from ._lib import call, id_violation_counter
+        W = self.world
+        flat = ids.reshape(-1).contiguous()
+        P = flat.numel()
+        if self._cap is None:                                      # first call only (synchronises): size the buckets
+            b = self._plan(flat, max(1024, P))                     # a bucket can never hold more than P ids
+            t = b['zero'][:W].max().reshape(1).to(torch.int64)
+            if W > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            self._cap = max(1024, int(int(t.item()) * self.cap_factor) + 64)
+        cap = self._cap
+        b = self._plan(flat, cap)
+        inverse = torch.empty(P, dtype=torch.int64, device=flat.device)
+        call('lk_shard_inverse', flat.data_ptr(), P, b['keys'].data_ptr(), b['vals'].data_ptr(), b['slots'], inverse.data_ptr())
+        self._overflow += b['zero'][W:]                            # device-side running count, read by check()
+        if W == 1:
+            recv = b['send']
+        else:
+            recv = b['recv']
+            dist.all_to_all_single(recv, b['send'], group=self.group)
+        id_violation_counter(self.local.device)
+        rows_out = b['rows_out'] if W > 1 else torch.empty_like(b['rows_out'])
+        call('lk_shard_gather', recv.data_ptr(), W * cap, W, self.local.data_ptr(), self.local.shape[0], self.local.shape[1], rows_out.data_ptr())
+        if W == 1:
+            rows = rows_out
+        else:
+            rows = torch.empty_like(rows_out)
+            dist.all_to_all_single(rows, rows_out, group=self.group)
+        return rows, inverse.reshape(ids.shape)
+
+    def check(self):
+        """Raise if any lookup since the last check overflowed a bucket (device->host read: call it where the host synchronises anyway)."""
+        if self._overflow is None:
+            return
+        n = int(self._overflow.item())
+        if n:
+            self._overflow.zero_()
+            raise RuntimeError(f'ShardedTable: {n} distinct ids did not fit the send buckets (capacity {self._cap}); construct with a larger cap_factor')
 
     def lookup(self, ids: torch.Tensor) -> torch.Tensor:
         """Dense result [*ids.shape, E]; invalid positions are zero rows (concat_inputer.py:108-112 semantics)."""

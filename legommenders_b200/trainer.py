@@ -222,6 +222,7 @@ class NativeNRMSStep:
         self.arena = None
         self.loss = torch.zeros((), dtype=torch.float32, device=opt.flat.device)
         self.calls = 0
+        self.check_every = 64
 
     def _ensure_arena(self, T, N, B, C):
         """Grow-only arena sized by the driver's own sizing pass, with 20% head-room so that it is queried rarely."""
@@ -267,6 +268,8 @@ class NativeNRMSStep:
             table, title_ids = self.sharded_table.lookup_unique(title_ids)
             if table.shape[0] == 0:
                 table = table.new_zeros((1, table.shape[1]))
+            if self.calls % self.check_every == 0 and hasattr(self.sharded_table, 'check'):
+                self.sharded_table.check()               # bucket overflow of the device lookup plan (a device->host read, hence rarely)
         call('lk_nrms_fwd_bwd', ptr(title_ids), ptr(pk.ids[self.cat_col]), ptr(pk.ids[self.special_col]), ptr(pk.cu),
              pk.n, pk.rows, pk.max_len, ptr(cu_u), B, C, max_u, ptr(table), table.shape[0], ptr(self.opt.flat), ptr(self.opt.grad),
              self.offsets.ctypes.data, self.D, self.heads, self.A, self.E, self.n_cats, self.n_special, float(de), float(da), int(seed),
