@@ -338,6 +338,26 @@ def main():
         ms_e2e, per_step_e2e, h2d_ids, d2h_e2e = ms_wire, per_step_wire, h2d, 4
     e2e_value = world_size * args.batch * args.steps / (ms_e2e / 1000.0)
 
+    # strong scaling (SURVEY §8e asks for both): the GLOBAL batch fixed at 512 impressions, 512 / N per rank, same data path as `value`
+    strong = None
+    if native is not None and not args.no_extra and not args.small and 512 % world_size == 0:
+        pb = 512 // world_size
+        dres_s = DeviceResampler(resampler, world, dev, neg_count=NEG, seed=4000 + rank, max_batch=pb)
+        rows_s = torch.from_numpy(rng.integers(0, world.n_train, size=(args.steps + 6, pb))).to(dev)
+
+        def strong_step(i):
+            dres_s.submit(rows_s[i + 1])
+            return step(dres_s.take())
+
+        dres_s.submit(rows_s[0])
+        for i in range(3):
+            strong_step(i)
+        ms_s, _, _, per_s = timed(strong_step, args.steps)
+        dres_s.take()
+        strong = dict(scaling='strong', global_batch=512, batch_per_gpu=pb, n_gpus=world_size, ms_per_step=ms_s / args.steps,
+                      impressions_per_s=512 * args.steps / (ms_s / 1000.0), ms_per_step_dist=per_s)
+        del dres_s
+
     # per-entry-point device time over two extra steps (CUDA events around every C-ABI call on the launching stream)
     # (every rank runs the two steps — they contain the gradient all-reduce — but only rank 0 times them)
     roof, shares = None, None
@@ -377,14 +397,15 @@ def main():
                          path='impression indices (pinned host) -> H2D -> lk_resample_batch (side stream, one step ahead) -> lk_pack_item_tokens -> lk_nrms_fwd_bwd -> allreduce -> Adam -> D2H loss (async copy every step, read by the host one step later)'
                          if native is not None else 'wire-format batch'),
                 e2e_wire_format=e2e_wire,
-                gpu_launches=launches, roofline=roof, kernel_ms_share=shares)
+                gpu_launches=launches, roofline=roof, kernel_ms_share=shares, strong_scaling=strong)
 
     if parity is not None:
         line['parity_check'] = parity
     if world_size > 1 and not args.small and not args.no_extra:
         extra = {}
         for name, fn in (('config4_sharded_table_train', lambda: config4_line(dev, rank, world_size, args.batch)),
-                         ('cached_eval_sharded', lambda: sharded_eval_line(dev, rank, world_size, model, resampler, world))):
+                         ('cached_eval_sharded', lambda: sharded_eval_line(dev, rank, world_size, model, resampler, world)),
+                         ('llm_item_path_sharded', lambda: config5_line(dev, rank, world_size, peaks()['hbm'], peaks()['tensor']))):
             try:                                                             # collective: every rank takes part
                 extra[name] = fn()
             except Exception as e:   # noqa: BLE001
@@ -593,6 +614,80 @@ def config4_line(dev, rank, W, batch, steps=20):
     return out
 
 
+def config5_line(dev, rank, W, hbm_peak, tensor_peak, n_items=1_000_000, E_llm=4096, U_sw=4096, k=10):
+    """Config 5 (BASELINE.json): frozen [1M, 4096] LLM item embeddings ROW-SHARDED over the ranks (contiguous blocks), projected locally to
+    256-d on the tensor cores, then the catalog sweep of 4096 replicated users with the per-user top-k fused into the epilogue
+    (lk_sweep_topk: no U x N score matrix exists) and one all-gather + k-way merge of the [U, k] candidates.  Device-timed, max over ranks."""
+    import torch.distributed as dist
+    from legommenders_b200 import ops, sharding
+    D = HIDDEN
+    a, b = sharding.item_slice(n_items, rank, W)
+    n_loc = b - a
+    g = torch.Generator(device=dev).manual_seed(55 + rank)
+    tab = torch.empty((n_loc, E_llm), dtype=torch.float32, device=dev).normal_(0, 1, generator=g)
+    gw = torch.Generator(device=dev).manual_seed(7)                  # replicated projection and users: same on every rank
+    Wp_f = torch.empty((D, E_llm), dtype=torch.float32, device=dev).normal_(0, 0.02, generator=gw)
+    bias = torch.zeros(D, dtype=torch.float32, device=dev)
+    users = torch.empty((U_sw, D), dtype=torch.float32, device=dev).normal_(0, 1, generator=gw)
+
+    def timed(fn, reps=3):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        if W > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+        if W > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    res = {}
+    ms_split = timed(lambda: res.__setitem__('tp', ops.split_planes(tab)), reps=2)      # fp32 .npy rows (embed.py) -> operand planes
+    tp = res.pop('tp')
+    ref_rows = torch.arange(0, n_loc, max(1, n_loc // 64), device=dev)[:64]
+    ref = (tab[ref_rows].double() @ Wp_f.double().t()).float()
+    del tab
+    Wp = ops.split_planes(Wp_f)
+    rep = torch.empty((n_loc, D), dtype=torch.float32, device=dev)
+    ms_p = timed(lambda: ops.tc_gemm(tp, Wp, False, n_loc, D, E_llm, out=rep, bias=bias))
+    err = float((rep[ref_rows] - ref).abs().max() / ref.abs().max())
+    del tp
+    Ip, Up = ops.split_planes(rep), ops.split_planes(users)
+    ms_s = timed(lambda: res.__setitem__('tk', sharding.catalog_topk(Up, Ip, k, item_offset=a)))
+    vals, idx = res['tk']
+    # spot check of the fused top-k against explicit scores for a few users (local shard only when W > 1 would miss winners: use the merged result
+    # against an all-gathered brute force on 8 users)
+    probe = users[:8]
+    loc = probe @ rep.t()
+    lv, li = torch.topk(loc, k, dim=1)
+    li = li + a
+    if W > 1:
+        gv = [torch.empty_like(lv) for _ in range(W)]; gi = [torch.empty_like(li) for _ in range(W)]
+        dist.all_gather(gv, lv.contiguous()); dist.all_gather(gi, li.contiguous())
+        lv, li = ops.merge_topk(torch.cat(gv, 1), torch.cat(gi, 1), k)
+    agree = float((idx[:8] == li).double().mean())
+    fl_p, fl_s = 2.0 * n_items * D * E_llm, 2.0 * U_sw * n_items * D
+    by_p = n_items * E_llm * 4 + n_items * D * 4
+    by_s = n_items * D * 4 + U_sw * D * 4                       # the sweep reads every projected item row once, algorithmically
+    return dict(items=n_items, items_per_rank=n_loc, embed_dim=E_llm, users=U_sw, k=k, n_gpus=W,
+                split_ms=ms_split, projection_ms=ms_p, projection_incl_split_ms=ms_split + ms_p,
+                projection=dict(items_per_s=n_items / ms_p * 1e3, items_per_s_incl_split=n_items / (ms_p + ms_split) * 1e3,
+                                tflops=fl_p / ms_p / 1e9 / 1.0, tensor_frac=fl_p / W / ms_p / 1e9 / tensor_peak,
+                                pipe_tensor_frac=3 * fl_p / W / ms_p / 1e9 / tensor_peak, hbm_frac=by_p / W / ms_p / 1e6 / hbm_peak,
+                                max_rel_err_vs_fp64=err),
+                sweep_topk=dict(ms=ms_s, scores_per_s=U_sw * n_items / ms_s * 1e3, tflops=fl_s / ms_s / 1e9,
+                                tensor_frac=fl_s / W / ms_s / 1e9 / tensor_peak, pipe_tensor_frac=3 * fl_s / W / ms_s / 1e9 / tensor_peak,
+                                top_k_agreement_with_brute_force=agree,
+                                note='per-rank tensor fractions; scores are never written: the 16.8 GB fp32 score matrix of the unfused sweep does not exist'),
+                note='lk_tc_gemm projection (tcgen05 split-bf16 x3) + lk_sweep_topk; tflops are whole-job algorithmic (the pipe executes 3 MMAs per product)')
+
+
 def hbm_bound_lines(dev, world, hbm_peak, model=None, resampler=None, tensor_peak=1400.0):
     """The HBM-bound pieces of the metric (BASELINE.json: cached-eval scores/s, gather HBM GB/s), each timed alone with CUDA events
     (5 repetitions after 2 warm-ups, inputs resident, a 256 MB write between repetitions to flush L2) and set against the measured
@@ -727,43 +822,10 @@ def hbm_bound_lines(dev, world, hbm_peak, model=None, resampler=None, tensor_pea
     def _():
         out['config4_sharded_table_train'] = config4_line(dev, 0, 1, 64)
 
-    # (2) LLM-embedding item path (config 5): frozen [1M, 4096] item table -> tensor-core projection to 256-d, then the catalog
-    # scoring sweep of 4096 users against the 1M projected items.  The frozen table is held as split-bf16 planes (same bytes as fp32).
+    # (2) LLM-embedding item path (config 5) on one GPU; the row-sharded N > 1 lines are in SCALE
     @guarded('llm_item_path')
     def _():
-        n_llm, E_llm, U_sw = 1_000_000, 4096, 4096
-        tab = torch.empty((n_llm, E_llm), dtype=torch.float32, device=dev).normal_(0, 1)
-        W = torch.empty((D, E_llm), dtype=torch.float32, device=dev).normal_(0, 0.02)
-        bias = torch.zeros(D, dtype=torch.float32, device=dev)
-        ops.split_planes(tab[:4096])
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); tp = ops.split_planes(tab); e1.record()
-        torch.cuda.synchronize()
-        ms_split = e0.elapsed_time(e1)
-        ref_rows = torch.arange(0, n_llm, n_llm // 64, device=dev)[:64]
-        ref = (tab[ref_rows].double() @ W.double().t()).float()
-        del tab
-        Wp = ops.split_planes(W)
-        rep = torch.empty((n_llm, D), dtype=torch.float32, device=dev)
-        ms_p = time_it(lambda: ops.tc_gemm(tp, Wp, False, n_llm, D, E_llm, out=rep, bias=bias), reps=3)
-        err = float((rep[ref_rows] - ref).abs().max() / ref.abs().max())
-        fl = 2.0 * n_llm * D * E_llm
-        by_p = n_llm * E_llm * 4 + n_llm * D * 4
-        del tp
-        Ip = ops.split_planes(rep)
-        Up = ops.split_planes(torch.randn(U_sw, D, generator=g).to(dev))
-        sc2 = torch.empty((U_sw, n_llm), dtype=torch.float32, device=dev)
-        ms_s = time_it(lambda: ops.tc_gemm(Up, Ip, False, U_sw, n_llm, D, out=sc2), reps=3)
-        by_s = U_sw * n_llm * 4 + n_llm * D * 4
-        out['llm_item_path'] = dict(
-            items=n_llm, embed_dim=E_llm, users=U_sw,
-            split_ms=ms_split, split_GBps=2 * n_llm * E_llm * 4 / ms_split / 1e6,
-            projection=dict(ms=ms_p, items_per_s=n_llm / ms_p * 1e3, tflops=fl / ms_p / 1e9, tensor_frac=fl / ms_p / 1e9 / tensor_peak,
-                            pipe_tensor_frac=3 * fl / ms_p / 1e9 / tensor_peak, algorithmic_GBps=by_p / ms_p / 1e6,
-                            hbm_frac=by_p / ms_p / 1e6 / hbm_peak, max_rel_err_vs_fp64=err),
-            scoring_sweep=dict(ms=ms_s, scores_per_s=U_sw * n_llm / ms_s * 1e3, tflops=fl / ms_s / 1e9, tensor_frac=fl / ms_s / 1e9 / tensor_peak,
-                               algorithmic_GBps=by_s / ms_s / 1e6, hbm_frac=by_s / ms_s / 1e6 / hbm_peak),
-            note='lk_tc_gemm (tcgen05 split-bf16 x3): the pipe executes 3 MMAs per algorithmic product; the sweep writes 16.8 GB of fp32 scores')
+        out['llm_item_path'] = config5_line(dev, 0, 1, hbm_peak, tensor_peak)
     return out
 
 

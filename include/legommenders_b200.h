@@ -217,6 +217,16 @@ int lk_tc_chain(const void* A_hi, const void* A_lo, int64_t lda, int64_t M, cons
  * 4 x 256 stamps of the last launch to the host (synchronises) */
 int lk_tc_chain_trace(long long* host_out, int cap);
 
+/* ---- catalog scoring sweep with fused per-user top-k (csrc/lk_sweep.cu; BASELINE config 5): for every user the k best items of
+ *      score[u, n] = <U[u,:], I[n,:]> (DotPredictor over the projected item table, model/predictors/dot_predictor.py:7-10) WITHOUT materialising
+ *      the U x N scores.  Operands as split-bf16 planes [rows, 256].  The items are cut into `ranges` contiguous ranges (lk_sweep_ranges);
+ *      out_val / out_idx [ranges, U, k] hold each range's k best per user (descending, ties towards the smaller item index; idx is the item's
+ *      row in I), to be merged by a k-way selection — across ranges, and across ranks when the item table is row-sharded. */
+#define LK_SWEEP_MAX_K 16
+int64_t lk_sweep_ranges(int64_t U, int64_t N);
+int lk_sweep_topk(const void* U_hi, const void* U_lo, int64_t ldu, int64_t U, const void* I_hi, const void* I_lo, int64_t ldi, int64_t N, int64_t D,
+                  int k, int64_t ranges, float* out_val, int32_t* out_idx, cudaStream_t stream);
+
 /* ---- NAML Conv1d(k,'same') as implicit-im2col GEMM — model/operators/cnn_operator.py:33-38,54-58.
  *      Wr[o, j*Cin+i] = W[o,i,j];  Wd[i, j*Cout+o] = W[o,i,taps-1-j];  rows = N*S token rows */
 int lk_conv1d_fwd(const float* X, const float* Wr, const float* bias, const int64_t* rowmask, float* Y, int64_t rows,

@@ -82,6 +82,8 @@ SIGNATURES = {
     'lk_shard_gather': ('pqipqqps', 'i'),
     'lk_resample_batch': ('pqiuppppppp' + 'qqq' + 'ppppp' + 'qs', 'i'),
     'lk_resample_reference': ('uqqpqiqp', 'i'),
+    'lk_sweep_ranges': ('qq', 'q'),
+    'lk_sweep_topk': ('ppqqppqqqiqpps', 'i'),
     'lk_tc_chain': ('ppqqpiis', 'i'),
     'lk_tc_chain_trace': ('pi', 'i'),
     'lk_nrms_arena_bytes': ('qqqqqqqqqq', 'z'),

@@ -5,6 +5,7 @@
 // The W1 GEMM (+bias+tanh) is done by the linear kernels; this file fuses everything after it.
 // One CTA owns one sequence; masked positions are never loaded.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "lk_common.cuh"
 #include "../../include/legommenders_b200.h"

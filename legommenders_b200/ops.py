@@ -188,6 +188,28 @@ def tc_chain(A: Planes, stages, b_mn=False):
     return outs
 
 
+def merge_topk(vals: torch.Tensor, idx: torch.Tensor, k: int):
+    """k-way selection over per-range (or per-rank) candidates: vals / idx [U, C] -> ([U, k], [U, k]); descending score, ties towards the
+    smaller item index (the order torch.topk / a stable descending sort of the full score row gives)."""
+    o1 = torch.argsort(idx, dim=1, stable=True)
+    v1, i1 = torch.gather(vals, 1, o1), torch.gather(idx, 1, o1)
+    o2 = torch.argsort(v1, dim=1, descending=True, stable=True)[:, :k]
+    return torch.gather(v1, 1, o2), torch.gather(i1, 1, o2)
+
+
+def sweep_topk(Up: Planes, Ip: Planes, k: int = 10, item_offset: int = 0):
+    """lk_sweep_topk + range merge: for every user row of `Up` the k best rows of `Ip` by dot product, scores never materialised.
+    -> (scores [U, k] fp32, item ids [U, k] int64 = row in Ip + item_offset)."""
+    U, N = Up.rows, Ip.rows
+    dev = Up.hi.device
+    R = query('lk_sweep_ranges', U, N)
+    pv = torch.empty((R, U, k), dtype=torch.float32, device=dev)
+    pi = torch.empty((R, U, k), dtype=torch.int32, device=dev)
+    call('lk_sweep_topk', ptr(Up.hi), ptr(Up.lo), Up.ld, U, ptr(Ip.hi), ptr(Ip.lo), Ip.ld, N, Up.cols, k, R, ptr(pv), ptr(pi))
+    vals, idx = merge_topk(pv.permute(1, 0, 2).reshape(U, R * k), pi.permute(1, 0, 2).reshape(U, R * k).to(torch.int64), k)
+    return vals, idx + item_offset
+
+
 def tc_gemm_ex(A: Planes, B: Planes, GM, GN, GK, b_mn=False, a_mn=False, out=None, store_c=True, bias=None, rowmask=None,
                rowmask_is_ids=False, act=0, drop_p=0.0, seed=0, accumulate=False, add0=None, add1=None, want_planes=False,
                want_colsum=False):

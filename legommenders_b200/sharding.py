@@ -189,6 +189,26 @@ class ShardedTable:
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# LLM-embedding catalog sweep (config 5)
+# ----------------------------------------------------------------------------------------------------------------
+def catalog_topk(user_planes, item_planes, k: int, item_offset: int = 0, group=None):
+    """Per-user top-k of the catalog with the item table ROW-SHARDED over the ranks (contiguous blocks: this rank holds the projected rows
+    [item_offset, item_offset + N_local) as split-bf16 planes; users are replicated).  The hot loop is local — `ops.sweep_topk`, scores never
+    materialised — and the only collective is an all-gather of the [U, k] candidates followed by a k-way merge.
+    -> (scores [U, k], global item ids [U, k]) identical on every rank."""
+    from . import ops
+    vals, idx = ops.sweep_topk(user_planes, item_planes, k, item_offset)
+    rank, world = _world(group)
+    if world > 1:
+        gv = [torch.empty_like(vals) for _ in range(world)]
+        gi = [torch.empty_like(idx) for _ in range(world)]
+        dist.all_gather(gv, vals.contiguous(), group=group)
+        dist.all_gather(gi, idx.contiguous(), group=group)
+        vals, idx = ops.merge_topk(torch.cat(gv, dim=1), torch.cat(gi, dim=1), k)
+    return vals, idx
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # cached evaluation (config 3)
 # ----------------------------------------------------------------------------------------------------------------
 def owned_rows(group_keys: torch.Tensor, rank: int, world: int) -> torch.Tensor:

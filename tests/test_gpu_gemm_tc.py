@@ -241,3 +241,32 @@ def test_tc_chain(ops, M, b_mn):
     assert rel(one[0]['f32'], mm(ad, wd[0]) + (0 if b_mn else bs[0].double())) <= 2e-5
     two = ops.tc_chain(A, [dict(w=W[0]), dict(w=W[1], want_f32=True)], b_mn=b_mn)
     assert rel(two[1]['f32'], mm(mm(ad, wd[0]), wd[1])) <= 2e-5
+
+
+@pytest.mark.parametrize('U,N,k', [(128, 128, 10), (300, 5000, 10), (70, 1000, 1), (4096, 40000, 16), (129, 131, 5)])
+def test_sweep_topk(ops, U, N, k):
+    """lk_sweep_topk (scores never materialised) against torch.topk of the fp64 score matrix: same items (ties and near-ties aside), scores
+    within the split-bf16 bar; ragged user / item tiles, several item ranges."""
+    g = torch.Generator().manual_seed(U + N + k)
+    u = torch.randn(U, 256, generator=g)
+    it = torch.randn(N, 256, generator=g)
+    if N >= 1000:
+        it[7] = it[3]                                   # an exact tie: the smaller item index must come first
+    vals, idx = ops.sweep_topk(ops.split_planes(u.cuda()), ops.split_planes(it.cuda()), k)
+    ref = u.double() @ it.double().t()
+    rv, ri = torch.sort(ref, dim=1, descending=True, stable=True)
+    rv, ri = rv[:, :k], ri[:, :k]
+    vals, idx = vals.cpu().double(), idx.cpu()
+    assert vals.shape == (U, k) and idx.dtype == torch.int64
+    scale = ref.abs().max().item()
+    assert (vals - rv).abs().max().item() <= 2e-5 * scale
+    got_scores = torch.gather(ref, 1, idx)              # the items returned really have (almost) the k best scores
+    assert (got_scores - rv).abs().max().item() <= 2e-5 * scale
+    assert (idx == ri).double().mean().item() >= 0.999   # rank swaps only between scores closer than the arithmetic resolves
+    for r in range(U):
+        assert len(set(idx[r].tolist())) == k
+    if N >= 1000:
+        rows = (idx == 7).any(dim=1) & (idx == 3).any(dim=1)
+        for r in torch.nonzero(rows).flatten().tolist():
+            pos3, pos7 = idx[r].tolist().index(3), idx[r].tolist().index(7)
+            assert pos3 < pos7
