@@ -27,10 +27,14 @@ namespace tc {
 // Two tile shapes.  128x128 (3 stages of 64 KB) is the general one.  128x256 (2 stages of 96 KB, the whole TMEM as the
 // double-buffered accumulator) reads every A tile once instead of twice; see pick_bn for where it pays.
 constexpr int ACC_STAGES = 2;
+// The operand ring is SIX slots of 32 KiB.  A k-block occupies [A_hi|A_lo] + [B_hi] + [B_lo] (three slots, BN = 256) or [A_hi|A_lo] + [B_hi|B_lo]
+// (two slots, BN = 128): finer slots keep ~190 KiB of loads in flight whatever the tile width.  (Round 1 used 2 x 96 KiB stages for BN = 256: the
+// producer ran a single k-block ahead and every k-block waited out an L2 round trip — 11 us per 128x256x256 tile against 5 us of MMA issue.)
+constexpr int SLOT_BYTES = 2 * TILE_BYTES;       // 32 KiB
+constexpr int SLOTS = 6;
 template <int BN> struct Cfg {
-  static constexpr int STAGES = BN == 256 ? 2 : 3;
-  static constexpr int TILE_B = BN * BK * 2;                    // one plane of the B tile
-  static constexpr int STAGE_BYTES = 2 * TILE_BYTES + 2 * TILE_B;   // A_hi, A_lo, B_hi, B_lo
+  static constexpr int TILE_B = BN * BK * 2;                    // one plane of the B tile (16 or 32 KiB)
+  static constexpr int SLOTS_PER_KB = BN == 256 ? 3 : 2;
   static constexpr int TMEM_COLS = ACC_STAGES * BN;             // fp32 accumulator columns (256 or 512)
   static constexpr int EPI_CHUNKS = BN / 4 / 16;                // 16-column chunks per epilogue warp
 };
@@ -39,10 +43,8 @@ constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;   // TMA warp, MMA warp, epilog
 constexpr int EPI_LD = 16;                 // staged epilogue rows are unpadded; an XOR swizzle of the 16-byte column keeps both
                                            // the row-per-lane writes and the 4-lanes-per-row reads free of bank conflicts
 constexpr int SMEM_BYTES = 3 * 4 * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 32 * EPI_LD * 4 /*epilogue staging*/;
-static_assert(Cfg<128>::STAGES * Cfg<128>::STAGE_BYTES == 3 * 4 * TILE_BYTES && Cfg<256>::STAGES * Cfg<256>::STAGE_BYTES == 3 * 4 * TILE_BYTES,
-              "both tile shapes use the same 192 KiB operand ring");
+static_assert(SLOTS * SLOT_BYTES == 3 * 4 * TILE_BYTES, "192 KiB operand ring");
 static_assert(SMEM_BYTES <= 227 * 1024, "tc_gemm shared memory budget");
-constexpr int MAX_STAGES = 3;
 
 struct Params {
   float* C;                 // [GM, ldc] (or split partials [splits, GM, GN] when partial != null)
@@ -188,13 +190,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const Params p) {
   pdl_trigger();   // the wait comes after the CTA set-up below (barriers, TMEM allocation, descriptor prefetch touch no global data)
   extern __shared__ uint8_t smem_raw[];
-  constexpr int STAGES = Cfg<BN>::STAGES, STAGE_BYTES = Cfg<BN>::STAGE_BYTES, TILE_B = Cfg<BN>::TILE_B, TMEM_COLS = Cfg<BN>::TMEM_COLS;
-  constexpr int OFF_BH = 2 * TILE_BYTES, OFF_BL = 2 * TILE_BYTES + TILE_B;      // A_hi at 0, A_lo at TILE_BYTES
+  constexpr int TILE_B = Cfg<BN>::TILE_B, TMEM_COLS = Cfg<BN>::TMEM_COLS;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024-byte alignment
-  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = bars;                     // [STAGES]
-  uint64_t* empty_bar = bars + MAX_STAGES;       // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * MAX_STAGES;   // [ACC_STAGES]
+  uint64_t* bars = (uint64_t*)(smem + SLOTS * SLOT_BYTES);
+  uint64_t* full_bar = bars;                     // [SLOTS]
+  uint64_t* empty_bar = bars + SLOTS;            // [SLOTS]
+  uint64_t* tfull_bar = bars + 2 * SLOTS;        // [ACC_STAGES]
   uint64_t* tempty_bar = tfull_bar + ACC_STAGES; // [ACC_STAGES]
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + ACC_STAGES);
 
@@ -208,7 +209,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapBl) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; i++) {
+    for (int i = 0; i < SLOTS; i++) {
       mbar_init(smem_u32(&full_bar[i]), 1);
       mbar_init(smem_u32(&empty_bar[i]), 1);
     }
@@ -239,11 +240,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         const int m0 = (rem / p.n_tiles) * BM, n0 = (rem % p.n_tiles) * BN;
         const int kb0 = split * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; kb++) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_expect_tx(fb, STAGE_BYTES);
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const int k0 = kb * BK;
+          // slot 1: both planes of the A tile
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, 2 * TILE_BYTES);
+          uint32_t sa = smem_u32(smem + stage * SLOT_BYTES);
           if (A_MN) {
             tma_load_2d(sa, &mapAh, fb, m0, k0);
             tma_load_2d(sa + TILE_BYTES / 2, &mapAh, fb, m0 + 64, k0);
@@ -253,17 +255,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
             tma_load_2d(sa, &mapAh, fb, k0, m0);
             tma_load_2d(sa + TILE_BYTES, &mapAl, fb, k0, m0);
           }
-          if (B_MN) {
+          if (++stage == SLOTS) { stage = 0; phase ^= 1; }
+          // slot(s) 2 (3): the B planes — one slot per plane for BN = 256, one slot for both for BN = 128
 #pragma unroll
-            for (int c = 0; c < BN / 64; c++) {            // 64 MN-elements x 64 k per box
-              tma_load_2d(sa + OFF_BH + c * (TILE_BYTES / 2), &mapBh, fb, n0 + 64 * c, k0);
-              tma_load_2d(sa + OFF_BL + c * (TILE_BYTES / 2), &mapBl, fb, n0 + 64 * c, k0);
+          for (int pl = 0; pl < 2; pl++) {
+            if (BN == 256 || pl == 0) {
+              mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+              fb = smem_u32(&full_bar[stage]);
+              mbar_expect_tx(fb, BN == 256 ? TILE_B : 2 * TILE_B);
+              sa = smem_u32(smem + stage * SLOT_BYTES);
             }
-          } else {
-            tma_load_2d(sa + OFF_BH, &mapBh, fb, k0, n0);
-            tma_load_2d(sa + OFF_BL, &mapBl, fb, k0, n0);
+            const uint32_t dst = sa + (BN == 256 ? 0 : pl * TILE_B);
+            const CUtensorMap* mb = pl ? &mapBl : &mapBh;
+            if (B_MN) {
+#pragma unroll
+              for (int c = 0; c < BN / 64; c++) tma_load_2d(dst + c * (TILE_BYTES / 2), mb, fb, n0 + 64 * c, k0);   // 64 MN-elements x 64 k per box
+            } else {
+              tma_load_2d(dst, mb, fb, k0, n0);
+            }
+            if (BN == 256 || pl == 1) {
+              if (++stage == SLOTS) { stage = 0; phase ^= 1; }
+            }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -282,21 +295,49 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; kb++) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          const int a_slot = stage;
+          mbar_wait(smem_u32(&full_bar[stage]), phase);            // A planes
+          const uint32_t sa = smem_u32(smem + stage * SLOT_BYTES);
+          if (++stage == SLOTS) { stage = 0; phase ^= 1; }
+          mbar_wait(smem_u32(&full_bar[stage]), phase);            // B_hi (BN = 256) or both B planes (BN = 128)
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = smem_u32(smem + stage * SLOT_BYTES);
+          const int bh_slot = stage;
+          if (++stage == SLOTS) { stage = 0; phase ^= 1; }
+          if (BN == 256) {
+            // hi plane first: A_lo·B_hi and A_hi·B_hi, then its slot goes back to the producer while the lo plane may still be in flight
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; k++) {
-            const uint64_t ah = make_desc(sa + k * a_kstep, A_MN);
-            const uint64_t al = make_desc(sa + TILE_BYTES + k * a_kstep, A_MN);
-            const uint64_t bh = make_desc(sa + OFF_BH + k * b_kstep, B_MN);
-            const uint64_t bl = make_desc(sa + OFF_BL + k * b_kstep, B_MN);
-            umma_bf16(d_tmem, al, bh, idesc, (kb > kb0 || k > 0) ? 1u : 0u);   // small terms first
-            umma_bf16(d_tmem, ah, bl, idesc, 1u);
-            umma_bf16(d_tmem, ah, bh, idesc, 1u);
+            for (int k = 0; k < BK / UMMA_K; k++) {
+              const uint64_t ah = make_desc(sa + k * a_kstep, A_MN), al = make_desc(sa + TILE_BYTES + k * a_kstep, A_MN);
+              const uint64_t bh = make_desc(sb + k * b_kstep, B_MN);
+              umma_bf16(d_tmem, al, bh, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_bf16(d_tmem, ah, bh, idesc, 1u);
+            }
+            umma_commit(smem_u32(&empty_bar[bh_slot]));
+            mbar_wait(smem_u32(&full_bar[stage]), phase);          // B_lo
+            tc_fence_after();
+            const uint32_t sl = smem_u32(smem + stage * SLOT_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; k++) {
+              const uint64_t ah = make_desc(sa + k * a_kstep, A_MN);
+              const uint64_t bl = make_desc(sl + k * b_kstep, B_MN);
+              umma_bf16(d_tmem, ah, bl, idesc, 1u);
+            }
+            umma_commit(smem_u32(&empty_bar[stage]));
+            umma_commit(smem_u32(&empty_bar[a_slot]));
+            if (++stage == SLOTS) { stage = 0; phase ^= 1; }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; k++) {
+              const uint64_t ah = make_desc(sa + k * a_kstep, A_MN), al = make_desc(sa + TILE_BYTES + k * a_kstep, A_MN);
+              const uint64_t bh = make_desc(sb + k * b_kstep, B_MN), bl = make_desc(sb + TILE_B + k * b_kstep, B_MN);
+              umma_bf16(d_tmem, al, bh, idesc, (kb > kb0 || k > 0) ? 1u : 0u);   // small terms first
+              umma_bf16(d_tmem, ah, bl, idesc, 1u);
+              umma_bf16(d_tmem, ah, bh, idesc, 1u);
+            }
+            umma_commit(smem_u32(&empty_bar[bh_slot]));
+            umma_commit(smem_u32(&empty_bar[a_slot]));
           }
-          umma_commit(smem_u32(&empty_bar[stage]));      // frees the smem stage once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(smem_u32(&tfull_bar[acc]));          // accumulator complete -> epilogue
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
@@ -306,7 +347,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     // ------------------------------------------------ epilogue (warps 2..9) ----------------------------------------
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int cg = (warp - 2) >> 2;         // which column group of the tile
-    float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * 32 * EPI_LD;
+    float* stage = reinterpret_cast<float*>(smem + SLOTS * SLOT_BYTES + 256) + (warp - 2) * 32 * EPI_LD;
     int acc = 0;
     uint32_t acc_phase = 0;
     const float inv_keep = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
