@@ -227,6 +227,15 @@ int64_t lk_sweep_ranges(int64_t U, int64_t N);
 int lk_sweep_topk(const void* U_hi, const void* U_lo, int64_t ldu, int64_t U, const void* I_hi, const void* I_lo, int64_t ldi, int64_t N, int64_t D,
                   int k, int64_t ranges, float* out_val, int32_t* out_idx, cudaStream_t stream);
 
+/* ---- GRU user encoder (LSTUR) — nn.GRU(1 layer, batch_first) over pack_padded_sequence, model/operators/gru_operator.py:25-54.
+ *      gi [B,S,3H] = x W_ih^T + b_ih for every step (one contraction, the caller's); whhT [H,3H] = W_hh transposed; len [B] valid steps.
+ *      Forward: last [B,H] = hidden state after step len-1; saved for the backward: hs [B,S,H], gates [B,S,3H] (r,z,n), hnp [B,S,H].
+ *      Backward: dlast -> dgi, dgh [B,S,3H] (zero beyond len); weight / bias / input gradients are contractions of those. */
+int lk_gru_fwd(const float* gi, const float* whhT, const float* bhh, const int32_t* len, float* last, float* hs, float* gates, float* hnp,
+               int64_t B, int64_t S, int64_t H, cudaStream_t stream);
+int lk_gru_bwd(const float* dlast, const float* whh, const int32_t* len, const float* hs, const float* gates, const float* hnp, float* dgi,
+               float* dgh, int64_t B, int64_t S, int64_t H, cudaStream_t stream);
+
 /* ---- NAML Conv1d(k,'same') as implicit-im2col GEMM — model/operators/cnn_operator.py:33-38,54-58.
  *      Wr[o, j*Cin+i] = W[o,i,j];  Wd[i, j*Cout+o] = W[o,i,taps-1-j];  rows = N*S token rows */
 int lk_conv1d_fwd(const float* X, const float* Wr, const float* bias, const int64_t* rowmask, float* Y, int64_t rows,

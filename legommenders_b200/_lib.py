@@ -84,6 +84,8 @@ SIGNATURES = {
     'lk_resample_reference': ('uqqpqiqp', 'i'),
     'lk_sweep_ranges': ('qq', 'q'),
     'lk_sweep_topk': ('ppqqppqqqiqpps', 'i'),
+    'lk_gru_fwd': ('pppppppp' + 'qqqs', 'i'),
+    'lk_gru_bwd': ('pppppppp' + 'qqqs', 'i'),
     'lk_tc_chain': ('ppqqpiis', 'i'),
     'lk_tc_chain_trace': ('pi', 'i'),
     'lk_nrms_arena_bytes': ('qqqqqqqqqq', 'z'),

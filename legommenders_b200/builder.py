@@ -25,7 +25,8 @@ MODEL_META = {
     'nrms': dict(item='Attention', user='Attention', predictor='Dot'),
     'naml': dict(item='CNN', user='Ada', predictor='Dot'),
     'llmid': dict(item=None, user='Ada', predictor='Dot'),          # id-based path with per-item LLM embeddings
-    'pool': dict(item='Pooling', user='Ada', predictor='Dot'),      # masked-mean item encoder (pooling_operator.py) + Ada users
+    'pool': dict(item='Pooling', user='Ada', predictor='Dot'),
+    'lstur': dict(item='CNNCat', user='GRU', predictor='Dot'),       # config/model/lstur.yaml      # masked-mean item encoder (pooling_operator.py) + Ada users
 }
 
 
@@ -44,6 +45,11 @@ def model_config(kind: str, hidden: int, heads: int = 8, additive: int = 256, dr
                     item_config=dict(dropout=dropout, kernel_size=3, additive_hidden_size=additive),
                     user_config=dict(additive_hidden_size=additive,
                                      inputer_config=dict(use_cls_token=False, use_sep_token=False)))
+    if kind == 'lstur':
+        return dict(use_item_content=True, hidden_size=hidden, item_hidden_size=hidden, neg_count=neg_count,
+                    use_neg_sampling=use_neg_sampling,
+                    item_config=dict(dropout=dropout, kernel_size=3, additive_hidden_size=additive),
+                    user_config=dict(inputer_config=dict(use_cls_token=False, use_sep_token=False)))
     if kind == 'pool':
         return dict(use_item_content=True, hidden_size=hidden, item_hidden_size=hidden, neg_count=neg_count,
                     use_neg_sampling=use_neg_sampling, item_config=dict(flatten=False, max_pooling=False),

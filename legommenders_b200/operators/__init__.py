@@ -3,8 +3,11 @@ from .attention_operator import AttentionOperator, AttentionOperatorConfig
 from .cnn_operator import CNNOperator, CNNOperatorConfig
 from .ada_operator import AdaOperator, AdaOperatorConfig
 from .pooling_operator import PoolingOperator, PoolingOperatorConfig
+from .cnn_cat_operator import CNNCatOperator, CNNCatOperatorConfig
+from .gru_operator import GRUOperator, GRUOperatorConfig
 
-REGISTRY = {'attention': AttentionOperator, 'cnn': CNNOperator, 'ada': AdaOperator, 'pooling': PoolingOperator}
+REGISTRY = {'attention': AttentionOperator, 'cnn': CNNOperator, 'ada': AdaOperator, 'pooling': PoolingOperator,
+            'cnncat': CNNCatOperator, 'gru': GRUOperator}
 
 
 def get(name: str):

@@ -536,6 +536,53 @@ def additive_attention(x, mask, w1, b1, w2, cu=None, max_len=None):
 
 
 # ----------------------------------------------------------------------------------------------------
+# GRU over padded sequences -> last hidden state (LSTUR user encoder)
+# ----------------------------------------------------------------------------------------------------
+class _GRULast(Function):
+    """nn.GRU(1 layer, batch_first) over pack_padded_sequence(x, lengths) -> h at each sequence's last valid step
+    (model/operators/gru_operator.py:40-52).  Input projection and all weight / input gradients are contractions (tensor cores when the
+    shapes allow); the recurrence itself is lk_gru_fwd / lk_gru_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, lengths, w_ih, w_hh, b_ih, b_hh):
+        x, w_ih, w_hh, b_ih, b_hh = _f32(x), _f32(w_ih), _f32(w_hh), _f32(b_ih), _f32(b_hh)
+        B, S, I = x.shape
+        H = w_hh.shape[1]
+        dev = x.device
+        x2 = x.reshape(B * S, I)
+        gi, xp = linear_fwd_raw(x2, w_ih, b_ih, None, ACT_NONE)
+        lens = lengths.to(dev, torch.int32).contiguous()
+        whhT = w_hh.t().contiguous()                      # layout only: [H, 3H] so that a warp reads consecutive recurrent weights
+        last = torch.empty((B, H), dtype=torch.float32, device=dev)
+        hs = torch.zeros((B, S, H), dtype=torch.float32, device=dev)        # rows beyond a sequence's length stay zero
+        gates = torch.zeros((B, S, 3 * H), dtype=torch.float32, device=dev)
+        hnp = torch.zeros((B, S, H), dtype=torch.float32, device=dev)
+        call('lk_gru_fwd', ptr(gi), ptr(whhT), ptr(b_hh), ptr(lens), ptr(last), ptr(hs), ptr(gates), ptr(hnp), B, S, H)
+        ctx.save_for_backward(x2, lens, w_ih, w_hh, hs, gates, hnp)
+        ctx.xp, ctx.dims = xp, (B, S, I, H)
+        return last
+
+    @staticmethod
+    def backward(ctx, dlast):
+        x2, lens, w_ih, w_hh, hs, gates, hnp = ctx.saved_tensors
+        B, S, I, H = ctx.dims
+        dev = x2.device
+        dgi = torch.empty((B * S, 3 * H), dtype=torch.float32, device=dev)
+        dgh = torch.empty((B * S, 3 * H), dtype=torch.float32, device=dev)
+        call('lk_gru_bwd', ptr(_f32(dlast)), ptr(w_hh), ptr(lens), ptr(hs), ptr(gates), ptr(hnp), ptr(dgi), ptr(dgh), B, S, H)
+        dw_ih, db_ih = linear_bwd_weight_raw(dgi, x2, xp=ctx.xp)
+        hprev = torch.cat([torch.zeros((B, 1, H), dtype=torch.float32, device=dev), hs[:, :-1]], dim=1).reshape(B * S, H)   # h_{t-1}: a shift
+        dw_hh, db_hh = linear_bwd_weight_raw(dgh, hprev)
+        dx = linear_bwd_data_raw(dgi, w_ih)
+        ctx.xp = None
+        return dx.view(B, S, I), None, dw_ih, dw_hh, db_ih, db_hh
+
+
+def gru_last_hidden(x, lengths, w_ih, w_hh, b_ih, b_hh):
+    return _GRULast.apply(x, lengths, w_ih, w_hh, b_ih, b_hh)
+
+
+# ----------------------------------------------------------------------------------------------------
 # Conv1d('same') + ReLU + mask (NAML)
 # ----------------------------------------------------------------------------------------------------
 class _Conv1dReluMask(Function):

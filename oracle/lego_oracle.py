@@ -217,6 +217,41 @@ def cnn_operator(state: dict, prefix: str, embeddings: "OrderedDict[str, torch.T
 # --------------------------------------------------------------------------------------------
 # a9 / a10 : AdaOperator, PoolingOperator
 # --------------------------------------------------------------------------------------------
+def cnn_cat_operator(state: dict, prefix: str, embeddings: "OrderedDict[str, torch.Tensor]", mask: "OrderedDict[str, torch.Tensor]") -> torch.Tensor:
+    """model/operators/cnn_cat_operator.py:23-38 (dropout 0): per column conv('same') -> ReLU -> mask -> additive attention, a single-token
+    column is its embedding; the per-column vectors are concatenated on the feature axis."""
+    outs = []
+    for col, e in embeddings.items():
+        if e.shape[1] > 1:
+            h = F.conv1d(e.permute(0, 2, 1), state[prefix + 'cnn.weight'], state[prefix + 'cnn.bias'], padding='same').permute(0, 2, 1)
+            h = F.relu(h) * mask[col].unsqueeze(-1)
+            outs.append(_additive(state, prefix, h, mask[col]))
+        else:
+            outs.append(e.squeeze(1))
+    return torch.cat(outs, dim=-1)
+
+
+def gru_operator(state: dict, prefix: str, x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """model/operators/gru_operator.py:40-52: nn.GRU(1 layer) over the first `len` steps of every sequence (pack_padded_sequence), last
+    hidden state, Linear.  Gate order (r, z, n); n = tanh(W_in x + b_in + r * (W_hn h + b_hn))."""
+    w_ih, w_hh = state[prefix + 'gru.weight_ih_l0'], state[prefix + 'gru.weight_hh_l0']
+    b_ih, b_hh = state[prefix + 'gru.bias_ih_l0'], state[prefix + 'gru.bias_hh_l0']
+    B, S, _ = x.shape
+    H = w_hh.shape[1]
+    lengths = mask.sum(dim=1)
+    h = x.new_zeros((B, H))
+    gi_all = x @ w_ih.t() + b_ih
+    for t in range(S):
+        gh = h @ w_hh.t() + b_hh
+        gi = gi_all[:, t]
+        r = torch.sigmoid(gi[:, :H] + gh[:, :H])
+        z = torch.sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+        n = torch.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+        hn = (1 - z) * n + z * h
+        h = torch.where((lengths > t).unsqueeze(1), hn, h)       # sequences that have ended keep their last state
+    return h @ state[prefix + 'linear.weight'].t() + state[prefix + 'linear.bias']
+
+
 def ada_operator(state: dict, prefix: str, x, mask) -> torch.Tensor:
     """model/operators/ada_operator.py:31-38."""
     return _additive(state, prefix, x, mask)
@@ -266,7 +301,7 @@ class ModelSpec:
 
     def __init__(self, kind: str, heads: int = 8, col_vocab: Optional[Dict[str, str]] = None,
                  use_neg_sampling: bool = True, item_vocab: str = 'item_id'):
-        assert kind in ('nrms', 'naml', 'llmid', 'pool')
+        assert kind in ('nrms', 'naml', 'llmid', 'pool', 'lstur')
         self.kind, self.heads = kind, heads
         self.col_vocab = col_vocab or {}
         self.use_neg_sampling = use_neg_sampling
@@ -292,6 +327,11 @@ def item_content(state: dict, spec: ModelSpec, tree: dict) -> torch.Tensor:
         am = OrderedDict((c, _flat(v)) for c, v in tree['attention_mask'].items())
         x = simple_embeddings(state, ids, am, spec.col_vocab)
         r = cnn_operator(state, 'item_op.', x, am)
+    elif spec.kind == 'lstur':
+        ids = OrderedDict((c, _flat(v)) for c, v in tree['input_ids'].items())
+        B = next(iter(tree['input_ids'].values())).shape[0]
+        am = OrderedDict((c, _flat(v)) for c, v in tree['attention_mask'].items())
+        r = cnn_cat_operator(state, 'item_op.', simple_embeddings(state, ids, am, spec.col_vocab), am)
     elif spec.kind == 'pool':
         ids = OrderedDict((c, _flat(v)) for c, v in tree['input_ids'].items())
         B = next(iter(tree['input_ids'].values())).shape[0]
@@ -313,6 +353,8 @@ def user_content(state: dict, spec: ModelSpec, batch: dict, clicks: Optional[tor
     m = batch['__clicks_mask__']
     if spec.kind == 'nrms':
         return attention_operator(state, 'user_op.', clicks, m, spec.heads)
+    if spec.kind == 'lstur':
+        return gru_operator(state, 'user_op.', clicks, m)
     return ada_operator(state, 'user_op.', clicks, m)
 
 
@@ -505,7 +547,7 @@ def state_shapes(kind: str, D: int, A: int, E: int, n_words: int, n_cats: int, n
         s[prefix + 'linear.bias'] = (D,)
         additive(prefix)
 
-    if kind in ('nrms', 'naml', 'pool'):
+    if kind in ('nrms', 'naml', 'pool', 'lstur'):
         s['embedding_vocab_table.glove.embedding.weight'] = (n_words, E)
         s['embedding_vocab_table.glove.linear.weight'] = (D, E)
         s['embedding_vocab_table.glove.linear.bias'] = (D,)
@@ -521,6 +563,18 @@ def state_shapes(kind: str, D: int, A: int, E: int, n_words: int, n_cats: int, n
         s['item_op.linear.bias'] = (D,)
         additive('item_op.')
         additive('user_op.')
+    elif kind == 'lstur':
+        s['item_op.cnn.weight'] = (D, D, 3)
+        s['item_op.cnn.bias'] = (D,)
+        s['item_op.linear.weight'] = (D, D)
+        s['item_op.linear.bias'] = (D,)
+        additive('item_op.')
+        s['user_op.gru.weight_ih_l0'] = (3 * D, 2 * D)
+        s['user_op.gru.weight_hh_l0'] = (3 * D, D)
+        s['user_op.gru.bias_ih_l0'] = (3 * D,)
+        s['user_op.gru.bias_hh_l0'] = (3 * D,)
+        s['user_op.linear.weight'] = (2 * D, D)
+        s['user_op.linear.bias'] = (2 * D,)
     elif kind == 'pool':
         additive('user_op.')
     else:

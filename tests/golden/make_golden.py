@@ -61,7 +61,7 @@ def run_case(name: str, c: dict):
     out['loss'] = np.float32(loss.item())
     for n, p in model.named_parameters():
         if p.requires_grad:
-            g = p.grad.detach().numpy()
+            g = p.grad.detach().numpy() if p.grad is not None else np.zeros(tuple(p.shape), dtype=np.float32)   # unused parameter (CNNCat's linear)
             if c.get('full_grads', True):
                 out['grad/' + n] = g
             else:

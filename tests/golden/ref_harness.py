@@ -76,6 +76,13 @@ def build_reference(world, model='nrms', hidden=256, neg_count=4, dropout=0.0, h
         user_cfg = dict(additive_hidden_size=additive,
                         inputer_config=dict(use_cls_token=False, use_sep_token=False))
         use_item_content = True
+    elif model == 'lstur':
+        from model.operators.cnn_cat_operator import CNNCatOperator
+        from model.operators.gru_operator import GRUOperator
+        item_cls, user_cls = CNNCatOperator, GRUOperator
+        item_cfg = dict(dropout=dropout, kernel_size=3, additive_hidden_size=additive)
+        user_cfg = dict(inputer_config=dict(use_cls_token=False, use_sep_token=False))
+        use_item_content = True
     elif model == 'pool':
         from model.operators.pooling_operator import PoolingOperator
         item_cls, user_cls = PoolingOperator, AdaOperator

@@ -84,7 +84,9 @@ def oracle_run(c, world, llm, batch, dtype=torch.float32):
     want = {}
     loss = O.forward(state, spec, copy.deepcopy(batch), want=want)
     loss.backward()
-    grads = {k: v.grad.detach().numpy() for k, v in state.items() if v.requires_grad}
+    # a parameter the forward never touches (CNNCat's inherited `linear`) has no gradient: zeros, as an optimiser would see it
+    grads = {k: (v.grad.detach().numpy() if v.grad is not None else np.zeros(tuple(v.shape), dtype=np.float32)) for k, v in state.items()
+             if v.requires_grad}
     with torch.no_grad():
         scores = O.forward(state, spec, copy.deepcopy(batch), return_scores=True)
     return dict(loss=float(loss.item()), grads=grads, scores=scores.numpy(), items=want['items'].detach().numpy(),

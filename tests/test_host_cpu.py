@@ -43,7 +43,7 @@ def test_ctypes_signatures_match_the_header_arity_and_structs():
     from legommenders_b200 import _lib, ops
     text = open(os.path.join(ROOT, 'include', 'legommenders_b200.h')).read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
-    decls = re.findall(r'\b(?:int|size_t|const char\*|void|unsigned long long)\s+(lk_\w+)\s*\(([^;{]*?)\)\s*;', text, flags=re.S)
+    decls = re.findall(r'\b(?:int|int64_t|size_t|const char\*|void|unsigned long long)\s+(lk_\w+)\s*\(([^;{]*?)\)\s*;', text, flags=re.S)
     assert len(decls) == len(_lib.SIGNATURES)
     for name, args in decls:
         a = args.strip()
@@ -55,6 +55,9 @@ def test_ctypes_signatures_match_the_header_arity_and_structs():
     body = re.search(r'typedef struct lk_gemm_epilogue \{(.*?)\} lk_gemm_epilogue;', text, flags=re.S).group(1)
     declared = re.findall(r'(\w+);', body)
     assert fields == declared, (fields, declared)
+    fields = [f[0] for f in ops.ChainStage._fields_]
+    body = re.search(r'typedef struct lk_chain_stage \{(.*?)\} lk_chain_stage;', text, flags=re.S).group(1)
+    assert fields == re.findall(r'(\w+);', body)
 
 
 def test_workspace_queries_do_not_need_a_gpu():
