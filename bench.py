@@ -274,7 +274,19 @@ def main():
     for i in range(max(args.warmup, 3, POOL)):
         step(devb[i % POOL])
     n_loop = args.steps + 4
-    rows_host = rng.integers(0, world.n_train, size=(n_loop, args.batch))
+    if world_size > 1:
+        # the GLOBAL batch of every step is drawn from one stream shared by all ranks and dealt out so that every rank packs (nearly) the
+        # same number of token rows (batching.balanced_partition): a data-parallel step waits for its slowest rank
+        from legommenders_b200.batching import balanced_partition, impression_costs
+        g_rng = np.random.default_rng(4242)
+        item_len_host = np.asarray([int(t['attention_mask'].sum()) for t in resampler.item_cache], dtype=np.int64)
+        cost = impression_costs(world, item_len_host, NEG)
+        rows_host = np.empty((n_loop, args.batch), dtype=np.int64)
+        for i in range(n_loop):
+            g_rows = g_rng.integers(0, world.n_train, size=world_size * args.batch)
+            rows_host[i] = g_rows[balanced_partition(cost[g_rows], world_size)[rank]]
+    else:
+        rows_host = rng.integers(0, world.n_train, size=(n_loop, args.batch))
     if native is not None:
         from legommenders_b200.batching import DeviceResampler
         dres = DeviceResampler(resampler, world, dev, neg_count=NEG, seed=3000 + rank, max_batch=args.batch)
@@ -390,7 +402,8 @@ def main():
                 warmup=args.warmup, ms_per_step=ms / args.steps, ms_per_step_dist=per_step, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', impl='b200',
                 config=dict(base_cfg, l2='per-step working set (~1 GB of activations) exceeds the 126 MB L2; every step samples a fresh batch (nothing memoised)',
-                            inputs='impression indices resident in HBM; negative sampling, history concat and token packing run inside every timed step'),
+                            inputs='impression indices resident in HBM; negative sampling, history concat and token packing run inside every timed step',
+                            placement='global batch dealt to the ranks by packed-token cost (serpentine)' if world_size > 1 else 'single rank'),
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit='impressions/s', h2d_bytes_per_step=h2d_ids, d2h_bytes_per_step=d2h_e2e,
                          ms_per_step=ms_e2e / args.steps, ms_per_step_dist=per_step_e2e,
@@ -816,6 +829,46 @@ def hbm_bound_lines(dev, world, hbm_peak, model=None, resampler=None, tensor_pea
         Env.train(); model.train()
         out['cache_build_device'] = dict(items=n_i, users=n_u, seconds=dt, items_and_users_per_s=(n_i + n_u) / dt,
                                          note='item pages: lk_pack_item_tokens + packed NRMS item encoder; user pages: lk_index_rows over the item cache + packed NRMS user encoder; wall clock incl. host offset arithmetic')
+
+    # config 1 (BASELINE.json configs[0]: NAML, the reference's CPU-runnable case) on the GPU through the plugin surface + torch.autograd:
+    # Conv1d('same') as the implicit-im2col SIMT kernel (fp32 FFMA), AdditiveAttention, Ada user encoder, fused dot + CE, FlatAdam
+    @guarded('naml_train')
+    def _():
+        from legommenders_b200 import Env, builder
+        from legommenders_b200.batching import BatchBuilder, tree_to_device
+        from legommenders_b200.trainer import FlatAdam
+        torch.manual_seed(11)
+        m2, r2, _ = builder.build_model(world, 'naml', hidden=HIDDEN, heads=HEADS, additive=ADDITIVE, dropout=DROPOUT, neg_count=NEG,
+                                        device_index=dev.index)
+        o2 = FlatAdam(m2, lr=1e-3)
+        Env.train(); m2.train()
+        bb2 = BatchBuilder(r2, world, neg_count=NEG, seed=3)
+        rng2 = np.random.default_rng(8)
+        pool2 = [tree_to_device(bb2.train_batch(rng2.integers(0, world.n_train, size=64)), dev, non_blocking=False) for _ in range(4)]
+
+        def one(i):
+            o2.zero_grad()
+            loss = m2(batch=pool2[i % 4])
+            loss.backward()
+            o2.step()
+            return loss
+
+        for i in range(4):
+            one(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        K2 = 10
+        e0.record()
+        for i in range(K2):
+            loss = one(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1) / K2
+        out['naml_train'] = dict(workload='NAML train step (CNN title encoder + additive attention, Ada user encoder, DotPredictor + CE), MIND-small shape, batch 64',
+                                 ms_per_step=ms2, impressions_per_s=64 / ms2 * 1e3, loss=float(loss.item()),
+                                 note='generic plugin path (model(batch); loss.backward(); FlatAdam.step()) on pre-built device batches; the conv runs on fp32 FFMA '
+                                      '(lk_conv1d_*), not on tensor cores; host-driven launches')
+        del m2, o2, pool2
 
     # config 4 on one GPU (the row-sharded table with a single shard: same kernels, no NVLink traffic); the N > 1 lines are in SCALE
     @guarded('config4_sharded_table_train')

@@ -282,3 +282,29 @@ class DeviceResampler:
         cu_u = np.zeros(len(rows) + 1, dtype=np.int32)
         np.cumsum([len(h) for h in hists], out=cu_u[1:])
         return items, cu, cu_u
+
+
+def balanced_partition(costs: np.ndarray, world: int) -> np.ndarray:
+    """Split a global batch into `world` equal-sized shares of (nearly) equal total cost -> index array [world, n // world].
+
+    Data-parallel steps end with an all-reduce, so every step waits for the rank with the most packed token rows; with impressions drawn
+    independently per rank the slowest of 8 is ≈ 8 % slower than the average (histories run from 1 to 50 clicks).  Sorting the GLOBAL batch by
+    cost and dealing it out in serpentine order gives every rank the same number of impressions and within a few rows the same number of token
+    rows.  Which impressions form the global batch — and therefore the averaged gradient — is unchanged; only their placement is."""
+    n = len(costs)
+    if n % world:
+        raise ValueError(f'global batch of {n} does not divide over {world} ranks')
+    order = np.argsort(-np.asarray(costs), kind='stable').reshape(n // world, world)
+    order[1::2] = order[1::2, ::-1].copy()                    # serpentine: 0..W-1, W-1..0, ...
+    return np.ascontiguousarray(order.T)
+
+
+def impression_costs(world, item_len: np.ndarray, neg_count: int = 4) -> np.ndarray:
+    """Expected packed token rows of every training impression: the tokens of its user's history items + the positive + an average
+    item for each sampled negative (host arithmetic, once per data set)."""
+    off = np.zeros(len(world.histories) + 1, dtype=np.int64)
+    np.cumsum([len(h) for h in world.histories], out=off[1:])
+    flat = np.concatenate([np.asarray(h, dtype=np.int64) for h in world.histories])
+    per_user = np.add.reduceat(item_len[flat], off[:-1]) if len(flat) else np.zeros(len(world.histories))
+    per_user[off[1:] == off[:-1]] = 0
+    return per_user[world.train_users] + item_len[world.train_pos] + neg_count * float(item_len.mean())

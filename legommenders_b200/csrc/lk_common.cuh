@@ -61,6 +61,13 @@ __device__ __forceinline__ bool id_in_range(int64_t id, int64_t rows, int32_t* v
   if (viol) atomicAdd(viol, 1);
   return false;
 }
+// warp-cooperative form: every lane holds the same id and evaluates the (register-only) test itself; lane 0 alone reports a violation.
+// No shuffle sits between the id load and the row loads that depend on it.
+__device__ __forceinline__ bool id_in_range_warp(int64_t id, int64_t rows, int32_t* viol, int lane) {
+  const bool ok = (uint64_t)id < (uint64_t)rows;
+  if (!ok && lane == 0 && viol) atomicAdd(viol, 1);
+  return ok;
+}
 
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -31,8 +31,7 @@ __global__ void __launch_bounds__(GW * 32) gather_rows_kernel(const int64_t* __r
   for (int64_t m = warp; m < M; m += nwarps) {
     int64_t id = ids[m];
     bool valid = mask ? (mask[m] > 0) : (id > -1);
-    if (valid && lane == 0) valid = id_in_range(id, V, viol);
-    valid = __shfl_sync(0xffffffffu, valid, 0);
+    if (valid) valid = id_in_range_warp(id, V, viol, lane);
     float* o = out + m * E;
     if (valid) {
       const float* src = table + id * (int64_t)E;
@@ -59,10 +58,7 @@ __global__ void __launch_bounds__(GW * 32) gather_split_kernel(const int64_t* __
   const int L4 = ld >> 2;
   for (int64_t m = warp; m < M; m += nwarps) {
     int64_t id = ids[m];
-    if (id > -1) {
-      bool ok = lane == 0 ? id_in_range(id, V, viol) : true;
-      if (!__shfl_sync(0xffffffffu, ok, 0)) id = -1;
-    }
+    if (id > -1 && !id_in_range_warp(id, V, viol, lane)) id = -1;
     const float* src = table + id * (int64_t)E;
     for (int c = lane; c < L4; c += 32) {
       float4 v = f4_zero();
@@ -96,7 +92,7 @@ __global__ void __launch_bounds__(GW * 32) gather_pool_kernel(const int64_t* __r
   const int64_t* idr = ids + n * S;
   const int64_t* mr = mask ? mask + n * S : nullptr;
   float4 acc = MODE == 1 ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : f4_zero();
-  int cnt = 0;
+  int cnt = 0, nbad = 0;
   for (int t0 = 0; t0 < S; t0 += 4) {
     float4 v[4];
     bool ok[4];
@@ -108,10 +104,9 @@ __global__ void __launch_bounds__(GW * 32) gather_pool_kernel(const int64_t* __r
       if (t < S) {
         int64_t id = idr[t];
         ok[u] = mr ? (mr[t] > 0) : (id > -1);
-        if (ok[u] && (uint64_t)id >= (uint64_t)V) {       // every lane sees the same id: lane 0 of column block 0 counts it
-          if (lane == 0 && blockIdx.y == 0 && viol) atomicAdd(viol, 1);
-          ok[u] = false;
-        }
+        const bool oob = ok[u] && (uint64_t)id >= (uint64_t)V;   // out of range: an invalid position, counted once after the loop
+        nbad += oob ? 1 : 0;                                     // (no branch or atomic between the four loads of a step)
+        ok[u] = ok[u] && !oob;
         if (ok[u] && col_ok) v[u] = ldg4(table + id * (int64_t)E + c);
       }
     }
@@ -127,6 +122,7 @@ __global__ void __launch_bounds__(GW * 32) gather_pool_kernel(const int64_t* __r
       }
     }
   }
+  if (nbad && lane == 0 && blockIdx.y == 0 && viol) atomicAdd(viol, nbad);   // every lane saw the same ids: lane 0 of column block 0 reports
   if (!col_ok) return;
   if (MODE == 0) {
     float inv = 1.0f / ((float)cnt + 1e-8f);

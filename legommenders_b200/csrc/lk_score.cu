@@ -139,13 +139,8 @@ __global__ void __launch_bounds__(SW * 32) cached_scores_kernel(const float* __r
     const bool two = r + 1 < R;
     int64_t ua = uid[r], ia = iid[r], ub = two ? uid[r + 1] : ua, ib = two ? iid[r + 1] : ia;
     // out-of-range ids (the reference raises IndexError): counted, scored as 0, never dereferenced
-    bool ok0 = true, ok1 = true;
-    if (lane == 0) {
-      ok0 = id_in_range(ua, n_users, viol) & id_in_range(ia, n_items, viol);
-      ok1 = !two || (id_in_range(ub, n_users, viol) & id_in_range(ib, n_items, viol));
-    }
-    ok0 = __shfl_sync(0xffffffffu, ok0, 0);
-    ok1 = __shfl_sync(0xffffffffu, ok1, 0);
+    const bool ok0 = id_in_range_warp(ua, n_users, viol, lane) & id_in_range_warp(ia, n_items, viol, lane);
+    const bool ok1 = !two || (id_in_range_warp(ub, n_users, viol, lane) & id_in_range_warp(ib, n_items, viol, lane));
     if (!ok0) ua = ia = 0;
     if (!ok1) ub = ib = 0;
     const float* u0 = U + ua * (int64_t)D;
@@ -176,8 +171,7 @@ __global__ void __launch_bounds__(SW * 32) index_rows_kernel(const float* __rest
   const int64_t nwarps = (int64_t)gridDim.x * SW;
   for (int64_t r = warp; r < R; r += nwarps) {
     const int64_t id = ids[r];
-    bool ok = lane == 0 ? id_in_range(id, V, viol) : true;
-    ok = __shfl_sync(0xffffffffu, ok, 0);
+    const bool ok = id_in_range_warp(id, V, viol, lane);
     const float* src = table + (ok ? id : 0) * (int64_t)D;
     for (int c = lane * 4; c < D; c += 128) st4(out + r * (int64_t)D + c, ok ? ldg4(src + c) : f4_zero());
   }

@@ -75,10 +75,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const int64_t* __restrict__
   for (int64_t j = warp; j < M; j += nwarps) {
     const int64_t id = ids[j];
     bool ok = id >= 0;
-    if (ok) {
-      bool in = lane == 0 ? id_in_range(id / W, local_rows, viol) : true;
-      ok = __shfl_sync(0xffffffffu, in, 0);
-    }
+    if (ok) ok = id_in_range_warp(id / W, local_rows, viol, lane);
     const float* src = local + (ok ? id / W : 0) * (int64_t)E;
     float* o = out + j * (int64_t)E;
     for (int c = lane; c < E4; c += 32) st4(o + c * 4, ok ? ldg4(src + c * 4) : f4_zero());

@@ -135,3 +135,21 @@ def _flat_bucket_allreduce(rank):
 
 def test_flat_bucket_allreduce_world2():
     spawn(_flat_bucket_allreduce)
+
+
+def test_balanced_partition_equalises_packed_rows():
+    """batching.balanced_partition: every rank gets the same number of impressions and (within a few rows) the same packed-token cost; the
+    global batch is only re-placed, never changed."""
+    from legommenders_b200.batching import balanced_partition
+    rng = np.random.default_rng(3)
+    for world, per in ((2, 64), (8, 64), (4, 5)):
+        cost = rng.integers(40, 1300, size=world * per).astype(np.float64)
+        part = balanced_partition(cost, world)
+        assert part.shape == (world, per)
+        assert sorted(part.reshape(-1).tolist()) == list(range(world * per))
+        sums = cost[part].sum(axis=1)
+        naive = cost.reshape(world, per).sum(axis=1)
+        assert sums.max() - sums.min() <= cost.max()                      # within one impression of each other
+        assert sums.max() - sums.min() <= naive.max() - naive.min()
+    with pytest.raises(ValueError):
+        balanced_partition(np.ones(10), 4)
