@@ -57,9 +57,9 @@ def peaks():
 
 
 def measured_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r1_traffic.json), or None."""
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r2_traffic.json), or None."""
     try:
-        return json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))[kernel]['dram_bytes_per_launch']
+        return json.load(open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')))[kernel]['dram_bytes_per_launch']
     except Exception:
         return None
 
@@ -388,10 +388,10 @@ def main():
         if gemm['ms'] > 0:
             ach = gemm['flops'] / (gemm['ms'] / 1e3) / 1e12
             tc = gemm['name'] == 'lk_tc_gemm'
-            roof = dict(bound='tensor', kernel='tc_gemm_kernel (tcgen05.mma, split-bf16 x3, fp32 TMEM accumulate)' if tc
+            roof = dict(bound='tensor', kernel='tcgen05 contractions: tc_gemm_kernel + chain_kernel (tcgen05.mma, split-bf16 x3, fp32 TMEM accumulate)' if tc
                         else 'gemm_simt_kernel (fp32 FFMA)', achieved=ach, peak=pk['tensor'],
-                        unit='TFLOP/s', frac=ach / pk['tensor'], traffic=measured_traffic('tc_gemm_kernel') if tc else None,
-                        traffic_note='dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the tc_gemm launches of one step (profiles/r1_traffic.json, ncu --set full)',
+                        unit='TFLOP/s', frac=ach / pk['tensor'], traffic=measured_traffic('tcgen05_contractions') if tc else None,
+                        traffic_note='dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over 40 consecutive tc_gemm_kernel / chain_kernel launches of a training step (profiles/r2_traffic.json, ncu --set full)',
                         pipe_tflops=3 * ach if tc else ach, pipe_frac=(3 * ach if tc else ach) / pk['tensor'], peak_source=pk['which'],
                         share_of_step=gemm['ms'] / max(sum(shares.values()), 1e-9), launches=gemm['calls'],
                         per_shape=gemm.get('per_shape'),
