@@ -227,6 +227,31 @@ int64_t lk_sweep_ranges(int64_t U, int64_t N);
 int lk_sweep_topk(const void* U_hi, const void* U_lo, int64_t ldu, int64_t U, const void* I_hi, const void* I_lo, int64_t ldi, int64_t N, int64_t D,
                   int k, int64_t ranges, float* out_val, int32_t* out_idx, cudaStream_t stream);
 
+/* ---- row-wise pieces of the BERT-style blocks of TransformerOperator / FastformerOperator (transformers BertModel behind
+ *      model/operators/transformer_operator.py:29-38; model/common/fastformer.py:146-226): y = LayerNorm(x + res) * w + b (res, xs nullable;
+ *      xs receives x + res for the backward), exact erf GELU (mode 0 forward, 1: dy * gelu'(x)), counter-based dropout (backward = the same
+ *      call on dy).  lk_layernorm_bwd leaves [lk_layernorm_bwd_parts(rows), 2*D] partials of (dw, db). */
+int lk_layernorm_fwd(const float* x, const float* res, const float* w, const float* b, float* y, float* xs, float* mean, float* rstd, int64_t rows,
+                     int64_t D, float eps, cudaStream_t stream);
+int64_t lk_layernorm_bwd_parts(int64_t rows);
+int lk_layernorm_bwd(const float* dy, const float* xs, const float* w, const float* mean, const float* rstd, float* dx, float* dwb_part, int64_t rows,
+                     int64_t D, cudaStream_t stream);
+int lk_gelu(const float* x, const float* dy, float* y, int64_t n, int mode, cudaStream_t stream);
+int lk_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, cudaStream_t stream);
+
+/* ---- MINER (csrc/lk_poly.cu): poly-attention pooling, model/operators/poly_attention_operator.py:52-56 (logits [B,S,C], mask [B,S], x [B,S,D] ->
+ *      out [B,C,D]; w [B,C,S] saved; masked positions carry the reference's 1e-30 logit, not -inf) and the target-aware predictor,
+ *      model/predictors/miner_predictor.py:30-64 (user, proj = gelu(Linear(user)) [B,C,D], items [B,K1,D] -> out [B,K1]; mode 0 weighted, 1 max, 2 mean;
+ *      sc, wt [B,K1,C] saved). */
+int lk_poly_pool_fwd(const float* logits, const int64_t* mask, const float* x, float* out, float* w, int64_t B, int64_t S, int64_t C, int64_t D,
+                     cudaStream_t stream);
+int lk_poly_pool_bwd(const float* dout, const float* w, const int64_t* mask, const float* x, float* dx, float* dlogits, int64_t B, int64_t S, int64_t C,
+                     int64_t D, cudaStream_t stream);
+int lk_miner_fwd(const float* user, const float* proj, const float* items, float* out, float* sc, float* wt, int64_t B, int64_t K1, int64_t C, int64_t D,
+                 int mode, cudaStream_t stream);
+int lk_miner_bwd(const float* dout, const float* user, const float* proj, const float* items, const float* sc, const float* wt, float* duser, float* dproj,
+                 float* ditems, int64_t B, int64_t K1, int64_t C, int64_t D, int mode, cudaStream_t stream);
+
 /* ---- GRU user encoder (LSTUR) — nn.GRU(1 layer, batch_first) over pack_padded_sequence, model/operators/gru_operator.py:25-54.
  *      gi [B,S,3H] = x W_ih^T + b_ih for every step (one contraction, the caller's); whhT [H,3H] = W_hh transposed; len [B] valid steps.
  *      Forward: last [B,H] = hidden state after step len-1; saved for the backward: hs [B,S,H], gates [B,S,3H] (r,z,n), hnp [B,S,H].

@@ -84,6 +84,15 @@ SIGNATURES = {
     'lk_resample_reference': ('uqqpqiqp', 'i'),
     'lk_sweep_ranges': ('qq', 'q'),
     'lk_sweep_topk': ('ppqqppqqqiqpps', 'i'),
+    'lk_layernorm_fwd': ('pppppppp' + 'qqfs', 'i'),
+    'lk_layernorm_bwd_parts': ('q', 'q'),
+    'lk_layernorm_bwd': ('ppppppp' + 'qqs', 'i'),
+    'lk_gelu': ('pppqis', 'i'),
+    'lk_dropout': ('ppqfus', 'i'),
+    'lk_poly_pool_fwd': ('ppppp' + 'qqqqs', 'i'),
+    'lk_poly_pool_bwd': ('pppppp' + 'qqqqs', 'i'),
+    'lk_miner_fwd': ('pppppp' + 'qqqqis', 'i'),
+    'lk_miner_bwd': ('ppppppppp' + 'qqqqis', 'i'),
     'lk_gru_fwd': ('pppppppp' + 'qqqs', 'i'),
     'lk_gru_bwd': ('pppppppp' + 'qqqs', 'i'),
     'lk_tc_chain': ('ppqqpiis', 'i'),

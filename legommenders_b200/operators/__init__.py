@@ -5,9 +5,11 @@ from .ada_operator import AdaOperator, AdaOperatorConfig
 from .pooling_operator import PoolingOperator, PoolingOperatorConfig
 from .cnn_cat_operator import CNNCatOperator, CNNCatOperatorConfig
 from .gru_operator import GRUOperator, GRUOperatorConfig
+from .transformer_operator import TransformerOperator, TransformerOperatorConfig
+from .poly_attention_operator import PolyAttentionOperator, PolyAttentionOperatorConfig
 
 REGISTRY = {'attention': AttentionOperator, 'cnn': CNNOperator, 'ada': AdaOperator, 'pooling': PoolingOperator,
-            'cnncat': CNNCatOperator, 'gru': GRUOperator}
+            'cnncat': CNNCatOperator, 'gru': GRUOperator, 'transformer': TransformerOperator, 'polyattention': PolyAttentionOperator}
 
 
 def get(name: str):

@@ -536,6 +536,158 @@ def additive_attention(x, mask, w1, b1, w2, cu=None, max_len=None):
 
 
 # ----------------------------------------------------------------------------------------------------
+# LayerNorm (+ residual), GELU, dropout — the row-wise pieces of the BERT-style blocks (Transformer / Fastformer operators)
+# ----------------------------------------------------------------------------------------------------
+class _LayerNorm(Function):
+    """y = LayerNorm(x + res) * w + b over the last axis (BertSelfOutput / BertOutput / BertEmbeddings, eps 1e-12)."""
+
+    @staticmethod
+    def forward(ctx, x, res, w, b, eps):
+        x, w, b = _f32(x), _f32(w), _f32(b)
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D)
+        r2 = _f32(res).reshape(-1, D) if res is not None else None
+        rows = x2.shape[0]
+        dev = x.device
+        y = torch.empty_like(x2)
+        xs = torch.empty_like(x2) if r2 is not None else None
+        mean = torch.empty(rows, dtype=torch.float32, device=dev)
+        rstd = torch.empty(rows, dtype=torch.float32, device=dev)
+        call('lk_layernorm_fwd', ptr(x2), ptr(r2), ptr(w), ptr(b), ptr(y), ptr(xs), ptr(mean), ptr(rstd), rows, D, float(eps))
+        ctx.save_for_backward(xs if xs is not None else x2, w, mean, rstd)
+        ctx.has_res, ctx.shape = res is not None, tuple(x.shape)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, w, mean, rstd = ctx.saved_tensors
+        rows, D = xs.shape
+        dy2 = _f32(dy).reshape(rows, D)
+        dx = torch.empty_like(xs)
+        nparts = query('lk_layernorm_bwd_parts', rows)
+        parts = torch.empty((nparts, 2 * D), dtype=torch.float32, device=xs.device)
+        call('lk_layernorm_bwd', ptr(dy2), ptr(xs), ptr(w), ptr(mean), ptr(rstd), ptr(dx), ptr(parts), rows, D)
+        dwb = colsum_raw(parts)
+        dxv = dx.view(ctx.shape)
+        return dxv, (dxv if ctx.has_res else None), dwb[:D].clone(), dwb[D:].clone(), None
+
+
+def layernorm(x, w, b, eps=1e-12, res=None):
+    return _LayerNorm.apply(x, res, w, b, eps)
+
+
+class _Gelu(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32(x)
+        y = torch.empty_like(x)
+        call('lk_gelu', ptr(x), None, ptr(y), x.numel(), 0)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        call('lk_gelu', ptr(x), ptr(_f32(dy)), ptr(dx), x.numel(), 1)
+        return dx
+
+
+def gelu(x):
+    """Exact (erf) GELU — transformers' ACT2FN['gelu'] (BertIntermediate) and F.gelu (miner_predictor.py:36)."""
+    return _Gelu.apply(x)
+
+
+class _Dropout(Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        x = _f32(x)
+        y = torch.empty_like(x)
+        call('lk_dropout', ptr(x), ptr(y), x.numel(), float(p), int(seed))
+        ctx.ps = (float(p), int(seed))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _f32(dy)
+        dx = torch.empty_like(dy)
+        call('lk_dropout', ptr(dy), ptr(dx), dy.numel(), ctx.ps[0], ctx.ps[1])
+        return dx, None, None
+
+
+def dropout(x, p, seed):
+    """nn.Dropout(p) with the library's counter-based stream; identity for p == 0."""
+    return x if p <= 0.0 else _Dropout.apply(x, p, seed)
+
+
+# ----------------------------------------------------------------------------------------------------
+# MINER: poly-attention pooling and the target-aware predictor
+# ----------------------------------------------------------------------------------------------------
+class _PolyPool(Function):
+    """out[b, c, :] = sum_s softmax_s(mask ? logits[b, s, c] : 1e-30) x[b, s, :]  (poly_attention_operator.py:52-56)."""
+
+    @staticmethod
+    def forward(ctx, logits, mask, x):
+        logits, x, mask = _f32(logits), _f32(x), _i64(mask)
+        B, S, C = logits.shape
+        D = x.shape[-1]
+        out = torch.empty((B, C, D), dtype=torch.float32, device=x.device)
+        w = torch.empty((B, C, S), dtype=torch.float32, device=x.device)
+        call('lk_poly_pool_fwd', ptr(logits), ptr(mask), ptr(x), ptr(out), ptr(w), B, S, C, D)
+        ctx.save_for_backward(w, mask, x)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        w, mask, x = ctx.saved_tensors
+        B, C, S = w.shape
+        D = x.shape[-1]
+        dx = torch.empty_like(x)
+        dlogits = torch.empty((B, S, C), dtype=torch.float32, device=x.device)
+        call('lk_poly_pool_bwd', ptr(_f32(dout)), ptr(w), ptr(mask), ptr(x), ptr(dx), ptr(dlogits), B, S, C, D)
+        return dlogits, None, dx
+
+
+def poly_pool(logits, mask, x):
+    return _PolyPool.apply(logits, mask, x)
+
+
+MINER_MODES = {'weighted': 0, 'max': 1, 'mean': 2}
+
+
+class _MinerScore(Function):
+    """miner_predictor.py:50-62: scores = items·userᵀ; weighted: sum_c softmax_c(items·projᵀ) * scores | max_c | mean_c."""
+
+    @staticmethod
+    def forward(ctx, user, proj, items, mode):
+        user, items = _f32(user), _f32(items)
+        proj = _f32(proj) if proj is not None else None
+        B, C, D = user.shape
+        K1 = items.shape[1]
+        dev = user.device
+        out = torch.empty((B, K1), dtype=torch.float32, device=dev)
+        sc = torch.empty((B, K1, C), dtype=torch.float32, device=dev)
+        wt = torch.empty((B, K1, C), dtype=torch.float32, device=dev)
+        call('lk_miner_fwd', ptr(user), ptr(proj), ptr(items), ptr(out), ptr(sc), ptr(wt), B, K1, C, D, mode)
+        ctx.save_for_backward(user, proj if proj is not None else user, items, sc, wt)
+        ctx.mode, ctx.has_proj = mode, proj is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        user, proj, items, sc, wt = ctx.saved_tensors
+        B, C, D = user.shape
+        K1 = items.shape[1]
+        du, dp, di = torch.empty_like(user), torch.empty_like(user), torch.empty_like(items)
+        call('lk_miner_bwd', ptr(_f32(dout)), ptr(user), ptr(proj), ptr(items), ptr(sc), ptr(wt), ptr(du), ptr(dp), ptr(di), B, K1, C, D, ctx.mode)
+        return du, (dp if ctx.has_proj else None), di, None
+
+
+def miner_score(user, proj, items, mode):
+    return _MinerScore.apply(user, proj, items, MINER_MODES[mode] if isinstance(mode, str) else mode)
+
+
+# ----------------------------------------------------------------------------------------------------
 # GRU over padded sequences -> last hidden state (LSTUR user encoder)
 # ----------------------------------------------------------------------------------------------------
 class _GRULast(Function):

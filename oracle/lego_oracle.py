@@ -252,6 +252,70 @@ def gru_operator(state: dict, prefix: str, x: torch.Tensor, mask: torch.Tensor) 
     return h @ state[prefix + 'linear.weight'].t() + state[prefix + 'linear.bias']
 
 
+def _layer_norm(x, w, b, eps=1e-12):
+    mu = x.mean(dim=-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def _gelu(x):
+    return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def bert_encoder(state: dict, prefix: str, x: torch.Tensor, mask: torch.Tensor, heads: int, layers: int) -> torch.Tensor:
+    """transformers BertModel.forward(inputs_embeds=x, attention_mask=mask).last_hidden_state with every dropout at 0
+    (modeling_bert.py: BertEmbeddings, BertSelfAttention, BertSelfOutput, BertIntermediate, BertOutput), restated:
+    h = LN(x + token_type[0] + position[0..S));  per layer: a = softmax(q k^T / sqrt(dh) + (1-mask)*(-inf)) v;
+    h1 = LN(dense(a) + h);  h = LN(dense(gelu(dense(h1))) + h1)."""
+    B, S, D = x.shape
+    dh = D // heads
+    p = prefix
+    h = x + state[p + 'embeddings.token_type_embeddings.weight'][0] + state[p + 'embeddings.position_embeddings.weight'][:S]
+    h = _layer_norm(h, state[p + 'embeddings.LayerNorm.weight'], state[p + 'embeddings.LayerNorm.bias'])
+    neg = torch.zeros(mask.shape, dtype=x.dtype).masked_fill(mask == 0, float('-inf'))[:, None, None, :]
+    for i in range(layers):
+        lp = f'{p}encoder.layer.{i}.'
+        def lin(name, t):
+            return t @ state[lp + name + '.weight'].t() + state[lp + name + '.bias']
+        q = lin('attention.self.query', h).view(B, S, heads, dh).transpose(1, 2)
+        k = lin('attention.self.key', h).view(B, S, heads, dh).transpose(1, 2)
+        v = lin('attention.self.value', h).view(B, S, heads, dh).transpose(1, 2)
+        att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh) + neg, dim=-1) @ v
+        att = att.transpose(1, 2).reshape(B, S, D)
+        h1 = _layer_norm(lin('attention.output.dense', att) + h, state[lp + 'attention.output.LayerNorm.weight'], state[lp + 'attention.output.LayerNorm.bias'])
+        ff = lin('output.dense', _gelu(lin('intermediate.dense', h1)))
+        h = _layer_norm(ff + h1, state[lp + 'output.LayerNorm.weight'], state[lp + 'output.LayerNorm.bias'])
+    return h
+
+
+def transformer_operator(state: dict, prefix: str, x, mask, heads: int, layers: int) -> torch.Tensor:
+    """model/operators/transformer_operator.py:46-61: BertModel -> Linear -> AdditiveAttention."""
+    h = bert_encoder(state, prefix + 'transformer.', x, mask, heads, layers)
+    out = h @ state[prefix + 'linear.weight'].t() + state[prefix + 'linear.bias']
+    return _additive(state, prefix, out, mask)
+
+
+def poly_attention_operator(state: dict, prefix: str, x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """model/operators/poly_attention_operator.py:45-58: weights = softmax_s(masked_fill(tanh(Linear(x))·codesᵀ, ~mask, 1e-30)) — the fill value
+    is a logit of ~0, not -inf; out [B, codes, D] = weights · x."""
+    proj = torch.tanh(x @ state[prefix + 'linear.weight'].t())
+    w = (proj @ state[prefix + 'context_codes'].t()).permute(0, 2, 1)
+    w = torch.where(mask.unsqueeze(1) > 0, w, torch.full_like(w, 1e-30))
+    return torch.softmax(w, dim=2) @ x
+
+
+def miner_predictor(state: dict, prefix: str, user: torch.Tensor, items: torch.Tensor, score_type: str = 'weighted') -> torch.Tensor:
+    """model/predictors/miner_predictor.py:30-62: scores = items·userᵀ [B, K+1, codes]; weighted: softmax_codes(items · gelu(Linear(user))ᵀ) * scores, summed."""
+    scores = items @ user.permute(0, 2, 1)
+    if score_type == 'max':
+        return scores.max(dim=2)[0]
+    if score_type == 'mean':
+        return scores.mean(dim=2)
+    proj = _gelu(user @ state[prefix + 'target_aware_attention.linear.weight'].t())
+    w = torch.softmax(items @ proj.permute(0, 2, 1), dim=2)
+    return (w * scores).sum(dim=2)
+
+
 def ada_operator(state: dict, prefix: str, x, mask) -> torch.Tensor:
     """model/operators/ada_operator.py:31-38."""
     return _additive(state, prefix, x, mask)
@@ -300,8 +364,9 @@ class ModelSpec:
     """What the oracle needs to know about a model (the yaml-level configuration)."""
 
     def __init__(self, kind: str, heads: int = 8, col_vocab: Optional[Dict[str, str]] = None,
-                 use_neg_sampling: bool = True, item_vocab: str = 'item_id'):
-        assert kind in ('nrms', 'naml', 'llmid', 'pool', 'lstur')
+                 use_neg_sampling: bool = True, item_vocab: str = 'item_id', layers: int = 0, score_type: str = 'weighted'):
+        assert kind in ('nrms', 'naml', 'llmid', 'pool', 'lstur', 'miner')
+        self.layers, self.score_type = layers, score_type
         self.kind, self.heads = kind, heads
         self.col_vocab = col_vocab or {}
         self.use_neg_sampling = use_neg_sampling
@@ -327,6 +392,11 @@ def item_content(state: dict, spec: ModelSpec, tree: dict) -> torch.Tensor:
         am = OrderedDict((c, _flat(v)) for c, v in tree['attention_mask'].items())
         x = simple_embeddings(state, ids, am, spec.col_vocab)
         r = cnn_operator(state, 'item_op.', x, am)
+    elif spec.kind == 'miner':
+        ids = {c: _flat(v) for c, v in tree['input_ids'].items()}
+        B = next(iter(tree['input_ids'].values())).shape[0]
+        mask = _flat(tree['attention_mask'])
+        r = transformer_operator(state, 'item_op.', concat_embeddings(state, ids, spec.col_vocab), mask, spec.heads, spec.layers)
     elif spec.kind == 'lstur':
         ids = OrderedDict((c, _flat(v)) for c, v in tree['input_ids'].items())
         B = next(iter(tree['input_ids'].values())).shape[0]
@@ -355,6 +425,8 @@ def user_content(state: dict, spec: ModelSpec, batch: dict, clicks: Optional[tor
         return attention_operator(state, 'user_op.', clicks, m, spec.heads)
     if spec.kind == 'lstur':
         return gru_operator(state, 'user_op.', clicks, m)
+    if spec.kind == 'miner':
+        return poly_attention_operator(state, 'user_op.', clicks, m)
     return ada_operator(state, 'user_op.', clicks, m)
 
 
@@ -371,7 +443,7 @@ def forward(state: dict, spec: ModelSpec, batch: dict, return_scores: bool = Fal
     if want is not None:
         want['items'], want['user'] = items, user
     if spec.use_neg_sampling:
-        scores = dot_scores(user, items)
+        scores = miner_predictor(state, 'predictor.', user, items, spec.score_type) if spec.kind == 'miner' else dot_scores(user, items)
         if return_scores:
             return scores
         return ce_loss(scores)
@@ -530,7 +602,8 @@ def adam_step(p, g, m, v, step: int, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
 # --------------------------------------------------------------------------------------------
 # parameter shapes / default initialisation for the CPU timing port
 # --------------------------------------------------------------------------------------------
-def state_shapes(kind: str, D: int, A: int, E: int, n_words: int, n_cats: int, n_items: int = 0) -> "OrderedDict[str, tuple]":
+def state_shapes(kind: str, D: int, A: int, E: int, n_words: int, n_cats: int, n_items: int = 0, layers: int = 0, codes: int = 0,
+                 code_dim: int = 0) -> "OrderedDict[str, tuple]":
     s = OrderedDict()
 
     def additive(prefix):
@@ -547,7 +620,7 @@ def state_shapes(kind: str, D: int, A: int, E: int, n_words: int, n_cats: int, n
         s[prefix + 'linear.bias'] = (D,)
         additive(prefix)
 
-    if kind in ('nrms', 'naml', 'pool', 'lstur'):
+    if kind in ('nrms', 'naml', 'pool', 'lstur', 'miner'):
         s['embedding_vocab_table.glove.embedding.weight'] = (n_words, E)
         s['embedding_vocab_table.glove.linear.weight'] = (D, E)
         s['embedding_vocab_table.glove.linear.bias'] = (D,)
@@ -563,6 +636,33 @@ def state_shapes(kind: str, D: int, A: int, E: int, n_words: int, n_cats: int, n
         s['item_op.linear.bias'] = (D,)
         additive('item_op.')
         additive('user_op.')
+    elif kind == 'miner':
+        s['embedding_vocab_table.' + SPECIAL_VOCAB + '.weight'] = (3, D)
+        t = 'item_op.transformer.'
+        s[t + 'embeddings.word_embeddings.weight'] = (1, D)
+        s[t + 'embeddings.position_embeddings.weight'] = (1024, D)
+        s[t + 'embeddings.token_type_embeddings.weight'] = (1, D)
+        s[t + 'embeddings.LayerNorm.weight'] = (D,)
+        s[t + 'embeddings.LayerNorm.bias'] = (D,)
+        for i in range(layers):
+            lp = f'{t}encoder.layer.{i}.'
+            for n, shp in (('attention.self.query', (D, D)), ('attention.self.key', (D, D)), ('attention.self.value', (D, D)),
+                           ('attention.output.dense', (D, D)), ('intermediate.dense', (4 * D, D)), ('output.dense', (D, 4 * D))):
+                s[lp + n + '.weight'] = shp
+                s[lp + n + '.bias'] = (shp[0],)
+            for n in ('attention.output.LayerNorm', 'output.LayerNorm'):
+                s[lp + n + '.weight'] = (D,)
+                s[lp + n + '.bias'] = (D,)
+        s[t + 'pooler.dense.weight'] = (D, D)
+        s[t + 'pooler.dense.bias'] = (D,)
+        s['item_op.linear.weight'] = (D, D)
+        s['item_op.linear.bias'] = (D,)
+        s['item_op.additive_attention.encoder.0.weight'] = (D, D)       # AdditiveAttention(hidden_size=hidden) in transformer_operator.py:40-43
+        s['item_op.additive_attention.encoder.0.bias'] = (D,)
+        s['item_op.additive_attention.encoder.2.weight'] = (1, D)
+        s['user_op.linear.weight'] = (code_dim, D)
+        s['user_op.context_codes'] = (codes, code_dim)
+        s['predictor.target_aware_attention.linear.weight'] = (D, D)
     elif kind == 'lstur':
         s['item_op.cnn.weight'] = (D, D, 3)
         s['item_op.cnn.bias'] = (D,)

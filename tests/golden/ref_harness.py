@@ -63,6 +63,7 @@ def build_reference(world, model='nrms', hidden=256, neg_count=4, dropout=0.0, h
 
     cm = ColumnMap(neg_col='neg')
     item_ut, user_ut = world.item_table(), world.user_table()
+    predictor_cls, predictor_cfg = DotPredictor, None
     if model == 'nrms':
         item_cls, user_cls = AttentionOperator, AttentionOperator
         item_cfg = dict(num_attention_heads=heads, attention_dropout=dropout, additive_hidden_size=additive,
@@ -76,6 +77,16 @@ def build_reference(world, model='nrms', hidden=256, neg_count=4, dropout=0.0, h
         user_cfg = dict(additive_hidden_size=additive,
                         inputer_config=dict(use_cls_token=False, use_sep_token=False))
         use_item_content = True
+    elif model == 'miner':
+        from model.operators.transformer_operator import TransformerOperator
+        from model.operators.poly_attention_operator import PolyAttentionOperator
+        from model.predictors.miner_predictor import MINERPredictor
+        item_cls, user_cls = TransformerOperator, PolyAttentionOperator
+        item_cfg = dict(num_attention_heads=heads, attention_dropout=dropout, num_hidden_layers=2,
+                        inputer_config=dict(use_cls_token=False, use_sep_token=True))
+        user_cfg = dict(num_context_codes=8, context_code_dim=24, inputer_config=dict(use_cls_token=False, use_sep_token=False))
+        use_item_content = True
+        predictor_cls, predictor_cfg = MINERPredictor, dict(score_type='weighted')
     elif model == 'lstur':
         from model.operators.cnn_cat_operator import CNNCatOperator
         from model.operators.gru_operator import GRUOperator
@@ -100,8 +111,8 @@ def build_reference(world, model='nrms', hidden=256, neg_count=4, dropout=0.0, h
         raise ValueError(model)
 
     cfg = LegoConfig(hidden_size=hidden, user_config=user_cfg, item_config=item_cfg, neg_count=neg_count,
-                     use_neg_sampling=use_neg_sampling, use_item_content=use_item_content, item_page_size=0)
-    cfg.set_component_classes(item_cls, user_cls, DotPredictor)
+                     use_neg_sampling=use_neg_sampling, use_item_content=use_item_content, item_page_size=0, predictor_config=predictor_cfg)
+    cfg.set_component_classes(item_cls, user_cls, predictor_cls)
     item_inputs = [world.title_col, 'category']
     cfg.set_item_ut(item_ut, item_inputs)
     cfg.set_user_ut(user_ut, ['history'])
@@ -125,6 +136,10 @@ def build_reference(world, model='nrms', hidden=256, neg_count=4, dropout=0.0, h
     cfg.build_components()
     cfg.register_inputer_vocabs()
     model_ = Legommender(cfg)
+    if dropout == 0.0:      # BertConfig.hidden_dropout_prob (0.1) is not reachable through the operator config: parity runs switch every dropout off
+        for m in model_.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
     resampler = Resampler(cfg)
     if tmp is not None:
         os.unlink(tmp.name)

@@ -58,13 +58,14 @@ def check_grads(c, grads: dict, ref_grads: dict, tol: float, golden=None):
 
 def case_spec(c, world):
     return O.ModelSpec(c['kind'], c['heads'], {world.title_col: world.word_vocab, 'category': 'category'},
-                       use_neg_sampling=c.get('use_neg_sampling', True))
+                       use_neg_sampling=c.get('use_neg_sampling', True), layers=c.get('layers', 0))
 
 
 def state_shapes(c, world, llm=None):
     """Parameter shapes of the reference model for a case, without importing the reference."""
     E = llm.shape[1] if c['kind'] == 'llmid' else world.embed_dim
-    return O.state_shapes(c['kind'], c['hidden'], c['additive'], E, world.n_words, world.n_cats, world.n_items)
+    return O.state_shapes(c['kind'], c['hidden'], c['additive'], E, world.n_words, world.n_cats, world.n_items, layers=c.get('layers', 0),
+                          codes=c.get('codes', 0), code_dim=c.get('code_dim', 0))
 
 
 def oracle_state(c, world, llm=None, dtype=torch.float32):
