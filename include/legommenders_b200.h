@@ -252,6 +252,17 @@ int lk_miner_fwd(const float* user, const float* proj, const float* items, float
 int lk_miner_bwd(const float* dout, const float* user, const float* proj, const float* items, const float* sc, const float* wt, float* duser, float* dproj,
                  float* ditems, int64_t B, int64_t K1, int64_t C, int64_t D, int mode, cudaStream_t stream);
 
+/* ---- Fastformer additive attention (csrc/lk_fast.cu; model/common/fastformer.py:96-143): per-head softmax pooling over the sequence with the
+ *      reference's additive -10000 mask (score [B,S,H], mask [B,S], v [B,S,D] -> out [B,D]; w [B,H,S] saved), the broadcast product
+ *      y[b,s,:] = a[b,s,:] * v[b,:] with its reduction dv[b,:] = sum_s dy*a, and an elementwise add. */
+int lk_head_pool_fwd(const float* score, const int64_t* mask, const float* v, float* out, float* w, int64_t B, int64_t S, int64_t H, int64_t D, float scale,
+                     cudaStream_t stream);
+int lk_head_pool_bwd(const float* dout, const float* w, const float* v, float* dv, float* dscore, int64_t B, int64_t S, int64_t H, int64_t D, float scale,
+                     cudaStream_t stream);
+int lk_bcast_mul(const float* a, const float* v, float* y, int64_t B, int64_t S, int64_t D, cudaStream_t stream);
+int lk_bcast_mul_dv(const float* dy, const float* a, float* dv, int64_t B, int64_t S, int64_t D, cudaStream_t stream);
+int lk_add(const float* a, const float* b, float* y, int64_t n, cudaStream_t stream);
+
 /* ---- GRU user encoder (LSTUR) — nn.GRU(1 layer, batch_first) over pack_padded_sequence, model/operators/gru_operator.py:25-54.
  *      gi [B,S,3H] = x W_ih^T + b_ih for every step (one contraction, the caller's); whhT [H,3H] = W_hh transposed; len [B] valid steps.
  *      Forward: last [B,H] = hidden state after step len-1; saved for the backward: hs [B,S,H], gates [B,S,3H] (r,z,n), hnp [B,S,H].

@@ -93,6 +93,11 @@ SIGNATURES = {
     'lk_poly_pool_bwd': ('pppppp' + 'qqqqs', 'i'),
     'lk_miner_fwd': ('pppppp' + 'qqqqis', 'i'),
     'lk_miner_bwd': ('ppppppppp' + 'qqqqis', 'i'),
+    'lk_head_pool_fwd': ('ppppp' + 'qqqqfs', 'i'),
+    'lk_head_pool_bwd': ('ppppp' + 'qqqqfs', 'i'),
+    'lk_bcast_mul': ('pppqqqs', 'i'),
+    'lk_bcast_mul_dv': ('pppqqqs', 'i'),
+    'lk_add': ('pppqs', 'i'),
     'lk_gru_fwd': ('pppppppp' + 'qqqs', 'i'),
     'lk_gru_bwd': ('pppppppp' + 'qqqs', 'i'),
     'lk_tc_chain': ('ppqqpiis', 'i'),

@@ -27,7 +27,8 @@ MODEL_META = {
     'llmid': dict(item=None, user='Ada', predictor='Dot'),          # id-based path with per-item LLM embeddings
     'pool': dict(item='Pooling', user='Ada', predictor='Dot'),
     'lstur': dict(item='CNNCat', user='GRU', predictor='Dot'),       # config/model/lstur.yaml
-    'miner': dict(item='Transformer', user='PolyAttention', predictor='MINER'),   # config/model/miner.yaml      # masked-mean item encoder (pooling_operator.py) + Ada users
+    'miner': dict(item='Transformer', user='PolyAttention', predictor='MINER'),   # config/model/miner.yaml
+    'fastformer': dict(item='Fastformer', user='Fastformer', predictor='Dot'),   # config/model/fastformer.yaml      # masked-mean item encoder (pooling_operator.py) + Ada users
 }
 
 
@@ -45,6 +46,13 @@ def model_config(kind: str, hidden: int, heads: int = 8, additive: int = 256, dr
                     use_neg_sampling=use_neg_sampling,
                     item_config=dict(dropout=dropout, kernel_size=3, additive_hidden_size=additive),
                     user_config=dict(additive_hidden_size=additive,
+                                     inputer_config=dict(use_cls_token=False, use_sep_token=False)))
+    if kind == 'fastformer':
+        return dict(use_item_content=True, hidden_size=hidden, item_hidden_size=hidden, neg_count=neg_count,
+                    use_neg_sampling=use_neg_sampling,
+                    item_config=dict(num_attention_heads=heads, num_hidden_layers=1, hidden_dropout_prob=dropout,
+                                     inputer_config=dict(use_cls_token=False, use_sep_token=False)),
+                    user_config=dict(num_attention_heads=heads, num_hidden_layers=1, hidden_dropout_prob=dropout,
                                      inputer_config=dict(use_cls_token=False, use_sep_token=False)))
     if kind == 'miner':
         return dict(use_item_content=True, hidden_size=hidden, item_hidden_size=hidden, neg_count=neg_count,

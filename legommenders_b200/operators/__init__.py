@@ -7,9 +7,10 @@ from .cnn_cat_operator import CNNCatOperator, CNNCatOperatorConfig
 from .gru_operator import GRUOperator, GRUOperatorConfig
 from .transformer_operator import TransformerOperator, TransformerOperatorConfig
 from .poly_attention_operator import PolyAttentionOperator, PolyAttentionOperatorConfig
+from .fastformer_operator import FastformerOperator, FastformerOperatorConfig
 
 REGISTRY = {'attention': AttentionOperator, 'cnn': CNNOperator, 'ada': AdaOperator, 'pooling': PoolingOperator,
-            'cnncat': CNNCatOperator, 'gru': GRUOperator, 'transformer': TransformerOperator, 'polyattention': PolyAttentionOperator}
+            'cnncat': CNNCatOperator, 'gru': GRUOperator, 'transformer': TransformerOperator, 'polyattention': PolyAttentionOperator, 'fastformer': FastformerOperator}
 
 
 def get(name: str):

@@ -688,6 +688,84 @@ def miner_score(user, proj, items, mode):
 
 
 # ----------------------------------------------------------------------------------------------------
+# Fastformer: per-head softmax pooling, broadcast product, add
+# ----------------------------------------------------------------------------------------------------
+class _HeadPool(Function):
+    """out[b, h*dh + j] = sum_s softmax_s(score[b, s, h] * scale - 10000 * (1 - mask[b, s])) v[b, s, h*dh + j]  (fastformer.py:103-116, 125-132)."""
+
+    @staticmethod
+    def forward(ctx, score, mask, v, scale):
+        score, v, mask = _f32(score), _f32(v), _i64(mask)
+        B, S, H = score.shape
+        D = v.shape[-1]
+        out = torch.empty((B, D), dtype=torch.float32, device=v.device)
+        w = torch.empty((B, H, S), dtype=torch.float32, device=v.device)
+        call('lk_head_pool_fwd', ptr(score), ptr(mask), ptr(v), ptr(out), ptr(w), B, S, H, D, float(scale))
+        ctx.save_for_backward(w, v)
+        ctx.scale = float(scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        w, v = ctx.saved_tensors
+        B, H, S = w.shape
+        D = v.shape[-1]
+        dv = torch.empty_like(v)
+        dscore = torch.empty((B, S, H), dtype=torch.float32, device=v.device)
+        call('lk_head_pool_bwd', ptr(_f32(dout)), ptr(w), ptr(v), ptr(dv), ptr(dscore), B, S, H, D, ctx.scale)
+        return dscore, None, dv, None
+
+
+def head_pool(score, mask, v, scale):
+    return _HeadPool.apply(score, mask, v, scale)
+
+
+class _BcastMul(Function):
+    """y[b, s, :] = a[b, s, :] * v[b, :]"""
+
+    @staticmethod
+    def forward(ctx, a, v):
+        a, v = _f32(a), _f32(v)
+        B, S, D = a.shape
+        y = torch.empty_like(a)
+        call('lk_bcast_mul', ptr(a), ptr(v), ptr(y), B, S, D)
+        ctx.save_for_backward(a, v)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, v = ctx.saved_tensors
+        B, S, D = a.shape
+        dy = _f32(dy)
+        da = torch.empty_like(a)
+        dv = torch.empty_like(v)
+        call('lk_bcast_mul', ptr(dy), ptr(v), ptr(da), B, S, D)
+        call('lk_bcast_mul_dv', ptr(dy), ptr(a), ptr(dv), B, S, D)
+        return da, dv
+
+
+def bcast_mul(a, v):
+    return _BcastMul.apply(a, v)
+
+
+class _Add(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _f32(a), _f32(b)
+        y = torch.empty_like(a)
+        call('lk_add', ptr(a), ptr(b), ptr(y), a.numel())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def add(a, b):
+    return _Add.apply(a, b)
+
+
+# ----------------------------------------------------------------------------------------------------
 # GRU over padded sequences -> last hidden state (LSTUR user encoder)
 # ----------------------------------------------------------------------------------------------------
 class _GRULast(Function):

@@ -295,6 +295,43 @@ def transformer_operator(state: dict, prefix: str, x, mask, heads: int, layers: 
     return _additive(state, prefix, out, mask)
 
 
+def fastformer_operator(state: dict, prefix: str, x: torch.Tensor, mask: torch.Tensor, heads: int, layers: int) -> torch.Tensor:
+    """model/operators/fastformer_operator.py:41-49 + model/common/fastformer.py:62-226 with every dropout at 0: position embeddings + LayerNorm,
+    `layers` x (FastSelfAttention -> BertSelfOutput -> BertIntermediate -> BertOutput), AttentionPooling, Linear.  The mask enters the two softmaxes
+    additively as (1 - mask) * (-10000)."""
+    B, S, D = x.shape
+    dh = D // heads
+    p = prefix + 'fastformer.'
+    m = mask.to(x.dtype)
+    ext = ((1.0 - m) * -10000.0).unsqueeze(1)                                   # [B, 1, S]
+
+    def lin(name, t):
+        return t @ state[name + '.weight'].t() + state[name + '.bias']
+
+    h = _layer_norm(x + state[p + 'position_embeddings.weight'][:S], state[p + 'LayerNorm.weight'], state[p + 'LayerNorm.bias'])
+    for i in range(layers):
+        lp = f'{p}encoders.{i}.'
+        sa = lp + 'attention.self.'
+        mq, mk = lin(sa + 'query', h), lin(sa + 'key', h)
+        qw = torch.softmax(lin(sa + 'query_att', mq).transpose(1, 2) / dh ** 0.5 + ext, dim=-1).unsqueeze(2)      # [B, heads, 1, S]
+        ql = mq.view(B, S, heads, dh).permute(0, 2, 1, 3)
+        pooled_q = (qw @ ql).transpose(1, 2).reshape(B, 1, D)
+        mixed = mk * pooled_q
+        kw = torch.softmax((lin(sa + 'key_att', mixed) / dh ** 0.5).transpose(1, 2) + ext, dim=-1).unsqueeze(2)
+        kl = mixed.view(B, S, heads, dh).permute(0, 2, 1, 3)
+        pooled_k = kw @ kl                                                        # [B, heads, 1, dh]
+        wv = (pooled_k * ql).transpose(1, 2).reshape(B, S, D)
+        so = lin(sa + 'transform', wv) + mq
+        att = _layer_norm(lin(lp + 'attention.output.dense', so) + h, state[lp + 'attention.output.LayerNorm.weight'], state[lp + 'attention.output.LayerNorm.bias'])
+        ff = lin(lp + 'output.dense', _gelu(lin(lp + 'intermediate.dense', att)))
+        h = _layer_norm(ff + att, state[lp + 'output.LayerNorm.weight'], state[lp + 'output.LayerNorm.bias'])
+    e = torch.tanh(lin(p + 'poolers.0.att_fc1', h))
+    alpha = torch.exp(lin(p + 'poolers.0.att_fc2', e)) * m.unsqueeze(2)
+    alpha = alpha / (alpha.sum(dim=1, keepdim=True) + 1e-8)
+    pooled = (h * alpha).sum(dim=1)
+    return pooled @ state[prefix + 'linear.weight'].t() + state[prefix + 'linear.bias']
+
+
 def poly_attention_operator(state: dict, prefix: str, x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """model/operators/poly_attention_operator.py:45-58: weights = softmax_s(masked_fill(tanh(Linear(x))·codesᵀ, ~mask, 1e-30)) — the fill value
     is a logit of ~0, not -inf; out [B, codes, D] = weights · x."""
@@ -365,7 +402,7 @@ class ModelSpec:
 
     def __init__(self, kind: str, heads: int = 8, col_vocab: Optional[Dict[str, str]] = None,
                  use_neg_sampling: bool = True, item_vocab: str = 'item_id', layers: int = 0, score_type: str = 'weighted'):
-        assert kind in ('nrms', 'naml', 'llmid', 'pool', 'lstur', 'miner')
+        assert kind in ('nrms', 'naml', 'llmid', 'pool', 'lstur', 'miner', 'fastformer')
         self.layers, self.score_type = layers, score_type
         self.kind, self.heads = kind, heads
         self.col_vocab = col_vocab or {}
@@ -392,6 +429,11 @@ def item_content(state: dict, spec: ModelSpec, tree: dict) -> torch.Tensor:
         am = OrderedDict((c, _flat(v)) for c, v in tree['attention_mask'].items())
         x = simple_embeddings(state, ids, am, spec.col_vocab)
         r = cnn_operator(state, 'item_op.', x, am)
+    elif spec.kind == 'fastformer':
+        ids = {c: _flat(v) for c, v in tree['input_ids'].items()}
+        B = next(iter(tree['input_ids'].values())).shape[0]
+        mask = _flat(tree['attention_mask'])
+        r = fastformer_operator(state, 'item_op.', concat_embeddings(state, ids, spec.col_vocab), mask, spec.heads, spec.layers)
     elif spec.kind == 'miner':
         ids = {c: _flat(v) for c, v in tree['input_ids'].items()}
         B = next(iter(tree['input_ids'].values())).shape[0]
@@ -427,6 +469,8 @@ def user_content(state: dict, spec: ModelSpec, batch: dict, clicks: Optional[tor
         return gru_operator(state, 'user_op.', clicks, m)
     if spec.kind == 'miner':
         return poly_attention_operator(state, 'user_op.', clicks, m)
+    if spec.kind == 'fastformer':
+        return fastformer_operator(state, 'user_op.', clicks, m, spec.heads, spec.layers)
     return ada_operator(state, 'user_op.', clicks, m)
 
 
@@ -620,7 +664,7 @@ def state_shapes(kind: str, D: int, A: int, E: int, n_words: int, n_cats: int, n
         s[prefix + 'linear.bias'] = (D,)
         additive(prefix)
 
-    if kind in ('nrms', 'naml', 'pool', 'lstur', 'miner'):
+    if kind in ('nrms', 'naml', 'pool', 'lstur', 'miner', 'fastformer'):
         s['embedding_vocab_table.glove.embedding.weight'] = (n_words, E)
         s['embedding_vocab_table.glove.linear.weight'] = (D, E)
         s['embedding_vocab_table.glove.linear.bias'] = (D,)
@@ -636,6 +680,29 @@ def state_shapes(kind: str, D: int, A: int, E: int, n_words: int, n_cats: int, n
         s['item_op.linear.bias'] = (D,)
         additive('item_op.')
         additive('user_op.')
+    elif kind == 'fastformer':
+        heads = codes                                    # (the caller passes the head count through `codes`)
+        for side in ('item_op.', 'user_op.'):
+            f = side + 'fastformer.'
+            for i in range(layers):
+                lp = f'{f}encoders.{i}.'
+                for n, shp in (('attention.self.query', (D, D)), ('attention.self.query_att', (heads, D)), ('attention.self.key', (D, D)),
+                               ('attention.self.key_att', (heads, D)), ('attention.self.transform', (D, D)), ('attention.output.dense', (D, D)),
+                               ('intermediate.dense', (4 * D, D)), ('output.dense', (D, 4 * D))):
+                    s[lp + n + '.weight'] = shp
+                    s[lp + n + '.bias'] = (shp[0],)
+                for n in ('attention.output.LayerNorm', 'output.LayerNorm'):
+                    s[lp + n + '.weight'] = (D,)
+                    s[lp + n + '.bias'] = (D,)
+            s[f + 'position_embeddings.weight'] = (1024, D)
+            s[f + 'LayerNorm.weight'] = (D,)
+            s[f + 'LayerNorm.bias'] = (D,)
+            s[f + 'poolers.0.att_fc1.weight'] = (D, D)
+            s[f + 'poolers.0.att_fc1.bias'] = (D,)
+            s[f + 'poolers.0.att_fc2.weight'] = (1, D)
+            s[f + 'poolers.0.att_fc2.bias'] = (1,)
+            s[side + 'linear.weight'] = (D, D)
+            s[side + 'linear.bias'] = (D,)
     elif kind == 'miner':
         s['embedding_vocab_table.' + SPECIAL_VOCAB + '.weight'] = (3, D)
         t = 'item_op.transformer.'

@@ -52,6 +52,8 @@ CASES = OrderedDict(
     # masked-mean PoolingOperator item encoder (a10) + Ada users
     # MINER: BERT-style Transformer item encoder (2 layers) + poly-attention user encoder (8 codes) + target-aware MINER predictor
     miner_small=dict(kind='miner', hidden=64, heads=8, additive=64, batch=6, seed=27, world=_small_world, layers=2, codes=8, code_dim=24),
+    # Fastformer item and user encoders (config/model/fastformer.yaml: one layer each, no SEP tokens)
+    fastformer_small=dict(kind='fastformer', hidden=64, heads=8, additive=64, batch=6, seed=28, world=_small_world, layers=1, cached_eval=True),
     # LSTUR: CNNCat item encoder (feature-axis concat of the columns) + GRU user encoder (config/model/lstur.yaml)
     lstur_small=dict(kind='lstur', hidden=64, heads=8, additive=32, batch=6, seed=26, world=_small_world),   # no cached eval: the reference's UserCacher placeholder is [users, hidden] but GRUOperator returns input_dim = 2*hidden (base_operator.py:52-53 vs gru_operator.py:54)
     pool_small=dict(kind='pool', hidden=64, heads=8, additive=32, batch=6, seed=25, world=_small_world, cached_eval=True),

@@ -77,6 +77,14 @@ def build_reference(world, model='nrms', hidden=256, neg_count=4, dropout=0.0, h
         user_cfg = dict(additive_hidden_size=additive,
                         inputer_config=dict(use_cls_token=False, use_sep_token=False))
         use_item_content = True
+    elif model == 'fastformer':
+        from model.operators.fastformer_operator import FastformerOperator
+        item_cls, user_cls = FastformerOperator, FastformerOperator
+        item_cfg = dict(num_attention_heads=heads, num_hidden_layers=1, hidden_dropout_prob=dropout,
+                        inputer_config=dict(use_cls_token=False, use_sep_token=False))
+        user_cfg = dict(num_attention_heads=heads, num_hidden_layers=1, hidden_dropout_prob=dropout,
+                        inputer_config=dict(use_cls_token=False, use_sep_token=False))
+        use_item_content = True
     elif model == 'miner':
         from model.operators.transformer_operator import TransformerOperator
         from model.operators.poly_attention_operator import PolyAttentionOperator

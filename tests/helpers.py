@@ -65,7 +65,7 @@ def state_shapes(c, world, llm=None):
     """Parameter shapes of the reference model for a case, without importing the reference."""
     E = llm.shape[1] if c['kind'] == 'llmid' else world.embed_dim
     return O.state_shapes(c['kind'], c['hidden'], c['additive'], E, world.n_words, world.n_cats, world.n_items, layers=c.get('layers', 0),
-                          codes=c.get('codes', 0), code_dim=c.get('code_dim', 0))
+                          codes=c.get('codes', c['heads'] if c['kind'] == 'fastformer' else 0), code_dim=c.get('code_dim', 0))
 
 
 def oracle_state(c, world, llm=None, dtype=torch.float32):
