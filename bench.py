@@ -830,15 +830,14 @@ def hbm_bound_lines(dev, world, hbm_peak, model=None, resampler=None, tensor_pea
         out['cache_build_device'] = dict(items=n_i, users=n_u, seconds=dt, items_and_users_per_s=(n_i + n_u) / dt,
                                          note='item pages: lk_pack_item_tokens + packed NRMS item encoder; user pages: lk_index_rows over the item cache + packed NRMS user encoder; wall clock incl. host offset arithmetic')
 
-    # config 1 (BASELINE.json configs[0]: NAML, the reference's CPU-runnable case) on the GPU through the plugin surface + torch.autograd:
-    # Conv1d('same') as the implicit-im2col SIMT kernel (fp32 FFMA), AdditiveAttention, Ada user encoder, fused dot + CE, FlatAdam
-    @guarded('naml_train')
-    def _():
+    # config 1 (BASELINE.json configs[0]: NAML, the reference's CPU-runnable case) and the neighbouring model families (LSTUR, MINER,
+    # Fastformer) on the GPU through the plugin surface + torch.autograd (model(batch); loss.backward(); FlatAdam.step()), pre-built device batches
+    def plugin_train_line(kind, note):
         from legommenders_b200 import Env, builder
         from legommenders_b200.batching import BatchBuilder, tree_to_device
         from legommenders_b200.trainer import FlatAdam
         torch.manual_seed(11)
-        m2, r2, _ = builder.build_model(world, 'naml', hidden=HIDDEN, heads=HEADS, additive=ADDITIVE, dropout=DROPOUT, neg_count=NEG,
+        m2, r2, _ = builder.build_model(world, kind, hidden=HIDDEN, heads=HEADS, additive=ADDITIVE, dropout=DROPOUT, neg_count=NEG,
                                         device_index=dev.index)
         o2 = FlatAdam(m2, lr=1e-3)
         Env.train(); m2.train()
@@ -864,11 +863,16 @@ def hbm_bound_lines(dev, world, hbm_peak, model=None, resampler=None, tensor_pea
         e1.record()
         torch.cuda.synchronize()
         ms2 = e0.elapsed_time(e1) / K2
-        out['naml_train'] = dict(workload='NAML train step (CNN title encoder + additive attention, Ada user encoder, DotPredictor + CE), MIND-small shape, batch 64',
-                                 ms_per_step=ms2, impressions_per_s=64 / ms2 * 1e3, loss=float(loss.item()),
-                                 note='generic plugin path (model(batch); loss.backward(); FlatAdam.step()) on pre-built device batches; the conv runs on fp32 FFMA '
-                                      '(lk_conv1d_*), not on tensor cores; host-driven launches')
         del m2, o2, pool2
+        return dict(ms_per_step=ms2, impressions_per_s=64 / ms2 * 1e3, loss=float(loss.item()), batch=64, note=note)
+
+    for kind, note in (('naml', 'NAML: CNN title encoder (conv on fp32 FFMA, lk_conv1d_*) + additive attention, Ada user encoder, DotPredictor + CE'),
+                       ('lstur', 'LSTUR: CNNCat item encoder + GRU user encoder (lk_gru_fwd/bwd)'),
+                       ('miner', 'MINER: 2-layer BERT-style Transformer item encoder + poly attention (8 codes) + target-aware predictor'),
+                       ('fastformer', 'Fastformer item and user encoders (1 layer each)')):
+        @guarded(kind + '_train')
+        def _(kind=kind, note=note):
+            out[kind + '_train'] = plugin_train_line(kind, note + '; generic plugin path, host-driven launches, MIND-small shape')
 
     # config 4 on one GPU (the row-sharded table with a single shard: same kernels, no NVLink traffic); the N > 1 lines are in SCALE
     @guarded('config4_sharded_table_train')

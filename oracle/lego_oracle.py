@@ -507,7 +507,7 @@ def build_item_cache(state: dict, spec: ModelSpec, item_trees: List[dict], page_
     with torch.no_grad():
         for s in range(0, len(item_trees), page_size):
             page = item_trees[s:s + page_size]
-            if spec.kind == 'nrms':
+            if spec.kind in ('nrms', 'miner', 'fastformer'):          # ConcatInputer: one mask for the concatenated sequence
                 tree = dict(input_ids={c: torch.stack([torch.as_tensor(p['input_ids'][c]) for p in page]).unsqueeze(1)
                                        for c in page[0]['input_ids']},
                             attention_mask=torch.stack([torch.as_tensor(p['attention_mask']) for p in page]).unsqueeze(1))

@@ -102,8 +102,8 @@ def item_trees(world, kind, title_len=None):
     out = []
     for i in range(len(tab)):
         s = tab[i]
-        if kind == 'nrms':
-            out.append(O.concat_layout(s, inputs, max_lens, use_cls_token=False, use_sep_token=True))
+        if kind in ('nrms', 'miner', 'fastformer'):          # ConcatInputer operators; Fastformer's yaml switches the SEP tokens off
+            out.append(O.concat_layout(s, inputs, max_lens, use_cls_token=False, use_sep_token=kind != 'fastformer'))
         else:
             out.append(O.simple_layout(s, inputs, max_lens))
     return out

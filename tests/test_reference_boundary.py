@@ -23,7 +23,14 @@ PLUGIN_FILES = {
     'b200plug/operators/b200attention_operator.py': "B200AttentionOperator = integration.plugin('attention')",
     'b200plug/operators/b200cnn_operator.py': "B200CNNOperator = integration.plugin('cnn')",
     'b200plug/operators/b200ada_operator.py': "B200AdaOperator = integration.plugin('ada')",
+    'b200plug/operators/b200pooling_operator.py': "B200PoolingOperator = integration.plugin('pooling')",
+    'b200plug/operators/b200cnncat_operator.py': "B200CNNCatOperator = integration.plugin('cnncat')",
+    'b200plug/operators/b200gru_operator.py': "B200GRUOperator = integration.plugin('gru')",
+    'b200plug/operators/b200transformer_operator.py': "B200TransformerOperator = integration.plugin('transformer')",
+    'b200plug/operators/b200fastformer_operator.py': "B200FastformerOperator = integration.plugin('fastformer')",
+    'b200plug/operators/b200polyattention_operator.py': "B200PolyAttentionOperator = integration.plugin('polyattention')",
     'b200plug/predictors/b200dot_predictor.py': "B200DotPredictor = integration.plugin('dot', kind='predictor')",
+    'b200plug/predictors/b200miner_predictor.py': "B200MINERPredictor = integration.plugin('miner', kind='predictor')",
 }
 
 
@@ -62,8 +69,9 @@ def test_classhub_discovers_plugins(plugin_tree):
     from model.operators.base_operator import BaseOperator as RefOp
     from legommenders_b200.operators.attention_operator import AttentionOperator
     ops_hub, pred_hub = discover()
-    assert sorted(ops_hub.list()) == ['b200ada', 'b200attention', 'b200cnn']      # yaml: meta.item: B200Attention -> lower()
-    assert pred_hub.list() == ['b200dot']
+    assert sorted(ops_hub.list()) == ['b200ada', 'b200attention', 'b200cnn', 'b200cnncat', 'b200fastformer', 'b200gru', 'b200polyattention',
+                                      'b200pooling', 'b200transformer']      # yaml: meta.item: B200Attention -> lower()
+    assert sorted(pred_hub.list()) == ['b200dot', 'b200miner']
     cls = ops_hub('B200Attention')
     assert issubclass(cls, RefOp) and issubclass(cls, AttentionOperator)
     assert not issubclass(AttentionOperator, RefOp)                                 # why the shim is needed at all
