@@ -319,8 +319,17 @@ def main():
             dres.take()
         dres.submit(rows_dev[0])
         l0 = _lib.load().lk_launch_count()
+        if world_size > 1:
+            opt.time_allreduce = []
         ms, w0, w1, per_step = timed(resident_step, args.steps)
         launches = int(_lib.load().lk_launch_count() - l0)
+        collective = None
+        if world_size > 1:
+            ts = sorted(a.elapsed_time(b) for a, b in opt.time_allreduce)
+            opt.time_allreduce = None
+            collective = dict(op=('lk_allreduce_p2p between two symmetric-memory barriers (NVLink peer memory)' if opt.symm is not None else 'ncclAllReduce') + ': sum of the flat gradient bucket', bytes=int(opt.grad.numel() * 4), ms_median=ts[len(ts) // 2], ms_min=ts[0],
+                              ms_max=ts[-1], note='CUDA events on the step stream around the collective of every timed step, this rank: from local gradients '
+                                                  'ready to reduced, i.e. the wait for the slowest rank + the transfer; it is not overlapped with compute')
         dres.take()
         dres.submit(rows_host[0])
         del losses_read[:]
@@ -411,6 +420,8 @@ def main():
                          if native is not None else 'wire-format batch'),
                 e2e_wire_format=e2e_wire,
                 gpu_launches=launches, roofline=roof, kernel_ms_share=shares, strong_scaling=strong)
+    if native is not None and world_size > 1:
+        line['collective'] = collective
 
     if parity is not None:
         line['parity_check'] = parity
@@ -459,6 +470,15 @@ def parity_self_check(dev, rank, W, model, native, opt, resampler, world, batch)
     native.fwd_bwd(dres.take(), training=False)
     g_dp = opt.grad.clone()
     dist.all_reduce(g_dp, op=dist.ReduceOp.SUM)
+    if opt.symm is not None:                                      # the timed step's own collective (lk_allreduce_p2p) against ncclAllReduce
+        opt.allreduce()
+        err = float((opt.grad - g_dp).abs().max() / g_dp.abs().max())
+        if not err <= 1e-6:
+            problems.append(f'peer-memory all-reduce differs from ncclAllReduce: {err:.2e}')
+        r0 = opt.grad.clone()
+        dist.broadcast(r0, src=0)
+        if not torch.equal(r0, opt.grad):
+            problems.append('peer-memory all-reduce: ranks hold different sums')
     g_dp /= W
     dres.submit(all_rows)
     loss_g = native.fwd_bwd(dres.take(), training=False).item()

@@ -76,6 +76,11 @@ int lk_shard_inverse(const int64_t* ids, int64_t P, const int64_t* keys, const i
                      cudaStream_t stream);
 int lk_shard_gather(const int64_t* ids, int64_t M, int W, const float* local, int64_t local_rows, int64_t E, float* out, cudaStream_t stream);
 
+/* ---- gradient all-reduce over NVLink peer memory (csrc/lk_allreduce.cu): every rank's flat gradient bucket is peer-mapped (symmetric memory);
+ *      this rank sums ITS 1/W slice over all W buckets (fixed order) and writes the (scaled) sum into all of them.  peer_ptrs: HOST array of W
+ *      device pointers, index = rank.  The caller provides the cross-rank barriers before (all gradients written) and after (all sums visible). */
+int lk_allreduce_p2p(void* const* peer_ptrs, int rank, int W, int64_t n, float scale, cudaStream_t stream);
+
 /* ---- device-side Resampler (csrc/lk_resample.cu) — loader/resampler.py:139-259 taken to the device: from B impression rows to the id lists
  *      and offsets of a packed training batch in ONE launch.  Negatives = min(K, len) distinct positions of the user's negative list in random
  *      order + uniform item ids (Philox4x32-10 keyed by (seed, impression row)); histories are the users' valid clicks (padding is never

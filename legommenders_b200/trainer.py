@@ -22,7 +22,12 @@ class FlatAdam:
         sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]      # keep every slice 16-byte aligned
         total = sum(sizes)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.symm = None
+        self.grad = self._peer_bucket(total, dev) if (self.world > 1 and dev.type == 'cuda') else None
+        if self.grad is None:
+            self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.m = torch.zeros(total, dtype=torch.float32, device=dev)
         self.v = torch.zeros(total, dtype=torch.float32, device=dev)
         off = 0
@@ -34,8 +39,42 @@ class FlatAdam:
             off += sz
         self.lr, self.betas, self.eps = lr, betas, eps
         self.step_count = 0
-        self.group = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.time_allreduce = None
+
+    def _peer_bucket(self, total, dev):
+        """The gradient bucket in symmetric memory (peer-mapped over NVLink by torch.distributed's rendezvous: plumbing) so that the all-reduce
+        can be this library's one-kernel slice reduction (lk_allreduce_p2p).  None -> NCCL all-reduce (LK_P2P_ALLREDUCE=0, or no peer access)."""
+        import ctypes
+        import os
+        if os.environ.get('LK_P2P_ALLREDUCE', '1') == '0':
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            group = self.group if self.group is not None else dist.group.WORLD
+            try:
+                symm_mem.enable_symm_mem_for_group(group.group_name)
+            except Exception:   # noqa: BLE001 — newer torch enables it on rendezvous
+                pass
+            grad = symm_mem.empty(total, dtype=torch.float32, device=dev)
+            grad.zero_()
+            self.symm = symm_mem.rendezvous(grad, group=group)
+            self._peer_ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in self.symm.buffer_ptrs])
+            return grad
+        except Exception as e:   # noqa: BLE001
+            import sys
+            print(f'[legommenders_b200] peer-memory gradient bucket unavailable ({type(e).__name__}: {e}); using ncclAllReduce', file=sys.stderr)
+            self.symm = None
+            return None
+
+    def _allreduce_now(self):
+        if self.symm is not None:
+            from ._lib import call
+            import ctypes
+            self.symm.barrier(channel=0)                       # every rank has written its gradients
+            call('lk_allreduce_p2p', ctypes.addressof(self._peer_ptrs), self.symm.rank, self.world, self.grad.numel(), 1.0)
+            self.symm.barrier(channel=1)                       # every slice's sum is visible everywhere
+        else:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
 
     def zero_grad(self):
         self.grad.zero_()
@@ -44,9 +83,17 @@ class FlatAdam:
                 raise RuntimeError('parameter .grad was detached from the flat buffer')
 
     def allreduce(self):
-        """Batch data-parallel: one flat-bucket NCCL allreduce (sum); the 1/world mean is folded into the Adam kernel."""
+        """Batch data-parallel: one all-reduce (sum) of the flat bucket — lk_allreduce_p2p over NVLink peer memory when the bucket is in
+        symmetric memory, ncclAllReduce otherwise; the 1/world mean is folded into the Adam kernel."""
         if self.world > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
+            if self.time_allreduce is not None:        # bench.py: CUDA events around the collective (local gradients ready -> reduced)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                self._allreduce_now()
+                e1.record()
+                self.time_allreduce.append((e0, e1))
+            else:
+                self._allreduce_now()
 
     def step(self, lr: float = None):
         self.step_count += 1

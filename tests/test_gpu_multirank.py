@@ -160,6 +160,30 @@ def _sharded_table_step(rank):
     assert torch.equal(opt.grad, g0)
 
 
+def _p2p_allreduce(rank):
+    """FlatAdam's peer-memory all-reduce (lk_allreduce_p2p between two symmetric-memory barriers) == ncclAllReduce of the same buckets,
+    bit-identical on all ranks, repeatedly (the barriers must order step k's reads before step k+1's writes)."""
+    from legommenders_b200.trainer import FlatAdam
+    dev = torch.device('cuda', rank)
+    m = torch.nn.Sequential(torch.nn.Linear(301, 257), torch.nn.Linear(257, 33)).to(dev)
+    opt = FlatAdam(m, lr=1e-3)
+    assert opt.symm is not None, 'gradient bucket is not in symmetric memory (peer access unavailable?)'
+    for it in range(20):
+        g = torch.Generator(device=dev).manual_seed(1000 * it + rank)
+        opt.grad.normal_(0, 1, generator=g)
+        want = opt.grad.clone()
+        dist.all_reduce(want)
+        opt.allreduce()
+        torch.testing.assert_close(opt.grad, want, rtol=1e-6, atol=1e-6)
+        other = opt.grad.clone()
+        dist.broadcast(other, src=0)
+        assert torch.equal(other, opt.grad)                      # every element summed once, by one rank
+
+
+def test_p2p_allreduce_matches_nccl():
+    spawn(_p2p_allreduce)
+
+
 def test_sharded_table_native_step_nccl():
     spawn(_sharded_table_step)
 
