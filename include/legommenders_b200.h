@@ -78,8 +78,13 @@ int lk_shard_gather(const int64_t* ids, int64_t M, int W, const float* local, in
 
 /* ---- gradient all-reduce over NVLink peer memory (csrc/lk_allreduce.cu): every rank's flat gradient bucket is peer-mapped (symmetric memory);
  *      this rank sums ITS 1/W slice over all W buckets (fixed order) and writes the (scaled) sum into all of them.  peer_ptrs: HOST array of W
- *      device pointers, index = rank.  The caller provides the cross-rank barriers before (all gradients written) and after (all sums visible). */
-int lk_allreduce_p2p(void* const* peer_ptrs, int rank, int W, int64_t n, float scale, cudaStream_t stream);
+ *      device pointers, index = rank.  flag_ptrs: HOST array of W device pointers to every rank's LK_ALLREDUCE_FLAG_WORDS int32 flag words
+ *      (symmetric memory, zeroed once): the cross-rank rendezvous before (all gradients written) and after (all sums visible) then happen
+ *      inside the launch, epoch = 1, 2, 3 ... per call and equal on all ranks.  flag_ptrs NULL: the caller brackets the launch with its own. */
+#define LK_ALLREDUCE_FLAG_WORDS 4096
+/* debugging aid: buf = device int64[148 * 6] (per block: SM clocks of launch->dependency, rendezvous, reduction, fence, rendezvous, total) or NULL */
+int lk_allreduce_set_trace(void* buf);
+int lk_allreduce_p2p(void* const* peer_ptrs, void* const* flag_ptrs, int epoch, int rank, int W, int64_t n, float scale, cudaStream_t stream);
 
 /* ---- device-side Resampler (csrc/lk_resample.cu) — loader/resampler.py:139-259 taken to the device: from B impression rows to the id lists
  *      and offsets of a packed training batch in ONE launch.  Negatives = min(K, len) distinct positions of the user's negative list in random

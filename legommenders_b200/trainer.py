@@ -51,14 +51,19 @@ class FlatAdam:
         try:
             import torch.distributed._symmetric_memory as symm_mem
             group = self.group if self.group is not None else dist.group.WORLD
-            try:
-                symm_mem.enable_symm_mem_for_group(group.group_name)
-            except Exception:   # noqa: BLE001 — newer torch enables it on rendezvous
-                pass
             grad = symm_mem.empty(total, dtype=torch.float32, device=dev)
             grad.zero_()
             self.symm = symm_mem.rendezvous(grad, group=group)
             self._peer_ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in self.symm.buffer_ptrs])
+            self._flag_ptrs = None
+            if os.environ.get('LK_P2P_FUSED_BARRIER', '1') != '0':
+                self._flags = symm_mem.empty(4096, dtype=torch.int32, device=dev)       # LK_ALLREDUCE_FLAG_WORDS
+                self._flags.zero_()
+                fh = symm_mem.rendezvous(self._flags, group=group)
+                self._flag_ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in fh.buffer_ptrs])
+                self._epoch = 0
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=group)                           # every rank's flags are zero before anybody signals
             return grad
         except Exception as e:   # noqa: BLE001
             import sys
@@ -70,8 +75,13 @@ class FlatAdam:
         if self.symm is not None:
             from ._lib import call
             import ctypes
+            if self._flag_ptrs is not None:                    # one launch: rendezvous, slice reduction, rendezvous
+                self._epoch += 1
+                call('lk_allreduce_p2p', ctypes.addressof(self._peer_ptrs), ctypes.addressof(self._flag_ptrs), self._epoch, self.symm.rank,
+                     self.world, self.grad.numel(), 1.0)
+                return
             self.symm.barrier(channel=0)                       # every rank has written its gradients
-            call('lk_allreduce_p2p', ctypes.addressof(self._peer_ptrs), self.symm.rank, self.world, self.grad.numel(), 1.0)
+            call('lk_allreduce_p2p', ctypes.addressof(self._peer_ptrs), None, 0, self.symm.rank, self.world, self.grad.numel(), 1.0)
             self.symm.barrier(channel=1)                       # every slice's sum is visible everywhere
         else:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
