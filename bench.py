@@ -327,7 +327,7 @@ def main():
         if world_size > 1:
             ts = sorted(a.elapsed_time(b) for a, b in opt.time_allreduce)
             opt.time_allreduce = None
-            collective = dict(op=('lk_allreduce_p2p (NVLink peer memory, ' + ('rendezvous inside the launch' if opt._flag_ptrs is not None else 'between two symmetric-memory barriers') + ')' if opt.symm is not None else 'ncclAllReduce') + ': sum of the flat gradient bucket', bytes=int(opt.grad.numel() * 4), ms_median=ts[len(ts) // 2], ms_min=ts[0],
+            collective = dict(op=('lk_allreduce_p2p (NVLink peer memory, ' + (('in-switch reduction via the multicast mapping, ' if opt._mc_ptr else '') + 'rendezvous inside the launch' if opt._flag_ptrs is not None else 'between two symmetric-memory barriers') + ')' if opt.symm is not None else 'ncclAllReduce') + ': sum of the flat gradient bucket', bytes=int(opt.grad.numel() * 4), ms_median=ts[len(ts) // 2], ms_min=ts[0],
                               ms_max=ts[-1], note='CUDA events on the step stream around the collective of every timed step, this rank: from local gradients '
                                                   'ready to reduced, i.e. the wait for the slowest rank + the transfer; it is not overlapped with compute')
         dres.take()

@@ -84,7 +84,10 @@ int lk_shard_gather(const int64_t* ids, int64_t M, int W, const float* local, in
 #define LK_ALLREDUCE_FLAG_WORDS 4096
 /* debugging aid: buf = device int64[148 * 6] (per block: SM clocks of launch->dependency, rendezvous, reduction, fence, rendezvous, total) or NULL */
 int lk_allreduce_set_trace(void* buf);
-int lk_allreduce_p2p(void* const* peer_ptrs, void* const* flag_ptrs, int epoch, int rank, int W, int64_t n, float scale, cudaStream_t stream);
+/* multicast_ptr (with flag_ptrs only): this rank's NVSwitch multicast mapping of the W buckets, or NULL.  Non-NULL: the slice is reduced in the
+ * switch (multimem.ld_reduce) and broadcast by it (multimem.st) — W times less NVLink traffic; the summation order is then the switch's. */
+int lk_allreduce_p2p(void* const* peer_ptrs, void* const* flag_ptrs, void* multicast_ptr, int epoch, int rank, int W, int64_t n, float scale,
+                     cudaStream_t stream);
 
 /* ---- device-side Resampler (csrc/lk_resample.cu) — loader/resampler.py:139-259 taken to the device: from B impression rows to the id lists
  *      and offsets of a packed training batch in ONE launch.  Negatives = min(K, len) distinct positions of the user's negative list in random

@@ -81,7 +81,7 @@ SIGNATURES = {
     'lk_shard_inverse': ('pqppqps', 'i'),
     'lk_shard_gather': ('pqipqqps', 'i'),
     'lk_allreduce_set_trace': ('p', 'i'),
-    'lk_allreduce_p2p': ('ppiiiqfs', 'i'),
+    'lk_allreduce_p2p': ('pppiiiqfs', 'i'),
     'lk_resample_batch': ('pqiuppppppp' + 'qqq' + 'ppppp' + 'qs', 'i'),
     'lk_resample_reference': ('uqqpqiqp', 'i'),
     'lk_sweep_ranges': ('qq', 'q'),

@@ -11,6 +11,7 @@ namespace lk {
 namespace ar {
 
 constexpr int MAXW = 16;
+constexpr long long kSpinLimitClk = 120ll * 1900000000ll;      // ~2 minutes of SM clocks
 struct Peers { float* p[MAXW]; };
 
 __device__ __forceinline__ float4 ld_sys(const float* a) {      // peer memory: system-scope, never from a stale L1 line
@@ -20,6 +21,17 @@ __device__ __forceinline__ float4 ld_sys(const float* a) {      // peer memory: 
 }
 __device__ __forceinline__ void st_sys(float* a, const float4& v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// The same two accesses through the NVSwitch multicast mapping of the bucket: the load is reduced IN THE SWITCH over all W replicas (one
+// 16-byte response instead of W), the store is replicated by the switch to all W buckets (one 16-byte request instead of W).
+__device__ __forceinline__ float4 ld_reduce_mc(const float* a) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_mc(float* a, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // Cross-rank rendezvous of block b with block b of every peer, through flag words in symmetric memory: flags[b * MAXW + r] of rank q is written
@@ -38,7 +50,16 @@ __device__ __forceinline__ void wait_peers(const Peers& flags, int rank, int W, 
   if ((int)threadIdx.x < W) {
     const int* f = (const int*)flags.p[rank] + (size_t)blockIdx.x * MAXW + threadIdx.x;
     int v;
-    do { asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); } while (v - epoch < 0);
+    const long long t0 = clock64();
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v - epoch >= 0) break;
+      if (clock64() - t0 > kSpinLimitClk) {                // a peer died or never launched: fail loudly instead of hanging the GPU
+        printf("lk_allreduce_p2p: rank %d block %d waited %llds for rank %d (flag %d, expected %d)\n", rank, (int)blockIdx.x,
+               kSpinLimitClk / 1900000000ll, (int)threadIdx.x, v, epoch);
+        __trap();
+      }
+    }
   }
   __syncthreads();
 }
@@ -48,7 +69,7 @@ __device__ __forceinline__ void wait_peers(const Peers& flags, int rank, int W, 
 // so when the grid completes every block of every peer is done with this rank's bucket: the next kernel on the stream may overwrite it.
 template <int WT, bool FENCE_ALL = false>
 __global__ void __launch_bounds__(1024) allreduce_fused_kernel(const __grid_constant__ Peers peers, const __grid_constant__ Peers flags, int rank, int W_rt, int64_t per4, int64_t n4,
-                                                              float scale, int epoch, long long* trace) {
+                                                              float scale, int epoch, long long* trace, float* mc) {
   const int W = WT > 0 ? WT : W_rt;
   long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
   if (trace) t0 = clock64();
@@ -60,6 +81,12 @@ __global__ void __launch_bounds__(1024) allreduce_fused_kernel(const __grid_cons
   const int64_t lo4 = (int64_t)rank * per4, hi4 = lo4 + per4 < n4 ? lo4 + per4 : n4;
   for (int64_t i = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 s;
+    if (mc != nullptr) {                                   // switch-side reduction and broadcast (the summation order is the switch's)
+      s = ld_reduce_mc(mc + i * 4);
+      s.x *= scale; s.y *= scale; s.z *= scale; s.w *= scale;
+      st_mc(mc + i * 4, s);
+      continue;
+    }
     if (WT > 0) {
       float4 v[WT > 0 ? WT : 1];
 #pragma unroll
@@ -113,7 +140,8 @@ int lk_allreduce_set_trace(void* buf) { g_ar_trace = (long long*)buf; return LK_
 // flag_ptrs: HOST array of W device pointers to each rank's flag words (LK_ALLREDUCE_FLAG_WORDS int32, zeroed once, symmetric memory), or NULL:
 //   with flags the rendezvous before and after the reduction are inside the launch (epoch = 1, 2, 3 ... per call, the same on every rank);
 //   without, the caller brackets the launch with its own cross-rank barriers.
-int lk_allreduce_p2p(void* const* peer_ptrs, void* const* flag_ptrs, int epoch, int rank, int W, int64_t n, float scale, cudaStream_t st) {
+int lk_allreduce_p2p(void* const* peer_ptrs, void* const* flag_ptrs, void* multicast_ptr, int epoch, int rank, int W, int64_t n, float scale,
+                     cudaStream_t st) {
   LK_REQUIRE(W >= 1 && W <= ar::MAXW && rank >= 0 && rank < W && n % 4 == 0, LK_ERR_ARG, "lk_allreduce_p2p: W=%d rank=%d n=%ld", W, rank, (long)n);
   if (n == 0) return LK_OK;
   ar::Peers peers, flags;
@@ -128,6 +156,8 @@ int lk_allreduce_p2p(void* const* peer_ptrs, void* const* flag_ptrs, int epoch, 
   const int64_t n4 = n / 4, per = (n4 + W - 1) / W;
   if (flag_ptrs) {
     LK_REQUIRE(epoch > 0, LK_ERR_ARG, "lk_allreduce_p2p: epoch starts at 1");
+    float* mc = (float*)multicast_ptr;
+    LK_REQUIRE((uintptr_t)mc % 16 == 0, LK_ERR_ARG, "lk_allreduce_p2p: multicast pointer alignment");
     // the SAME grid on every rank (blocks pair up across ranks), one block per SM at most; one float4 per thread when the slice allows it:
     // the reduction is latency-bound (a round trip over NVSwitch per load), so parallelism rather than a grid-stride loop
     static const int thr_env = getenv("LK_AR_THREADS") ? atoi(getenv("LK_AR_THREADS")) : 0;
@@ -136,13 +166,14 @@ int lk_allreduce_p2p(void* const* peer_ptrs, void* const* flag_ptrs, int epoch, 
     if (blocks > kNumSMs) blocks = kNumSMs;
     static_assert(kNumSMs * ar::MAXW <= LK_ALLREDUCE_FLAG_WORDS, "flag words");
     switch (W) {
-      case 2: LK_LAUNCH((ar::allreduce_fused_kernel<2>), (unsigned)blocks, threads, 0, st, peers, flags, rank, W, per, n4, scale, epoch, g_ar_trace); break;
-      case 4: LK_LAUNCH((ar::allreduce_fused_kernel<4>), (unsigned)blocks, threads, 0, st, peers, flags, rank, W, per, n4, scale, epoch, g_ar_trace); break;
-      case 8: LK_LAUNCH((ar::allreduce_fused_kernel<8>), (unsigned)blocks, threads, 0, st, peers, flags, rank, W, per, n4, scale, epoch, g_ar_trace); break;
-      default: LK_LAUNCH((ar::allreduce_fused_kernel<0>), (unsigned)blocks, threads, 0, st, peers, flags, rank, W, per, n4, scale, epoch, g_ar_trace);
+      case 2: LK_LAUNCH((ar::allreduce_fused_kernel<2>), (unsigned)blocks, threads, 0, st, peers, flags, rank, W, per, n4, scale, epoch, g_ar_trace, mc); break;
+      case 4: LK_LAUNCH((ar::allreduce_fused_kernel<4>), (unsigned)blocks, threads, 0, st, peers, flags, rank, W, per, n4, scale, epoch, g_ar_trace, mc); break;
+      case 8: LK_LAUNCH((ar::allreduce_fused_kernel<8>), (unsigned)blocks, threads, 0, st, peers, flags, rank, W, per, n4, scale, epoch, g_ar_trace, mc); break;
+      default: LK_LAUNCH((ar::allreduce_fused_kernel<0>), (unsigned)blocks, threads, 0, st, peers, flags, rank, W, per, n4, scale, epoch, g_ar_trace, mc);
     }
     return check_launch("allreduce_p2p");
   }
+  LK_REQUIRE(multicast_ptr == nullptr, LK_ERR_ARG, "lk_allreduce_p2p: the multicast path needs the flag words");
   const int64_t lo4 = (int64_t)rank * per, hi4 = lo4 + per < n4 ? lo4 + per : n4;
   if (lo4 >= hi4) return LK_OK;
   int64_t blocks = (hi4 - lo4 + 511) / 512;

@@ -56,12 +56,16 @@ class FlatAdam:
             self.symm = symm_mem.rendezvous(grad, group=group)
             self._peer_ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in self.symm.buffer_ptrs])
             self._flag_ptrs = None
+            self._mc_ptr = None
             if os.environ.get('LK_P2P_FUSED_BARRIER', '1') != '0':
                 self._flags = symm_mem.empty(4096, dtype=torch.int32, device=dev)       # LK_ALLREDUCE_FLAG_WORDS
                 self._flags.zero_()
                 fh = symm_mem.rendezvous(self._flags, group=group)
                 self._flag_ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in fh.buffer_ptrs])
                 self._epoch = 0
+                mc = int(getattr(self.symm, 'multicast_ptr', 0) or 0)
+                if mc and os.environ.get('LK_P2P_MULTIMEM', '1') != '0':
+                    self._mc_ptr = mc                              # NVSwitch multicast mapping: in-switch reduction + broadcast
             torch.cuda.synchronize(dev)
             dist.barrier(group=group)                           # every rank's flags are zero before anybody signals
             return grad
@@ -77,11 +81,11 @@ class FlatAdam:
             import ctypes
             if self._flag_ptrs is not None:                    # one launch: rendezvous, slice reduction, rendezvous
                 self._epoch += 1
-                call('lk_allreduce_p2p', ctypes.addressof(self._peer_ptrs), ctypes.addressof(self._flag_ptrs), self._epoch, self.symm.rank,
+                call('lk_allreduce_p2p', ctypes.addressof(self._peer_ptrs), ctypes.addressof(self._flag_ptrs), self._mc_ptr, self._epoch, self.symm.rank,
                      self.world, self.grad.numel(), 1.0)
                 return
             self.symm.barrier(channel=0)                       # every rank has written its gradients
-            call('lk_allreduce_p2p', ctypes.addressof(self._peer_ptrs), None, 0, self.symm.rank, self.world, self.grad.numel(), 1.0)
+            call('lk_allreduce_p2p', ctypes.addressof(self._peer_ptrs), None, None, 0, self.symm.rank, self.world, self.grad.numel(), 1.0)
             self.symm.barrier(channel=1)                       # every slice's sum is visible everywhere
         else:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)

@@ -32,14 +32,19 @@ def timeit(fn, iters=200):
 
 
 out = {}
-for mode in ('fused', 'bracketed', 'nccl'):
+for mode in ('fused', 'fused_multimem', 'bracketed', 'nccl'):
     os.environ['LK_P2P_ALLREDUCE'] = '0' if mode == 'nccl' else '1'
-    os.environ['LK_P2P_FUSED_BARRIER'] = '1' if mode == 'fused' else '0'
+    os.environ['LK_P2P_FUSED_BARRIER'] = '1' if mode.startswith('fused') else '0'
+    os.environ['LK_P2P_MULTIMEM'] = '1' if mode == 'fused_multimem' else '0'
     m = torch.nn.Linear(n, 1, bias=False).to(dev)
     opt = FlatAdam(m)
     opt.grad.fill_(1.0)
+    if mode == 'fused_multimem':
+        out['multicast'] = bool(opt._mc_ptr)
+        opt.grad.fill_(float(rank + 1)); opt.allreduce(); torch.cuda.synchronize()
+        out['multimem_sum_ok'] = bool((opt.grad == W * (W + 1) / 2).all())
     out[mode + '_us'] = timeit(opt.allreduce)
-    if mode == 'fused' and os.environ.get('LK_AR_TRACE'):
+    if mode.startswith('fused') and os.environ.get('LK_AR_TRACE'):
         from legommenders_b200 import _lib
         tr = torch.zeros(148 * 6, dtype=torch.int64, device=dev)
         _lib.load().lk_allreduce_set_trace(tr.data_ptr())
@@ -49,8 +54,8 @@ for mode in ('fused', 'bracketed', 'nccl'):
         _lib.load().lk_allreduce_set_trace(None)
         t = tr.view(148, 6).cpu()
         t = t[t[:, 5] > 0]
-        out['trace_clk_median'] = dict(zip(['dep', 'rdv_in', 'reduce', 'fence', 'rdv_out', 'total'], t.median(0).values.tolist()))
-        out['trace_clk_max'] = dict(zip(['dep', 'rdv_in', 'reduce', 'fence', 'rdv_out', 'total'], t.max(0).values.tolist()))
+        out[mode + '_clk_median'] = dict(zip(['dep', 'rdv_in', 'reduce', 'fence', 'rdv_out', 'total'], t.median(0).values.tolist()))
+        out[mode + '_clk_max'] = dict(zip(['dep', 'rdv_in', 'reduce', 'fence', 'rdv_out', 'total'], t.max(0).values.tolist()))
     del opt, m
 if rank == 0:
     print(json.dumps(dict(W=W, floats=n, threads=os.environ.get('LK_AR_THREADS', 'auto'), **out)))
