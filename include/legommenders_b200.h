@@ -170,6 +170,10 @@ typedef struct lk_split_seg {
   int64_t rows, cols, ld_in, ld_out;
 } lk_split_seg;
 int lk_split_bf16_multi(const lk_split_seg* segs, int n_segs, cudaStream_t stream);
+/* Conv1d(k,'same') on the tensor cores (model/operators/cnn_operator.py:54-58): planes of the im2col image of X [rows, C] (sequences of S
+ * rows): Xcol[r, j*C + c] = X[r + j - taps/2, c] inside r's sequence, else 0; hi/lo [rows, ld_out >= taps*C].  Y = Xcol·Wrᵀ is then one
+ * lk_tc_gemm (bias / ReLU / dropout / row-mask epilogue), dX = im2col(dY)·Wdᵀ another, dW = dYᵀ·Xcol the third (Wr, Wd as for lk_conv1d_*). */
+int lk_im2col_split_bf16(const float* X, int64_t rows, int64_t S, int64_t C, int taps, void* hi, void* lo, int64_t ld_out, cudaStream_t stream);
 size_t lk_tc_gemm_workspace_bytes(int64_t GM, int64_t GN, int64_t GK);
 /* Fused epilogue of lk_tc_gemm_ex, applied in this order to every result element r[m,n] of A·B:
  *   r += bias[n];  r = act(r);  r *= dropout(seed, m*GN+n);  r *= rowmask(m);  r += add_tab0[add_ids0[m], n] (+ add_tab1 ...)  where id > -1;

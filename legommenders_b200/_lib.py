@@ -44,6 +44,7 @@ SIGNATURES = {
     'lk_splitk_reduce': ('ppqqqiis', 'i'),
     'lk_split_bf16_workspace_bytes': ('qq', 'z'),
     'lk_split_bf16': ('pqqqppqippzs', 'i'),
+    'lk_im2col_split_bf16': ('pqqqippqs', 'i'),
     'lk_split_bf16_multi': ('pis', 'i'),
     'lk_split_bf16_partial': ('pqqqppqps', 'i'),
     'lk_colsum_finish_multi': ('pis', 'i'),

@@ -375,6 +375,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   }
 }
 
+// im2col image of [rows, C] token rows (sequences of S rows) as split-bf16 planes: four columns per thread, consecutive threads on
+// consecutive columns of one output row (8-byte stores per plane, 16-byte loads; every input row is read `taps` times, from L1/L2)
+__global__ void __launch_bounds__(256) im2col_split_kernel(const float* __restrict__ X, int64_t rows, int S, int C, int taps,
+                                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t ld_out) {
+  pdl_prologue();
+  const int ld4 = (int)(ld_out >> 2), half = taps >> 1, width = taps * C;
+  const int64_t total = rows * ld4;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / ld4;
+    const int col = (int)(idx - r * ld4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < width) {
+      const int j = col / C, c = col - j * C;
+      const int s = (int)(r % S) + j - half;
+      if (s >= 0 && s < S) v = __ldg(reinterpret_cast<const float4*>(X + (r + j - half) * C + c));
+    }
+    uint2 h, l;
+    split4(v, h, l);
+    *reinterpret_cast<uint2*>(hi + r * ld_out + col) = h;
+    *reinterpret_cast<uint2*>(lo + r * ld_out + col) = l;
+  }
+}
+
 // fp32 -> (hi, lo) bf16 planes, output pitch ld_out (>= cols, multiple of 8, pad columns zeroed).  A block owns SPLIT_ROWS
 // rows x 256 columns (32 column-threads x 8 elements, 8 row-threads); optionally it also emits per-block column sums of the
 // fp32 input (the bias gradient db = sum_m dY[m,:] rides on the pass that has to read dY anyway).
@@ -606,6 +629,21 @@ int lk_split_bf16_partial(const float* X, int64_t rows, int64_t cols, int64_t ld
   dim3 grid((unsigned)((ld_out + 255) / 256), (unsigned)nparts);
   LK_LAUNCH((split_bf16_kernel), grid, 256, 0, st, X, rows, (int)cols, ld_in, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_out, part);
   return check_launch("split_bf16_partial");
+}
+
+// Conv1d(k, 'same') as ONE contraction (model/operators/cnn_operator.py:54-58): the operand planes of the im2col image of X.
+//   Xcol[r, j*C + c] = X[r + j - taps/2, c] when that row is inside r's sequence (fixed length S), else 0
+// so that Y = Xcol · Wrᵀ with Wr[o, j*C + c] = W[o, c, j] and, with X := dY and the flipped kernel, dX = dYcol · Wdᵀ.
+int lk_im2col_split_bf16(const float* X, int64_t rows, int64_t S, int64_t C, int taps, void* hi, void* lo, int64_t ld_out, cudaStream_t st) {
+  LK_REQUIRE(S > 0 && rows % S == 0 && C % 4 == 0 && taps > 0 && (taps & 1), LK_ERR_SHAPE,
+             "lk_im2col_split_bf16: rows=%ld S=%ld C=%ld taps=%d (C %% 4 == 0, odd taps, whole sequences)", (long)rows, (long)S, (long)C, taps);
+  LK_REQUIRE(ld_out % 8 == 0 && ld_out >= taps * C, LK_ERR_SHAPE, "lk_im2col_split_bf16: output pitch %ld", (long)ld_out);
+  if (rows == 0) return LK_OK;
+  const int64_t total = rows * (ld_out / 4);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+  LK_LAUNCH((im2col_split_kernel), (unsigned)blocks, 256, 0, st, X, rows, (int)S, (int)C, taps, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_out);
+  return check_launch("im2col_split_bf16");
 }
 
 int lk_split_bf16_multi(const lk_split_seg* segs, int n_segs, cudaStream_t st) {

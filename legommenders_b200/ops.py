@@ -74,6 +74,15 @@ class SplitSeg(ctypes.Structure):
                 ('cols', ctypes.c_int64), ('ld_in', ctypes.c_int64), ('ld_out', ctypes.c_int64)]
 
 
+def im2col_planes(x2: torch.Tensor, S: int, taps: int) -> Planes:
+    """Planes of the im2col image [rows, taps*C] of token rows x2 [rows, C] (sequences of S rows, zero beyond their ends)."""
+    rows, C = x2.shape
+    ld = (taps * C + 7) // 8 * 8
+    buf = torch.empty((2, rows, ld), dtype=torch.bfloat16, device=x2.device)
+    call('lk_im2col_split_bf16', ptr(x2), rows, S, C, taps, ptr(buf[0]), ptr(buf[1]), ld)
+    return Planes(buf[0], buf[1], rows, taps * C, ld)
+
+
 def split_planes_multi(mats):
     """Planes of several fp32 matrices (e.g. all weights of a step) in ONE launch (lk_split_bf16_multi)."""
     segs = (SplitSeg * len(mats))()
@@ -124,6 +133,9 @@ def weight_planes(w: torch.Tensor, transpose: bool = False) -> Planes:
 
 def invalidate_weight_planes():
     _wplanes.clear()
+
+
+CONV_TC_FWD = os.environ.get('LK_CONV_TC_FWD', '0') == '1'
 
 
 def tc_ok(M, N, K) -> bool:
@@ -825,9 +837,19 @@ class _Conv1dReluMask(Function):
         Cout, _, taps = w.shape
         wr = w.permute(0, 2, 1).contiguous().view(Cout, taps * Cin)       # Wr[o, j*Cin+i] = W[o,i,j] (layout only)
         rm = _i64(mask.reshape(-1)) if mask is not None else None
-        y = torch.empty((N * S, Cout), dtype=torch.float32, device=x.device)
-        x2 = x.reshape(N * S, Cin)
-        call('lk_conv1d_fwd', ptr(x2), ptr(wr), ptr(b), ptr(rm), ptr(y), N * S, S, Cin, Cout, taps, ACT_RELU, float(drop_p), int(seed))
+        x2 = x.reshape(N * S, Cin).contiguous()
+        # Backward (two thirds of the work) always runs as tcgen05 contractions over im2col planes when the shape allows.  The forward does
+        # so only on request (CONV_TC_FWD): ReLU's gate is a step function of the pre-activation, and the ~1e-5 relative error of the
+        # split-bf16 product flips it for a few hundred of the ~1e8 elements of a NAML batch (|pre| < 1e-5) — each flip is an O(1) error
+        # in one dPre element, which shows up at 5e-3 in small bias gradients (measured on naml_full).  The fp32 FFMA forward flips
+        # 100x fewer gates, like any fp32 implementation of the reference does against another.
+        ctx.tc = tc_ok(N * S, Cout, taps * Cin) and Cin % 4 == 0 and Cout % 4 == 0
+        if ctx.tc and CONV_TC_FWD:
+            y = tc_gemm(im2col_planes(x2, S, taps), split_planes(wr), False, N * S, Cout, taps * Cin, bias=b, rowmask=rm, act=ACT_RELU,
+                        drop_p=drop_p, seed=seed)
+        else:
+            y = torch.empty((N * S, Cout), dtype=torch.float32, device=x.device)
+            call('lk_conv1d_fwd', ptr(x2), ptr(wr), ptr(b), ptr(rm), ptr(y), N * S, S, Cin, Cout, taps, ACT_RELU, float(drop_p), int(seed))
         ctx.save_for_backward(x2, w, y, rm)
         ctx.dims = (N, S, Cin, Cout, taps)
         ctx.drop_p, ctx.seed = drop_p, seed
@@ -839,6 +861,15 @@ class _Conv1dReluMask(Function):
         N, S, Cin, Cout, taps = ctx.dims
         dy2 = act_bwd_raw(_f32(dy).reshape(N * S, Cout), y, rm, ACT_RELU, ctx.drop_p, ctx.seed)
         dx = dw = db = None
+        if ctx.tc:
+            if ctx.needs_input_grad[0]:
+                wd = w.flip(2).permute(1, 2, 0).contiguous().view(Cin, taps * Cout)   # Wd[i, j*Cout+o] = W[o,i,taps-1-j]
+                dx = tc_gemm(im2col_planes(dy2, S, taps), split_planes(wd), False, N * S, Cin, taps * Cout).view(N, S, Cin)
+            if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+                dyp, db = split_planes(dy2, colsum=True)
+                dwr = tc_gemm(dyp, im2col_planes(x2, S, taps), True, Cout, taps * Cin, N * S)
+                dw = dwr.view(Cout, taps, Cin).permute(0, 2, 1).contiguous()
+            return dx, dw, db, None, None, None
         if ctx.needs_input_grad[0]:
             wd = w.flip(2).permute(1, 2, 0).contiguous().view(Cin, taps * Cout)   # Wd[i, j*Cout+o] = W[o,i,taps-1-j]
             dx = torch.empty((N * S, Cin), dtype=torch.float32, device=dy.device)

@@ -161,8 +161,14 @@ def test_linear_split_reduction_large_m(ops, engine):
     assert rel(xg.grad, dy.double() @ w.double()) <= gemm_tol(engine, 3e-6)
 
 
-@pytest.mark.parametrize('N_,S,Cin,Cout', [(5, 30, 64, 64), (3, 7, 32, 48), (9, 2, 256, 256)])
-def test_conv1d_relu_mask(ops, N_, S, Cin, Cout):
+@pytest.mark.parametrize('N_,S,Cin,Cout', [(5, 30, 64, 64), (3, 7, 32, 48), (9, 2, 256, 256), (40, 30, 256, 256), (13, 31, 300, 256), (70, 5, 64, 48)])
+@pytest.mark.parametrize('drop', [0.0, 0.2])
+@pytest.mark.parametrize('tc_fwd', [False, True])
+def test_conv1d_relu_mask(ops, engine, monkeypatch, N_, S, Cin, Cout, drop, tc_fwd):
+    """Under engine 'tc' the three larger shapes (rows >= 256) run their backward as tcgen05 contractions over im2col planes, and with
+    tc_fwd (LK_CONV_TC_FWD=1) the forward too; everything runs on the FFMA kernels under 'simt'.  With dropout the kept set is read back
+    from the output (the mask is a pure function of (seed, element))."""
+    monkeypatch.setattr(ops, 'CONV_TC_FWD', tc_fwd)
     g = torch.Generator().manual_seed(S + Cin)
     x = torch.randn(N_, S, Cin, generator=g)
     w = torch.randn(Cout, Cin, 3, generator=g) / (3 * Cin) ** 0.5
@@ -170,15 +176,21 @@ def test_conv1d_relu_mask(ops, N_, S, Cin, Cout):
     lens = torch.randint(0, S + 1, (N_,), generator=g)
     mask = (torch.arange(S)[None, :] < lens[:, None]).long()
     dy = torch.randn(N_, S, Cout, generator=g)
+    xg, wg, bg = (dev(t).requires_grad_(True) for t in (x, w, b))
+    y = ops.conv1d_relu_mask(xg, wg, bg, dev(mask), drop_p=drop, seed=77)
+    y.backward(dev(dy))
     xc, wc, bc = (t.double().requires_grad_(True) for t in (x, w, b))
     yr = torch.relu(F.conv1d(xc.permute(0, 2, 1), wc, bc, padding=1).permute(0, 2, 1)) * mask.unsqueeze(-1)
+    if drop:
+        keep = ((y.detach().cpu() != 0) | (yr.detach() == 0)).double()          # dropped = reference non-zero, result zero
+        frac = 1.0 - float(keep[yr.detach() != 0].mean()) if (yr != 0).any() else drop
+        assert abs(frac - drop) < 0.05
+        yr = yr * keep / (1.0 - drop)
     yr.backward(dy.double())
-    xg, wg, bg = (dev(t).requires_grad_(True) for t in (x, w, b))
-    y = ops.conv1d_relu_mask(xg, wg, bg, dev(mask))
-    y.backward(dev(dy))
-    assert rel(y, yr) <= 3e-6
-    assert rel(xg.grad, xc.grad) <= 3e-6
-    assert rel(wg.grad, wc.grad) <= 1e-5
+    tc = engine == 'tc' and N_ * S >= 256
+    assert rel(y, yr) <= (4e-5 if tc and tc_fwd else 3e-6)
+    assert rel(xg.grad, xc.grad) <= (4e-5 if tc else 3e-6)
+    assert rel(wg.grad, wc.grad) <= (4e-5 if tc else 1e-5)
     assert rel(bg.grad, bc.grad) <= 1e-5
 
 
