@@ -896,13 +896,24 @@ def hbm_bound_lines(dev, world, hbm_peak, model=None, resampler=None, tensor_pea
         del m2, o2, pool2
         return dict(ms_per_step=ms2, impressions_per_s=64 / ms2 * 1e3, loss=float(loss.item()), batch=64, note=note)
 
-    for kind, note in (('naml', 'NAML: CNN title encoder (conv on fp32 FFMA, lk_conv1d_*) + additive attention, Ada user encoder, DotPredictor + CE'),
+    for kind, note in (('naml', 'NAML: CNN title encoder (conv forward on fp32 FFMA lk_conv1d_fwd, input and weight gradients as tcgen05 contractions over im2col planes) + additive attention, Ada user encoder, DotPredictor + CE'),
                        ('lstur', 'LSTUR: CNNCat item encoder + GRU user encoder (lk_gru_fwd/bwd)'),
                        ('miner', 'MINER: 2-layer BERT-style Transformer item encoder + poly attention (8 codes) + target-aware predictor'),
                        ('fastformer', 'Fastformer item and user encoders (1 layer each)')):
         @guarded(kind + '_train')
         def _(kind=kind, note=note):
             out[kind + '_train'] = plugin_train_line(kind, note + '; generic plugin path, host-driven launches, MIND-small shape')
+
+    @guarded('naml_train_tc_forward')
+    def _():
+        from legommenders_b200 import ops as _ops
+        old = _ops.CONV_TC_FWD
+        _ops.CONV_TC_FWD = True
+        try:
+            out['naml_train_tc_forward'] = plugin_train_line('naml', 'NAML with LK_CONV_TC_FWD=1: the conv forward on the tensor cores as well (not the parity '
+                                                             'configuration: ReLU gates within 1e-5 of zero may flip, see ops._Conv1dReluMask)')
+        finally:
+            _ops.CONV_TC_FWD = old
 
     # config 4 on one GPU (the row-sharded table with a single shard: same kernels, no NVLink traffic); the N > 1 lines are in SCALE
     @guarded('config4_sharded_table_train')
