@@ -1140,6 +1140,7 @@ int lk_mha_bwd(const float* qkv, const int64_t* mask, const int32_t* cu, const f
       if (tc_path_ok(p, S)) {
         const bool small = tc_small_launch(N, H, S);
         const int JW = small ? 2 : 1;   // 2 x 128 threads keep the 168 registers the kernel needs (4 would cap it at 128 and spill)
+        // (measured, r2: forcing 4 CTAs/SM on the JW = 1 kernel = 128 registers, 260 B of spills: 187 -> 234 us per launch — rejected)
         const size_t smem = ((size_t)(2 + JW) * S * tcm::TCP + 4 * tcm::TC_MAX_L + (size_t)JW * 4 * 64) * sizeof(float);
         LK_REQUIRE(smem <= 227 * 1024, LK_ERR_SHAPE, "lk_mha_bwd: tiles (%zu B) do not fit shared memory", smem);
         static bool attr = false;
