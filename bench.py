@@ -820,9 +820,23 @@ def hbm_bound_lines(dev, world, hbm_peak, model=None, resampler=None, tensor_pea
         ms_e = time_it(run, reps=3)
         cacher.item.repr = cacher.user.repr = None
         cacher.item.cached = cacher.user.cached = False
-        out['cached_eval_e2e'] = dict(rows=R, ms=ms_e, scores_per_s=R / ms_e * 1e3, h2d_bytes=int(4 * 8 * R), d2h_bytes=5 * 8,
+        out['cached_eval_e2e'] = dict(rows=R, ms=ms_e, scores_per_s=R / ms_e * 1e3, h2d_bytes=int(3 * 8 * R), d2h_bytes=5 * 8,
                                       metrics={k: round(float(v), 4) for k, v in res['m'].items()},
-                                      note='evaluate(): H2D of user/item/label ids, scoring, GAUC/MRR/NDCG@1,5,10, D2H of the means')
+                                      note='evaluate(): H2D of user/item/label ids (int64, as the reference holds them; the group key is the user '
+                                           'id and is copied once), scoring, GAUC/MRR/NDCG@1,5,10, D2H of the means')
+        cacher.item.repr, cacher.user.repr = I, U
+        cacher.item.cached = cacher.user.cached = True
+        hu32, hi32, hl32 = (torch.from_numpy(a.astype(np.int32)).pin_memory() for a in (world.eval_users, world.eval_items, world.eval_click))
+
+        def run32():
+            res['m32'] = ev.evaluate(model, hu32, hi32, hl32)[0]
+        ms_32 = time_it(run32, reps=3)
+        cacher.item.repr = cacher.user.repr = None
+        cacher.item.cached = cacher.user.cached = False
+        out['cached_eval_e2e_int32'] = dict(rows=R, ms=ms_32, scores_per_s=R / ms_32 * 1e3, h2d_bytes=int(3 * 4 * R), d2h_bytes=5 * 8,
+                                            metrics_equal=bool(res['m32'] == res['m']),
+                                            note='the same call with the evaluation ids held as int32 in pinned host memory: half the PCIe '
+                                                 'bytes, widened on the device')
 
     # (a15) item-representation cache build through the cacher contract (positional content list, pages of cache_page_size)
     @guarded('item_cache_build')

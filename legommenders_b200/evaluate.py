@@ -130,6 +130,7 @@ def evaluate(model, user_ids, item_ids, labels, groups=None, metrics: Sequence[s
     presharded=True: the rows passed in are already this rank's share (`sharding.owned_rows` applied once to the evaluation set, SURVEY §8e
     "rows pre-partitioned by group"); only the metric reduction is collective then."""
     rank, world = sharding._world(group) if shard else (0, 1)      # shard=False: this rank evaluates every row itself (needs full caches)
+    same_groups = groups is None or groups is user_ids          # config/data/mind.yaml:24: the group key IS the user id -> one copy, not two
     groups = user_ids if groups is None else groups
     user_ids, item_ids, labels, groups = (torch.as_tensor(t).reshape(-1) for t in (user_ids, item_ids, labels, groups))
     rows: Optional[torch.Tensor] = None
@@ -147,8 +148,12 @@ def evaluate(model, user_ids, item_ids, labels, groups=None, metrics: Sequence[s
         scores = torch.empty(0, dtype=torch.float32, device=Env.device)
         vals, pool.n_groups = OrderedDict((k, 0.0) for k in metrics), 0
     else:
-        scores = cached_scores(model, user_ids, item_ids)
-        vals = pool.calculate(scores, labels, groups)
+        # every id array crosses PCIe once, in the integer width the host holds (int32 halves the bytes), and is widened on the device
+        def up(t):
+            return t.to(Env.device, non_blocking=True).to(torch.int64)
+        uid, iid, lab = up(user_ids), up(item_ids), up(labels)
+        scores = cached_scores(model, uid, iid)
+        vals = pool.calculate(scores, lab, uid if same_groups else up(groups))
     if world > 1:
         local = torch.tensor(list(vals.values()), dtype=torch.float64, device=Env.device)
         means, _ = sharding.reduce_group_means(local, pool.n_groups, group)

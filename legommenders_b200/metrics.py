@@ -45,8 +45,8 @@ class MetricPool:
         """scores: fp32 [R]; labels, groups: int64 [R] — device tensors are used in place, anything else is copied up once."""
         dev = Env.device
         s = torch.as_tensor(scores, dtype=torch.float32).to(dev).contiguous()
-        y = torch.as_tensor(labels, dtype=torch.int64).to(dev).contiguous()
-        g = torch.as_tensor(groups, dtype=torch.int64).to(dev).contiguous()
+        y = torch.as_tensor(labels).to(dev).to(torch.int64).contiguous()          # widened on the device, not on the host
+        g = torch.as_tensor(groups).to(dev).to(torch.int64).contiguous()
         R = s.numel()
         if not (y.numel() == R and g.numel() == R):
             raise ValueError('scores, labels and groups must have the same length')
