@@ -327,9 +327,11 @@ int lk_additive_pool_bwd(const float* X, const float* Hd, const float* w2, const
  * row-dot partials s_part [rows, 4] instead of Hd·w2 (packed rows only) */
 int lk_additive_pool_fwd_planes(const void* X_hi, const void* X_lo, int64_t ldx, const float* s_part, const int32_t* cu, float* out, float* alpha,
                                 int64_t N, int64_t S, int64_t D, cudaStream_t stream);
+/* dpre goes to fp32 rows (dpre) and / or straight to the split-bf16 planes the next contractions read (dpre_hi/lo, pitch ld_dpre), in which
+ * case dpre_colsum_part [N, A] (nullable) receives the per-sequence column sums of dpre (the b1 gradient, see lk_colsum_finish_multi) */
 int lk_additive_pool_bwd_planes(const void* X_hi, const void* X_lo, int64_t ldx, const float* Hd, const float* w2, const float* alpha, const int32_t* cu,
-                                const float* dOut, float* dX, float* dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A,
-                                cudaStream_t stream);
+                                const float* dOut, float* dX, float* dpre, void* dpre_hi, void* dpre_lo, int64_t ld_dpre, float* dpre_colsum_part,
+                                float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A, cudaStream_t stream);
 /* PoolingOperator on gathered embeddings — model/operators/pooling_operator.py:46-56 (mode 0 mean, 1 max) */
 int lk_masked_pool(const float* X, const int64_t* mask, float* out, int64_t N, int64_t S, int64_t D, int mode,
                    cudaStream_t stream);

@@ -61,7 +61,7 @@ SIGNATURES = {
     'lk_mha_bwd': ('ppppppppppqqqqfus', 'i'),
     'lk_additive_pool_fwd': ('pppppppqqqqs', 'i'),
     'lk_additive_pool_fwd_planes': ('ppqpppp' + 'qqqs', 'i'),
-    'lk_additive_pool_bwd_planes': ('ppqpppppppp' + 'qqqqs', 'i'),
+    'lk_additive_pool_bwd_planes': ('ppqppppppp' + 'ppqp' + 'p' + 'qqqqs', 'i'),
     'lk_additive_pool_bwd': ('pppppppppqqqqis', 'i'),
     'lk_masked_pool': ('pppqqqis', 'i'),
     'lk_masked_mean_pool_bwd': ('pppqqqs', 'i'),

@@ -109,11 +109,33 @@ __global__ void __launch_bounds__(AT) additive_pool_fwd_kernel(const RowSrc X, c
   }
 }
 
+// (hi, lo) bf16 planes of four floats (the operand format of the tcgen05 contractions, lk_tc.cuh:split4)
+__device__ __forceinline__ void split4_planes(const float4& v, uint2& hi, uint2& lo) {
+  uint32_t h01, h23, l01, l23;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h01) : "f"(v.y), "f"(v.x));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h23) : "f"(v.w), "f"(v.z));
+  const float r0 = v.x - __uint_as_float(h01 << 16), r1 = v.y - __uint_as_float(h01 & 0xffff0000u);
+  const float r2 = v.z - __uint_as_float(h23 << 16), r3 = v.w - __uint_as_float(h23 & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l01) : "f"(r1), "f"(r0));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l23) : "f"(r3), "f"(r2));
+  hi = make_uint2(h01, h23);
+  lo = make_uint2(l01, l23);
+}
+
+// Where dpre goes: fp32 rows, or directly the split-bf16 planes the next contractions read (dpre·W1 and dpreᵀ·lin) together with the
+// per-sequence column sums of dpre (the b1 gradient) — the separate split pass over dpre and the fp32 copy then never exist.
+struct DpreOut {
+  float* f32;
+  __nv_bfloat16 *hi, *lo;
+  int64_t ld;
+  float* colsum_part;            // [N, A] with planes
+};
+
 // dX[t,:] (+)= alpha[t] * dOut ;  dpre[t,:] = ds[t] * w2 * (1 - h^2) ;  dw2_part[n,:] = sum_t ds[t] * h[t,:]
 __global__ void __launch_bounds__(AT) additive_pool_bwd_kernel(const RowSrc X, const float* __restrict__ Hd,
                                                                const float* __restrict__ w2, const float* __restrict__ alpha,
                                                                const int* __restrict__ cu, const float* __restrict__ dOut,
-                                                               float* __restrict__ dX, float* __restrict__ dpre,
+                                                               float* __restrict__ dX, const DpreOut dp,
                                                                float* __restrict__ dw2_part, int Smax, int D, int A,
                                                                int accumulate_dx) {
   pdl_prologue();
@@ -122,7 +144,10 @@ __global__ void __launch_bounds__(AT) additive_pool_bwd_kernel(const RowSrc X, c
   const int64_t n = blockIdx.x;
   const int64_t r0 = cu ? cu[n] : n * Smax;
   const int S = cu ? cu[n + 1] - cu[n] : Smax;
-  Hd += r0 * A; alpha += r0; dX += r0 * D; dpre += r0 * A;
+  Hd += r0 * A; alpha += r0; dX += r0 * D;
+  float* dpre = dp.f32 ? dp.f32 + r0 * A : nullptr;
+  __nv_bfloat16* dhi = dp.hi ? dp.hi + r0 * dp.ld : nullptr;
+  __nv_bfloat16* dlo = dp.hi ? dp.lo + r0 * dp.ld : nullptr;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   for (int t = threadIdx.x; t < S; t += AT) al_s[t] = alpha[t];
   __syncthreads();
@@ -155,7 +180,7 @@ __global__ void __launch_bounds__(AT) additive_pool_bwd_kernel(const RowSrc X, c
   const ColSplit sp = col_split(A);
   for (int q0 = 0; q0 < sp.cq; q0 += AT) {
     const int q = q0 + sp.q;
-    float4 acc = f4_zero();
+    float4 acc = f4_zero(), bsum = f4_zero();
     if (sp.active && q < sp.cq) {
       const float4 wv = ldg4(w2 + q * 4);
 #pragma unroll 4
@@ -168,11 +193,22 @@ __global__ void __launch_bounds__(AT) additive_pool_bwd_kernel(const RowSrc X, c
           o.x = ds * wv.x * (1.f - h.x * h.x); o.y = ds * wv.y * (1.f - h.y * h.y);
           o.z = ds * wv.z * (1.f - h.z * h.z); o.w = ds * wv.w * (1.f - h.w * h.w);
         }
-        st4(dpre + t * (int64_t)A + q * 4, o);
+        if (dpre) st4(dpre + t * (int64_t)A + q * 4, o);
+        if (dhi) {
+          uint2 h2, l2;
+          split4_planes(o, h2, l2);
+          *reinterpret_cast<uint2*>(dhi + t * dp.ld + q * 4) = h2;
+          *reinterpret_cast<uint2*>(dlo + t * dp.ld + q * 4) = l2;
+          f4_add(bsum, o);
+        }
       }
     }
     acc = group_sum(acc, sp, red);
     if (sp.rg == 0 && sp.active && q < sp.cq) st4(dw2_part + n * (int64_t)A + q * 4, acc);
+    if (dp.colsum_part) {
+      bsum = group_sum(bsum, sp, red);
+      if (sp.rg == 0 && sp.active && q < sp.cq) st4(dp.colsum_part + n * (int64_t)A + q * 4, bsum);
+    }
   }
 }
 
@@ -238,7 +274,9 @@ static int pool_fwd(const RowSrc& X, const float* Hd, const float* s_part, const
   return check_launch("additive_pool_fwd");
 }
 static int pool_bwd(const RowSrc& X, const float* Hd, const float* w2, const float* alpha, const int32_t* cu, const float* dOut, float* dX,
-                    float* dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A, int accumulate_dx, cudaStream_t st) {
+                    const DpreOut& dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A, int accumulate_dx, cudaStream_t st) {
+  LK_REQUIRE(dpre.f32 || dpre.hi, LK_ERR_ARG, "lk_additive_pool_bwd: no destination for dpre");
+  LK_REQUIRE(!dpre.hi || (dpre.lo && dpre.ld % 4 == 0 && dpre.ld >= A), LK_ERR_ARG, "lk_additive_pool_bwd: dpre planes (both, pitch %% 4 == 0, >= A)");
   LK_REQUIRE(D % 4 == 0 && A % 4 == 0, LK_ERR_SHAPE, "lk_additive_pool_bwd: D=%ld, A=%ld must be multiples of 4", (long)D, (long)A);
   LK_REQUIRE(S <= MAXS, LK_ERR_SHAPE, "lk_additive_pool_bwd: S=%ld exceeds %d", (long)S, MAXS);
   if (N == 0) return LK_OK;
@@ -255,7 +293,8 @@ int lk_additive_pool_fwd(const float* X, const float* Hd, const float* w2, const
 int lk_additive_pool_bwd(const float* X, const float* Hd, const float* w2, const float* alpha, const int32_t* cu, const float* dOut,
                          float* dX, float* dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A, int accumulate_dx,
                          cudaStream_t st) {
-  return pool_bwd(RowSrc{X, nullptr, nullptr, 0}, Hd, w2, alpha, cu, dOut, dX, dpre, dw2_part, N, S, D, A, accumulate_dx, st);
+  return pool_bwd(RowSrc{X, nullptr, nullptr, 0}, Hd, w2, alpha, cu, dOut, dX, DpreOut{dpre, nullptr, nullptr, 0, nullptr}, dw2_part, N, S, D, A,
+                  accumulate_dx, st);
 }
 
 int lk_additive_pool_fwd_planes(const void* X_hi, const void* X_lo, int64_t ldx, const float* s_part, const int32_t* cu, float* out, float* alpha,
@@ -266,11 +305,12 @@ int lk_additive_pool_fwd_planes(const void* X_hi, const void* X_lo, int64_t ldx,
 }
 
 int lk_additive_pool_bwd_planes(const void* X_hi, const void* X_lo, int64_t ldx, const float* Hd, const float* w2, const float* alpha, const int32_t* cu,
-                                const float* dOut, float* dX, float* dpre, float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A,
-                                cudaStream_t st) {
+                                const float* dOut, float* dX, float* dpre, void* dpre_hi, void* dpre_lo, int64_t ld_dpre, float* dpre_colsum_part,
+                                float* dw2_part, int64_t N, int64_t S, int64_t D, int64_t A, cudaStream_t st) {
   LK_REQUIRE(X_hi && X_lo && ldx % 4 == 0 && ldx >= D && cu, LK_ERR_ARG, "lk_additive_pool_bwd_planes: packed rows as planes");
-  return pool_bwd(RowSrc{nullptr, (const __nv_bfloat16*)X_hi, (const __nv_bfloat16*)X_lo, ldx}, Hd, w2, alpha, cu, dOut, dX, dpre, dw2_part, N, S, D, A, 0,
-                  st);
+  LK_REQUIRE(!dpre_colsum_part || dpre_hi, LK_ERR_ARG, "lk_additive_pool_bwd_planes: the column-sum partials ride on the plane output");
+  return pool_bwd(RowSrc{nullptr, (const __nv_bfloat16*)X_hi, (const __nv_bfloat16*)X_lo, ldx}, Hd, w2, alpha, cu, dOut, dX,
+                  DpreOut{dpre, (__nv_bfloat16*)dpre_hi, (__nv_bfloat16*)dpre_lo, ld_dpre, dpre_colsum_part}, dw2_part, N, S, D, A, 0, st);
 }
 
 int lk_masked_pool(const float* X, const int64_t* mask, float* out, int64_t N, int64_t S, int64_t D, int mode, cudaStream_t st) {

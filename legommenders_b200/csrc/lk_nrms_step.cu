@@ -240,7 +240,7 @@ struct EncPartials { float *dw2p, *b1p, *linbp, *outbp, *binp; };
 static EncPartials alloc_partials(Ctx& c, int64_t T, int64_t N, int64_t D, int64_t A) {
   EncPartials q;
   q.dw2p = c.a.f32(N * A);                          // per-sequence partials of dw2
-  q.b1p = c.a.f32(split_colsum_parts(T) * A);
+  q.b1p = c.a.f32((split_colsum_parts(T) > N ? split_colsum_parts(T) : N) * A);     // per-sequence (chained) or per-64-row-block partials
   q.linbp = c.a.f32(gemm_colsum_parts(T) * D);
   q.outbp = c.a.f32(gemm_colsum_parts(T) * D);
   q.binp = c.a.f32(N * 3 * D);                      // per-sequence column sums of dqkv
@@ -252,13 +252,19 @@ static void enc_bwd(Ctx& c, const EncSaved& s, const EncWeights& w, const EncPla
   const int64_t T = s.T, N = s.N;
   const size_t mark = c.a.off;
   float* dlin = c.a.f32(T * D);
-  float* dpre = c.a.f32(T * A);
-  if (s.chained) STEP(lk_additive_pool_bwd_planes(s.linp.hi, s.linp.lo, s.linp.ld, s.hid, w.w2, s.alpha, s.cu, drep, dlin, dpre, q.dw2p, N, s.S, D, A, c.st));
-  else STEP(lk_additive_pool_bwd(s.lin, s.hid, w.w2, s.alpha, s.cu, drep, dlin, dpre, q.dw2p, N, s.S, D, A, 0, c.st));
-  defer_colsum(c, q.dw2p, w.g_w2, N, A, A);
   PlaneBuf dprep = alloc_planes(c, T, A);
-  STEP(lk_split_bf16_partial(dpre, T, A, A, dprep.hi, dprep.lo, dprep.ld, q.b1p, c.st));
-  defer_colsum(c, q.b1p, w.g_b1, split_colsum_parts(T), A, A);
+  if (s.chained) {
+    // dpre leaves the pooling backward as operand planes + per-sequence column sums: no fp32 dpre, no split pass
+    STEP(lk_additive_pool_bwd_planes(s.linp.hi, s.linp.lo, s.linp.ld, s.hid, w.w2, s.alpha, s.cu, drep, dlin, nullptr, dprep.hi, dprep.lo, dprep.ld,
+                                     q.b1p, q.dw2p, N, s.S, D, A, c.st));
+    defer_colsum(c, q.b1p, w.g_b1, N, A, A);
+  } else {
+    float* dpre = c.a.f32(T * A);
+    STEP(lk_additive_pool_bwd(s.lin, s.hid, w.w2, s.alpha, s.cu, drep, dlin, dpre, q.dw2p, N, s.S, D, A, 0, c.st));
+    STEP(lk_split_bf16_partial(dpre, T, A, A, dprep.hi, dprep.lo, dprep.ld, q.b1p, c.st));
+    defer_colsum(c, q.b1p, w.g_b1, split_colsum_parts(T), A, A);
+  }
+  defer_colsum(c, q.dw2p, w.g_w2, N, A, A);
   gemm_wgrad(c, dprep, s.linp, w.g_w1, T, A, D, side);
   if (s.chained) {
     // dpre -> dlin (= alpha*drep + dpre·W1) -> dout -> dctx in one kernel; the two intermediate tiles leave only as the planes the weight

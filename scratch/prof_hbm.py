@@ -54,6 +54,6 @@ rep = torch.empty(N, D, device=dev); alpha = torch.empty(T, device=dev)
 drep = torch.randn(N, D, generator=g).to(dev); dlin = torch.empty(T, D, device=dev); dpre = torch.empty(T, D, device=dev); dw2p = torch.empty(N, D, device=dev)
 for _ in range(2):
     cold(); call('lk_additive_pool_fwd_planes', ptr(P.hi), ptr(P.lo), P.ld, ptr(sp), ptr(cu), ptr(rep), ptr(alpha), N, 40, D)
-    cold(); call('lk_additive_pool_bwd_planes', ptr(P.hi), ptr(P.lo), P.ld, ptr(hid), ptr(w2), ptr(alpha), ptr(cu), ptr(drep), ptr(dlin), ptr(dpre), ptr(dw2p), N, 40, D, D)
+    cold(); call('lk_additive_pool_bwd_planes', ptr(P.hi), ptr(P.lo), P.ld, ptr(hid), ptr(w2), ptr(alpha), ptr(cu), ptr(drep), ptr(dlin), ptr(dpre), None, None, 0, None, ptr(dw2p), N, 40, D, D)
 torch.cuda.synchronize()
 print('done')
