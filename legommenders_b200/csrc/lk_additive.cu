@@ -55,7 +55,8 @@ __device__ __forceinline__ float4 load4(const RowSrc& X, int64_t row, int D, int
                      __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16), __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u));
 }
 
-__global__ void __launch_bounds__(AT) additive_pool_fwd_kernel(const RowSrc X, const float* __restrict__ Hd, const float* __restrict__ s_part,
+template <int OCC>
+__global__ void __launch_bounds__(AT, OCC) additive_pool_fwd_kernel(const RowSrc X, const float* __restrict__ Hd, const float* __restrict__ s_part,
                                                                const float* __restrict__ w2, const int64_t* __restrict__ mask,
                                                                const int* __restrict__ cu, float* __restrict__ out,
                                                                float* __restrict__ alpha, int Smax, int D, int A) {
@@ -132,7 +133,8 @@ struct DpreOut {
 };
 
 // dX[t,:] (+)= alpha[t] * dOut ;  dpre[t,:] = ds[t] * w2 * (1 - h^2) ;  dw2_part[n,:] = sum_t ds[t] * h[t,:]
-__global__ void __launch_bounds__(AT) additive_pool_bwd_kernel(const RowSrc X, const float* __restrict__ Hd,
+template <int OCC>
+__global__ void __launch_bounds__(AT, OCC) additive_pool_bwd_kernel(const RowSrc X, const float* __restrict__ Hd,
                                                                const float* __restrict__ w2, const float* __restrict__ alpha,
                                                                const int* __restrict__ cu, const float* __restrict__ dOut,
                                                                float* __restrict__ dX, const DpreOut dp,
@@ -264,13 +266,20 @@ using namespace lk;
 
 extern "C" {
 
+// 8 CTAs per SM (32 registers) instead of 4: these kernels wait on memory between block barriers, more resident sequences hide it
+static bool pool_occ8() {
+  static const bool v = !(getenv("LK_POOL_OCC") && atoi(getenv("LK_POOL_OCC")) == 4);
+  return v;
+}
+
 static int pool_fwd(const RowSrc& X, const float* Hd, const float* s_part, const float* w2, const int64_t* mask, const int32_t* cu, float* out,
                     float* alpha, int64_t N, int64_t S, int64_t D, int64_t A, cudaStream_t st) {
   LK_REQUIRE(D % 4 == 0 && A % 4 == 0, LK_ERR_SHAPE, "lk_additive_pool_fwd: D=%ld, A=%ld must be multiples of 4", (long)D, (long)A);
   LK_REQUIRE(S <= MAXS, LK_ERR_SHAPE, "lk_additive_pool_fwd: S=%ld exceeds %d", (long)S, MAXS);
   LK_REQUIRE(Hd || s_part, LK_ERR_ARG, "lk_additive_pool_fwd: needs the hidden rows or their w2 row dots");
   if (N == 0) return LK_OK;
-  LK_LAUNCH((additive_pool_fwd_kernel), (unsigned)N, AT, 0, st, X, Hd, s_part, w2, mask, cu, out, alpha, (int)S, (int)D, (int)A);
+  if (pool_occ8()) LK_LAUNCH((additive_pool_fwd_kernel<8>), (unsigned)N, AT, 0, st, X, Hd, s_part, w2, mask, cu, out, alpha, (int)S, (int)D, (int)A);
+  else LK_LAUNCH((additive_pool_fwd_kernel<4>), (unsigned)N, AT, 0, st, X, Hd, s_part, w2, mask, cu, out, alpha, (int)S, (int)D, (int)A);
   return check_launch("additive_pool_fwd");
 }
 static int pool_bwd(const RowSrc& X, const float* Hd, const float* w2, const float* alpha, const int32_t* cu, const float* dOut, float* dX,
@@ -280,8 +289,10 @@ static int pool_bwd(const RowSrc& X, const float* Hd, const float* w2, const flo
   LK_REQUIRE(D % 4 == 0 && A % 4 == 0, LK_ERR_SHAPE, "lk_additive_pool_bwd: D=%ld, A=%ld must be multiples of 4", (long)D, (long)A);
   LK_REQUIRE(S <= MAXS, LK_ERR_SHAPE, "lk_additive_pool_bwd: S=%ld exceeds %d", (long)S, MAXS);
   if (N == 0) return LK_OK;
-  LK_LAUNCH((additive_pool_bwd_kernel), (unsigned)N, AT, 0, st, X, Hd, w2, alpha, cu, dOut, dX, dpre, dw2_part, (int)S, (int)D, (int)A,
-                                                      accumulate_dx);
+  if (pool_occ8())
+    LK_LAUNCH((additive_pool_bwd_kernel<8>), (unsigned)N, AT, 0, st, X, Hd, w2, alpha, cu, dOut, dX, dpre, dw2_part, (int)S, (int)D, (int)A, accumulate_dx);
+  else
+    LK_LAUNCH((additive_pool_bwd_kernel<4>), (unsigned)N, AT, 0, st, X, Hd, w2, alpha, cu, dOut, dX, dpre, dw2_part, (int)S, (int)D, (int)A, accumulate_dx);
   return check_launch("additive_pool_bwd");
 }
 
