@@ -108,8 +108,9 @@ int lk_resample_reference(uint64_t seed, int64_t row, int64_t pos, const int64_t
 /* backward of the whole ConcatInputer embedding stage (concat_inputer.py:105-113 + embedding_hub.py:95-96) in one pass over
  * dx [T,D]:  dP = dx·dropout(seed)·(title id > -1) as split-bf16 planes [T, ld] (operand of the projection weight gradient),
  * g_bias [D] = column sums of dP, g_cat [n_cats, D] / g_special [n_special, D] = per-id sums of dx.  Deterministic.
- * With all three gradient pointers null the per-block partials [ceil(T/128), (1+n_cats+n_special)*D] stay in `workspace`
+ * With all three gradient pointers null the per-block partials [lk_concat_embed_bwd_blocks(T), (1+n_cats+n_special)*D] stay in `workspace`
  * (row layout: bias | categories | special tokens) for a later lk_colsum_finish_multi. */
+int64_t lk_concat_embed_bwd_blocks(int64_t T);
 size_t lk_concat_embed_bwd_workspace_bytes(int64_t T, int64_t D, int64_t n_cats, int64_t n_special);
 int lk_concat_embed_bwd(const float* dx, const int64_t* title_ids, const int64_t* cat_ids, const int64_t* special_ids, int64_t T,
                         int64_t D, int64_t n_cats, int64_t n_special, float drop_p, uint64_t seed, void* dp_hi, void* dp_lo, int64_t ld,

@@ -33,6 +33,7 @@ SIGNATURES = {
     'lk_scatter_add_workspace_bytes': ('qqq', 'z'),
     'lk_scatter_add_sorted': ('ppppqpqqqipzs', 'i'),
     'lk_pack_item_tokens': ('ppippqqs', 'i'),
+    'lk_concat_embed_bwd_blocks': ('q', 'q'),
     'lk_concat_embed_bwd_workspace_bytes': ('qqqq', 'z'),
     'lk_concat_embed_bwd': ('ppppqqqqfuppqppppzs', 'i'),
     'lk_linear_fwd': ('pppppqqqiifus', 'i'),

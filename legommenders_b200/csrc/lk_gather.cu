@@ -272,18 +272,25 @@ static size_t small_ws_bytes(int64_t P, int64_t V, int64_t E) { return (size_t)(
 //   x[t] = valid(title[t]) · dropout(W·glove[title[t]] + b) + cat_table[cat[t]] + special_table[sp[t]]
 //   => dP[t]   = dx[t] · dropout · valid     -> split-bf16 planes (operand of the projection's weight gradient) + column sums (db)
 //      dcat[c] = Σ_{t: cat[t]=c} dx[t],   dspecial likewise              (deterministic: block partials, fixed-order finish)
-// A block owns EB_ROWS consecutive rows; EB_LANES row-lanes walk them in order with private shared accumulators.
+// A block owns eb_rows(T) consecutive rows; EB_LANES row-lanes walk them in order with private shared accumulators.  The rows per block
+// are chosen so that the grid is ONE balanced wave of the 2 blocks per SM the shared accumulators allow (128-row blocks at T = 42.6 k
+// were 333 blocks on 296 slots: a full second wave for 37 blocks).
 // ------------------------------------------------------------------------------------------------
-constexpr int EB_ROWS = 128, EB_LANES = 4;
+constexpr int EB_MAX_ROWS = 512, EB_MIN_ROWS = 32, EB_LANES = 4;
+static int eb_rows(int64_t T) {
+  int64_t r = (T + 2 * kNumSMs - 1) / (2 * kNumSMs);
+  r = (r + EB_LANES - 1) / EB_LANES * EB_LANES;
+  return (int)(r < EB_MIN_ROWS ? EB_MIN_ROWS : r > EB_MAX_ROWS ? EB_MAX_ROWS : r);
+}
 
 __global__ void __launch_bounds__(256) concat_embed_bwd_kernel(const float* __restrict__ dx, const int64_t* __restrict__ title,
                                                                const int64_t* __restrict__ cat, const int64_t* __restrict__ special,
                                                                int64_t T, int D, int Vc, int Vs, float drop_p, unsigned long long seed,
                                                                __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld,
-                                                               float* __restrict__ part) {
+                                                               float* __restrict__ part, int EB_ROWS) {
   pdl_prologue();
   extern __shared__ __align__(16) float sm[];           // [EB_LANES][1 + Vc + Vs][D]
-  __shared__ int s_title[EB_ROWS], s_cat[EB_ROWS], s_sp[EB_ROWS];
+  __shared__ int s_title[EB_MAX_ROWS], s_cat[EB_MAX_ROWS], s_sp[EB_MAX_ROWS];
   const int D4 = D >> 2, NT = 1 + Vc + Vs;
   const int cols = blockDim.x / EB_LANES;
   const int rl = threadIdx.x / cols, ct = threadIdx.x - rl * cols;
@@ -470,8 +477,10 @@ int lk_pack_item_tokens(const int64_t* const* tables, int64_t* const* outs, int 
   return check_launch("pack_item_tokens");
 }
 
+int64_t lk_concat_embed_bwd_blocks(int64_t T) { return T > 0 ? (T + eb_rows(T) - 1) / eb_rows(T) : 0; }
+
 size_t lk_concat_embed_bwd_workspace_bytes(int64_t T, int64_t D, int64_t n_cats, int64_t n_special) {
-  return (size_t)((T + EB_ROWS - 1) / EB_ROWS) * (1 + n_cats + n_special) * D * sizeof(float) + 256;
+  return (size_t)lk_concat_embed_bwd_blocks(T) * (1 + n_cats + n_special) * D * sizeof(float) + 256;
 }
 
 int lk_concat_embed_bwd(const float* dx, const int64_t* title_ids, const int64_t* cat_ids, const int64_t* special_ids, int64_t T,
@@ -483,13 +492,13 @@ int lk_concat_embed_bwd(const float* dx, const int64_t* title_ids, const int64_t
   LK_REQUIRE(smem <= 200 * 1024, LK_ERR_SHAPE, "lk_concat_embed_bwd: tables with %d rows do not fit the shared accumulators", NT - 1);
   LK_REQUIRE(workspace && workspace_bytes >= lk_concat_embed_bwd_workspace_bytes(T, D, n_cats, n_special), LK_ERR_ARG,
              "lk_concat_embed_bwd: workspace too small");
-  const int nblk = (int)((T + EB_ROWS - 1) / EB_ROWS);
+  const int nblk = (int)lk_concat_embed_bwd_blocks(T);
   if (T > 0) {
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(concat_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
     LK_LAUNCH((concat_embed_bwd_kernel), nblk, 256, smem, st, dx, title_ids, cat_ids, special_ids, T, (int)D, (int)n_cats, (int)n_special, drop_p,
                                                      (unsigned long long)seed, (__nv_bfloat16*)dp_hi, (__nv_bfloat16*)dp_lo, (int)ld,
-                                                     (float*)workspace);
+                                                     (float*)workspace, eb_rows(T));
   }
   if (!g_bias && !g_cat && !g_special) return check_launch("concat_embed_bwd");   // deferred: the caller reduces workspace[nblk, NT*D] itself
   const float* part = (const float*)workspace;

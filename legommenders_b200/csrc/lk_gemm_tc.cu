@@ -508,6 +508,14 @@ __global__ void __launch_bounds__(1024) colsum_finish_multi_kernel(const ColsumJ
     float s0 = 0.f, s1 = 0.f;
     if (c < j.cols) {
       int64_t i = pl;
+      // eight independent loads in flight per lane: the per-sequence partials (thousands of rows) made this loop a chain of exposed
+      // memory latencies with two
+      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (; i + 224 < j.nparts; i += 256) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) a[u] += __ldg(j.part + (i + 32 * u) * j.stride + c);
+      }
+      s0 = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
       for (; i + 32 < j.nparts; i += 64) { s0 += j.part[i * j.stride + c]; s1 += j.part[(i + 32) * j.stride + c]; }
       if (i < j.nparts) s0 += j.part[i * j.stride + c];
     }

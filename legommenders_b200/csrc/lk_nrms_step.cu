@@ -440,7 +440,7 @@ static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const 
   STEP(lk_concat_embed_bwd(dx, title_ids, cat_ids, special_ids, T, D, n_cats, n_special, drop_embed, s_embed, dpp.hi, dpp.lo, dpp.ld, nullptr,
                            nullptr, nullptr, ebp, eb_bytes, st));
   {
-    const int64_t nblk = (T + 127) / 128, stride = (1 + n_cats + n_special) * D;
+    const int64_t nblk = lk_concat_embed_bwd_blocks(T), stride = (1 + n_cats + n_special) * D;
     defer_colsum(c, ebp, G(1), nblk, D, stride);
     defer_colsum(c, ebp + D, G(2), nblk, n_cats * D, stride);
     defer_colsum(c, ebp + (1 + n_cats) * D, G(3), nblk, n_special * D, stride);
