@@ -344,6 +344,7 @@ int lk_masked_mean_pool_bwd(const float* dOut, const int64_t* mask, float* dX, i
 int lk_dot_scores(const float* U, const float* V, float* scores, int64_t B, int64_t C, int64_t D, cudaStream_t stream);
 int lk_dot_ce_fwd(const float* U, const float* V, float* scores, float* probs, float* rowloss, float* loss, int64_t B,
                   int64_t C, int64_t D, cudaStream_t stream);
+/* dloss: device scalar (the gradient of the mean loss), or NULL for 1 */
 int lk_dot_ce_bwd(const float* U, const float* V, const float* probs, const float* dloss, float* dU, float* dV, int64_t B,
                   int64_t C, int64_t D, cudaStream_t stream);
 int lk_dot_bwd(const float* U, const float* V, const float* dS, float* dU, float* dV, int64_t B, int64_t C, int64_t D,

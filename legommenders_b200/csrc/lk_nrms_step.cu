@@ -423,11 +423,9 @@ static int nrms_run(bool dry, size_t* high_out, const int64_t* title_ids, const 
   STEP(lk_dot_ce_fwd(su.rep, si.rep, scores, probs, rowloss, loss_out, B, C, D, st));
 
   // ---- backward ---------------------------------------------------------------------------------------------------------
-  float* one = c.a.f32(1);
-  STEP(lk_fill_f32(one, 1.0f, 1, st));
   float* drep = c.a.f32(n_items * D);
   float* duser = c.a.f32(B * D);
-  STEP(lk_dot_ce_bwd(su.rep, si.rep, probs, one, duser, drep, B, C, D, st));          // dV -> drep[0 : B*C]
+  STEP(lk_dot_ce_bwd(su.rep, si.rep, probs, nullptr /* dloss = 1 */, duser, drep, B, C, D, st));          // dV -> drep[0 : B*C]
   const EncPartials qu = alloc_partials(c, Tu, B, D, A), qi = alloc_partials(c, T, n_items, D, A);
   const size_t eb_bytes = lk_concat_embed_bwd_workspace_bytes(T, D, n_cats, n_special);
   float* ebp = (float*)c.a.take(eb_bytes);                                               // per-block partials of the embedding-stage gradients

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(SW * 32) dot_ce_bwd_kernel(const float* __rest
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * SW + (threadIdx.x >> 5);
   if (b >= B) return;
-  const float gs = dloss[0] / (float)B;
+  const float gs = (dloss ? dloss[0] : 1.f) / (float)B;
   const float* u = U + b * (int64_t)D;
   for (int d = lane * 4; d < D; d += 128) {
     const float4 uv = ldg4(u + d);
