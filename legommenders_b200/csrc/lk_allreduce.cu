@@ -1,9 +1,10 @@
 // Gradient all-reduce over NVLink peer memory (data-parallel training): the flat gradient bucket of every rank lives in symmetric
-// memory (peer-mapped over NVSwitch); one kernel per rank reduces ITS 1/W slice by reading that slice from all W buffers (fixed order
-// 0..W-1: every element is summed once, by one rank, so all ranks end up with bit-identical gradients) and writes the sum back into all W
-// buffers.  3.5 MB on 8 GPUs: 3 MB in and 3 MB out per rank over NVLink instead of a ring / tree of NCCL steps (measured 63-71 us per step for
-// ncclAllReduce at this size, profiles/r2_05).  The caller brackets the kernel with two cross-rank barriers (gradients ready / sums visible);
-// they are the symmetric-memory handle's device-side barriers, enqueued on the same stream.
+// memory (peer-mapped over NVSwitch, plus the switch's multicast mapping).  One kernel per rank reduces ITS 1/W slice — in the switch
+// (multimem.ld_reduce over the W replicas) or by reading the slice from all W buffers in rank order — and writes the sum into all W buffers
+// (multimem.st, or W peer stores).  Every element is summed once, by one rank, so all ranks end up with bit-identical gradients.
+// The two cross-rank rendezvous (gradients ready / sums visible) are flag words in symmetric memory polled inside the same launch
+// (allreduce_fused_kernel); with flag_ptrs == NULL the caller brackets the plain slice kernel with its own barriers instead.
+// 3.49 MB on 8 GPUs: 23.4 us (multicast) / 29.5 us (peer loads) against 50.6 us for ncclAllReduce, profiles/r2_05_allreduce.md.
 #include "lk_common.cuh"
 #include "../../include/legommenders_b200.h"
 
